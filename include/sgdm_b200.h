@@ -1,0 +1,144 @@
+/* sgdm_b200.h — C ABI of libsgdm_b200.so (sm_100a).
+ *
+ * The drop-in boundary of the guided reverse-diffusion hot path.  Everything crossing it
+ * is a plain pointer, size or scalar: no torch types, no C++ types, no exceptions.  All
+ * device pointers are CUDA device memory of the current device; `stream` is a
+ * cudaStream_t passed as void* (the host passes torch.cuda.current_stream().cuda_stream).
+ * Every function returns 0 on success and non-zero on failure; sgdm_last_error() then
+ * returns a message.  No function synchronises the device or the stream.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   sgdm_create / sgdm_load_param   UNetModel.__init__ + load_state_dict
+ *                                   (dynamic/diffusionmodules/openaimodel.py:496-835,
+ *                                    openaimodel_ca.py:479-836)
+ *   sgdm_forward                    UNetModel.forward (openaimodel.py:904-956,
+ *                                    openaimodel_ca.py:917-1033)
+ *   sgdm_forward_guided + sgdm_mix  UNetModel.forward_with_cond_scale + get_guided_score
+ *                                   (openaimodel.py:853-902, openaimodel_ca.py:871-915)
+ *   sgdm_ddim_step                  DDIMSampler.p_sample_ddim / p_sample_plms
+ *                                   (diffusion/sampler/ddim_plms_sampler.py:345-391,482-525)
+ *   sgdm_ddpm_step                  Schedule_DDPM.p_mean_variance + p_sample
+ *                                   (diffusion/sampler/ddpm_sampler.py:154-192)
+ *   sgdm_to_uint8                   clip_unnormalize_to_zero_to_255 (diffusion_utils/util.py:99-100)
+ *   sgdm_k_*                        single-kernel entry points used by the unit parity tests
+ */
+#ifndef SGDM_B200_H
+#define SGDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgdm_engine* sgdm_handle;
+
+#define SGDM_KIND_UNET_FAST 0   /* dynamic.diffusionmodules.openaimodel.UNetModel    */
+#define SGDM_KIND_UNETCA_FAST 1 /* dynamic.diffusionmodules.openaimodel_ca.UNetModel */
+#define SGDM_SCALE_IMAGEN 0
+#define SGDM_SCALE_CFG 1
+
+typedef struct sgdm_config {
+  int32_t kind;
+  int32_t image_size, in_channels, out_channels, model_channels, num_res_blocks;
+  int32_t n_channel_mult;
+  int32_t channel_mult[8];
+  int32_t n_attention_resolutions;
+  int32_t attention_resolutions[8];
+  int32_t num_heads;
+  int32_t resblock_updown;
+  int32_t cond_dim;
+  int32_t layout_dim;     /* 0 | clusterlayout: 1 | stegoclusterlayout: 27 */
+  int32_t context_dim;    /* unetca_fast: 32 */
+  int32_t cond_token_num; /* unetca_fast: 1 */
+} sgdm_config;
+
+const char* sgdm_last_error(void);
+const char* sgdm_version(void);
+/* "f16" (default build) or "bf16": the 16-bit GEMM operand type; accumulation is fp32 */
+const char* sgdm_operand_dtype(void);
+
+/* Host-only: builds the layer list and the parameter inventory. No CUDA call is made. */
+int sgdm_create(const sgdm_config* cfg, sgdm_handle* out);
+int sgdm_destroy(sgdm_handle h);
+
+/* Parameter inventory == the reference module's state_dict (same names, same shapes). */
+int sgdm_param_count(sgdm_handle h);
+const char* sgdm_param_name(sgdm_handle h, int i);
+int sgdm_param_shape(sgdm_handle h, int i, int64_t* dims /* >= 4 */, int* ndim);
+
+/* Copies / packs one fp32 parameter (device pointer, contiguous) into the engine.
+ * The engine never keeps `data`; call again after the parameter changes (EMA swap). */
+int sgdm_load_param(sgdm_handle h, const char* name, const float* data, const int64_t* shape, int ndim,
+                    void* stream);
+/* Number of parameters not loaded yet (0 = ready). */
+int sgdm_params_missing(sgdm_handle h);
+/* freqs[i] = exp(-ln(10000) * i / half), i < model_channels/2, computed by the host with the
+ * reference's own fp32 expression (dynamic/diffusionmodules/util.py:160-163). Host pointer. */
+int sgdm_set_timestep_freqs(sgdm_handle h, const float* host_freqs, int n);
+
+/* eps = UNet(x, t, cond, layout) with a per-sample drop mask (1 = use the null embeddings).
+ *   x [B, C, H, W] fp32 NCHW | t [B] int64 | cond [B, cond_dim] fp32 or NULL |
+ *   layout [B, L, H, W] fp32 or NULL | drop [B] uint8 or NULL (= keep all) | eps_out [B, C, H, W] fp32 */
+int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
+                 const float* layout, const uint8_t* drop, int B, float* eps_out);
+
+/* Conditional and unconditional passes as ONE batched launch sequence (rows [0,B) keep
+ * the condition, rows [B,2B) use the null embeddings).  Writes the engine-owned result
+ * pointers (valid until the next forward on this handle): eps_c, eps_u [B, C, H, W] fp32. */
+int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
+                        const float* layout, int B, const float** eps_c, const float** eps_u);
+
+/* eps = (1-w) eps_u + w eps_c (imagen) | (1+w) eps_c - w eps_u (cfg); w scalar, or per sample
+ * when w_per_sample != NULL ([B] fp32 device). */
+int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+             int scale_type, float* eps_out, int B, int64_t per_sample);
+
+/* One DDIM / PLMS update, optionally fused with the guidance mix (eps_u may be NULL: eps = eps_c).
+ * coef = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma_t, temperature}. */
+int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+                   int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                   float* x_out, float* x0_out /* may be NULL */, float* eps_out /* may be NULL */, int B,
+                   int64_t per_sample);
+/* One ancestral DDPM update. coef = {sqrt_recip_ac[t], sqrt_recipm1_ac[t], post_mean_coef1[t],
+ * post_mean_coef2[t], (t!=0)*exp(0.5*post_logvar[t]), temperature}. */
+int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+                   int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                   float* x_out, float* x0_out /* may be NULL */, int B, int64_t per_sample);
+/* PLMS multistep eps combination (ddim_plms_sampler.py:432-459): out = (sum_k coefs[k]*terms[k]) / div,
+ * n_terms <= 4; `terms` and `coefs` are HOST arrays (of device pointers / floats). */
+int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const float* coefs, float div, float* out,
+                 int64_t n);
+int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
+
+/* Count of kernels launched by this library since load (claim for bench.py `gpu_launches`). */
+int64_t sgdm_launch_count(void);
+/* bring-up switch: 1 routes every conv through the CUDA-core checker kernel (tests only) */
+int sgdm_debug_set_naive_conv(int on);
+
+/* ---- single-kernel entry points (unit parity tests). 16-bit tensors are `op` = fp16 (or bf16). ---- */
+/* conv / GEMM: in [B,Hin,Win,Cin] op NHWC; in2 optional [B,Hout,Wout,C2]; w packed [Npad][ks*ks*Cin + C2] op */
+int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, const void* in2, int C2,
+                const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
+                const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
+                int naive);
+/* packs a torch conv weight [Cout,Cin,ks,ks] fp32 into dst[co][k_off + tap*cin_pad + ci] (row length ktot) */
+int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad,
+                       int ktot, int k_off);
+int sgdm_k_groupnorm(void* stream, const float* src0, const float* src1, int B, int H, int W, int C0, int C1,
+                     const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
+                     int resample, void* out_op, void* raw_out_op, float* pool_out);
+int sgdm_k_layernorm(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
+                     void* out_op, float* out_f32, int64_t rows, int C);
+int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_head_stride, const void* k,
+                     int64_t k_row_stride, int k_head_stride, const void* v, int64_t v_row_stride,
+                     int v_head_stride, const void* k_extra, const void* v_extra, int n_extra, void* out,
+                     int64_t o_row_stride, int B, int T, int heads, int D, float scale);
+int sgdm_k_linear_f32(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
+                      float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate);
+int sgdm_k_cast(void* stream, const float* src, void* dst_op, int B, int H, int W, int C, int up2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGDM_B200_H */

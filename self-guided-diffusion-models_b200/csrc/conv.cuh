@@ -1,0 +1,71 @@
+// Implicit-GEMM convolution / GEMM on tcgen05 (sm_100a): host-side description.
+//
+// Replaces the reference's nn.Conv2d 3x3 (s1/s2, pad 1), nn.Conv2d 1x1, nn.Conv1d(k=1)
+// and nn.Linear call sites (dynamic/diffusionmodules/openaimodel.py:245-287,349-357,
+// openaimodel_ca.py:101-181, crossattetion_lr.py:70-79) — SURVEY.md §2.3 rows K3/K4.
+//
+//   D[M = B*Hout*Wout, N = Cout] = sum over K-blocks of A[M, 64] * W[N, 64]^T
+//   K-blocks = (tap r,s) x (64-channel chunk of the NHWC source)  [+ 1x1 chunks of a
+//   second "skip" source accumulated into the same TMEM tile: fused skip_connection]
+//
+// A tiles are fetched with 4-D tiled TMA boxes (64ch, bw, bh, bn) at coordinates shifted
+// by the tap offset; out-of-bounds pixels are zero-filled by TMA, which implements the
+// conv padding for free (no im2col buffer).  Stride-2 convs use TMA elementStrides.
+#pragma once
+#include "common.cuh"
+
+namespace sgdm {
+
+struct ConvDesc {
+  // main source: NHWC op_t [B, Hin, Win, Cin], Cin % 64 == 0
+  const op_t* in = nullptr;
+  int B = 0, Hin = 0, Win = 0, Cin = 0;
+  // optional 1x1 skip source at OUTPUT resolution: NHWC op_t [B, Hout, Wout, C2], C2 % 64 == 0
+  const op_t* in2 = nullptr;
+  int C2 = 0;
+  // packed weights: op_t [Npad][Ktot], Ktot = ks*ks*Cin + C2, K order = (tap, cin) then skip cin
+  const op_t* w = nullptr;
+  int ks = 3, stride = 1, pad = 1;
+  int Hout = 0, Wout = 0, Cout = 0;
+  // epilogue
+  const float* bias = nullptr;  // [Cout]
+  const float* res = nullptr;   // fp32 NHWC residual, see res_mode
+  int res_mode = 0;             // 0 none | 1 same shape | 2 nearest-2x upsampled source [B,Hout/2,Wout/2,Cout]
+  float* out_f32 = nullptr;     // NHWC fp32 [B,Hout,Wout,Cout]
+  op_t* out_op = nullptr;       // NHWC op_t
+  float* out_nchw = nullptr;    // NCHW fp32 [B,Cout,Hout,Wout] (final conv, Cout = 3)
+  int block_n = 128;            // 16 or a multiple of 32, <= 256; Npad = roundup(Cout, block_n)
+};
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap tmA;
+  CUtensorMap tmA2;
+  CUtensorMap tmB;
+  int M_total, HW, Wout, Hout;
+  int stride, pad, ks, taps;
+  int kc1, kc2;
+  int N_total, block_n, n_tiles, m_tiles;
+  const float* bias;
+  const float* res;
+  int res_mode;
+  float* out_f32;
+  op_t* out_op;
+  float* out_nchw;
+};
+
+struct ConvLaunch {
+  ConvKernelParams p;
+  int grid = 0;
+  ConvDesc desc;  // kept for the naive checker path
+};
+
+// Builds the TMA descriptors and launch geometry.  Returns 0 on success; on failure
+// writes a message into err (size errlen).
+int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen);
+int conv_launch(const ConvLaunch& l, cudaStream_t stream);
+// CUDA-core checker with identical semantics (test / bring-up only; never on the product path).
+int conv_launch_naive(const ConvDesc& d, cudaStream_t stream);
+
+inline int conv_npad(int cout, int block_n) { return (cout + block_n - 1) / block_n * block_n; }
+
+}  // namespace sgdm

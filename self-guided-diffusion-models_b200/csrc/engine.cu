@@ -1,0 +1,1180 @@
+// Engine: layer list, parameter inventory / packing, per-batch launch plan, C ABI.
+//
+// The host side mirrors the reference constructors (openaimodel.py:634-835,
+// openaimodel_ca.py:645-836) to derive (a) the parameter inventory — identical to the
+// reference module's state_dict — and (b) a static launch plan per batch size: an ordered
+// list of kernel launches over engine-owned workspace.  A forward is then a replay of that
+// list on the caller's stream (no allocation, no host sync, no Python in the loop).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/sgdm_b200.h"
+#include "attn.cuh"
+#include "conv.cuh"
+#include "kernels.cuh"
+
+using namespace sgdm;
+
+static thread_local char g_err[1024] = "";
+static int64_t g_launches = 0;
+static int g_naive_conv = 0;
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CUDA_TRY(x)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+typedef std::function<int(cudaStream_t)> Op;
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::function<int(const float*, cudaStream_t)> load;  // null: accepted and ignored (unused by forward)
+  bool loaded = false;
+};
+
+struct ResW {
+  int cin = 0, cout = 0;
+  bool up = false, down = false, skip = false;
+  float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
+  float *b1 = nullptr, *b2 = nullptr, *bskip = nullptr, *bfused = nullptr;
+  op_t *w1 = nullptr, *w2 = nullptr;
+  int emb_off = 0;
+};
+struct AttnW {  // AttentionBlock
+  int ch = 0;
+  float *norm_w = nullptr, *norm_b = nullptr, *bqkv = nullptr, *bproj = nullptr;
+  op_t *wqkv = nullptr, *wproj = nullptr;
+};
+struct AttnLRW {  // Attention_LR
+  int ch = 0, dh = 0;
+  float *norm_g = nullptr, *norm_b = nullptr, *ctx_ln_w = nullptr, *ctx_ln_b = nullptr, *ctx_w = nullptr,
+        *ctx_b = nullptr, *null_kv = nullptr, *out_g = nullptr, *out_b = nullptr;
+  op_t *wqkv = nullptr, *wout = nullptr;
+};
+struct ConvW {
+  int cin = 0, cin_pad = 0, cout = 0;
+  op_t* w = nullptr;
+  float* b = nullptr;
+};
+enum LayerKind { L_CONV_IN, L_RES, L_ATTN, L_DOWN, L_UP };
+struct Layer {
+  LayerKind kind;
+  int idx;
+};
+
+struct Act {
+  float* p = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Plan {
+  int Bp = 0;
+  std::vector<Op> ops;
+  std::vector<void*> owned;
+  // prologue inputs are bound per call through these
+  PrepDesc prep;
+  float* eps = nullptr;        // [Bp, Cout, H, W] fp32 NCHW
+  unsigned char* drop = nullptr;
+  size_t bytes = 0;
+  ~Plan() {
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+struct sgdm_engine {
+  sgdm_config cfg;
+  bool ca = false;
+  int mc = 0, E = 0, NE = 0, heads = 0;
+  int in_ch_total = 0;  // image + layout channels of the first conv
+  std::vector<Param> params;
+  std::unordered_map<std::string, int> pidx;
+  std::vector<std::vector<Layer>> in_blocks, out_blocks;
+  std::vector<Layer> mid;
+  std::vector<ResW> res;
+  std::vector<AttnW> attn;
+  std::vector<AttnLRW> attn_lr;
+  std::vector<ConvW> convs;  // first conv, down/up convs
+  ConvW conv_out;
+  // fp32 prologue / misc weights
+  std::map<std::string, float*> f32;
+  op_t* w_emb = nullptr;   // [NE][E] all ResBlock emb_layers stacked
+  float* b_emb = nullptr;  // [NE]
+  float* out_gn_w = nullptr;
+  float* out_gn_b = nullptr;
+  float* freqs = nullptr;
+  int* ci_map_first = nullptr;
+  std::vector<void*> owned;
+  bool device_ready = false;
+  std::map<int, std::unique_ptr<Plan>> plans;
+  const float* last_eps_c = nullptr;
+
+  ~sgdm_engine() {
+    plans.clear();
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------ topology
+int pick_block_n(int cout) {
+  if (cout < 16) return 16;
+  for (int bn : {256, 128, 64, 32})
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+void add_param(sgdm_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  e->pidx[name] = static_cast<int>(e->params.size());
+  Param p;
+  p.name = name;
+  p.shape = std::move(shape);
+  e->params.push_back(std::move(p));
+}
+
+int add_res(sgdm_engine* e, const std::string& p, int cin, int cout, bool up, bool down) {
+  ResW r;
+  r.cin = cin; r.cout = cout; r.up = up; r.down = down; r.skip = cin != cout;
+  r.emb_off = e->NE;
+  e->NE += 2 * cout;
+  add_param(e, p + ".in_layers.0.weight", {cin});
+  add_param(e, p + ".in_layers.0.bias", {cin});
+  add_param(e, p + ".in_layers.2.weight", {cout, cin, 3, 3});
+  add_param(e, p + ".in_layers.2.bias", {cout});
+  add_param(e, p + ".emb_layers.1.weight", {2 * cout, e->E});
+  add_param(e, p + ".emb_layers.1.bias", {2 * cout});
+  add_param(e, p + ".out_layers.0.weight", {cout});
+  add_param(e, p + ".out_layers.0.bias", {cout});
+  add_param(e, p + ".out_layers.3.weight", {cout, cout, 3, 3});
+  add_param(e, p + ".out_layers.3.bias", {cout});
+  if (r.skip) {
+    add_param(e, p + ".skip_connection.weight", {cout, cin, 1, 1});
+    add_param(e, p + ".skip_connection.bias", {cout});
+  }
+  e->res.push_back(r);
+  return static_cast<int>(e->res.size()) - 1;
+}
+
+int add_attn(sgdm_engine* e, const std::string& p, int ch) {
+  if (!e->ca) {
+    AttnW a;
+    a.ch = ch;
+    add_param(e, p + ".norm.weight", {ch});
+    add_param(e, p + ".norm.bias", {ch});
+    add_param(e, p + ".qkv.weight", {3 * ch, ch, 1});
+    add_param(e, p + ".qkv.bias", {3 * ch});
+    add_param(e, p + ".proj_out.weight", {ch, ch, 1});
+    add_param(e, p + ".proj_out.bias", {ch});
+    e->attn.push_back(a);
+    return static_cast<int>(e->attn.size()) - 1;
+  }
+  AttnLRW a;
+  a.ch = ch;
+  a.dh = ch / e->heads;
+  const int ctx = e->cfg.context_dim;
+  add_param(e, p + ".null_kv", {2, a.dh});
+  add_param(e, p + ".norm.gamma", {ch});
+  add_param(e, p + ".norm.beta", {ch});
+  add_param(e, p + ".to_q.weight", {a.dh * e->heads, ch});
+  add_param(e, p + ".to_kv.weight", {2 * a.dh, ch});
+  add_param(e, p + ".to_context.0.weight", {ctx});
+  add_param(e, p + ".to_context.0.bias", {ctx});
+  add_param(e, p + ".to_context.1.weight", {2 * a.dh, ctx});
+  add_param(e, p + ".to_context.1.bias", {2 * a.dh});
+  add_param(e, p + ".to_out.0.weight", {ch, a.dh * e->heads});
+  add_param(e, p + ".to_out.1.gamma", {ch});
+  add_param(e, p + ".to_out.1.beta", {ch});
+  e->attn_lr.push_back(a);
+  return static_cast<int>(e->attn_lr.size()) - 1;
+}
+
+int add_conv(sgdm_engine* e, const std::string& p, int cin, int cout) {
+  ConvW c;
+  c.cin = cin;
+  c.cin_pad = (cin + 63) / 64 * 64;
+  c.cout = cout;
+  add_param(e, p + ".weight", {cout, cin, 3, 3});
+  add_param(e, p + ".bias", {cout});
+  e->convs.push_back(c);
+  return static_cast<int>(e->convs.size()) - 1;
+}
+
+bool in_list(const int32_t* v, int n, int x) {
+  for (int i = 0; i < n; ++i)
+    if (v[i] == x) return true;
+  return false;
+}
+
+int build_topology(sgdm_engine* e) {
+  const sgdm_config& c = e->cfg;
+  e->ca = c.kind == SGDM_KIND_UNETCA_FAST;
+  e->mc = c.model_channels;
+  e->heads = c.num_heads;
+  const int mc = e->mc, ted = 4 * mc;
+  if (c.kind != SGDM_KIND_UNET_FAST && c.kind != SGDM_KIND_UNETCA_FAST) return fail("unknown kind %d", c.kind);
+  if (mc % 64) return fail("model_channels must be a multiple of 64 (got %d)", mc);
+  if (c.n_channel_mult < 1 || c.n_channel_mult > 8) return fail("bad channel_mult");
+  if (e->ca && (c.cond_token_num != 1 || c.context_dim <= 0 || c.cond_dim <= 0))
+    return fail("unetca_fast: only cond_token_num == 1 with context_dim > 0 is supported (openaimodel_ca.py:960)");
+  if (!e->ca && c.layout_dim > 1) return fail("unet_fast supports clusterlayout (layout_dim 1) only (openaimodel.py:623)");
+  if (2 * c.in_channels + c.layout_dim > 64) return fail("too many input channels");
+
+  // ---- top-level parameters, in the reference's registration order
+  if (!e->ca) {
+    if (c.cond_dim > 0) add_param(e, "null_cond_emb", {1, c.cond_dim});
+    if (c.layout_dim > 0) add_param(e, "null_layout_emb", {1, 1, c.image_size, c.image_size});
+    add_param(e, "time_embed.0.weight", {ted, mc});
+    add_param(e, "time_embed.0.bias", {ted});
+    add_param(e, "time_embed.2.weight", {ted, ted});
+    add_param(e, "time_embed.2.bias", {ted});
+    if (c.cond_dim > 0) {
+      add_param(e, "mlp_cond.0.weight", {ted / 2, c.cond_dim});
+      add_param(e, "mlp_cond.0.bias", {ted / 2});
+      add_param(e, "mlp_cond.2.weight", {ted / 2, ted / 2});
+      add_param(e, "mlp_cond.2.bias", {ted / 2});
+    }
+    e->E = ted + (c.cond_dim > 0 ? ted / 2 : 0);
+  } else {
+    const int ctx = c.context_dim;
+    add_param(e, "null_cond_emb", {1, c.cond_dim});
+    if (c.layout_dim > 0) add_param(e, "null_layout_emb", {1, 1, c.image_size, c.image_size});
+    add_param(e, "time_embed.0.weight", {ted, mc});
+    add_param(e, "time_embed.0.bias", {ted});
+    add_param(e, "time_embed.2.weight", {ted, ted});
+    add_param(e, "time_embed.2.bias", {ted});
+    add_param(e, "norm_cond.weight", {ctx});
+    add_param(e, "norm_cond.bias", {ctx});
+    add_param(e, "to_time_tokens.0.weight", {mc, mc});
+    add_param(e, "to_time_tokens.0.bias", {mc});
+    add_param(e, "to_time_tokens.2.weight", {ctx * 8, mc});
+    add_param(e, "to_time_tokens.2.bias", {ctx * 8});
+    add_param(e, "cond_mlp.0.weight", {ted, c.cond_dim});
+    add_param(e, "cond_mlp.0.bias", {ted});
+    add_param(e, "cond_mlp.2.weight", {ted, ted});
+    add_param(e, "cond_mlp.2.bias", {ted});
+    add_param(e, "to_cond_tokens.0.weight", {ctx * 8, c.cond_dim});
+    add_param(e, "to_cond_tokens.0.bias", {ctx * 8});
+    // to_cond_tokens_2d is built by the reference for every cond_token_num > 0 but only used
+    // when cond_token_num > 1 (openaimodel_ca.py:605-614,998): accepted, never read.
+    const int mid = static_cast<int>(sqrt(static_cast<double>(ctx) * c.cond_dim));
+    add_param(e, "to_cond_tokens_2d.0.weight", {mid, c.cond_dim});
+    add_param(e, "to_cond_tokens_2d.0.bias", {mid});
+    add_param(e, "to_cond_tokens_2d.2.weight", {mid, mid});
+    add_param(e, "to_cond_tokens_2d.2.bias", {mid});
+    add_param(e, "to_cond_tokens_2d.4.weight", {mid, mid});
+    add_param(e, "to_cond_tokens_2d.4.bias", {mid});
+    add_param(e, "to_cond_tokens_2d.6.weight", {ctx, mid});
+    add_param(e, "to_cond_tokens_2d.6.bias", {ctx});
+    e->E = ted;
+  }
+  e->in_ch_total = c.in_channels + c.layout_dim;
+
+  const bool updown = c.resblock_updown != 0;
+  char buf[128];
+  auto name = [&](const char* fmt, int a, int b) {
+    snprintf(buf, sizeof(buf), fmt, a, b);
+    return std::string(buf);
+  };
+  // input blocks
+  e->in_blocks.push_back({Layer{L_CONV_IN, add_conv(e, "input_blocks.0.0", e->in_ch_total, mc)}});
+  std::vector<int> chans{mc};
+  int ch = mc, ds = 1;
+  for (int level = 0; level < c.n_channel_mult; ++level) {
+    const int mult = c.channel_mult[level];
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      const int i = static_cast<int>(e->in_blocks.size());
+      std::vector<Layer> layers;
+      layers.push_back({L_RES, add_res(e, name("input_blocks.%d.%d", i, 0), ch, mult * mc, false, false)});
+      ch = mult * mc;
+      if (in_list(c.attention_resolutions, c.n_attention_resolutions, ds))
+        layers.push_back({L_ATTN, add_attn(e, name("input_blocks.%d.%d", i, 1), ch)});
+      e->in_blocks.push_back(layers);
+      chans.push_back(ch);
+    }
+    if (level != c.n_channel_mult - 1) {
+      const int i = static_cast<int>(e->in_blocks.size());
+      if (updown) {
+        e->in_blocks.push_back({Layer{L_RES, add_res(e, name("input_blocks.%d.%d", i, 0), ch, ch, false, true)}});
+      } else {
+        e->in_blocks.push_back({Layer{L_DOWN, add_conv(e, name("input_blocks.%d.%d", i, 0) + ".op", ch, ch)}});
+      }
+      chans.push_back(ch);
+      ds *= 2;
+    }
+  }
+  e->mid.push_back({L_RES, add_res(e, "middle_block.0", ch, ch, false, false)});
+  e->mid.push_back({L_ATTN, add_attn(e, "middle_block.1", ch)});
+  e->mid.push_back({L_RES, add_res(e, "middle_block.2", ch, ch, false, false)});
+  for (int level = c.n_channel_mult - 1; level >= 0; --level) {
+    const int mult = c.channel_mult[level];
+    for (int i = 0; i <= c.num_res_blocks; ++i) {
+      const int ich = chans.back();
+      chans.pop_back();
+      const int o = static_cast<int>(e->out_blocks.size());
+      std::vector<Layer> layers;
+      layers.push_back({L_RES, add_res(e, name("output_blocks.%d.%d", o, 0), ch + ich, mc * mult, false, false)});
+      ch = mc * mult;
+      if (in_list(c.attention_resolutions, c.n_attention_resolutions, ds))
+        layers.push_back({L_ATTN, add_attn(e, name("output_blocks.%d.%d", o, static_cast<int>(layers.size())), ch)});
+      if (level && i == c.num_res_blocks) {
+        const int li = static_cast<int>(layers.size());
+        if (updown) layers.push_back({L_RES, add_res(e, name("output_blocks.%d.%d", o, li), ch, ch, true, false)});
+        else layers.push_back({L_UP, add_conv(e, name("output_blocks.%d.%d", o, li) + ".conv", ch, ch)});
+        ds /= 2;
+      }
+      e->out_blocks.push_back(layers);
+    }
+  }
+  add_param(e, "out.0.weight", {ch});
+  add_param(e, "out.0.bias", {ch});
+  add_param(e, "out.2.weight", {c.out_channels, mc, 3, 3});
+  add_param(e, "out.2.bias", {c.out_channels});
+  if (ch != mc) return fail("unexpected final channel count %d", ch);
+  e->conv_out.cin = mc;
+  e->conv_out.cin_pad = mc;
+  e->conv_out.cout = c.out_channels;
+  if (e->NE % 128) return fail("emb width %d not a multiple of 128", e->NE);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ device setup
+template <typename T>
+int dalloc(sgdm_engine* e, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16));
+  if (zero) CUDA_TRY(cudaMemset(q, 0, n * sizeof(T)));
+  e->owned.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int64_t numel(const std::vector<int64_t>& s) {
+  int64_t n = 1;
+  for (auto d : s) n *= d;
+  return n;
+}
+
+// loader factories -----------------------------------------------------------------------
+std::function<int(const float*, cudaStream_t)> copy_loader(float* dst, int64_t n) {
+  return [dst, n](const float* src, cudaStream_t s) {
+    return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+  };
+}
+std::function<int(const float*, cudaStream_t)> pack_loader(op_t* dst, int cout, int cin, int ks, int cin_pad,
+                                                           int ktot, int k_off, const int* ci_map = nullptr) {
+  return [=](const float* src, cudaStream_t s) {
+    ++g_launches;
+    return pack_conv_weight_launch(src, dst, cout, cin, ks, cin_pad, ktot, k_off, ci_map, s);
+  };
+}
+
+int bind_loader(sgdm_engine* e, const std::string& name, std::function<int(const float*, cudaStream_t)> fn) {
+  auto it = e->pidx.find(name);
+  if (it == e->pidx.end()) return fail("internal: unknown param %s", name.c_str());
+  e->params[it->second].load = std::move(fn);
+  return 0;
+}
+int bind_f32(sgdm_engine* e, const std::string& name, float** slot) {
+  auto it = e->pidx.find(name);
+  if (it == e->pidx.end()) return fail("internal: unknown param %s", name.c_str());
+  const int64_t n = numel(e->params[it->second].shape);
+  if (dalloc(e, slot, n)) return 1;
+  e->f32[name] = *slot;
+  return bind_loader(e, name, copy_loader(*slot, n));
+}
+
+int setup_device(sgdm_engine* e) {
+  if (e->device_ready) return 0;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail("sgdm_b200 kernels are built for sm_100a only; device is sm_%d%d (no fallback path)", prop.major,
+                prop.minor);
+  const sgdm_config& c = e->cfg;
+  float* tmp = nullptr;
+  // prologue fp32 weights
+  std::vector<std::string> plain;
+  for (auto& p : e->params) {
+    const std::string& n = p.name;
+    if (n.rfind("time_embed.", 0) == 0 || n.rfind("mlp_cond.", 0) == 0 || n.rfind("cond_mlp.", 0) == 0 ||
+        n.rfind("to_time_tokens.", 0) == 0 || n.rfind("to_cond_tokens.0", 0) == 0 || n.rfind("norm_cond.", 0) == 0 ||
+        n == "null_cond_emb" || n == "null_layout_emb")
+      plain.push_back(n);
+  }
+  for (auto& n : plain)
+    if (bind_f32(e, n, &tmp)) return 1;
+  if (bind_f32(e, "out.0.weight", &e->out_gn_w) || bind_f32(e, "out.0.bias", &e->out_gn_b)) return 1;
+
+  // fused emb projection
+  if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E) || dalloc(e, &e->b_emb, e->NE)) return 1;
+
+  // first conv channel map: dst [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0] <- src [x(Cimg) | layout(L)]
+  {
+    std::vector<int> m(64, -1);
+    for (int i = 0; i < c.in_channels; ++i) { m[i] = i; m[c.in_channels + i] = i; }
+    for (int l = 0; l < c.layout_dim; ++l) m[2 * c.in_channels + l] = c.in_channels + l;
+    if (dalloc(e, &e->ci_map_first, 64)) return 1;
+    CUDA_TRY(cudaMemcpy(e->ci_map_first, m.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
+  }
+
+  auto prefix_of = [&](const std::vector<std::vector<Layer>>& blocks, const char* base, size_t bi, size_t li) {
+    char b[96];
+    snprintf(b, sizeof(b), "%s.%zu.%zu", base, bi, li);
+    return std::string(b);
+  };
+  auto setup_layer = [&](const Layer& L, const std::string& p) -> int {
+    if (L.kind == L_RES) {
+      ResW& r = e->res[L.idx];
+      if (bind_f32(e, p + ".in_layers.0.weight", &r.gn1_w) || bind_f32(e, p + ".in_layers.0.bias", &r.gn1_b) ||
+          bind_f32(e, p + ".out_layers.0.weight", &r.gn2_w) || bind_f32(e, p + ".out_layers.0.bias", &r.gn2_b) ||
+          bind_f32(e, p + ".in_layers.2.bias", &r.b1))
+        return 1;
+      const int k1 = 9 * r.cin, k2 = 9 * r.cout + (r.skip ? r.cin : 0);
+      const int np = conv_npad(r.cout, pick_block_n(r.cout));
+      if (dalloc(e, &r.w1, static_cast<size_t>(np) * k1) || dalloc(e, &r.w2, static_cast<size_t>(np) * k2)) return 1;
+      if (bind_loader(e, p + ".in_layers.2.weight", pack_loader(r.w1, r.cout, r.cin, 3, r.cin, k1, 0))) return 1;
+      if (bind_loader(e, p + ".out_layers.3.weight", pack_loader(r.w2, r.cout, r.cout, 3, r.cout, k2, 0))) return 1;
+      if (dalloc(e, &r.b2, r.cout) || dalloc(e, &r.bfused, r.cout)) return 1;
+      float *b2 = r.b2, *bf = r.bfused;
+      const int co = r.cout;
+      if (r.skip) {
+        if (dalloc(e, &r.bskip, r.cout)) return 1;
+        float* bs = r.bskip;
+        if (bind_loader(e, p + ".skip_connection.weight", pack_loader(r.w2, r.cout, r.cin, 1, r.cin, k2, 9 * r.cout)))
+          return 1;
+        if (bind_loader(e, p + ".skip_connection.bias", [=](const float* src, cudaStream_t s) {
+              if (cudaMemcpyAsync(bs, src, co * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return 1;
+              ++g_launches;
+              return add_bias_launch(b2, bs, bf, co, s);
+            }))
+          return 1;
+        if (bind_loader(e, p + ".out_layers.3.bias", [=](const float* src, cudaStream_t s) {
+              if (cudaMemcpyAsync(b2, src, co * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return 1;
+              ++g_launches;
+              return add_bias_launch(b2, bs, bf, co, s);
+            }))
+          return 1;
+      } else {
+        if (bind_loader(e, p + ".out_layers.3.bias", [=](const float* src, cudaStream_t s) {
+              if (cudaMemcpyAsync(b2, src, co * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return 1;
+              return cudaMemcpyAsync(bf, src, co * sizeof(float), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+            }))
+          return 1;
+      }
+      if (bind_loader(e, p + ".emb_layers.1.weight",
+               pack_loader(e->w_emb + static_cast<size_t>(r.emb_off) * e->E, 2 * r.cout, e->E, 1, e->E, e->E, 0)))
+        return 1;
+      if (bind_loader(e, p + ".emb_layers.1.bias", copy_loader(e->b_emb + r.emb_off, 2 * r.cout))) return 1;
+    } else if (L.kind == L_ATTN && !e->ca) {
+      AttnW& a = e->attn[L.idx];
+      const int C = a.ch;
+      if (bind_f32(e, p + ".norm.weight", &a.norm_w) || bind_f32(e, p + ".norm.bias", &a.norm_b) ||
+          bind_f32(e, p + ".qkv.bias", &a.bqkv) || bind_f32(e, p + ".proj_out.bias", &a.bproj))
+        return 1;
+      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(3 * C, pick_block_n(3 * C))) * C) ||
+          dalloc(e, &a.wproj, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * C))
+        return 1;
+      if (bind_loader(e, p + ".qkv.weight", pack_loader(a.wqkv, 3 * C, C, 1, C, C, 0)) ||
+          bind_loader(e, p + ".proj_out.weight", pack_loader(a.wproj, C, C, 1, C, C, 0)))
+        return 1;
+    } else if (L.kind == L_ATTN) {
+      AttnLRW& a = e->attn_lr[L.idx];
+      const int C = a.ch, inner = a.dh * e->heads, nq = inner + 2 * a.dh;
+      if (bind_f32(e, p + ".norm.gamma", &a.norm_g) || bind_f32(e, p + ".norm.beta", &a.norm_b) ||
+          bind_f32(e, p + ".to_context.0.weight", &a.ctx_ln_w) || bind_f32(e, p + ".to_context.0.bias", &a.ctx_ln_b) ||
+          bind_f32(e, p + ".to_context.1.weight", &a.ctx_w) || bind_f32(e, p + ".to_context.1.bias", &a.ctx_b) ||
+          bind_f32(e, p + ".null_kv", &a.null_kv) || bind_f32(e, p + ".to_out.1.gamma", &a.out_g) ||
+          bind_f32(e, p + ".to_out.1.beta", &a.out_b))
+        return 1;
+      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(nq, pick_block_n(nq))) * C) ||
+          dalloc(e, &a.wout, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * inner))
+        return 1;
+      if (bind_loader(e, p + ".to_q.weight", pack_loader(a.wqkv, inner, C, 1, C, C, 0)) ||
+          bind_loader(e, p + ".to_kv.weight", pack_loader(a.wqkv + static_cast<size_t>(inner) * C, 2 * a.dh, C, 1, C, C, 0)) ||
+          bind_loader(e, p + ".to_out.0.weight", pack_loader(a.wout, C, inner, 1, inner, inner, 0)))
+        return 1;
+    } else {  // conv layers: first conv, Downsample.op, Upsample.conv
+      ConvW& cw = e->convs[L.idx];
+      const std::string pp = L.kind == L_DOWN ? p + ".op" : L.kind == L_UP ? p + ".conv" : p;
+      const int ktot = 9 * cw.cin_pad;
+      if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
+      if (bind_f32(e, pp + ".bias", &cw.b)) return 1;
+      const int* map = L.kind == L_CONV_IN ? e->ci_map_first : nullptr;
+      if (bind_loader(e, pp + ".weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0, map))) return 1;
+    }
+    return 0;
+  };
+  for (size_t bi = 0; bi < e->in_blocks.size(); ++bi)
+    for (size_t li = 0; li < e->in_blocks[bi].size(); ++li)
+      if (setup_layer(e->in_blocks[bi][li], prefix_of(e->in_blocks, "input_blocks", bi, li))) return 1;
+  for (size_t li = 0; li < e->mid.size(); ++li) {
+    char b[64];
+    snprintf(b, sizeof(b), "middle_block.%zu", li);
+    if (setup_layer(e->mid[li], b)) return 1;
+  }
+  for (size_t bi = 0; bi < e->out_blocks.size(); ++bi)
+    for (size_t li = 0; li < e->out_blocks[bi].size(); ++li)
+      if (setup_layer(e->out_blocks[bi][li], prefix_of(e->out_blocks, "output_blocks", bi, li))) return 1;
+  {
+    ConvW& cw = e->conv_out;
+    const int ktot = 9 * cw.cin_pad;
+    if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
+    if (bind_f32(e, "out.2.bias", &cw.b)) return 1;
+    if (bind_loader(e, "out.2.weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0))) return 1;
+  }
+  if (dalloc(e, &e->freqs, e->mc / 2 + 1)) return 1;
+  e->device_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ plan builder
+struct Builder {
+  sgdm_engine* e;
+  Plan* plan;
+  bool dry;
+  int Bp;
+  // scratch roles (max over uses, computed in the dry pass)
+  std::map<std::string, size_t> need;
+  std::map<std::string, void*> have;
+  size_t stream_bytes = 0;
+  char* stream_base = nullptr;
+  size_t stream_off = 0;
+  int err = 0;
+
+  void* scratch(const std::string& role, size_t bytes) {
+    if (dry) {
+      size_t& n = need[role];
+      if (bytes > n) n = bytes;
+      return nullptr;
+    }
+    return have[role];
+  }
+  float* stream_alloc(size_t elems) {
+    const size_t bytes = (elems * sizeof(float) + 255) / 256 * 256;
+    if (dry) {
+      stream_bytes += bytes;
+      return nullptr;
+    }
+    float* p = reinterpret_cast<float*>(stream_base + stream_off);
+    stream_off += bytes;
+    return p;
+  }
+  void push(Op op) {
+    if (!dry) plan->ops.push_back(std::move(op));
+  }
+
+  void conv(ConvDesc d) {
+    d.B = Bp;
+    d.block_n = pick_block_n(d.Cout);
+    if (dry) return;
+    auto l = std::make_shared<ConvLaunch>();
+    char msg[256];
+    if (conv_prepare(d, l.get(), msg, sizeof(msg))) {
+      fail("%s", msg);
+      err = 1;
+      return;
+    }
+    push([l](cudaStream_t s) {
+      ++g_launches;
+      return g_naive_conv ? conv_launch_naive(l->desc, s) : conv_launch(*l, s);
+    });
+  }
+  void gn(GnDesc d) {
+    d.B = Bp;
+    d.chunks = gn_chunks_for(Bp, d.H * d.W, d.C0 + d.C1);
+    d.partial = static_cast<double*>(scratch("gn_partial", static_cast<size_t>(Bp) * 16 * 32 * 2 * sizeof(double)));
+    if (dry) return;
+    push([d](cudaStream_t s) {
+      g_launches += 2;
+      return gn_launch(d, s);
+    });
+  }
+
+  // ResBlock._forward (openaimodel.py:300-320)
+  Act resblock(const ResW& r, Act a, Act b) {
+    const int C = a.C + b.C, H = a.H, W = a.W;
+    const int Ho = r.down ? H / 2 : r.up ? H * 2 : H, Wo = r.down ? W / 2 : r.up ? W * 2 : W;
+    const size_t px_in = static_cast<size_t>(Bp) * H * W, px_out = static_cast<size_t>(Bp) * Ho * Wo;
+    op_t* g1 = static_cast<op_t*>(scratch("gn_out", px_out * C * sizeof(op_t)));
+    op_t* raw = r.skip ? static_cast<op_t*>(scratch("raw_op", px_in * C * sizeof(op_t))) : nullptr;
+    float* pooled = r.down ? static_cast<float*>(scratch("pooled", px_out * C * sizeof(float))) : nullptr;
+    GnDesc g;
+    g.src0 = a.p; g.src1 = b.p; g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
+    g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
+    g.out = g1; g.raw_out = raw; g.pool_out = pooled;
+    gn(g);
+    float* h1 = static_cast<float*>(scratch("h1", px_out * r.cout * sizeof(float)));
+    ConvDesc c1;
+    c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
+    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_f32 = h1;
+    conv(c1);
+    op_t* g2 = static_cast<op_t*>(scratch("gn_out", px_out * r.cout * sizeof(op_t)));
+    GnDesc gg;
+    gg.src0 = h1; gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
+    gg.film = dry ? nullptr : emb_out + r.emb_off; gg.film_stride = e->NE; gg.silu = 1; gg.out = g2;
+    gn(gg);
+    Act o;
+    o.C = r.cout; o.H = Ho; o.W = Wo;
+    o.p = stream_alloc(px_out * r.cout);
+    ConvDesc c2;
+    c2.in = g2; c2.Hin = Ho; c2.Win = Wo; c2.Cin = r.cout; c2.w = r.w2; c2.ks = 3; c2.stride = 1; c2.pad = 1;
+    c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p;
+    if (r.skip) {
+      c2.in2 = raw; c2.C2 = C; c2.bias = r.bfused;
+    } else {
+      c2.bias = r.bfused;
+      c2.res = r.down ? pooled : a.p;
+      c2.res_mode = r.up ? 2 : 1;
+    }
+    conv(c2);
+    return o;
+  }
+
+  // AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:365-371,403-420)
+  Act attention(const AttnW& w, Act a) {
+    const int C = a.C, T = a.H * a.W, dh = C / e->heads;
+    const size_t rows = static_cast<size_t>(Bp) * T;
+    op_t* g = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
+    GnDesc gd;
+    gd.src0 = a.p; gd.H = a.H; gd.W = a.W; gd.C0 = C; gd.gamma = w.norm_w; gd.beta = w.norm_b; gd.silu = 0; gd.out = g;
+    gn(gd);
+    op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * 3 * C * sizeof(op_t)));
+    ConvDesc c1;
+    c1.in = g; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
+    c1.Hout = a.H; c1.Wout = a.W; c1.Cout = 3 * C; c1.bias = w.bqkv; c1.out_op = qkv;
+    conv(c1);
+    op_t* att = static_cast<op_t*>(scratch("att", rows * C * sizeof(op_t)));
+    AttnDesc ad;
+    ad.q = qkv; ad.q_row_stride = 3 * C; ad.q_head_stride = 3 * dh;
+    ad.k = dry ? nullptr : qkv + dh; ad.k_row_stride = 3 * C; ad.k_head_stride = 3 * dh;
+    ad.v = dry ? nullptr : qkv + 2 * dh; ad.v_row_stride = 3 * C; ad.v_head_stride = 3 * dh;
+    ad.out = att; ad.o_row_stride = C; ad.B = Bp; ad.T = T; ad.heads = e->heads; ad.D = dh;
+    ad.scale = 1.0f / sqrtf(static_cast<float>(dh));  // (ch^-1/4 on q) * (ch^-1/4 on k)
+    push([ad](cudaStream_t s) {
+      ++g_launches;
+      return attn_launch(ad, s);
+    });
+    Act o = a;
+    o.p = stream_alloc(rows * C);
+    ConvDesc c2;
+    c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = C; c2.w = w.wproj; c2.ks = 1; c2.stride = 1; c2.pad = 0;
+    c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.bias = w.bproj; c2.res = a.p; c2.res_mode = 1; c2.out_f32 = o.p;
+    conv(c2);
+    return o;
+  }
+
+  // Attention_LR.forward (crossattetion_lr.py:81-142)
+  Act attention_lr(const AttnLRW& w, Act a) {
+    const int C = a.C, T = a.H * a.W, dh = w.dh, inner = dh * e->heads, nq = inner + 2 * dh;
+    const size_t rows = static_cast<size_t>(Bp) * T;
+    op_t* ln = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
+    {
+      const float* x = a.p;
+      const float *g = w.norm_g, *b = w.norm_b;
+      push([=](cudaStream_t s) {
+        ++g_launches;
+        return layernorm_launch(x, g, b, nullptr, ln, nullptr, static_cast<long>(rows), C, s);
+      });
+    }
+    op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * nq * sizeof(op_t)));
+    ConvDesc c1;
+    c1.in = ln; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
+    c1.Hout = a.H; c1.Wout = a.W; c1.Cout = nq; c1.out_op = qkv;
+    conv(c1);
+    op_t* ck = static_cast<op_t*>(scratch("ctx_k", static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
+    op_t* cv = static_cast<op_t*>(scratch("ctx_v", static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
+    CtxDesc cd;
+    cd.time_tokens = time_tokens; cd.cond_tokens = cond_tokens;
+    cd.norm_w = dry ? nullptr : e->f32["norm_cond.weight"]; cd.norm_b = dry ? nullptr : e->f32["norm_cond.bias"];
+    cd.ln_w = w.ctx_ln_w; cd.ln_b = w.ctx_ln_b; cd.lin_w = w.ctx_w; cd.lin_b = w.ctx_b; cd.null_kv = w.null_kv;
+    cd.Bp = Bp; cd.ctx = e->cfg.context_dim; cd.dh = dh; cd.k_out = ck; cd.v_out = cv;
+    push([cd](cudaStream_t s) {
+      ++g_launches;
+      return context_kv_launch(cd, s);
+    });
+    op_t* att = static_cast<op_t*>(scratch("att", rows * inner * sizeof(op_t)));
+    AttnDesc ad;
+    ad.q = qkv; ad.q_row_stride = nq; ad.q_head_stride = dh;
+    ad.k = dry ? nullptr : qkv + inner; ad.k_row_stride = nq; ad.k_head_stride = 0;
+    ad.v = dry ? nullptr : qkv + inner + dh; ad.v_row_stride = nq; ad.v_head_stride = 0;
+    ad.k_extra = ck; ad.v_extra = cv; ad.n_extra = 17;
+    ad.out = att; ad.o_row_stride = inner; ad.B = Bp; ad.T = T; ad.heads = e->heads; ad.D = dh;
+    ad.scale = 1.0f / sqrtf(static_cast<float>(dh));
+    push([ad](cudaStream_t s) {
+      ++g_launches;
+      return attn_launch(ad, s);
+    });
+    float* tmp = static_cast<float*>(scratch("h1", rows * C * sizeof(float)));
+    ConvDesc c2;
+    c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = inner; c2.w = w.wout; c2.ks = 1; c2.stride = 1; c2.pad = 0;
+    c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.out_f32 = tmp;
+    conv(c2);
+    Act o = a;
+    o.p = stream_alloc(rows * C);
+    {
+      const float* x = a.p;
+      const float *g = w.out_g, *b = w.out_b;
+      float* op = o.p;
+      push([=](cudaStream_t s) {
+        ++g_launches;
+        return layernorm_launch(tmp, g, b, x, nullptr, op, static_cast<long>(rows), C, s);
+      });
+    }
+    return o;
+  }
+
+  // Downsample (conv3x3 s2) / Upsample (nearest + conv3x3) of unetca_fast (openaimodel_ca.py:101-181)
+  Act resample_conv(const ConvW& cw, Act a, bool up) {
+    const int Hc = up ? a.H * 2 : a.H, Wc = up ? a.W * 2 : a.W;  // conv input size
+    const int Ho = up ? Hc : a.H / 2, Wo = up ? Wc : a.W / 2;
+    op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * Hc * Wc * a.C * sizeof(op_t)));
+    {
+      const float* src = a.p;
+      const int B = Bp, H = a.H, W = a.W, C = a.C, u = up ? 1 : 0;
+      push([=](cudaStream_t s) {
+        ++g_launches;
+        return cast_launch(src, raw, B, H, W, C, u, s);
+      });
+    }
+    Act o;
+    o.C = cw.cout; o.H = Ho; o.W = Wo;
+    o.p = stream_alloc(static_cast<size_t>(Bp) * Ho * Wo * cw.cout);
+    ConvDesc c;
+    c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
+    c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
+    conv(c);
+    return o;
+  }
+
+  // buffers shared across the walk
+  float* emb_out = nullptr;
+  float* time_tokens = nullptr;
+  float* cond_tokens = nullptr;
+
+  Act run_layers(const std::vector<Layer>& layers, Act h, Act skip) {
+    bool first = true;
+    for (const Layer& L : layers) {
+      Act none;
+      switch (L.kind) {
+        case L_RES: h = resblock(e->res[L.idx], h, first ? skip : none); break;
+        case L_ATTN: h = e->ca ? attention_lr(e->attn_lr[L.idx], h) : attention(e->attn[L.idx], h); break;
+        case L_DOWN: h = resample_conv(e->convs[L.idx], h, false); break;
+        case L_UP: h = resample_conv(e->convs[L.idx], h, true); break;
+        default: break;
+      }
+      first = false;
+    }
+    return h;
+  }
+
+  void build() {
+    const sgdm_config& c = e->cfg;
+    const int mc = e->mc, ted = 4 * mc, H = c.image_size, W = c.image_size;
+    const size_t px = static_cast<size_t>(Bp) * H * W;
+    // ---- prologue buffers
+    op_t* x_in = static_cast<op_t*>(scratch("x_in", px * 64 * sizeof(op_t)));
+    float* t_emb = static_cast<float*>(scratch("t_emb", static_cast<size_t>(Bp) * mc * sizeof(float)));
+    float* cond_m = static_cast<float*>(scratch("cond_m", static_cast<size_t>(Bp) * (c.cond_dim + 1) * sizeof(float)));
+    float* hid = static_cast<float*>(scratch("hid", static_cast<size_t>(Bp) * ted * sizeof(float)));
+    float* emb = static_cast<float*>(scratch("emb", static_cast<size_t>(Bp) * e->E * sizeof(float)));
+    op_t* emb_act = static_cast<op_t*>(scratch("emb_act", static_cast<size_t>(Bp) * e->E * sizeof(op_t)));
+    emb_out = static_cast<float*>(scratch("emb_out", static_cast<size_t>(Bp) * e->NE * sizeof(float)));
+    unsigned char* drop = static_cast<unsigned char*>(scratch("drop", Bp));
+    float* eps = static_cast<float*>(scratch("eps", px * c.out_channels * sizeof(float)));
+    if (!dry) {
+      plan->drop = drop;
+      plan->eps = eps;
+      PrepDesc& pd = plan->prep;
+      pd.null_cond = c.cond_dim > 0 ? e->f32["null_cond_emb"] : nullptr;
+      pd.null_layout = c.layout_dim > 0 ? e->f32["null_layout_emb"] : nullptr;
+      pd.freqs = e->freqs;
+      pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = c.cond_dim; pd.mc = mc;
+      pd.x_in = x_in; pd.t_emb = t_emb; pd.cond_masked = cond_m; pd.drop = drop;
+    }
+    auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,
+                   int silu_out, int accumulate) {
+      if (dry) return;
+      const float* Wt = e->f32[std::string(wname) + ".weight"];
+      const float* bs = e->f32[std::string(wname) + ".bias"];
+      const int M = Bp;
+      push([=](cudaStream_t s) {
+        ++g_launches;
+        return linear_f32_launch(in, in_stride, Wt, bs, out, out_stride, M, N, K, silu_out, accumulate, s);
+      });
+    };
+    // time_embed (openaimodel.py:570-574,921-923)
+    lin(t_emb, mc, "time_embed.0", hid, ted, ted, mc, 1, 0);
+    lin(hid, ted, "time_embed.2", emb, e->E, ted, ted, 0, 0);
+    if (!e->ca) {
+      if (c.cond_dim > 0) {  // mlp_cond, concatenated after the time embedding (:602-607,941-942)
+        lin(cond_m, c.cond_dim, "mlp_cond.0", hid, ted, ted / 2, c.cond_dim, 1, 0);
+        lin(hid, ted, "mlp_cond.2", emb + ted, e->E, ted / 2, ted / 2, 0, 0);
+      }
+    } else {
+      const int ctx = c.context_dim;
+      // cond_mlp ADDED to the time embedding (openaimodel_ca.py:594-598,976-977)
+      lin(cond_m, c.cond_dim, "cond_mlp.0", hid, ted, ted, c.cond_dim, 1, 0);
+      lin(hid, ted, "cond_mlp.2", emb, e->E, ted, ted, 0, 1);
+      // to_time_tokens / to_cond_tokens (:586-604,942,972)
+      time_tokens = static_cast<float*>(scratch("time_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float)));
+      cond_tokens = static_cast<float*>(scratch("cond_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float)));
+      lin(t_emb, mc, "to_time_tokens.0", hid, ted, mc, mc, 1, 0);
+      lin(hid, ted, "to_time_tokens.2", time_tokens, 8 * ctx, 8 * ctx, mc, 0, 0);
+      lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
+    }
+    // all ResBlock emb_layers = SiLU + Linear, as one GEMM (openaimodel.py:262-268,309)
+    {
+      const long n = static_cast<long>(Bp) * e->E;
+      push([=](cudaStream_t s) {
+        ++g_launches;
+        return silu_cast_launch(emb, emb_act, n, s);
+      });
+      ConvDesc d;
+      d.in = emb_act; d.Hin = 1; d.Win = 1; d.Cin = e->E; d.w = e->w_emb; d.ks = 1; d.stride = 1; d.pad = 0;
+      d.Hout = 1; d.Wout = 1; d.Cout = e->NE; d.bias = e->b_emb; d.out_f32 = emb_out;
+      conv(d);
+    }
+    // ---- UNet body
+    std::vector<Act> hs;
+    Act h;
+    {
+      const ConvW& cw = e->convs[e->in_blocks[0][0].idx];
+      h.C = cw.cout; h.H = H; h.W = W;
+      h.p = stream_alloc(px * cw.cout);
+      ConvDesc d;
+      d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
+      d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
+      conv(d);
+      hs.push_back(h);
+    }
+    Act none;
+    for (size_t bi = 1; bi < e->in_blocks.size(); ++bi) {
+      h = run_layers(e->in_blocks[bi], h, none);
+      hs.push_back(h);
+    }
+    h = run_layers(e->mid, h, none);
+    for (auto& layers : e->out_blocks) {
+      Act skip = hs.back();
+      hs.pop_back();
+      h = run_layers(layers, h, skip);
+    }
+    // out = GN + SiLU + conv3x3 -> eps NCHW (openaimodel.py:830-835,956)
+    op_t* g = static_cast<op_t*>(scratch("gn_out", px * h.C * sizeof(op_t)));
+    GnDesc gd;
+    gd.src0 = h.p; gd.H = H; gd.W = W; gd.C0 = h.C; gd.gamma = e->out_gn_w; gd.beta = e->out_gn_b; gd.silu = 1; gd.out = g;
+    gn(gd);
+    ConvDesc d;
+    d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
+    d.Hout = H; d.Wout = W; d.Cout = c.out_channels; d.bias = e->conv_out.b; d.out_nchw = eps;
+    conv(d);
+  }
+};
+
+int get_plan(sgdm_engine* e, int Bp, Plan** out) {
+  auto it = e->plans.find(Bp);
+  if (it != e->plans.end()) {
+    *out = it->second.get();
+    return 0;
+  }
+  // keep at most 3 plans alive (workspace is large)
+  while (e->plans.size() >= 3) e->plans.erase(e->plans.begin());
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->Bp = Bp;
+  Builder b;
+  b.e = e; b.plan = plan.get(); b.Bp = Bp;
+  b.dry = true;
+  b.build();
+  size_t total = b.stream_bytes;
+  for (auto& kv : b.need) total += (kv.second + 255) / 256 * 256;
+  char* base = nullptr;
+  cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&base), total);
+  if (ce != cudaSuccess) return fail("workspace of %zu MiB for batch rows %d: %s", total >> 20, Bp, cudaGetErrorString(ce));
+  plan->owned.push_back(base);
+  plan->bytes = total;
+  size_t off = 0;
+  for (auto& kv : b.need) {
+    b.have[kv.first] = base + off;
+    off += (kv.second + 255) / 256 * 256;
+  }
+  b.stream_base = base + off;
+  b.stream_off = 0;
+  b.dry = false;
+  b.build();
+  if (b.err) return 1;
+  *out = plan.get();
+  e->plans[Bp] = std::move(plan);
+  return 0;
+}
+
+int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t, const float* cond,
+                const float* layout, const uint8_t* drop, int B, int Bp, Plan** plan_out) {
+  if (!e->device_ready) return fail("no parameters loaded");
+  for (auto& p : e->params)
+    if (!p.loaded) return fail("parameter %s was never loaded", p.name.c_str());
+  if (e->cfg.cond_dim > 0 && cond == nullptr) return fail("cond is required (cond_dim=%d)", e->cfg.cond_dim);
+  if (e->cfg.layout_dim > 0 && layout == nullptr) return fail("layout is required (layout_dim=%d)", e->cfg.layout_dim);
+  Plan* plan = nullptr;
+  if (get_plan(e, Bp, &plan)) return 1;
+  if (drop) {
+    CUDA_TRY(cudaMemcpyAsync(plan->drop, drop, Bp, cudaMemcpyDeviceToDevice, s));
+  } else if (Bp == 2 * B) {
+    CUDA_TRY(cudaMemsetAsync(plan->drop, 0, B, s));
+    CUDA_TRY(cudaMemsetAsync(plan->drop + B, 1, B, s));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(plan->drop, 0, Bp, s));
+  }
+  PrepDesc pd = plan->prep;
+  pd.x = x; pd.t = reinterpret_cast<const long long*>(t); pd.cond = cond; pd.layout = layout; pd.B = B;
+  g_launches += 2;
+  if (prep_launch(pd, s)) return fail("prep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (size_t i = 0; i < plan->ops.size(); ++i)
+    if (plan->ops[i](s)) {
+      cudaError_t ce = cudaGetLastError();
+      return fail("launch %zu of %zu failed: %s", i, plan->ops.size(), cudaGetErrorString(ce));
+    }
+  *plan_out = plan;
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================================================= C ABI
+extern "C" {
+
+const char* sgdm_last_error(void) { return g_err; }
+const char* sgdm_version(void) { return "sgdm_b200 0.1.0 (sm_100a)"; }
+const char* sgdm_operand_dtype(void) {
+#ifdef SGDM_OPERAND_BF16
+  return "bf16";
+#else
+  return "f16";
+#endif
+}
+int64_t sgdm_launch_count(void) { return g_launches; }
+int sgdm_debug_set_naive_conv(int on) {
+  g_naive_conv = on;
+  return 0;
+}
+
+int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
+  if (!cfg || !out) return fail("null argument");
+  std::unique_ptr<sgdm_engine> e(new sgdm_engine());
+  e->cfg = *cfg;
+  if (build_topology(e.get())) return 1;
+  *out = e.release();
+  return 0;
+}
+int sgdm_destroy(sgdm_handle h) {
+  delete h;
+  return 0;
+}
+int sgdm_param_count(sgdm_handle h) { return h ? static_cast<int>(h->params.size()) : -1; }
+const char* sgdm_param_name(sgdm_handle h, int i) {
+  if (!h || i < 0 || i >= static_cast<int>(h->params.size())) return nullptr;
+  return h->params[i].name.c_str();
+}
+int sgdm_param_shape(sgdm_handle h, int i, int64_t* dims, int* ndim) {
+  if (!h || i < 0 || i >= static_cast<int>(h->params.size())) return fail("bad param index");
+  *ndim = static_cast<int>(h->params[i].shape.size());
+  for (int k = 0; k < *ndim; ++k) dims[k] = h->params[i].shape[k];
+  return 0;
+}
+int sgdm_params_missing(sgdm_handle h) {
+  int n = 0;
+  for (auto& p : h->params) n += p.loaded ? 0 : 1;
+  return n;
+}
+int sgdm_load_param(sgdm_handle h, const char* name, const float* data, const int64_t* shape, int ndim,
+                    void* stream) {
+  if (!h || !name || !data) return fail("null argument");
+  if (setup_device(h)) return 1;
+  auto it = h->pidx.find(name);
+  if (it == h->pidx.end()) return fail("unexpected parameter '%s'", name);
+  Param& p = h->params[it->second];
+  bool ok = ndim == static_cast<int>(p.shape.size());
+  for (int k = 0; ok && k < ndim; ++k) ok = shape[k] == p.shape[k];
+  if (!ok) return fail("shape mismatch for '%s'", name);
+  if (p.load && p.load(data, static_cast<cudaStream_t>(stream)))
+    return fail("loading '%s' failed: %s", name, cudaGetErrorString(cudaGetLastError()));
+  p.loaded = true;
+  return 0;
+}
+int sgdm_set_timestep_freqs(sgdm_handle h, const float* host_freqs, int n) {
+  if (setup_device(h)) return 1;
+  if (n != h->mc / 2) return fail("expected %d frequencies, got %d", h->mc / 2, n);
+  CUDA_TRY(cudaMemcpy(h->freqs, host_freqs, n * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
+                 const float* layout, const uint8_t* drop, int B, float* eps_out) {
+  Plan* plan = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (run_forward(h, s, x, t, cond, layout, drop, B, B, &plan)) return 1;
+  const size_t n = static_cast<size_t>(B) * h->cfg.out_channels * h->cfg.image_size * h->cfg.image_size;
+  CUDA_TRY(cudaMemcpyAsync(eps_out, plan->eps, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
+                        const float* layout, int B, const float** eps_c, const float** eps_u) {
+  Plan* plan = nullptr;
+  if (run_forward(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, nullptr, B, 2 * B, &plan)) return 1;
+  const size_t n = static_cast<size_t>(B) * h->cfg.out_channels * h->cfg.image_size * h->cfg.image_size;
+  *eps_c = plan->eps;
+  *eps_u = plan->eps + n;
+  return 0;
+}
+
+static MixDesc make_mix(const float* eps_c, const float* eps_u, float w, const float* wps, int scale_type) {
+  MixDesc m;
+  m.eps_c = eps_c; m.eps_u = eps_u; m.w = w; m.w_per_sample = wps; m.scale_type = scale_type;
+  return m;
+}
+int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+             int scale_type, float* eps_out, int B, int64_t per_sample) {
+  ++g_launches;
+  if (mix_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), eps_out, B, per_sample,
+                 static_cast<cudaStream_t>(stream)))
+    return fail("mix launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+                   int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                   float* x_out, float* x0_out, float* eps_out, int B, int64_t per_sample) {
+  DdimCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};
+  ++g_launches;
+  if (ddim_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, x, noise, x_out, x0_out, eps_out, B,
+                       per_sample, static_cast<cudaStream_t>(stream)))
+    return fail("ddim step launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+                   int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                   float* x_out, float* x0_out, int B, int64_t per_sample) {
+  DdpmCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};
+  ++g_launches;
+  if (ddpm_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, x, noise, x_out, x0_out, B,
+                       per_sample, static_cast<cudaStream_t>(stream)))
+    return fail("ddpm step launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const float* coefs, float div, float* out,
+                 int64_t n) {
+  ++g_launches;
+  return lincomb_launch(terms, coefs, n_terms, div, out, n, static_cast<cudaStream_t>(stream))
+             ? fail("lincomb launch failed")
+             : 0;
+}
+int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n) {
+  ++g_launches;
+  return to_uint8_launch(x, out, n, static_cast<cudaStream_t>(stream)) ? fail("to_uint8 launch failed") : 0;
+}
+
+// ---- single-kernel entry points ------------------------------------------------------------
+int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, const void* in2, int C2,
+                const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
+                const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
+                int naive) {
+  ConvDesc d;
+  d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = Hin; d.Win = Win; d.Cin = Cin;
+  d.in2 = static_cast<const op_t*>(in2); d.C2 = C2; d.w = static_cast<const op_t*>(w);
+  d.ks = ks; d.stride = stride; d.pad = ks == 3 ? 1 : 0; d.Hout = Hout; d.Wout = Wout; d.Cout = Cout;
+  d.bias = bias; d.res = res; d.res_mode = res_mode; d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
+  d.out_nchw = out_nchw; d.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
+  ++g_launches;
+  if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
+  ConvLaunch l;
+  char msg[256];
+  if (conv_prepare(d, &l, msg, sizeof(msg))) return fail("%s", msg);
+  if (conv_launch(l, static_cast<cudaStream_t>(stream)))
+    return fail("conv launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad, int ktot,
+                       int k_off) {
+  ++g_launches;
+  return pack_conv_weight_launch(w, static_cast<op_t*>(dst), Cout, Cin, ks, cin_pad, ktot, k_off, nullptr,
+                                 static_cast<cudaStream_t>(stream))
+             ? fail("pack launch failed")
+             : 0;
+}
+int sgdm_k_groupnorm(void* stream, const float* src0, const float* src1, int B, int H, int W, int C0, int C1,
+                     const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
+                     int resample, void* out_op, void* raw_out_op, float* pool_out) {
+  GnDesc d;
+  d.src0 = src0; d.src1 = src1; d.B = B; d.H = H; d.W = W; d.C0 = C0; d.C1 = C1; d.gamma = gamma; d.beta = beta;
+  d.film = film; d.film_stride = film_stride; d.silu = silu; d.resample = resample;
+  d.out = static_cast<op_t*>(out_op); d.raw_out = static_cast<op_t*>(raw_out_op); d.pool_out = pool_out;
+  d.chunks = gn_chunks_for(B, H * W, C0 + C1);
+  double* partial = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * d.chunks * 64 * sizeof(double)));
+  d.partial = partial;
+  g_launches += 2;
+  const int rc = gn_launch(d, static_cast<cudaStream_t>(stream));
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // test entry point only: frees its scratch
+  cudaFree(partial);
+  return rc ? fail("groupnorm launch: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+}
+int sgdm_k_layernorm(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
+                     void* out_op, float* out_f32, int64_t rows, int C) {
+  ++g_launches;
+  return layernorm_launch(x, gamma, beta, res, static_cast<op_t*>(out_op), out_f32, rows, C,
+                          static_cast<cudaStream_t>(stream))
+             ? fail("layernorm launch failed")
+             : 0;
+}
+int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_head_stride, const void* k,
+                     int64_t k_row_stride, int k_head_stride, const void* v, int64_t v_row_stride,
+                     int v_head_stride, const void* k_extra, const void* v_extra, int n_extra, void* out,
+                     int64_t o_row_stride, int B, int T, int heads, int D, float scale) {
+  AttnDesc a;
+  a.q = static_cast<const op_t*>(q); a.q_row_stride = q_row_stride; a.q_head_stride = q_head_stride;
+  a.k = static_cast<const op_t*>(k); a.k_row_stride = k_row_stride; a.k_head_stride = k_head_stride;
+  a.v = static_cast<const op_t*>(v); a.v_row_stride = v_row_stride; a.v_head_stride = v_head_stride;
+  a.k_extra = static_cast<const op_t*>(k_extra); a.v_extra = static_cast<const op_t*>(v_extra); a.n_extra = n_extra;
+  a.out = static_cast<op_t*>(out); a.o_row_stride = o_row_stride; a.B = B; a.T = T; a.heads = heads; a.D = D;
+  a.scale = scale;
+  ++g_launches;
+  return attn_launch(a, static_cast<cudaStream_t>(stream))
+             ? fail("attention launch: %s", cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+int sgdm_k_linear_f32(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
+                      float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate) {
+  ++g_launches;
+  return linear_f32_launch(in, in_stride, W, bias, out, out_stride, M, N, K, silu_out, accumulate,
+                           static_cast<cudaStream_t>(stream))
+             ? fail("linear launch failed")
+             : 0;
+}
+int sgdm_k_cast(void* stream, const float* src, void* dst_op, int B, int H, int W, int C, int up2) {
+  ++g_launches;
+  return cast_launch(src, static_cast<op_t*>(dst_op), B, H, W, C, up2, static_cast<cudaStream_t>(stream))
+             ? fail("cast launch failed")
+             : 0;
+}
+
+}  // extern "C"

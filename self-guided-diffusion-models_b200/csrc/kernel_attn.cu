@@ -1,0 +1,200 @@
+// Fused attention (flash-style online softmax, warp-shuffle row reductions).
+//
+// Replaces QKVAttentionLegacy (openaimodel.py:403-420: 8 heads, per-head [q|k|v] channel
+// blocks, q and k each scaled by ch^-1/4) and the attention core of Attention_LR
+// (crossattetion_lr.py:88-137: multi-query, ONE shared k/v head, keys = [16 context |
+// 1 null | T self], q scaled by d^-1/2) — SURVEY.md §2.3 rows K6/K7.
+//
+// One CTA = 64 queries of one (sample, head); 4 warps x 16 query rows.  K and V of the
+// sample (T_kv <= 320 rows incl. the extra context/null rows) are staged once in shared
+// memory; S = QK^T and O = PV run on mma.sync m16n8k16 (16-bit operands, fp32 accumulate);
+// the softmax is computed in fp32 over key chunks of 64 with running max / sum.
+// Attention is ~1 % of the UNet FLOPs.
+#include "attn.cuh"
+
+namespace sgdm {
+
+#ifdef SGDM_OPERAND_BF16
+#define SGDM_MMA "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32"
+#else
+#define SGDM_MMA "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32"
+#endif
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(SGDM_MMA " {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_kernel(const AttnDesc a, int tkv_pad) {
+  constexpr int LD = D + 8;  // padded row: conflict-free ldmatrix
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  op_t* sK = reinterpret_cast<op_t*>(smem_attn);
+  op_t* sV = sK + static_cast<long>(tkv_pad) * LD;
+  op_t* sQ = sV + static_cast<long>(tkv_pad) * LD;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tkv = a.n_extra + a.T;
+  constexpr int CPR = D / 8;  // 16-byte chunks per row
+
+  // ---- stage K, V (extra rows first, then the T self rows) and the Q tile
+  for (int i = threadIdx.x; i < tkv_pad * CPR; i += 128) {
+    const int row = i / CPR, ch = i - row * CPR;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (row < a.n_extra) {
+      const long o = (static_cast<long>(n) * a.n_extra + row) * D + ch * 8;
+      kv = *reinterpret_cast<const uint4*>(a.k_extra + o);
+      vv = *reinterpret_cast<const uint4*>(a.v_extra + o);
+    } else if (row < Tkv) {
+      const long tok = static_cast<long>(n) * a.T + (row - a.n_extra);
+      kv = *reinterpret_cast<const uint4*>(a.k + tok * a.k_row_stride + h * a.k_head_stride + ch * 8);
+      vv = *reinterpret_cast<const uint4*>(a.v + tok * a.v_row_stride + h * a.v_head_stride + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + row * LD + ch * 8) = kv;
+    *reinterpret_cast<uint4*>(sV + row * LD + ch * 8) = vv;
+  }
+  for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
+    const int row = i / CPR, ch = i - row * CPR;
+    uint4 qv = make_uint4(0, 0, 0, 0);
+    if (q0 + row < a.T)
+      qv = *reinterpret_cast<const uint4*>(a.q + (static_cast<long>(n) * a.T + q0 + row) * a.q_row_stride +
+                                           h * a.q_head_stride + ch * 8);
+    *reinterpret_cast<uint4*>(sQ + row * LD + ch * 8) = qv;
+  }
+  __syncthreads();
+
+  // ---- Q fragments (A operand, 16 x D per warp)
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks)
+    ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 15)) * LD + ks * 16 + (lane >> 4) * 8);
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sl = a.scale * 1.4426950408889634f;  // logits in log2 units
+  const int mi = lane >> 3, lr = lane & 7;
+
+  const int nchunks = (Tkv + 63) / 64;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldsm_x4(b, sK + (kc * 64 + np * 16 + (mi >> 1) * 8 + lr) * LD + ks * 16 + (mi & 1) * 8);
+        mma16816(s[2 * np], qf[ks], b[0], b[1]);
+        mma16816(s[2 * np + 1], qf[ks], b[2], b[3]);
+      }
+    }
+    // scale, mask, running max
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kc * 64 + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = key + (j & 1) < Tkv;
+        s[nt][j] = ok ? s[nt][j] * sl : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - m0), p1 = exp2f(s[nt][1] - m0);
+      const float p2 = exp2f(s[nt][2] - m1), p3 = exp2f(s[nt][3] - m1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_op2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_op2(p2, p3);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int ndp = 0; ndp < D / 16; ++ndp) {
+        uint32_t b[4];
+        ldsm_x4_t(b, sV + (kc * 64 + kk * 16 + (mi & 1) * 8 + lr) * LD + (ndp * 2 + (mi >> 1)) * 8);
+        mma16816(o[2 * ndp], pf[kk], b[0], b[1]);
+        mma16816(o[2 * ndp + 1], pf[kk], b[2], b[3]);
+      }
+    }
+  }
+  // ---- finalise: row sums across the 4 lanes of a row, normalise, store
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    const int d = nd * 8 + (lane & 3) * 2;
+    if (r0 < a.T)
+      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r0) * a.o_row_stride + h * D + d) =
+          pack_op2(o[nd][0] * i0, o[nd][1] * i0);
+    if (r1 < a.T)
+      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r1) * a.o_row_stride + h * D + d) =
+          pack_op2(o[nd][2] * i1, o[nd][3] * i1);
+  }
+}
+
+int attn_launch(const AttnDesc& a, cudaStream_t s) {
+  const int Tkv = a.n_extra + a.T;
+  const int tkv_pad = (Tkv + 63) / 64 * 64;
+  if (a.D != 32 && a.D != 64) return 1;
+  const int LD = a.D + 8;
+  const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + 64) * LD * sizeof(op_t);
+  if (smem > 200 * 1024) return 1;
+  const dim3 grid((a.T + 63) / 64, a.heads, a.B);
+  static size_t max_set[2] = {0, 0};  // opt-in dynamic smem limit, raised on demand
+  if (a.D == 64) {
+    if (smem > max_set[0]) {
+      if (cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return 1;
+      max_set[0] = smem;
+    }
+    attn_kernel<64><<<grid, 128, smem, s>>>(a, tkv_pad);
+  } else {
+    if (smem > max_set[1]) {
+      if (cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return 1;
+      max_set[1] = smem;
+    }
+    attn_kernel<32><<<grid, 128, smem, s>>>(a, tkv_pad);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace sgdm

@@ -1,0 +1,357 @@
+// tcgen05 + TMA implicit-GEMM convolution (see conv.cuh).
+//
+// CTA = 192 threads, persistent over (m_tile, n_tile) work items, 1 CTA / SM:
+//   warp 0 (one lane)  TMA producer : 4-stage ring of {A 128x64, B block_n x 64} tiles
+//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per stage,
+//                                     accumulating in one of two TMEM accumulator stages
+//   warps 2..5         epilogue     : tcgen05.ld -> +bias (+residual) -> global store,
+//                                     overlapping the next tile's MMAs
+// Roofline: tensor pipe.  FLOPs per launch = 2 * M_total * Cout * Ktot.
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv.cuh"
+
+namespace sgdm {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 64 * 2;   // 16 KB
+constexpr int kBBytesMax = 256 * 64 * 2;   // 32 KB
+constexpr int kBarBytes = 256;
+constexpr int kConvSmem = 1024 + kStages * (kABytes + kBBytesMax) + kBarBytes;
+constexpr int kConvThreads = 192;
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytesMax));
+  uint64_t* full = bars;             // [kStages] TMA -> MMA
+  uint64_t* empty = bars + kStages;  // [kStages] MMA -> TMA
+  uint64_t* tfull = bars + 2 * kStages;       // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int block_n = p.block_n;
+  // two accumulator stages of block_n fp32 columns each; allocation must be a power of 2 >= 32
+  uint32_t ncols = 32;
+  while (ncols < 2u * block_n) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (p.kc2) tma_prefetch_desc(&p.tmA2);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int KB = p.taps * p.kc1 + p.kc2;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = kABytes + block_n * 128;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int p0 = m_tile * kTileM;
+        const int img = p0 / p.HW;
+        const int y0 = (p0 - img * p.HW) / p.Wout;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          if (kb < p.taps * p.kc1) {
+            const int tap = kb / p.kc1;
+            const int cc = kb - tap * p.kc1;
+            const int r = tap / p.ks;
+            const int s = tap - r * p.ks;
+            tma_load_4d(&p.tmA, &full[stage], sA + stage * kABytes, cc * 64, s - p.pad,
+                        y0 * p.stride + r - p.pad, img);
+          } else {
+            const int cc = kb - p.taps * p.kc1;
+            tma_load_4d(&p.tmA2, &full[stage], sA + stage * kABytes, cc * 64, 0, y0, img);
+          }
+          tma_load_2d(&p.tmB, &full[stage], sB + stage * kBBytesMax, kb * 64, n_tile * block_n);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = umma_idesc(kTileM, block_n);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * block_n;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBBytesMax);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);            // frees the smem stage when these MMAs retire
+          if (kb == KB - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_tile * kTileM + row;
+      const bool valid = m < p.M_total;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * block_n;
+      long res_row = 0;
+      int img = 0, pix = 0;
+      if (valid) {
+        img = m / p.HW;
+        pix = m - img * p.HW;
+        if (p.res_mode == 2) {
+          const int y = pix / p.Wout, x = pix - y * p.Wout;
+          res_row = (static_cast<long>(img) * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+        } else {
+          res_row = m;
+        }
+      }
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t v[32];
+        const int nc = min(32, block_n - c0);
+        if (nc == 32) tmem_ld_32x32(taddr + c0, v);
+        else tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int col0 = n_tile * block_n + c0;
+        if (p.out_nchw != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (j < nc && col < p.N_total) {
+              float a = __uint_as_float(v[j]);
+              if (p.bias) a += p.bias[col];
+              p.out_nchw[(static_cast<long>(img) * p.N_total + col) * p.HW + pix] = a;
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j >= nc) break;
+          const int col = col0 + j;
+          if (col >= p.N_total) break;
+          float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (p.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.res_mode) {
+            const float4 r = *reinterpret_cast<const float4*>(p.res + res_row * p.N_total + col);
+            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+          }
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
+          if (p.out_op) {
+            uint2 h = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
+            *reinterpret_cast<uint2*>(p.out_op + static_cast<long>(m) * p.N_total + col) = h;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------ host
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+#ifdef SGDM_OPERAND_BF16
+#define SGDM_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#else
+#define SGDM_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#endif
+
+static int encode_nhwc(CUtensorMap* tm, const op_t* base, int B, int H, int W, int C, int bw, int bh, int bn,
+                       int stride, char* err, int errlen) {
+  auto fn = get_encode_fn();
+  if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(tm, SGDM_TMA_DTYPE, 4, const_cast<op_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled(A: B%d H%d W%d C%d box %dx%dx%d s%d) failed: %d", B, H, W, C, bw,
+             bh, bn, stride, (int)r);
+    return 1;
+  }
+  return 0;
+}
+
+int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
+  memset(&out->p, 0, sizeof(out->p));
+  out->desc = d;
+  ConvKernelParams& p = out->p;
+  auto fail = [&](const char* msg) { snprintf(err, errlen, "conv_prepare: %s", msg); return 1; };
+  if (d.Cin % 64 || (d.in2 && d.C2 % 64)) return fail("channel counts must be multiples of 64");
+  if (!(d.ks == 1 || d.ks == 3) || !(d.stride == 1 || d.stride == 2)) return fail("unsupported ks/stride");
+  if (d.block_n != 16 && (d.block_n % 32 || d.block_n > 256 || d.block_n <= 0)) return fail("bad block_n");
+  if (d.Wout > 128 || (128 % d.Wout) != 0) return fail("Wout must divide 128");
+  const int HW = d.Hout * d.Wout;
+  if (!((HW % 128) == 0 || (128 % HW) == 0)) return fail("Hout*Wout must divide or be a multiple of 128");
+  if (d.out_nchw == nullptr && (d.Cout % 4)) return fail("Cout % 4 != 0 needs the NCHW epilogue");
+  if (d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
+  const int bw = d.Wout;
+  const int bh = min(d.Hout, 128 / bw);
+  const int bn = 128 / (bw * bh);
+  if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, bh, bn, d.stride, err, errlen)) return 1;
+  if (d.in2) {
+    if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
+  }
+  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
+  const int npad = conv_npad(d.Cout, d.block_n);
+  {
+    auto fn = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)d.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&p.tmB, SGDM_TMA_DTYPE, 2, const_cast<op_t*>(d.w), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(err, errlen, "cuTensorMapEncodeTiled(B: K%d N%d) failed: %d", Ktot, npad, (int)r);
+      return 1;
+    }
+  }
+  p.M_total = d.B * HW;
+  p.HW = HW;
+  p.Wout = d.Wout;
+  p.Hout = d.Hout;
+  p.stride = d.stride;
+  p.pad = d.pad;
+  p.ks = d.ks;
+  p.taps = d.ks * d.ks;
+  p.kc1 = d.Cin / 64;
+  p.kc2 = d.in2 ? d.C2 / 64 : 0;
+  p.N_total = d.Cout;
+  p.block_n = d.block_n;
+  p.n_tiles = npad / d.block_n;
+  p.m_tiles = (p.M_total + kTileM - 1) / kTileM;
+  p.bias = d.bias;
+  p.res = d.res;
+  p.res_mode = d.res ? d.res_mode : 0;
+  p.out_f32 = d.out_f32;
+  p.out_op = d.out_op;
+  p.out_nchw = d.out_nchw;
+  const int total = p.m_tiles * p.n_tiles;
+  out->grid = total < kNumSMs ? total : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  return 0;
+}
+
+int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+  conv_gemm_kernel<<<l.grid, kConvThreads, kConvSmem, stream>>>(l.p);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// --------------------------------------------------------------------- CUDA-core checker
+__global__ void conv_naive_kernel(ConvDesc d, int npad) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long M = static_cast<long>(d.B) * d.Hout * d.Wout;
+  if (idx >= M * d.Cout) return;
+  const int col = idx % d.Cout;
+  const long m = idx / d.Cout;
+  const int HW = d.Hout * d.Wout;
+  const int img = m / HW, pix = m % HW, y = pix / d.Wout, x = pix % d.Wout;
+  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
+  const op_t* wrow = d.w + static_cast<long>(col) * Ktot;
+  float acc = 0.f;
+  for (int r = 0; r < d.ks; ++r)
+    for (int s = 0; s < d.ks; ++s) {
+      const int iy = y * d.stride + r - d.pad, ix = x * d.stride + s - d.pad;
+      if (iy < 0 || iy >= d.Hin || ix < 0 || ix >= d.Win) continue;
+      const op_t* a = d.in + ((static_cast<long>(img) * d.Hin + iy) * d.Win + ix) * d.Cin;
+      const op_t* w = wrow + (r * d.ks + s) * d.Cin;
+      for (int c = 0; c < d.Cin; ++c) acc += from_op(a[c]) * from_op(w[c]);
+    }
+  if (d.in2) {
+    const op_t* a = d.in2 + m * d.C2;
+    const op_t* w = wrow + d.ks * d.ks * d.Cin;
+    for (int c = 0; c < d.C2; ++c) acc += from_op(a[c]) * from_op(w[c]);
+  }
+  if (d.bias) acc += d.bias[col];
+  if (d.res && d.res_mode == 1) acc += d.res[m * d.Cout + col];
+  if (d.res && d.res_mode == 2)
+    acc += d.res[((static_cast<long>(img) * (d.Hout / 2) + y / 2) * (d.Wout / 2) + x / 2) * d.Cout + col];
+  if (d.out_f32) d.out_f32[m * d.Cout + col] = acc;
+  if (d.out_op) d.out_op[m * d.Cout + col] = to_op(acc);
+  if (d.out_nchw) d.out_nchw[(static_cast<long>(img) * d.Cout + col) * HW + pix] = acc;
+}
+
+int conv_launch_naive(const ConvDesc& d, cudaStream_t stream) {
+  const long total = static_cast<long>(d.B) * d.Hout * d.Wout * d.Cout;
+  const int threads = 256;
+  conv_naive_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      d, conv_npad(d.Cout, d.block_n));
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace sgdm

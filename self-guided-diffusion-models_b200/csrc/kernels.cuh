@@ -1,0 +1,121 @@
+// Launch wrappers of the non-GEMM kernels (HBM-bound elementwise / reduction work).
+// All activations are NHWC; the residual stream is fp32, GEMM operands are op_t.
+#pragma once
+#include "common.cuh"
+
+namespace sgdm {
+
+// ---- K1/K2: GroupNorm(32) [+FiLM] [+SiLU] [+2x2 avg-pool | nearest 2x] ------------------
+// Reference: GroupNorm32 (diffusionmodules/util.py:199-216) + SiLU + ResBlock FiLM
+// `out_norm(h) * (1 + scale) + shift` (openaimodel.py:312-316), avg_pool2d / nearest
+// upsample of up/down ResBlocks (:253-258,301-306), skip concat th.cat([h, hs.pop()], 1) (:950).
+struct GnDesc {
+  const float* src0 = nullptr;  // fp32 NHWC [B, H, W, C0]
+  const float* src1 = nullptr;  // optional second concat source [B, H, W, C1]
+  int B = 0, H = 0, W = 0, C0 = 0, C1 = 0;
+  const float* gamma = nullptr;  // [C0+C1]
+  const float* beta = nullptr;
+  const float* film = nullptr;   // optional fp32 [B, film_stride]: scale at [c], shift at [C + c]
+  long film_stride = 0;
+  int silu = 1;
+  int resample = 0;              // 0 none | 1 avg-pool 2x2 | 2 nearest 2x
+  double* partial = nullptr;     // scratch [B][chunks][32][2]
+  int chunks = 1;
+  op_t* out = nullptr;           // NHWC op_t [B, H', W', C]
+  op_t* raw_out = nullptr;       // optional op_t copy of the un-normalised concat input (for the 1x1 skip conv)
+  float* pool_out = nullptr;     // optional fp32 avg-pooled raw input (residual of a down ResBlock)
+};
+int gn_chunks_for(int B, int HW, int C);
+int gn_launch(const GnDesc& d, cudaStream_t s);
+
+// ---- LayerNorm over channels (Attention_LR, crossattetion_lr.py:36-43) -------------------
+// mode 0: out_op = LN(x)*gamma+beta ; mode 1: out_f32 = res + LN(x)*gamma+beta
+int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
+                     float* out_f32, long rows, int C, cudaStream_t s);
+
+// ---- casts --------------------------------------------------------------------------------
+// fp32 NHWC -> op_t NHWC, optionally nearest-2x upsampled (Upsample, openaimodel_ca.py:121-131)
+int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s);
+// dst[i] = op(silu(src[i]))   (ResBlock.emb_layers[0], openaimodel.py:262-263)
+int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s);
+
+// ---- fp32 small linear: out[m, n] (+)= act(bias[n] + sum_k in[m,k] W[n,k]) -----------------
+int linear_f32_launch(const float* in, long in_stride, const float* W, const float* bias, float* out,
+                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s);
+
+// ---- prologue: CFG batch assembly (C1/C3/C4 rows of SURVEY §8a) ------------------------------
+struct PrepDesc {
+  const float* x = nullptr;          // fp32 NCHW [B, Cimg, H, W]
+  const long long* t = nullptr;      // int64 [B]
+  const float* cond = nullptr;       // fp32 [B, cond_dim] (may be null when cond_dim == 0)
+  const float* layout = nullptr;     // fp32 [B, L, H, W]   (null when L == 0)
+  const unsigned char* drop = nullptr;  // [Bp] 1 = replace cond/layout by the null embeddings
+  const float* null_cond = nullptr;  // [cond_dim]
+  const float* null_layout = nullptr;   // [H*W]
+  const float* freqs = nullptr;      // [mc/2] host-computed exp(-ln(1e4) i / half) (util.py:160-163)
+  int B = 0, Bp = 0;                 // Bp = B or 2B; row r reads sample r % B
+  int Cimg = 3, H = 0, W = 0, L = 0, cond_dim = 0, mc = 0;
+  op_t* x_in = nullptr;              // NHWC op_t [Bp, H, W, 64]: [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0]
+  float* t_emb = nullptr;            // [Bp, mc]  [cos | sin]
+  float* cond_masked = nullptr;      // [Bp, cond_dim]
+};
+int prep_launch(const PrepDesc& d, cudaStream_t s);
+
+// context K/V for Attention_LR: norm_cond LayerNorm over [time tokens | cond tokens]
+// (openaimodel_ca.py:973,1017) then per-site to_context = LayerNorm + Linear(ctx -> 2*dh)
+// (crossattetion_lr.py:75,103-106), null_kv appended as key 16 (:95-97).
+struct CtxDesc {
+  const float* time_tokens = nullptr;  // [Bp, 8*ctx]
+  const float* cond_tokens = nullptr;  // [Bp, 8*ctx]
+  const float* norm_w = nullptr;       // norm_cond [ctx]
+  const float* norm_b = nullptr;
+  const float* ln_w = nullptr;         // to_context.0 [ctx]
+  const float* ln_b = nullptr;
+  const float* lin_w = nullptr;        // to_context.1 [2*dh, ctx]
+  const float* lin_b = nullptr;        // [2*dh]
+  const float* null_kv = nullptr;      // [2, dh]
+  int Bp = 0, ctx = 32, dh = 64;
+  op_t* k_out = nullptr;               // [Bp, 17, dh]
+  op_t* v_out = nullptr;
+};
+int context_kv_launch(const CtxDesc& d, cudaStream_t s);
+
+// ---- K10: guidance mix + sampler updates (fp32, bit-faithful op order) ----------------------
+// eps = (1-w) eps_u + w eps_c  ('imagen') | (1+w) eps_c - w eps_u ('cfg')   (openaimodel.py:853-859)
+struct MixDesc {
+  const float* eps_c = nullptr;
+  const float* eps_u = nullptr;  // null: eps = eps_c (single pass)
+  float w = 0.f;
+  const float* w_per_sample = nullptr;  // optional [B] (tensor cond_scale [B,1,1,1])
+  int scale_type = 0;                    // 0 imagen | 1 cfg
+};
+int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStream_t s);
+
+// Host-computed fp32 scalars, each produced with the reference's own dtype chain:
+//   sqrt_one_minus_at = ddim_sqrt_one_minus_alphas[i]; sqrt_at = fp32 sqrt(ddim_alphas[i]);
+//   sqrt_a_prev = fp32 sqrt(fp32(ddim_alphas_prev[i])); dir_coef = fp32 sqrt(1 - a_prev - sigma^2)
+struct DdimCoef { float sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t, temperature; int clip; };
+// p_sample_ddim arithmetic (ddim_plms_sampler.py:360-391) fused with the mix.
+int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const float* x, const float* noise, float* x_out,
+                     float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s);
+
+// nonzero_sigma = (t != 0) * exp(0.5 * posterior_log_variance_clipped[t]) (fp32, host-computed)
+struct DdpmCoef { float sqrt_recip, sqrt_recipm1, coef1, coef2, nonzero_sigma, temperature; int clip; };
+// p_mean_variance + p_sample arithmetic (ddpm_sampler.py:154-192) fused with the mix.
+int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const float* x, const float* noise, float* x_out,
+                     float* x0_out, int B, long per_sample, cudaStream_t s);
+
+// ((x+1)*127.5).clamp(0,255).to(uint8)  (diffusion_utils/util.py:99-100)
+int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s);
+
+// out = (c0*a0 + c1*a1 + ...)/div, left to right (PLMS, ddim_plms_sampler.py:432-459)
+int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s);
+
+// ---- weight packing --------------------------------------------------------------------------
+// torch conv weight fp32 [Cout, Cin, ks, ks] -> op_t dst[co][k_off + (r*ks+s)*cin_pad + ci] (row length ktot);
+// channels ci >= Cin (padding) are left untouched (buffers are zero-initialised).
+int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
+                            const int* ci_map, cudaStream_t s);
+int add_bias_launch(const float* a, const float* b, float* out, int n, cudaStream_t s);
+
+}  // namespace sgdm

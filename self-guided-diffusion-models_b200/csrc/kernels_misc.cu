@@ -1,0 +1,572 @@
+// HBM-bound kernels: GroupNorm(+FiLM+SiLU+resample), LayerNorm, casts, the fp32 prologue
+// (timestep embedding, null substitution, small MLPs), the fused guidance-mix + sampler
+// update, uint8 conversion and weight packing.  See kernels.cuh for the reference lines.
+#include "kernels.cuh"
+
+namespace sgdm {
+
+#define SGDM_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
+
+// =========================================================================== GroupNorm
+// Pass 1: per (sample, chunk of pixels) partial sum / sum-of-squares per group.
+// Thread = (float4 channel column q, pixel lane pl); fp32 per-thread partials over at most
+// a few hundred elements, combined in double -> deterministic and cancellation-safe.
+__global__ void gn_stats_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int HW, int C0,
+                                int C1, int chunks, int PL, double* __restrict__ partial) {
+  __shared__ float s_sum[1024];
+  __shared__ float s_sq[1024];
+  const int C = C0 + C1, C4 = C >> 2;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+  const int ppc = HW / chunks;
+  const int c = q * 4;
+  const float* base;
+  int cs, co;
+  if (c < C0) { base = src0 + static_cast<long>(n) * HW * C0; cs = C0; co = c; }
+  else { base = src1 + static_cast<long>(n) * HW * C1; cs = C1; co = c - C0; }
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int px = chunk * ppc + pl; px < (chunk + 1) * ppc; px += PL) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long>(px) * cs + co));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+  }
+  // layout [pl][C]
+  float* ps = s_sum + pl * C + c;
+  float* pq = s_sq + pl * C + c;
+  ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
+  pq[0] = ss.x; pq[1] = ss.y; pq[2] = ss.z; pq[3] = ss.w;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x, cpg = C / 32;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < PL; ++l)
+      for (int k = 0; k < cpg; ++k) {
+        a += static_cast<double>(s_sum[l * C + g * cpg + k]);
+        b += static_cast<double>(s_sq[l * C + g * cpg + k]);
+      }
+    double* out = partial + ((static_cast<long>(n) * chunks + chunk) * 32 + g) * 2;
+    out[0] = a;
+    out[1] = b;
+  }
+}
+
+struct GnApplyArgs {
+  const float* src0; const float* src1;
+  int H, W, C0, C1;
+  const float* gamma; const float* beta; const float* film; long film_stride;
+  int silu, resample, chunks;
+  const double* partial;
+  op_t* out; op_t* raw_out; float* pool_out;
+};
+
+__device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, int c, float (&v)[8]) {
+  const int HW = a.H * a.W;
+  const float* p = (c < a.C0) ? a.src0 + (static_cast<long>(n) * HW + pix) * a.C0 + c
+                              : a.src1 + (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
+  uint4 o = make_uint4(pack_op2(y[0], y[1]), pack_op2(y[2], y[3]), pack_op2(y[4], y[5]), pack_op2(y[6], y[7]));
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+// Pass 2: normalise + affine (+FiLM) (+SiLU), write op_t NHWC, optionally pooled / upsampled.
+__global__ void gn_apply_kernel(const GnApplyArgs a) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  if (threadIdx.x < 32) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < a.chunks; ++k) {
+      const double* pp = a.partial + ((static_cast<long>(n) * a.chunks + k) * 32 + threadIdx.x) * 2;
+      s += pp[0];
+      q += pp[1];
+    }
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int Ho = a.resample == 1 ? a.H >> 1 : a.H, Wo = a.resample == 1 ? a.W >> 1 : a.W;
+  const long items = static_cast<long>(Ho) * Wo * C8;  // iterate over input pixels (pooled: output pixels)
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= items) return;
+  const int cg = idx % C8;
+  const int pix = idx / C8;
+  const int c = cg * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float ga = __ldg(a.gamma + c + j) * s_rstd[g];
+    sc[j] = ga;
+    sh[j] = __ldg(a.beta + c + j) - s_mean[g] * ga;
+  }
+  float fs[8], fb[8];
+  const bool film = a.film != nullptr;
+  if (film) {
+    const float* f = a.film + static_cast<long>(n) * a.film_stride;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { fs[j] = 1.0f + __ldg(f + c + j); fb[j] = __ldg(f + C + c + j); }
+  }
+  auto xform = [&](const float (&v)[8], float (&y)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      if (film) t = t * fs[j] + fb[j];
+      y[j] = a.silu ? silu(t) : t;
+    }
+  };
+  float v[8], y[8];
+  if (a.resample == 0) {
+    gn_load8(a, n, pix, c, v);
+    xform(v, y);
+    store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y);
+    if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v);
+  } else if (a.resample == 1) {
+    const int yo = pix / Wo, xo = pix - yo * Wo;
+    float acc[8], racc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] = 0.f; racc[j] = 0.f; }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        gn_load8(a, n, (2 * yo + dy) * a.W + 2 * xo + dx, c, v);
+        xform(v, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j] += y[j]; racc[j] += v[j]; }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] *= 0.25f; racc[j] *= 0.25f; }
+    const long o = (static_cast<long>(n) * Ho * Wo + pix) * C + c;
+    store8_op(a.out + o, acc);
+    if (a.pool_out) {
+      *reinterpret_cast<float4*>(a.pool_out + o) = make_float4(racc[0], racc[1], racc[2], racc[3]);
+      *reinterpret_cast<float4*>(a.pool_out + o + 4) = make_float4(racc[4], racc[5], racc[6], racc[7]);
+    }
+  } else {
+    gn_load8(a, n, pix, c, v);
+    xform(v, y);
+    const int yi = pix / a.W, xi = pix - yi * a.W;
+    const int W2 = a.W * 2;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        store8_op(a.out + ((static_cast<long>(n) * a.H * 2 + 2 * yi + dy) * W2 + 2 * xi + dx) * C + c, y);
+  }
+}
+
+int gn_chunks_for(int B, int HW, int C) {
+  const int C4 = C / 4;
+  const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
+  int chunks = 1;
+  // enough CTAs to fill the chip at small batch, while keeping >= PL pixels per chunk
+  while (B * chunks < 2 * kNumSMs && chunks < 16 && HW / (chunks * 2) >= PL && (HW % (chunks * 2)) == 0) chunks *= 2;
+  return chunks;
+}
+
+int gn_launch(const GnDesc& d, cudaStream_t s) {
+  const int C = d.C0 + d.C1, HW = d.H * d.W;
+  if (C % 32 || C > 1024 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;
+  const int C4 = C / 4;
+  const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
+  gn_stats_kernel<<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+  GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
+                d.silu, d.resample, d.chunks, d.partial, d.out, d.raw_out, d.pool_out};
+  const long items = (d.resample == 1 ? static_cast<long>(HW) / 4 : static_cast<long>(HW)) * (C / 8);
+  gn_apply_kernel<<<dim3(static_cast<unsigned>((items + 255) / 256), d.B), 256, 0, s>>>(a);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== LayerNorm
+// One warp per row of C channels (C % 128 == 0, C <= 1024); two-pass in registers.
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ res,
+                                 op_t* __restrict__ out_op, float* __restrict__ out_f32, long rows, int C) {
+  const long row = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = C >> 7;  // float4 per lane
+  float4 v[8];
+  float s = 0.f;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  for (int j = 0; j < nv; ++j) {
+    v[j] = __ldg(xr + j * 32 + lane);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int j = 0; j < nv; ++j) {
+    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+  for (int j = 0; j < nv; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y = make_float4((v[j].x - mean) * rstd * g.x + b.x, (v[j].y - mean) * rstd * g.y + b.y,
+                           (v[j].z - mean) * rstd * g.z + b.z, (v[j].w - mean) * rstd * g.w + b.w);
+    if (out_f32) {
+      if (res) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(res + row * C + c));
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+    } else {
+      *reinterpret_cast<uint2*>(out_op + row * C + c) = make_uint2(pack_op2(y.x, y.y), pack_op2(y.z, y.w));
+    }
+  }
+}
+int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
+                     float* out_f32, long rows, int C, cudaStream_t s) {
+  if (C % 128 || C > 1024) return 1;
+  const long threads = rows * 32;
+  layernorm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(x, gamma, beta, res, out_op, out_f32,
+                                                                              rows, C);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== casts
+__global__ void cast_kernel(const float* __restrict__ src, op_t* __restrict__ dst, int H, int W, int C, int up2,
+                            long items) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= items) return;
+  const int C8 = C >> 3;
+  const int cg = idx % C8;
+  const long pixg = idx / C8;  // global input pixel index (n*H*W + y*W + x)
+  const float* p = src + pixg * C + cg * 8;
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+  const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  if (!up2) {
+    store8_op(dst + pixg * C + cg * 8, v);
+  } else {
+    const long n = pixg / (static_cast<long>(H) * W);
+    const int pix = pixg - n * H * W;
+    const int y = pix / W, x = pix - y * W;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx)
+        store8_op(dst + ((n * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * C + cg * 8, v);
+  }
+}
+int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s) {
+  if (C % 8) return 1;
+  const long items = static_cast<long>(B) * H * W * (C / 8);
+  cast_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, s>>>(src, dst, H, W, C, up2, items);
+  return SGDM_LAUNCH_OK();
+}
+
+__global__ void silu_cast_kernel(const float* __restrict__ src, op_t* __restrict__ dst, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = to_op(silu(src[i]));
+}
+int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s) {
+  silu_cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== fp32 linear
+// 64x64 output tile per 256-thread CTA, 4x4 per thread, K staged 16 at a time through smem.
+__global__ void linear_f32_kernel(const float* __restrict__ in, long in_stride, const float* __restrict__ W,
+                                  const float* __restrict__ bias, float* __restrict__ out, long out_stride, int M,
+                                  int N, int K, int silu_out, int accumulate) {
+  __shared__ float As[16][65];
+  __shared__ float Ws[16][65];
+  const int tm = blockIdx.y * 64, tn = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;
+      const int m = tm + r, n = tn + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? in[m * in_stride + k] : 0.f;
+      Ws[kk][r] = (n < N && k < K) ? W[static_cast<long>(n) * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int m = tm + ty * 4 + i;
+    if (m >= M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int n = tn + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (silu_out) v = silu(v);
+      float* o = out + m * out_stride + n;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+int linear_f32_launch(const float* in, long in_stride, const float* W, const float* bias, float* out,
+                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s) {
+  linear_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, s>>>(in, in_stride, W, bias, out, out_stride, M, N,
+                                                                      K, silu_out, accumulate);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== prologue
+// x (NCHW fp32) -> NHWC op_t with 64 channels: [x_hi | x_lo | layout | 0].  x_lo = x - x_hi
+// restores the precision lost by the 16-bit rounding of the image (its weights duplicate
+// the image-channel weights), so the first conv sees x to ~2^-21.
+__global__ void prep_x_kernel(const PrepDesc d) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const int HW = d.H * d.W;
+  if (idx >= static_cast<long>(d.Bp) * HW) return;
+  const int r = idx / HW, pix = idx - static_cast<long>(r) * HW;
+  const int b = r % d.B;
+  const bool drop = d.drop && d.drop[r];
+  __align__(16) op_t v[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) v[j] = to_op(0.f);
+  for (int c = 0; c < d.Cimg; ++c) {
+    const float xv = d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pix];
+    const op_t hi = to_op(xv);
+    v[c] = hi;
+    v[d.Cimg + c] = to_op(xv - from_op(hi));
+  }
+  for (int l = 0; l < d.L; ++l) {
+    const float lv = drop ? d.null_layout[pix] : d.layout[(static_cast<long>(b) * d.L + l) * HW + pix];
+    v[2 * d.Cimg + l] = to_op(lv);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(d.x_in + idx * 64);
+  const uint4* srcv = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = srcv[j];
+}
+__global__ void prep_emb_kernel(const PrepDesc d) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const int half = d.mc / 2;
+  const long n_t = static_cast<long>(d.Bp) * half;
+  const long n_c = static_cast<long>(d.Bp) * d.cond_dim;
+  if (idx < n_t) {
+    const int r = idx / half, i = idx - static_cast<long>(r) * half;
+    const float arg = __fmul_rn(static_cast<float>(d.t[r % d.B]), d.freqs[i]);
+    d.t_emb[static_cast<long>(r) * d.mc + i] = cosf(arg);
+    d.t_emb[static_cast<long>(r) * d.mc + half + i] = sinf(arg);
+    if ((d.mc & 1) && i == 0) d.t_emb[static_cast<long>(r) * d.mc + d.mc - 1] = 0.f;
+  } else if (idx < n_t + n_c) {
+    const long k = idx - n_t;
+    const int r = k / d.cond_dim, j = k - static_cast<long>(r) * d.cond_dim;
+    const bool drop = d.drop && d.drop[r];
+    d.cond_masked[k] = drop ? d.null_cond[j] : d.cond[static_cast<long>(r % d.B) * d.cond_dim + j];
+  }
+}
+int prep_launch(const PrepDesc& d, cudaStream_t s) {
+  if (2 * d.Cimg + d.L > 64) return 1;
+  const long npx = static_cast<long>(d.Bp) * d.H * d.W;
+  prep_x_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
+  const long ne = static_cast<long>(d.Bp) * (d.mc / 2) + static_cast<long>(d.Bp) * d.cond_dim;
+  prep_emb_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, s>>>(d);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== context K/V
+__global__ void context_kv_kernel(const CtxDesc d) {
+  extern __shared__ float sm[];
+  const int ctx = d.ctx, dh = d.dh;
+  float* tok = sm;            // [16][ctx]
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < 16 * ctx; i += blockDim.x) {
+    const int t = i / ctx, j = i - t * ctx;
+    tok[i] = t < 8 ? d.time_tokens[(static_cast<long>(n) * 8 + t) * ctx + j]
+                   : d.cond_tokens[(static_cast<long>(n) * 8 + (t - 8)) * ctx + j];
+  }
+  __syncthreads();
+  // two LayerNorms back to back (norm_cond, then to_context.0), one thread per token
+  if (threadIdx.x < 16) {
+    float* row = tok + threadIdx.x * ctx;
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* w = pass == 0 ? d.norm_w : d.ln_w;
+      const float* b = pass == 0 ? d.norm_b : d.ln_b;
+      float mean = 0.f;
+      for (int j = 0; j < ctx; ++j) mean += row[j];
+      mean /= ctx;
+      float var = 0.f;
+      for (int j = 0; j < ctx; ++j) { const float dlt = row[j] - mean; var += dlt * dlt; }
+      const float rstd = rsqrtf(var / ctx + 1e-5f);
+      for (int j = 0; j < ctx; ++j) row[j] = (row[j] - mean) * rstd * w[j] + b[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 2 * dh; i += blockDim.x) {
+    const int t = i / (2 * dh), o = i - t * 2 * dh;
+    float acc = d.lin_b[o];
+    const float* w = d.lin_w + static_cast<long>(o) * ctx;
+    for (int j = 0; j < ctx; ++j) acc += tok[t * ctx + j] * w[j];
+    if (o < dh) d.k_out[(static_cast<long>(n) * 17 + t) * dh + o] = to_op(acc);
+    else d.v_out[(static_cast<long>(n) * 17 + t) * dh + (o - dh)] = to_op(acc);
+  }
+  for (int o = threadIdx.x; o < dh; o += blockDim.x) {
+    d.k_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(d.null_kv[o]);
+    d.v_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(d.null_kv[dh + o]);
+  }
+}
+int context_kv_launch(const CtxDesc& d, cudaStream_t s) {
+  context_kv_kernel<<<d.Bp, 128, 16 * d.ctx * sizeof(float), s>>>(d);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== guidance mix + sampler updates
+// All arithmetic uses explicit round-to-nearest intrinsics in the reference's operation
+// order (no FMA contraction), so that given identical eps the update is bit-identical to
+// the unfused torch ops it replaces.
+__device__ __forceinline__ float mix1(const MixDesc& m, float ec, float eu, float w, float ow) {
+  if (m.eps_u == nullptr) return ec;
+  if (m.scale_type == 0) return __fadd_rn(__fmul_rn(ow, eu), __fmul_rn(w, ec));  // (1-w) z + w zc
+  return __fsub_rn(__fmul_rn(ow, ec), __fmul_rn(w, eu));                        // (1+w) zc - w z
+}
+__device__ __forceinline__ void mix_coeffs(const MixDesc& m, int b, float& w, float& ow) {
+  w = m.w_per_sample ? m.w_per_sample[b] : m.w;
+  ow = m.scale_type == 0 ? __fsub_rn(1.0f, w) : __fadd_rn(1.0f, w);
+}
+
+__global__ void mix_kernel(const MixDesc m, float* __restrict__ out, long per_sample, long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float w, ow;
+  mix_coeffs(m, static_cast<int>(i / per_sample), w, ow);
+  out[i] = mix1(m, m.eps_c[i], m.eps_u ? m.eps_u[i] : 0.f, w, ow);
+}
+int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStream_t s) {
+  const long total = B * per_sample;
+  mix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, eps_out, per_sample, total);
+  return SGDM_LAUNCH_OK();
+}
+
+__global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const float* __restrict__ x,
+                                 const float* __restrict__ noise, float* __restrict__ x_out,
+                                 float* __restrict__ x0_out, float* __restrict__ eps_out, long per_sample,
+                                 long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float w, ow;
+  mix_coeffs(m, static_cast<int>(i / per_sample), w, ow);
+  const float e = mix1(m, m.eps_c[i], m.eps_u ? m.eps_u[i] : 0.f, w, ow);
+  // pred_x0 = (x - sqrt(1-a_t) e) / sqrt(a_t)
+  float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(c.sqrt_one_minus_at, e)), c.sqrt_at);
+  if (c.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float dir = __fmul_rn(c.dir_coef, e);                              // sqrt(1 - a_prev - sigma^2) e
+  const float nz = __fmul_rn(__fmul_rn(c.sigma_t, noise[i]), c.temperature);  // sigma * noise * temperature
+  x_out[i] = __fadd_rn(__fadd_rn(__fmul_rn(c.sqrt_a_prev, x0), dir), nz);
+  if (x0_out) x0_out[i] = x0;
+  if (eps_out) eps_out[i] = e;
+}
+int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const float* x, const float* noise, float* x_out,
+                     float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s) {
+  const long total = B * per_sample;
+  ddim_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, x, noise, x_out, x0_out, eps_out,
+                                                                             per_sample, total);
+  return SGDM_LAUNCH_OK();
+}
+
+__global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const float* __restrict__ x,
+                                 const float* __restrict__ noise, float* __restrict__ x_out,
+                                 float* __restrict__ x0_out, long per_sample, long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float w, ow;
+  mix_coeffs(m, static_cast<int>(i / per_sample), w, ow);
+  const float e = mix1(m, m.eps_c[i], m.eps_u ? m.eps_u[i] : 0.f, w, ow);
+  const float xi = x[i];
+  float x0 = __fsub_rn(__fmul_rn(c.sqrt_recip, xi), __fmul_rn(c.sqrt_recipm1, e));
+  if (c.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float mean = __fadd_rn(__fmul_rn(c.coef1, x0), __fmul_rn(c.coef2, xi));
+  const float nz = __fmul_rn(noise[i], c.temperature);
+  x_out[i] = __fadd_rn(mean, __fmul_rn(c.nonzero_sigma, nz));  // nonzero_mask * exp(0.5 logvar) * noise
+  if (x0_out) x0_out[i] = x0;
+}
+int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const float* x, const float* noise, float* x_out,
+                     float* x0_out, int B, long per_sample, cudaStream_t s) {
+  const long total = B * per_sample;
+  ddpm_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, x, noise, x_out, x0_out,
+                                                                             per_sample, total);
+  return SGDM_LAUNCH_OK();
+}
+
+__global__ void to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float v = __fmul_rn(__fadd_rn(x[i], 1.0f), 127.5f);
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  out[i] = static_cast<unsigned char>(v);  // truncation, like .to(torch.uint8)
+}
+int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s) {
+  to_uint8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, out, n);
+  return SGDM_LAUNCH_OK();
+}
+
+
+// PLMS multistep combination (ddim_plms_sampler.py:432-459): out = (c0 a0 + c1 a1 + ...) / div,
+// evaluated left to right with separately rounded products, like the unfused torch expression.
+struct LincombArgs { const float* a[4]; float c[4]; int n_terms; float div; };
+__global__ void lincomb_kernel(const LincombArgs g, float* __restrict__ out, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float acc = __fmul_rn(g.c[0], g.a[0][i]);
+  for (int k = 1; k < g.n_terms; ++k) acc = __fadd_rn(acc, __fmul_rn(g.c[k], g.a[k][i]));
+  out[i] = __fdiv_rn(acc, g.div);
+}
+int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s) {
+  if (n_terms < 1 || n_terms > 4) return 1;
+  LincombArgs g;
+  for (int k = 0; k < 4; ++k) { g.a[k] = k < n_terms ? a[k] : nullptr; g.c[k] = k < n_terms ? c[k] : 0.f; }
+  g.n_terms = n_terms;
+  g.div = div;
+  lincomb_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(g, out, n);
+  return SGDM_LAUNCH_OK();
+}
+
+// =========================================================================== weight packing
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin, int ks,
+                                        int cin_pad, int ktot, int k_off, const int* __restrict__ ci_map) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
+  if (idx >= total) return;
+  const int cj = idx % cin_pad;
+  const int tap = (idx / cin_pad) % (ks * ks);
+  const int co = idx / (static_cast<long>(cin_pad) * ks * ks);
+  const int ci = ci_map ? ci_map[cj] : (cj < Cin ? cj : -1);
+  if (ci < 0) return;
+  const int r = tap / ks, s = tap - r * ks;
+  dst[static_cast<long>(co) * ktot + k_off + tap * cin_pad + cj] =
+      to_op(w[((static_cast<long>(co) * Cin + ci) * ks + r) * ks + s]);
+}
+int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
+                            const int* ci_map, cudaStream_t s) {
+  const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
+  pack_conv_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ks, cin_pad,
+                                                                                   ktot, k_off, ci_map);
+  return SGDM_LAUNCH_OK();
+}
+__global__ void add_bias_kernel(const float* a, const float* b, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
+}
+int add_bias_launch(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+  add_bias_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, out, n);
+  return SGDM_LAUNCH_OK();
+}
+
+}  // namespace sgdm

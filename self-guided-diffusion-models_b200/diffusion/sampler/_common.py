@@ -1,0 +1,160 @@
+"""Shared pieces of the sampler mirrors: schedule tables and the fused step driver."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ...dynamic.diffusionmodules._unet_base import EngineUNet, _is_number
+
+
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    """float64 numpy betas, same expressions as dynamic/diffusionmodules/util.py:23-43."""
+    if schedule == "linear":
+        betas = torch.linspace(linear_start**0.5, linear_end**0.5, n_timestep, dtype=torch.float64) ** 2
+    elif schedule == "cosine":
+        timesteps = torch.arange(n_timestep + 1, dtype=torch.float64) / n_timestep + cosine_s
+        alphas = timesteps / (1 + cosine_s) * np.pi / 2
+        alphas = torch.cos(alphas).pow(2)
+        alphas = alphas / alphas[0]
+        betas = 1 - alphas[1:] / alphas[:-1]
+        betas = np.clip(betas, a_min=0, a_max=0.999)
+    elif schedule == "sqrt_linear":
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64)
+    elif schedule == "sqrt":
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64) ** 0.5
+    else:
+        raise ValueError(f"schedule '{schedule}' unknown.")
+    return betas.numpy()
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=False):
+    """util.py:46-60."""
+    if ddim_discr_method == "uniform":
+        c = num_ddpm_timesteps // num_ddim_timesteps
+        ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+    elif ddim_discr_method == "quad":
+        ddim_timesteps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * 0.8), num_ddim_timesteps)) ** 2).astype(int)
+    else:
+        raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
+    return ddim_timesteps + 1
+
+
+def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=False):
+    """util.py:63-74 — alphas: fp32 torch; alphas_prev: float64 numpy; sigmas: their mix."""
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return sigmas, alphas, alphas_prev
+
+
+def log_indices(total, log_num_per_prog):
+    return torch.linspace(0, total, log_num_per_prog, dtype=torch.int).cpu().numpy().tolist()
+
+
+class GuidedEps:
+    """Binds (model, cond, layout, cond_scale) for one trajectory and produces, per step, the
+    eps pointers the fused update kernels consume.
+
+    If `denoise_sample_fn` is the bound `forward_with_cond_scale` of an sgdm_b200 UNet, the
+    conditional and unconditional scores stay in engine memory and the guidance mix is fused
+    into the sampler update kernel.  Any other callable is invoked as the reference does
+    (`denoise_sample_fn(x, t, **kwargs)`) and its result is fed to the same kernel.
+    """
+
+    def __init__(self, denoise_sample_fn, kwargs, device):
+        self.fn = denoise_sample_fn
+        self.kwargs = dict(kwargs or {})
+        self.device = torch.device(device)
+        model = getattr(denoise_sample_fn, "__sgdm_model__", None)
+        if model is None:
+            owner = getattr(denoise_sample_fn, "__self__", None)
+            if isinstance(owner, EngineUNet) and getattr(denoise_sample_fn, "__name__", "") == "forward_with_cond_scale":
+                model = owner
+        extra = set(self.kwargs) - {"cond", "layout", "cond_scale"}
+        self.model = model if (model is not None and not extra) else None
+        self.w, self.w_ptr, self.mode = 0.0, None, "generic"
+        self._keep = []
+        if self.model is not None:
+            m = self.model
+            cs = self.kwargs.get("cond_scale")
+            if _is_number(cs, m._FLOAT_SHORTCUT) and cs == 1:
+                self.mode = "cond"
+            elif _is_number(cs, m._FLOAT_SHORTCUT) and cs == 0:
+                self.mode = "uncond"
+            else:
+                self.mode = "guided"
+                if torch.is_tensor(cs):
+                    wt = cs.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+                    self._keep.append(wt)
+                    self.w_ptr = wt.data_ptr()
+                else:
+                    self.w = float(cs)
+            self.scale_type = m._scale_type()
+            m.sync_weights()
+            self._prepared = None
+
+    def _prepare(self, x, t):
+        m = self.model
+        if self._prepared is None:  # cond / layout are constant over the trajectory: convert once
+            _, _, cond, layout = m._prep_inputs(x, t, self.kwargs.get("cond"), self.kwargs.get("layout"))
+            self._prepared = (cond, layout)
+        return self._prepared
+
+    def __call__(self, x, t):
+        """-> (eps_c_ptr, eps_u_ptr or None, w, w_ptr, scale_type)"""
+        if self.model is None:
+            eps = self.fn(x, t, **self.kwargs)
+            eps = eps.detach().float().contiguous()
+            self._keep = [eps]
+            return eps.data_ptr(), None, 0.0, None, 0
+        m = self.model
+        cond, layout = self._prepare(x, t)
+        if self.mode == "guided":
+            pc, pu = m.guided_pair_ptrs(x, t, cond, layout)
+            return pc, pu, self.w, self.w_ptr, self.scale_type
+        B = x.shape[0]
+        drop = torch.full((B,), 1 if self.mode == "uncond" else 0, dtype=torch.uint8, device=x.device)
+        eps = torch.empty_like(x)
+        _lib.check(_lib.lib().sgdm_forward(m._h, _lib.current_stream(x.device), x.data_ptr(), t.data_ptr(),
+                                           _lib.ptr(cond), _lib.ptr(layout), drop.data_ptr(), B, eps.data_ptr()))
+        self._keep = [eps, drop]
+        return eps.data_ptr(), None, 0.0, None, 0
+
+
+def coef6(*vals):
+    return (C.c_float * 6)(*[float(v) for v in vals])
+
+
+def check_supported(sampling_kwargs):
+    if sampling_kwargs.get("dtp", 1) < 1.0:
+        raise NotImplementedError("dynamic thresholding (dtp < 1) is not built into the fused update yet")
+    if sampling_kwargs.get("noise_dropout", 0) > 0.0:
+        raise NotImplementedError("noise_dropout > 0 is not built into the fused update yet")
+    vis = sampling_kwargs.get("vis", None)
+    for flag in ("condscale", "interp", "chainvis", "scoremix_vis"):
+        if vis is not None and hasattr(vis, flag) and getattr(vis, flag):
+            raise NotImplementedError(f"paper-visualisation branch vis.{flag} is out of scope")
+
+
+class NoiseSource:
+    """Per-trajectory noise: a host-supplied tape {'x_T', 'noise'[k]} (parity runs) or the
+    same torch.randn draws the reference makes on the device."""
+
+    def __init__(self, shape, device, tape=None):
+        self.shape, self.device, self.k = tuple(shape), torch.device(device), 0
+        self.tape = tape
+        if tape is not None:
+            self._noise = tape["noise"].to(self.device, torch.float32, non_blocking=True)
+
+    def x_T(self):
+        if self.tape is not None:
+            return self.tape["x_T"].to(self.device, torch.float32).contiguous().clone()
+        return torch.randn(self.shape, device=self.device)
+
+    def next(self):
+        if self.tape is not None:
+            n = self._noise[self.k]
+            self.k += 1
+            return n
+        return torch.randn(self.shape, device=self.device)
