@@ -89,20 +89,21 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u);
 
-/* eps = (1-w) eps_u + w eps_c (imagen) | (1+w) eps_c - w eps_u (cfg); w scalar, or per sample
- * when w_per_sample != NULL ([B] fp32 device). */
-int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+/* eps = (1-w) eps_u + w eps_c (imagen) | (1+w) eps_c - w eps_u (cfg); w scalar (a double, like the
+ * Python number the reference multiplies with: 1-w is formed in double, then rounded to fp32), or
+ * per sample when w_per_sample != NULL ([B] fp32 device; 1-w is then an fp32 op). */
+int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
              int scale_type, float* eps_out, int B, int64_t per_sample);
 
 /* One DDIM / PLMS update, optionally fused with the guidance mix (eps_u may be NULL: eps = eps_c).
  * coef = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma_t, temperature}. */
-int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out /* may be NULL */, float* eps_out /* may be NULL */, int B,
                    int64_t per_sample);
 /* One ancestral DDPM update. coef = {sqrt_recip_ac[t], sqrt_recipm1_ac[t], post_mean_coef1[t],
  * post_mean_coef2[t], (t!=0)*exp(0.5*post_logvar[t]), temperature}. */
-int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out /* may be NULL */, int B, int64_t per_sample);
 /* PLMS multistep eps combination (ddim_plms_sampler.py:432-459): out = (sum_k coefs[k]*terms[k]) / div,
@@ -110,6 +111,13 @@ int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float w
 int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const float* coefs, float div, float* out,
                  int64_t n);
 int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
+
+/* Per-launch timing of one forward (bench.py roofline): with profiling on, the next forward
+ * brackets every launch of its plan with CUDA events on `stream` and synchronises at the end.
+ * Each record: kernel family, measured ms, algorithmic FLOPs and algorithmic HBM bytes. */
+int sgdm_set_profiling(sgdm_handle h, int on);
+int sgdm_profile_count(sgdm_handle h);
+int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double* flops, double* bytes);
 
 /* Count of kernels launched by this library since load (claim for bench.py `gpu_launches`). */
 int64_t sgdm_launch_count(void);

@@ -38,7 +38,7 @@ KIND_UNET_FAST = 0
 KIND_UNETCA_FAST = 1
 SCALE_TYPES = {"imagen": 0, "cfg": 1}
 
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol declared in include/sgdm_b200.h
 PROTOTYPES = {
@@ -55,11 +55,14 @@ PROTOTYPES = {
     "sgdm_set_timestep_freqs": (_i, [_vp, _vp, _i]),
     "sgdm_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgdm_forward_guided": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_vp)]),
-    "sgdm_mix": (_i, [_vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i64]),
-    "sgdm_ddim_step": (_i, [_vp, _vp, _vp, _f, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64]),
-    "sgdm_ddpm_step": (_i, [_vp, _vp, _vp, _f, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64]),
+    "sgdm_mix": (_i, [_vp, _vp, _vp, _d, _vp, _i, _vp, _i, _i64]),
+    "sgdm_ddim_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64]),
+    "sgdm_ddpm_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64]),
     "sgdm_lincomb": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_f), _f, _vp, _i64]),
     "sgdm_to_uint8": (_i, [_vp, _vp, _vp, _i64]),
+    "sgdm_set_profiling": (_i, [_vp, _i]),
+    "sgdm_profile_count": (_i, [_vp]),
+    "sgdm_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
     "sgdm_launch_count": (_i64, []),
     "sgdm_debug_set_naive_conv": (_i, [_i]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),

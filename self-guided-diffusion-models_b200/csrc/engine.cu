@@ -86,9 +86,17 @@ struct Act {
   int C = 0, H = 0, W = 0;
 };
 
+struct OpMeta {
+  const char* kind;  // kernel family
+  double flops;      // algorithmic FLOPs (2*MAC, real channel counts) of this launch
+  double bytes;      // algorithmic HBM bytes (read + write) of this launch
+};
+
 struct Plan {
   int Bp = 0;
   std::vector<Op> ops;
+  std::vector<OpMeta> meta;
+  std::vector<float> prof_ms;  // filled by a profiled replay
   std::vector<void*> owned;
   // prologue inputs are bound per call through these
   PrepDesc prep;
@@ -127,7 +135,8 @@ struct sgdm_engine {
   std::vector<void*> owned;
   bool device_ready = false;
   std::map<int, std::unique_ptr<Plan>> plans;
-  const float* last_eps_c = nullptr;
+  bool profiling = false;
+  Plan* last_profiled = nullptr;
 
   ~sgdm_engine() {
     plans.clear();
@@ -582,11 +591,13 @@ struct Builder {
     stream_off += bytes;
     return p;
   }
-  void push(Op op) {
-    if (!dry) plan->ops.push_back(std::move(op));
+  void push(Op op, const char* kind = "misc", double flops = 0, double bytes = 0) {
+    if (dry) return;
+    plan->ops.push_back(std::move(op));
+    plan->meta.push_back(OpMeta{kind, flops, bytes});
   }
 
-  void conv(ConvDesc d) {
+  void conv(ConvDesc d, int real_cin = 0) {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
     if (dry) return;
@@ -597,20 +608,28 @@ struct Builder {
       err = 1;
       return;
     }
+    const double M = static_cast<double>(Bp) * d.Hout * d.Wout;
+    const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin) + (d.in2 ? d.C2 : 0);
+    const double flops = 2.0 * M * d.Cout * k_real;
+    const double in_px = static_cast<double>(Bp) * d.Hin * d.Win;
+    const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * d.C2 * 2 : 0) +
+                         M * d.Cout * ((d.out_f32 || d.out_nchw) ? 4 : 2) + (d.res ? M * d.Cout * 4 / (d.res_mode == 2 ? 4 : 1) : 0);
     push([l](cudaStream_t s) {
       ++g_launches;
       return g_naive_conv ? conv_launch_naive(l->desc, s) : conv_launch(*l, s);
-    });
+    }, d.ks == 3 ? "conv3x3" : "gemm1x1", flops, bytes);
   }
   void gn(GnDesc d) {
     d.B = Bp;
     d.chunks = gn_chunks_for(Bp, d.H * d.W, d.C0 + d.C1);
     d.partial = static_cast<double*>(scratch("gn_partial", static_cast<size_t>(Bp) * 16 * 32 * 2 * sizeof(double)));
     if (dry) return;
+    const double el = static_cast<double>(Bp) * d.H * d.W * (d.C0 + d.C1);
+    const double out_el = d.resample == 1 ? el / 4 : d.resample == 2 ? el * 4 : el;
     push([d](cudaStream_t s) {
       g_launches += 2;
       return gn_launch(d, s);
-    });
+    }, "groupnorm", 0, el * 4 * 2 + out_el * 2 + (d.raw_out ? el * 2 : 0) + (d.pool_out ? out_el * 4 : 0));
   }
 
   // ResBlock._forward (openaimodel.py:300-320)
@@ -676,7 +695,7 @@ struct Builder {
     push([ad](cudaStream_t s) {
       ++g_launches;
       return attn_launch(ad, s);
-    });
+    }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * T * dh, static_cast<double>(rows) * 4 * C * 2);
     Act o = a;
     o.p = stream_alloc(rows * C);
     ConvDesc c2;
@@ -726,7 +745,8 @@ struct Builder {
     push([ad](cudaStream_t s) {
       ++g_launches;
       return attn_launch(ad, s);
-    });
+    }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * (T + 17) * dh,
+         static_cast<double>(rows) * (nq + inner) * 2);
     float* tmp = static_cast<float*>(scratch("h1", rows * C * sizeof(float)));
     ConvDesc c2;
     c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = inner; c2.w = w.wout; c2.ks = 1; c2.stride = 1; c2.pad = 0;
@@ -867,7 +887,7 @@ struct Builder {
       ConvDesc d;
       d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
       d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
-      conv(d);
+      conv(d, cw.cin);
       hs.push_back(h);
     }
     Act none;
@@ -950,11 +970,26 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
   pd.x = x; pd.t = reinterpret_cast<const long long*>(t); pd.cond = cond; pd.layout = layout; pd.B = B;
   g_launches += 2;
   if (prep_launch(pd, s)) return fail("prep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  for (size_t i = 0; i < plan->ops.size(); ++i)
+  std::vector<cudaEvent_t> ev;
+  if (e->profiling) {
+    ev.resize(plan->ops.size() + 1);
+    for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
+    CUDA_TRY(cudaEventRecord(ev[0], s));
+  }
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (plan->ops[i](s)) {
       cudaError_t ce = cudaGetLastError();
-      return fail("launch %zu of %zu failed: %s", i, plan->ops.size(), cudaGetErrorString(ce));
+      return fail("launch %zu (%s) of %zu failed: %s", i, plan->meta[i].kind, plan->ops.size(), cudaGetErrorString(ce));
     }
+    if (e->profiling) CUDA_TRY(cudaEventRecord(ev[i + 1], s));
+  }
+  if (e->profiling) {  // profiling replays synchronise; never enabled inside a timed region
+    CUDA_TRY(cudaStreamSynchronize(s));
+    plan->prof_ms.assign(plan->ops.size(), 0.f);
+    for (size_t i = 0; i < plan->ops.size(); ++i) CUDA_TRY(cudaEventElapsedTime(&plan->prof_ms[i], ev[i], ev[i + 1]));
+    for (auto& x : ev) cudaEventDestroy(x);
+    e->last_profiled = plan;
+  }
   *plan_out = plan;
   return 0;
 }
@@ -1029,6 +1064,22 @@ int sgdm_set_timestep_freqs(sgdm_handle h, const float* host_freqs, int n) {
   return 0;
 }
 
+int sgdm_set_profiling(sgdm_handle h, int on) {
+  h->profiling = on != 0;
+  return 0;
+}
+int sgdm_profile_count(sgdm_handle h) { return h->last_profiled ? static_cast<int>(h->last_profiled->ops.size()) : 0; }
+int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double* flops, double* bytes) {
+  Plan* p = h->last_profiled;
+  if (!p || i < 0 || i >= static_cast<int>(p->ops.size()) || p->prof_ms.size() != p->ops.size())
+    return fail("no profile recorded");
+  *kind = p->meta[i].kind;
+  *ms = p->prof_ms[i];
+  *flops = p->meta[i].flops;
+  *bytes = p->meta[i].bytes;
+  return 0;
+}
+
 int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                  const float* layout, const uint8_t* drop, int B, float* eps_out) {
   Plan* plan = nullptr;
@@ -1048,12 +1099,13 @@ int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64
   return 0;
 }
 
-static MixDesc make_mix(const float* eps_c, const float* eps_u, float w, const float* wps, int scale_type) {
+static MixDesc make_mix(const float* eps_c, const float* eps_u, double w, const float* wps, int scale_type) {
   MixDesc m;
-  m.eps_c = eps_c; m.eps_u = eps_u; m.w = w; m.w_per_sample = wps; m.scale_type = scale_type;
+  m.eps_c = eps_c; m.eps_u = eps_u; m.w = static_cast<float>(w); m.w_per_sample = wps; m.scale_type = scale_type;
+  m.ow = static_cast<float>(scale_type == 0 ? 1.0 - w : 1.0 + w);
   return m;
 }
-int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
              int scale_type, float* eps_out, int B, int64_t per_sample) {
   ++g_launches;
   if (mix_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), eps_out, B, per_sample,
@@ -1061,7 +1113,7 @@ int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, float w, cons
     return fail("mix launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
-int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out, float* eps_out, int B, int64_t per_sample) {
   DdimCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};
@@ -1071,7 +1123,7 @@ int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float w
     return fail("ddim step launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
-int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float w, const float* w_per_sample,
+int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out, int B, int64_t per_sample) {
   DdpmCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};

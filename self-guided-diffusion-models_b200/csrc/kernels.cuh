@@ -85,7 +85,8 @@ int context_kv_launch(const CtxDesc& d, cudaStream_t s);
 struct MixDesc {
   const float* eps_c = nullptr;
   const float* eps_u = nullptr;  // null: eps = eps_c (single pass)
-  float w = 0.f;
+  float w = 0.f;   // fp32(w)
+  float ow = 1.f;  // host-computed fp32(1 - w) ('imagen') or fp32(1 + w) ('cfg'), from the DOUBLE w like torch
   const float* w_per_sample = nullptr;  // optional [B] (tensor cond_scale [B,1,1,1])
   int scale_type = 0;                    // 0 imagen | 1 cfg
 };

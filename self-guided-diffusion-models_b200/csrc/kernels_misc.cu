@@ -165,11 +165,13 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
 }
 
 int gn_chunks_for(int B, int HW, int C) {
+  // Depends on the per-sample shape ONLY (never on the batch): the fp32 summation order, and with
+  // it every output bit, is then independent of how samples are batched together.
+  (void)B;
   const int C4 = C / 4;
   const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
   int chunks = 1;
-  // enough CTAs to fill the chip at small batch, while keeping >= PL pixels per chunk
-  while (B * chunks < 2 * kNumSMs && chunks < 16 && HW / (chunks * 2) >= PL && (HW % (chunks * 2)) == 0) chunks *= 2;
+  while (chunks < 16 && HW / (chunks * 2) >= 4 * PL && (HW % (chunks * 2)) == 0) chunks *= 2;
   return chunks;
 }
 
@@ -438,8 +440,13 @@ __device__ __forceinline__ float mix1(const MixDesc& m, float ec, float eu, floa
   return __fsub_rn(__fmul_rn(ow, ec), __fmul_rn(w, eu));                        // (1+w) zc - w z
 }
 __device__ __forceinline__ void mix_coeffs(const MixDesc& m, int b, float& w, float& ow) {
-  w = m.w_per_sample ? m.w_per_sample[b] : m.w;
-  ow = m.scale_type == 0 ? __fsub_rn(1.0f, w) : __fadd_rn(1.0f, w);
+  if (m.w_per_sample) {  // fp32 tensor cond_scale: (1 -/+ w) is an fp32 tensor op in the reference
+    w = m.w_per_sample[b];
+    ow = m.scale_type == 0 ? __fsub_rn(1.0f, w) : __fadd_rn(1.0f, w);
+  } else {               // Python-number cond_scale: (1 -/+ w) evaluated in double, then cast
+    w = m.w;
+    ow = m.ow;
+  }
 }
 
 __global__ void mix_kernel(const MixDesc m, float* __restrict__ out, long per_sample, long total) {

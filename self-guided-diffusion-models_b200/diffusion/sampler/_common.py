@@ -62,7 +62,7 @@ class GuidedEps:
     (`denoise_sample_fn(x, t, **kwargs)`) and its result is fed to the same kernel.
     """
 
-    def __init__(self, denoise_sample_fn, kwargs, device):
+    def __init__(self, denoise_sample_fn, kwargs, device, fresh_weights=True):
         self.fn = denoise_sample_fn
         self.kwargs = dict(kwargs or {})
         self.device = torch.device(device)
@@ -91,6 +91,8 @@ class GuidedEps:
                 else:
                     self.w = float(cs)
             self.scale_type = m._scale_type()
+            if fresh_weights:  # once per trajectory: also catches `.data` writes (ema_scope)
+                m.invalidate_weight_cache()
             m.sync_weights()
             self._prepared = None
 

@@ -56,6 +56,39 @@ class Schedule_DDPM(nn.Module):
         reg("posterior_mean_coef1", betas * np.sqrt(alphas_cumprod_prev) / (1.0 - alphas_cumprod))
         reg("posterior_mean_coef2", (1.0 - alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - alphas_cumprod))
 
+
+    @torch.no_grad()
+    def p_sample(self, x, t, clip_denoised=False, repeat_noise=False, temperature=1.0, noise_dropout=0.0,
+                 sampling_kwargs=None, denoise_sample_fn=None, denoise_sample_fn_kwargs=None, noise=None,
+                 index=None, **kwargs):
+        """One reverse step (ddpm_sampler.py:175-192): guided eps + fused posterior update.
+        `t` must be batch-uniform (it always is while sampling); pass `index` = that timestep to
+        avoid reading it back from the device.  `noise` is an optional host-supplied draw."""
+        check_supported(sampling_kwargs)
+        if noise_dropout > 0.0 or repeat_noise:
+            raise NotImplementedError("noise_dropout / repeat_noise")
+        i = int(t[0]) if index is None else int(index)
+        device = x.device
+        if not hasattr(self, "_step_tab") or self._step_tab[0] is not self.posterior_log_variance_clipped:
+            tab = {k: getattr(self, k).detach().cpu() for k in
+                   ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                    "posterior_mean_coef2", "posterior_log_variance_clipped")}
+            tab["sigma"] = (0.5 * tab["posterior_log_variance_clipped"]).exp()
+            self._step_tab = (self.posterior_log_variance_clipped, tab)
+        tab = self._step_tab[1]
+        eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device, fresh_weights=False)
+        x = x.detach().float().contiguous()
+        pc, pu, w, w_ptr, st = eps_src(x, t.to(device=device, dtype=torch.long).contiguous())
+        nz = torch.randn(x.shape, device=device) if noise is None else noise.to(device, torch.float32).contiguous()
+        out, x0 = torch.empty_like(x), torch.empty_like(x)
+        c = coef6(tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i],
+                  tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
+                  tab["sigma"][i] if i != 0 else 0.0, temperature)
+        _lib.check(_lib.lib().sgdm_ddpm_step(_lib.current_stream(device), pc, pu, w, w_ptr, st, c,
+                                             1 if sampling_kwargs["clip_denoised"] else 0, x.data_ptr(), nz.data_ptr(),
+                                             out.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel()))
+        return out, x0, None
+
     @torch.no_grad()
     def sample(self, shape, sampling_kwargs=None, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,
                condition_kwargs=None, noise_tape=None, **kwargs):

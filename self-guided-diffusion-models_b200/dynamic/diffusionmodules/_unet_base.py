@@ -144,6 +144,13 @@ class EngineUNet(nn.Module):
         self.dtype = torch.float32
 
     # ------------------------------------------------------------------ weights
+    def invalidate_weight_cache(self):
+        """Forget the packed copies: the next call re-packs every tensor.  Needed only after writes
+        that bypass autograd's version counter (`param.data.copy_(...)`, as the reference's
+        `ema_scope` does, dynamic/ema.py:46-53); the samplers call this at the start of every
+        trajectory, so sampling under `ema_scope` is always correct."""
+        self._loaded_sig = {}
+
     def sync_weights(self, force=False):
         """(Re)pack every tensor whose storage or version changed since the last call."""
         lib = _lib.lib()

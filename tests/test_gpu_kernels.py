@@ -1,0 +1,377 @@
+"""Unit parity of every CUDA kernel, called through the C ABI (ctypes), against torch fp32.
+
+The 16-bit operand tensors are rounded ONCE (to the library's operand dtype) and the torch
+reference consumes the rounded values in fp32, so the comparison isolates the kernel's own
+arithmetic (fp32 accumulation order): tolerances are ~1e-4 relative, far below the
+operand-rounding error budget measured end to end in test_gpu_e2e.py.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from sgdm_b200 import _lib
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    lib = _lib.lib()
+    lib._op = torch.float16 if lib.sgdm_operand_dtype() == b"f16" else torch.bfloat16
+    return lib
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def ck(lib, rc):
+    assert rc == 0, lib.sgdm_last_error().decode()
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def pack_weight(lib, w, extra=None, block_n=None):
+    """torch conv weight [Co,Ci,k,k] (+ optional 1x1 skip weight [Co,C2,1,1]) -> packed op tensor."""
+    Co, Ci, ks, _ = w.shape
+    C2 = 0 if extra is None else extra.shape[1]
+    ktot = ks * ks * Ci + C2
+    bn = block_n or next((b for b in (256, 128, 64, 32) if Co % b == 0), 16)
+    npad = (Co + bn - 1) // bn * bn
+    dst = torch.zeros(npad, ktot, dtype=lib._op, device="cuda")
+    ck(lib, lib.sgdm_k_pack_weight(S(), P(w.contiguous()), P(dst), Co, Ci, ks, Ci, ktot, 0))
+    if extra is not None:
+        ck(lib, lib.sgdm_k_pack_weight(S(), P(extra.contiguous()), P(dst), Co, C2, 1, C2, ktot, ks * ks * Ci))
+    return dst, bn
+
+
+def run_conv(lib, x_nhwc, w_packed, bn, ks, stride, Cout, Hout, Wout, bias=None, in2=None, res=None, res_mode=0,
+             out="f32", naive=0):
+    B, Hin, Win, Cin = x_nhwc.shape
+    C2 = 0 if in2 is None else in2.shape[-1]
+    o32 = oop = onchw = None
+    if out == "f32":
+        o32 = torch.full((B, Hout, Wout, Cout), float("nan"), device="cuda")
+    elif out == "op":
+        oop = torch.zeros((B, Hout, Wout, Cout), dtype=lib._op, device="cuda")
+    else:
+        onchw = torch.full((B, Cout, Hout, Wout), float("nan"), device="cuda")
+    ck(lib, lib.sgdm_k_conv(S(), P(x_nhwc), B, Hin, Win, Cin, P(in2), C2, P(w_packed), ks, stride, Hout, Wout, Cout,
+                            P(bias), P(res), res_mode, P(o32), P(oop), P(onchw), bn, naive))
+    torch.cuda.synchronize()
+    return o32 if o32 is not None else (oop if oop is not None else onchw)
+
+
+CONV_CASES = [
+    # (B, H, W, Cin, Cout, ks, stride, skipC, res_mode, out, note)
+    (2, 16, 16, 64, 128, 3, 1, 0, 0, "f32", "3x3 basic, tile = half image"),
+    (1, 64, 64, 64, 128, 3, 1, 0, 1, "f32", "64x64: tile = 2 image rows, residual"),
+    (4, 8, 8, 128, 256, 3, 1, 0, 0, "f32", "8x8: tile spans 2 images, N=256"),
+    (16, 4, 4, 256, 256, 3, 1, 0, 1, "f32", "4x4: tile spans 8 images"),
+    (3, 32, 32, 128, 128, 3, 1, 0, 0, "op", "16-bit output, odd batch"),
+    (2, 16, 16, 192, 64, 3, 1, 0, 0, "f32", "Cin=192 (3 chunks), N=64"),
+    (2, 32, 32, 128, 128, 3, 2, 0, 0, "f32", "stride 2 (TMA elementStrides)"),
+    (2, 16, 16, 256, 256, 3, 2, 0, 0, "f32", "stride 2 -> 8x8"),
+    (2, 16, 16, 128, 256, 3, 1, 384, 0, "f32", "fused 1x1 skip source (K = 9*128 + 384)"),
+    (2, 16, 16, 128, 128, 3, 1, 0, 2, "f32", "residual from nearest-2x upsampled source"),
+    (2, 16, 16, 512, 1536, 1, 1, 0, 0, "op", "1x1 qkv GEMM"),
+    (2, 16, 16, 512, 640, 1, 1, 0, 0, "op", "1x1, N=640 (5 tiles of 128)"),
+    (2, 16, 16, 256, 320, 1, 1, 0, 0, "op", "1x1, N=320 (5 tiles of 64)"),
+    (200, 1, 1, 384, 512, 1, 1, 0, 0, "f32", "linear, M=200 (ragged last tile)"),
+    (5, 1, 1, 768, 1024, 1, 1, 0, 0, "f32", "linear, tiny M"),
+    (2, 32, 32, 64, 3, 3, 1, 0, 0, "nchw", "final conv: N=3 padded to 16, NCHW epilogue"),
+    (1, 64, 64, 128, 3, 3, 1, 0, 0, "nchw", "final conv at 64x64"),
+    (33, 16, 16, 64, 64, 3, 1, 0, 0, "f32", "66 tiles, ragged batch (B=33)"),
+    (5, 64, 64, 64, 128, 3, 1, 0, 1, "f32", "160 tiles > 148 CTAs: second tile on some CTAs"),
+    (40, 32, 32, 128, 256, 3, 1, 128, 0, "f32", "320 tiles x N=256: persistent loop, both TMEM stages, phase flips"),
+    (37, 16, 16, 512, 512, 1, 1, 0, 1, "f32", "74 m-tiles x 2 n-tiles"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[-1] for c in CONV_CASES])
+def test_conv_tcgen05_vs_torch(L, case):
+    B, H, W, Cin, Cout, ks, stride, skipC, res_mode, out, note = case
+    g = torch.Generator(device="cuda").manual_seed(hash(note) % 2**31)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    w = (torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * ks * ks))
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    Ho, Wo = H // stride, W // stride
+    in2 = wskip = None
+    if skipC:
+        in2 = torch.randn(B, Ho, Wo, skipC, device="cuda", generator=g).to(L._op)
+        wskip = torch.randn(Cout, skipC, 1, 1, device="cuda", generator=g) / math.sqrt(skipC)
+    res = None
+    if res_mode == 1:
+        res = torch.randn(B, Ho, Wo, Cout, device="cuda", generator=g)
+    elif res_mode == 2:
+        res = torch.randn(B, Ho // 2, Wo // 2, Cout, device="cuda", generator=g)
+    wp, bn = pack_weight(L, w, wskip)
+    # reference on the rounded operands
+    wr = w.to(L._op).float()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wr, bias, stride=stride, padding=1 if ks == 3 else 0)
+    if skipC:
+        ref = ref + F.conv2d(in2.float().permute(0, 3, 1, 2), wskip.to(L._op).float())
+    if res_mode == 1:
+        ref = ref + res.permute(0, 3, 1, 2)
+    elif res_mode == 2:
+        ref = ref + F.interpolate(res.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for naive in (1, 0):
+        got = run_conv(L, x, wp, bn, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
+        got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
+        assert torch.isfinite(got).all(), f"non-finite output ({'naive' if naive else 'tcgen05'})"
+        e = relerr(got, ref)
+        print(f"[conv {note}] {'naive ' if naive else 'tcgen05'} rel_l2={e:.3e}")
+        assert e < (2e-3 if out == "op" else 2e-5), f"{'naive' if naive else 'tcgen05'} conv mismatch {e}"
+
+
+def test_conv_rejects_bad_shapes(L):
+    x = torch.zeros(1, 16, 16, 48, dtype=L._op, device="cuda")
+    w = torch.zeros(64, 9 * 48, dtype=L._op, device="cuda")
+    o = torch.zeros(1, 16, 16, 64, device="cuda")
+    rc = L.sgdm_k_conv(S(), P(x), 1, 16, 16, 48, None, 0, P(w), 3, 1, 16, 16, 64, None, None, 0, P(o), None, None, 64, 0)
+    assert rc != 0 and b"multiples of 64" in L.sgdm_last_error()
+
+
+GN_CASES = [
+    # (B, H, W, C0, C1, film, silu, resample, raw, note)
+    (2, 16, 16, 128, 0, False, 1, 0, False, "plain GN+SiLU"),
+    (3, 32, 32, 64, 0, True, 1, 0, False, "C=64 (2 ch/group), FiLM"),
+    (2, 16, 16, 256, 128, False, 1, 0, True, "concat 256+128 (12 ch/group straddles the sources), raw copy"),
+    (2, 8, 8, 512, 256, True, 1, 0, False, "concat 512+256 = 768 (24 ch/group)"),
+    (2, 8, 8, 512, 512, False, 1, 0, True, "concat 1024"),
+    (2, 16, 16, 128, 64, False, 1, 0, True, "concat 192 (6 ch/group)"),
+    (2, 16, 16, 256, 0, False, 0, 0, False, "no SiLU (attention norm)"),
+    (2, 32, 32, 128, 0, False, 1, 1, False, "avg-pool 2x2 after SiLU + pooled raw"),
+    (2, 8, 8, 256, 0, False, 1, 2, False, "nearest 2x after SiLU"),
+    (1, 64, 64, 128, 0, True, 1, 0, False, "64x64, B=1 (multi-chunk stats)"),
+    (5, 4, 4, 256, 0, False, 1, 0, False, "4x4 images"),
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES, ids=[c[-1] for c in GN_CASES])
+def test_groupnorm(L, case):
+    B, H, W, C0, C1, film, silu, resample, raw, note = case
+    C = C0 + C1
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(B, H, W, C0, device="cuda", generator=g) * 2 + 0.5
+    b = torch.randn(B, H, W, C1, device="cuda", generator=g) * 0.5 - 1 if C1 else None
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    fl = torch.randn(B, 2 * C + 8, device="cuda", generator=g) * 0.3 if film else None
+    Ho, Wo = (H // 2, W // 2) if resample == 1 else (H * 2, W * 2) if resample == 2 else (H, W)
+    out = torch.zeros(B, Ho, Wo, C, dtype=L._op, device="cuda")
+    raw_out = torch.zeros(B, H, W, C, dtype=L._op, device="cuda") if raw else None
+    pool = torch.zeros(B, Ho, Wo, C, device="cuda") if resample == 1 else None
+    ck(L, L.sgdm_k_groupnorm(S(), P(a), P(b), B, H, W, C0, C1, P(gamma), P(beta), P(fl), 2 * C + 8 if film else 0,
+                             silu, resample, P(out), P(raw_out), P(pool)))
+    torch.cuda.synchronize()
+    x = torch.cat([a, b], -1) if C1 else a
+    xc = x.permute(0, 3, 1, 2)
+    ref = F.group_norm(xc, 32, gamma, beta, eps=1e-5)
+    if film:
+        ref = ref * (1 + fl[:, :C, None, None]) + fl[:, C:2 * C, None, None]
+    if silu:
+        ref = F.silu(ref)
+    if resample == 1:
+        ref = F.avg_pool2d(ref, 2, 2)
+    elif resample == 2:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+    e = relerr(out.float().permute(0, 3, 1, 2), ref)
+    print(f"[gn {note}] rel_l2={e:.3e}")
+    assert e < 1e-3  # output is rounded to the 16-bit operand type (2^-11 relative for fp16)
+    if raw:
+        assert relerr(raw_out.float(), x) < 1e-3
+    if pool is not None:
+        assert relerr(pool.permute(0, 3, 1, 2), F.avg_pool2d(xc, 2, 2)) < 1e-6
+
+
+ATTN_CASES = [
+    # (B, T, heads, D, n_extra, mqa, note)
+    (2, 256, 8, 64, 0, False, "legacy qkv layout, T=256 d=64 (cfg2)"),
+    (3, 64, 8, 32, 0, False, "legacy, T=64 d=32 (cfg1)"),
+    (2, 16, 8, 32, 0, False, "T=16 < one query tile"),
+    (2, 256, 8, 64, 17, True, "multi-query + 17 context/null keys (Attention_LR)"),
+    (2, 16, 8, 32, 17, True, "MQA, T=16 d=32"),
+    (1, 100, 4, 64, 5, True, "ragged T=100"),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[c[-1] for c in ATTN_CASES])
+def test_attention(L, case):
+    B, T, H, D, nx, mqa, note = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    C = H * D
+    if not mqa:
+        qkv = torch.randn(B, T, 3 * C, device="cuda", generator=g).to(L._op)
+        out = torch.zeros(B, T, C, dtype=L._op, device="cuda")
+        ck(L, L.sgdm_k_attention(S(), qkv.data_ptr(), 3 * C, 3 * D, qkv.data_ptr() + 2 * D, 3 * C, 3 * D,
+                                 qkv.data_ptr() + 4 * D, 3 * C, 3 * D, None, None, 0, P(out), C, B, T, H, D,
+                                 1 / math.sqrt(D)))
+        torch.cuda.synchronize()
+        # QKVAttentionLegacy on [N, H*3*D, T]
+        x = qkv.float().permute(0, 2, 1)
+        q, k, v = x.reshape(B * H, 3 * D, T).split(D, dim=1)
+        s = 1 / math.sqrt(math.sqrt(D))
+        w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), -1)
+        ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T).permute(0, 2, 1)
+    else:
+        nq = C + 2 * D
+        buf = torch.randn(B, T, nq, device="cuda", generator=g).to(L._op)
+        kx = torch.randn(B, nx, D, device="cuda", generator=g).to(L._op)
+        vx = torch.randn(B, nx, D, device="cuda", generator=g).to(L._op)
+        out = torch.zeros(B, T, C, dtype=L._op, device="cuda")
+        ck(L, L.sgdm_k_attention(S(), buf.data_ptr(), nq, D, buf.data_ptr() + 2 * C, nq, 0,
+                                 buf.data_ptr() + 2 * (C + D), nq, 0, P(kx), P(vx), nx, P(out), C, B, T, H, D,
+                                 D ** -0.5))
+        torch.cuda.synchronize()
+        q = buf[..., :C].float().reshape(B, T, H, D).permute(0, 2, 1, 3) * D ** -0.5
+        k = torch.cat([kx.float(), buf[..., C:C + D].float()], 1)
+        v = torch.cat([vx.float(), buf[..., C + D:].float()], 1)
+        attn = torch.einsum("bhid,bjd->bhij", q, k).softmax(-1)
+        ref = torch.einsum("bhij,bjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(B, T, C)
+    e = relerr(out.float(), ref)
+    print(f"[attn {note}] rel_l2={e:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert e < 3e-3  # P and the output are rounded to 16 bits
+
+
+def test_layernorm(L):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for rows, C in ((500, 512), (33, 256), (7, 1024), (64, 128)):
+        x = torch.randn(rows, C, device="cuda", generator=g) * 3 + 1
+        ga = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+        be = 0.1 * torch.randn(C, device="cuda", generator=g)
+        res = torch.randn(rows, C, device="cuda", generator=g)
+        o1 = torch.zeros(rows, C, dtype=L._op, device="cuda")
+        o2 = torch.zeros(rows, C, device="cuda")
+        ck(L, L.sgdm_k_layernorm(S(), P(x), P(ga), P(be), None, P(o1), None, rows, C))
+        ck(L, L.sgdm_k_layernorm(S(), P(x), P(ga), P(be), P(res), None, P(o2), rows, C))
+        torch.cuda.synchronize()
+        ref = F.layer_norm(x, (C,), ga, be)
+        assert relerr(o1.float(), ref) < 1e-3
+        assert relerr(o2, ref + res) < 1e-5
+
+
+def test_linear_f32(L):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for M, N, K in ((32, 512, 128), (5, 256, 1000), (130, 70, 33), (512, 256, 5000)):
+        x = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+        b = torch.randn(N, device="cuda", generator=g)
+        out = torch.zeros(M, N + 3, device="cuda")
+        ck(L, L.sgdm_k_linear_f32(S(), P(x), K, P(W), P(b), P(out), N + 3, M, N, K, 1, 0))
+        ck(L, L.sgdm_k_linear_f32(S(), P(x), K, P(W), P(b), P(out), N + 3, M, N, K, 0, 1))
+        torch.cuda.synchronize()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        lin = F.linear(x.double(), W.double(), b.double())
+        ref = (F.silu(lin) + lin).float()
+        assert relerr(out[:, :N], ref) < 1e-5
+        assert out[:, N:].abs().max() == 0
+    # one-hot input: the first Linear is an exact column gather
+    idx = torch.randint(0, 1000, (16,), device="cuda", generator=g)
+    oh = F.one_hot(idx, 1000).float()
+    W = torch.randn(256, 1000, device="cuda", generator=g)
+    b = torch.randn(256, device="cuda", generator=g)
+    out = torch.zeros(16, 256, device="cuda")
+    ck(L, L.sgdm_k_linear_f32(S(), P(oh), 1000, P(W), P(b), P(out), 256, 16, 256, 1000, 0, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(out, W[:, idx].t() + b)
+
+
+def test_cast_and_upsample(L):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(3, 8, 8, 128, device="cuda", generator=g)
+    a = torch.zeros(3, 8, 8, 128, dtype=L._op, device="cuda")
+    b = torch.zeros(3, 16, 16, 128, dtype=L._op, device="cuda")
+    ck(L, L.sgdm_k_cast(S(), P(x), P(a), 3, 8, 8, 128, 0))
+    ck(L, L.sgdm_k_cast(S(), P(x), P(b), 3, 8, 8, 128, 1))
+    torch.cuda.synchronize()
+    assert torch.equal(a, x.to(L._op))
+    up = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(b, up.to(L._op))
+
+
+def test_sampler_update_kernels_bit_exact(L):
+    """The fused mix+update kernels reproduce the unfused torch fp32 arithmetic of the
+    reference bit for bit (oracle/sampler.py restates ddim_plms_sampler.py:360-391 and
+    ddpm_sampler.py:154-192)."""
+    import ctypes as C
+
+    from oracle import sampler as osamp
+    from oracle import schedule as osched
+
+    g = torch.Generator().manual_seed(21)
+    B, shape = 4, (4, 3, 16, 16)
+    x, ec, eu, nz = (torch.randn(shape, generator=g) for _ in range(4))
+    xd, ecd, eud, nzd = (t.cuda() for t in (x, ec, eu, nz))
+    per = x[0].numel()
+    tab = osched.ddpm_tables(1000)
+    for eta in (0.0, 1.0):
+        dt = osched.ddim_tables(tab["alphas_cumprod"], 10, 1000, eta)
+        for index in (0, 4, 9):
+            for w in (2.0, 0.3):
+                e = (1 - w) * eu + w * ec
+                kw = dict(clip_denoised=True, dtp=1, temperature=1.0, noise_dropout=0)
+                ref_x, ref_x0 = osamp._ddim_update(x, e, dt, index, nz, kw)
+                z = torch.zeros(())
+                a_t = torch.full_like(z, dt["alphas"][index]); a_p = torch.full_like(z, dt["alphas_prev"][index])
+                sg = torch.full_like(z, dt["sigmas"][index]); s1 = torch.full_like(z, dt["sqrt_one_minus_alphas"][index])
+                coef = (C.c_float * 6)(s1.item(), a_t.sqrt().item(), a_p.sqrt().item(),
+                                       (1.0 - a_p - sg**2).sqrt().item(), sg.item(), 1.0)
+                xo, x0o, eo = (torch.empty_like(xd) for _ in range(3))
+                ck(L, L.sgdm_ddim_step(S(), P(ecd), P(eud), w, None, 0, coef, 1, P(xd), P(nzd), P(xo), P(x0o), P(eo),
+                                       B, per))
+                torch.cuda.synchronize()
+                assert torch.equal(eo.cpu(), e), "guidance mix not bit-exact"
+                assert torch.equal(x0o.cpu(), ref_x0), "pred_x0 not bit-exact"
+                assert torch.equal(xo.cpu(), ref_x), "x_prev not bit-exact"
+    # DDPM
+    for i in (0, 1, 500, 999):
+        w = 2.0
+        e = (1 - w) * eu + w * ec
+        t = torch.full((B,), i, dtype=torch.long)
+        x0 = osamp._ext(tab["sqrt_recip_alphas_cumprod"], t, x) * x - osamp._ext(tab["sqrt_recipm1_alphas_cumprod"], t, x) * e
+        x0 = x0.clamp(-1, 1)
+        mean = osamp._ext(tab["posterior_mean_coef1"], t, x) * x0 + osamp._ext(tab["posterior_mean_coef2"], t, x) * x
+        logvar = osamp._ext(tab["posterior_log_variance_clipped"], t, x)
+        nonzero = (1 - (t == 0).float()).reshape(B, 1, 1, 1)
+        ref = mean + nonzero * (0.5 * logvar).exp() * (nz * 1.0)
+        sig = (0.5 * tab["posterior_log_variance_clipped"]).exp()
+        coef = (C.c_float * 6)(tab["sqrt_recip_alphas_cumprod"][i].item(), tab["sqrt_recipm1_alphas_cumprod"][i].item(),
+                               tab["posterior_mean_coef1"][i].item(), tab["posterior_mean_coef2"][i].item(),
+                               sig[i].item() if i else 0.0, 1.0)
+        xo, x0o = torch.empty_like(xd), torch.empty_like(xd)
+        ck(L, L.sgdm_ddpm_step(S(), P(ecd), P(eud), w, None, 0, coef, 1, P(xd), P(nzd), P(xo), P(x0o), B, per))
+        torch.cuda.synchronize()
+        assert torch.equal(x0o.cpu(), x0)
+        assert torch.equal(xo.cpu(), ref)
+    # per-sample tensor cond_scale and the 'cfg' scale type
+    wt = torch.linspace(0.5, 3.0, B)
+    out = torch.empty_like(xd)
+    ck(L, L.sgdm_mix(S(), P(ecd), P(eud), 0.0, P(wt.cuda()), 0, P(out), B, per))
+    assert torch.equal(out.cpu(), (1 - wt.view(B, 1, 1, 1)) * eu + wt.view(B, 1, 1, 1) * ec)
+    ck(L, L.sgdm_mix(S(), P(ecd), P(eud), 0.1, None, 1, P(out), B, per))
+    assert torch.equal(out.cpu(), (1 + 0.1) * ec - 0.1 * eu)
+    # uint8 conversion
+    v = torch.randn(10000, generator=g) * 1.5
+    o8 = torch.empty(10000, dtype=torch.uint8, device="cuda")
+    ck(L, L.sgdm_to_uint8(S(), P(v.cuda()), P(o8), 10000))
+    assert torch.equal(o8.cpu(), osamp.to_uint8(v))
+    # PLMS combination
+    ptrs = (C.c_void_p * 4)(P(xd), P(ecd), P(eud), P(nzd))
+    cf = (C.c_float * 4)(55.0, -59.0, 37.0, -9.0)
+    ck(L, L.sgdm_lincomb(S(), 4, ptrs, cf, 24.0, P(out), xd.numel()))
+    assert torch.equal(out.cpu(), (55 * x - 59 * ec + 37 * eu - 9 * nz) / 24)
