@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline steps (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write the per-launch profile of one step to this JSON file")
     ap.add_argument("--ncu", action="store_true", help="minimal run for profiling under ncu: warm-up + timed steps only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -350,10 +351,18 @@ def main():
         torch.cuda.synchronize()
         _lib.check(lib.sgdm_set_profiling(model._h, 0))
         kind, ms, fl, by = C.c_char_p(), C.c_double(), C.c_double(), C.c_double()
+        ops = []
         for j in range(lib.sgdm_profile_count(model._h)):
             _lib.check(lib.sgdm_profile_get(model._h, j, C.byref(kind), C.byref(ms), C.byref(fl), C.byref(by)))
+            ops.append(dict(i=j, kind=kind.value.decode(), ms=round(ms.value, 4), gflop=round(fl.value / 1e9, 2),
+                            mbytes=round(by.value / 1e6, 1),
+                            tflops=round(fl.value / (ms.value * 1e-3) / 1e12, 1) if ms.value > 0 and fl.value else None,
+                            gbs=round(by.value / (ms.value * 1e-3) / 1e9, 1) if ms.value > 0 and by.value else None))
             f = fam.setdefault(kind.value.decode(), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
             f["ms"] += ms.value; f["flops"] += fl.value; f["bytes"] += by.value; f["launches"] += 1
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as fh:
+                json.dump(ops, fh, indent=0)
         pk = peaks()
         conv = dict(ms=0.0, flops=0.0, launches=0)
         for k_ in ("conv3x3", "gemm1x1"):

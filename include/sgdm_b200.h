@@ -133,8 +133,9 @@ int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, 
 /* packs a torch conv weight [Cout,Cin,ks,ks] fp32 into dst[co][k_off + tap*cin_pad + ci] (row length ktot) */
 int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad,
                        int ktot, int k_off);
-int sgdm_k_groupnorm(void* stream, const float* src0, const float* src1, int B, int H, int W, int C0, int C1,
-                     const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
+/* src0: fp32 NHWC, or op NHWC when src0_is_op (then src1 must be NULL) */
+int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W, int C0,
+                     int C1, const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
                      int resample, void* out_op, void* raw_out_op, float* pool_out);
 int sgdm_k_layernorm(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
                      void* out_op, float* out_f32, int64_t rows, int C);

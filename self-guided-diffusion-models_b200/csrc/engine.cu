@@ -629,7 +629,7 @@ struct Builder {
     push([d](cudaStream_t s) {
       g_launches += 2;
       return gn_launch(d, s);
-    }, "groupnorm", 0, el * 4 * 2 + out_el * 2 + (d.raw_out ? el * 2 : 0) + (d.pool_out ? out_el * 4 : 0));
+    }, "groupnorm", 0, el * (d.src0_is_op ? 2 : 4) * 2 + out_el * 2 + (d.raw_out ? el * 2 : 0) + (d.pool_out ? out_el * 4 : 0));
   }
 
   // ResBlock._forward (openaimodel.py:300-320)
@@ -645,14 +645,16 @@ struct Builder {
     g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
     g.out = g1; g.raw_out = raw; g.pool_out = pooled;
     gn(g);
-    float* h1 = static_cast<float*>(scratch("h1", px_out * r.cout * sizeof(float)));
+    // h1 only feeds the second GroupNorm: kept in the 16-bit operand type (halves its HBM traffic;
+    // measured cost on eps: rel-L2 1.65e-3 -> 1.96e-3, DESIGN.md "operand precision")
+    op_t* h1 = static_cast<op_t*>(scratch("h1", px_out * r.cout * sizeof(op_t)));
     ConvDesc c1;
     c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
-    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_f32 = h1;
+    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_op = h1;
     conv(c1);
     op_t* g2 = static_cast<op_t*>(scratch("gn_out", px_out * r.cout * sizeof(op_t)));
     GnDesc gg;
-    gg.src0 = h1; gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
+    gg.src0 = h1; gg.src0_is_op = 1; gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
     gg.film = dry ? nullptr : emb_out + r.emb_off; gg.film_stride = e->NE; gg.silu = 1; gg.out = g2;
     gn(gg);
     Act o;
@@ -747,7 +749,7 @@ struct Builder {
       return attn_launch(ad, s);
     }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * (T + 17) * dh,
          static_cast<double>(rows) * (nq + inner) * 2);
-    float* tmp = static_cast<float*>(scratch("h1", rows * C * sizeof(float)));
+    float* tmp = static_cast<float*>(scratch("tmpf", rows * C * sizeof(float)));
     ConvDesc c2;
     c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = inner; c2.w = w.wout; c2.ks = 1; c2.stride = 1; c2.pad = 0;
     c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.out_f32 = tmp;
@@ -1173,11 +1175,11 @@ int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Ci
              ? fail("pack launch failed")
              : 0;
 }
-int sgdm_k_groupnorm(void* stream, const float* src0, const float* src1, int B, int H, int W, int C0, int C1,
-                     const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
+int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W, int C0,
+                     int C1, const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
                      int resample, void* out_op, void* raw_out_op, float* pool_out) {
   GnDesc d;
-  d.src0 = src0; d.src1 = src1; d.B = B; d.H = H; d.W = W; d.C0 = C0; d.C1 = C1; d.gamma = gamma; d.beta = beta;
+  d.src0 = src0; d.src0_is_op = src0_is_op; d.src1 = src1; d.B = B; d.H = H; d.W = W; d.C0 = C0; d.C1 = C1; d.gamma = gamma; d.beta = beta;
   d.film = film; d.film_stride = film_stride; d.silu = silu; d.resample = resample;
   d.out = static_cast<op_t*>(out_op); d.raw_out = static_cast<op_t*>(raw_out_op); d.pool_out = pool_out;
   d.chunks = gn_chunks_for(B, H * W, C0 + C1);

@@ -20,7 +20,9 @@ constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 64 * 2;   // 16 KB
 constexpr int kBBytesMax = 256 * 64 * 2;   // 32 KB
 constexpr int kBarBytes = 256;
-constexpr int kConvSmem = 1024 + kStages * (kABytes + kBBytesMax) + kBarBytes;
+constexpr int kStgLd = 36;                          // staging row stride in floats (32 + 4: conflict-free)
+constexpr int kStgBytes = 4 * 32 * kStgLd * 4;      // one 32x32 fp32 sub-tile per epilogue warp
+constexpr int kConvSmem = 1024 + kStages * (kABytes + kBBytesMax) + kBarBytes + kStgBytes;
 constexpr int kConvThreads = 192;
 
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull = bars + 2 * kStages;       // [2] MMA -> epilogue
   uint64_t* tempty = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* stg_all = reinterpret_cast<float*>(smem + kStages * (kABytes + kBBytesMax) + kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,8 +129,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter).  A 32x32 fp32 sub-tile is read
+    // from TMEM (thread = row), transposed through a private smem staging tile, and written
+    // back with thread = (row group, column quad) so that every global load / store instruction
+    // of the warp touches whole 128-byte row segments (bias, residual and output alike).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
+    float* stg = stg_all + (warp - 2) * 32 * kStgLd;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles;
@@ -135,62 +142,94 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = m_tile * kTileM + row;
-      const bool valid = m < p.M_total;
+      const int m_base = m_tile * kTileM + quarter * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * block_n;
-      long res_row = 0;
-      int img = 0, pix = 0;
-      if (valid) {
-        img = m / p.HW;
-        pix = m - img * p.HW;
-        if (p.res_mode == 2) {
-          const int y = pix / p.Wout, x = pix - y * p.Wout;
-          res_row = (static_cast<long>(img) * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
-        } else {
-          res_row = m;
-        }
-      }
       for (int c0 = 0; c0 < block_n; c0 += 32) {
         uint32_t v[32];
         const int nc = min(32, block_n - c0);
         if (nc == 32) tmem_ld_32x32(taddr + c0, v);
         else tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
-        if (!valid) continue;
         const int col0 = n_tile * block_n + c0;
-        if (p.out_nchw != nullptr) {
+        if (p.out_nchw != nullptr) {  // final conv: lanes = adjacent pixels -> already coalesced
+          const int m = m_base + lane;
+          if (m < p.M_total) {
+            const int img = m / p.HW, pix = m - img * p.HW;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (j < nc && col < p.N_total) {
-              float a = __uint_as_float(v[j]);
-              if (p.bias) a += p.bias[col];
-              p.out_nchw[(static_cast<long>(img) * p.N_total + col) * p.HW + pix] = a;
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (j < nc && col < p.N_total) {
+                float a = __uint_as_float(v[j]);
+                if (p.bias) a += p.bias[col];
+                p.out_nchw[(static_cast<long>(img) * p.N_total + col) * p.HW + pix] = a;
+              }
             }
           }
           continue;
         }
+        float4* srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j >= nc) break;
-          const int col = col0 + j;
-          if (col >= p.N_total) break;
-          float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (p.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+        for (int j = 0; j < 8; ++j)
+          if (4 * j < nc)
+            srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        if (p.out_f32) {
+          // 8 lanes per row (float4 each), 4 rows per instruction
+          const int cq = (lane & 7) * 4;
+          const int col = col0 + cq;
+          const bool col_ok = cq < nc && col < p.N_total;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && p.bias) b = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int rl = rr + (lane >> 3);
+            const int m = m_base + rl;
+            if (!col_ok || m >= p.M_total) continue;
+            float4 a = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            if (p.res_mode) {
+              long rrow = m;
+              if (p.res_mode == 2) {
+                const int img = m / p.HW, pix = m - img * p.HW;
+                const int y = pix / p.Wout, x = pix - y * p.Wout;
+                rrow = (static_cast<long>(img) * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+              }
+              const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + rrow * p.N_total + col));
+              a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            }
+            *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
           }
-          if (p.res_mode) {
-            const float4 r = *reinterpret_cast<const float4*>(p.res + res_row * p.N_total + col);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        } else {
+          // 16-bit output: 4 lanes per row (8 columns = 16 bytes each), 8 rows per instruction
+          const int cq = (lane & 3) * 8;
+          const int col = col0 + cq;
+          const bool col_ok = cq < nc && col < p.N_total;
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (col_ok && p.bias) {
+            b0 = *reinterpret_cast<const float4*>(p.bias + col);
+            b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
           }
-          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
-          if (p.out_op) {
-            uint2 h = make_uint2(pack_op2(a.x, a.y), pack_op2(a.z, a.w));
-            *reinterpret_cast<uint2*>(p.out_op + static_cast<long>(m) * p.N_total + col) = h;
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 8) {
+            const int rl = rr + (lane >> 2);
+            const int m = m_base + rl;
+            if (!col_ok || m >= p.M_total) continue;
+            float4 a0 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+            float4 a1 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq + 4);
+            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+            if (p.res_mode == 1) {
+              const float* rp = p.res + static_cast<long>(m) * p.N_total + col;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+              a0.x += r0.x; a0.y += r0.y; a0.z += r0.z; a0.w += r0.w;
+              a1.x += r1.x; a1.y += r1.y; a1.z += r1.z; a1.w += r1.w;
+            }
+            const uint4 h = make_uint4(pack_op2(a0.x, a0.y), pack_op2(a0.z, a0.w), pack_op2(a1.x, a1.y), pack_op2(a1.z, a1.w));
+            *reinterpret_cast<uint4*>(p.out_op + static_cast<long>(m) * p.N_total + col) = h;
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -251,7 +290,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.Wout > 128 || (128 % d.Wout) != 0) return fail("Wout must divide 128");
   const int HW = d.Hout * d.Wout;
   if (!((HW % 128) == 0 || (128 % HW) == 0)) return fail("Hout*Wout must divide or be a multiple of 128");
-  if (d.out_nchw == nullptr && (d.Cout % 4)) return fail("Cout % 4 != 0 needs the NCHW epilogue");
+  if (d.out_nchw == nullptr && (d.Cout % 8)) return fail("Cout % 8 != 0 needs the NCHW epilogue");
+  if ((d.out_f32 != nullptr) + (d.out_op != nullptr) + (d.out_nchw != nullptr) != 1) return fail("exactly one output");
+  if (d.out_op && d.res && d.res_mode == 2) return fail("res_mode 2 needs the fp32 output");
   if (d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
   const int bw = d.Wout;
   const int bh = min(d.Hout, 128 / bw);

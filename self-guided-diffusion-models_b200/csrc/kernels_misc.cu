@@ -8,11 +8,28 @@ namespace sgdm {
 #define SGDM_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
 // =========================================================================== GroupNorm
+// Two HBM-bound passes (roofline: read 4 B + read 4 B + write 2 B per element, 2+2+2 for a
+// 16-bit source).  Both passes give every thread a FIXED channel slice and walk pixels with
+// several independent 128-bit loads in flight; all reduction orders depend on the per-sample
+// shape only, so results are bit-identical however samples are batched.
+//
 // Pass 1: per (sample, chunk of pixels) partial sum / sum-of-squares per group.
-// Thread = (float4 channel column q, pixel lane pl); fp32 per-thread partials over at most
-// a few hundred elements, combined in double -> deterministic and cancellation-safe.
-__global__ void gn_stats_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int HW, int C0,
-                                int C1, int chunks, int PL, double* __restrict__ partial) {
+// Thread = (4-channel column q, pixel lane pl); fp32 per-thread partials over at most a few
+// hundred elements, combined in double -> deterministic and cancellation-safe.
+template <bool kHalfIn>
+__device__ __forceinline__ float4 gn_ld4(const void* base, long off) {
+  if (kHalfIn) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(static_cast<const op_t*>(base) + off));
+    const float2 a = unpack_op2(r.x), b = unpack_op2(r.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + off));
+}
+
+template <bool kHalfIn>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ src0, const float* __restrict__ src1,
+                                                       int HW, int C0, int C1, int chunks, int PL,
+                                                       double* __restrict__ partial) {
   __shared__ float s_sum[1024];
   __shared__ float s_sq[1024];
   const int C = C0 + C1, C4 = C >> 2;
@@ -20,21 +37,40 @@ __global__ void gn_stats_kernel(const float* __restrict__ src0, const float* __r
   const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
   const int ppc = HW / chunks;
   const int c = q * 4;
-  const float* base;
-  int cs, co;
-  if (c < C0) { base = src0 + static_cast<long>(n) * HW * C0; cs = C0; co = c; }
-  else { base = src1 + static_cast<long>(n) * HW * C1; cs = C1; co = c - C0; }
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int px = chunk * ppc + pl; px < (chunk + 1) * ppc; px += PL) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long>(px) * cs + co));
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+  const bool first = c < C0;
+  const long cs = first ? C0 : C1;
+  const long base_off = static_cast<long>(n) * HW * cs + (first ? c : c - C0);
+  const void* base = first ? src0 : static_cast<const void*>(src1);
+  float4 s[4], ss[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { s[u] = make_float4(0.f, 0.f, 0.f, 0.f); ss[u] = s[u]; }
+  const int px_end = (chunk + 1) * ppc;
+  int px = chunk * ppc + pl;
+  for (; px + 3 * PL < px_end; px += 4 * PL) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      v[u] = (first && kHalfIn) ? gn_ld4<true>(base, base_off + static_cast<long>(px + u * PL) * cs)
+                                : gn_ld4<false>(base, base_off + static_cast<long>(px + u * PL) * cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w;
+      ss[u].x += v[u].x * v[u].x; ss[u].y += v[u].y * v[u].y; ss[u].z += v[u].z * v[u].z; ss[u].w += v[u].w * v[u].w;
+    }
   }
-  // layout [pl][C]
+  for (; px < px_end; px += PL) {
+    const float4 v = (first && kHalfIn) ? gn_ld4<true>(base, base_off + static_cast<long>(px) * cs)
+                                        : gn_ld4<false>(base, base_off + static_cast<long>(px) * cs);
+    s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+    ss[0].x += v.x * v.x; ss[0].y += v.y * v.y; ss[0].z += v.z * v.z; ss[0].w += v.w * v.w;
+  }
+  // layout [pl][C]; the 4 unroll slots are folded in a fixed order
   float* ps = s_sum + pl * C + c;
   float* pq = s_sq + pl * C + c;
-  ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
-  pq[0] = ss.x; pq[1] = ss.y; pq[2] = ss.z; pq[3] = ss.w;
+  ps[0] = (s[0].x + s[1].x) + (s[2].x + s[3].x); ps[1] = (s[0].y + s[1].y) + (s[2].y + s[3].y);
+  ps[2] = (s[0].z + s[1].z) + (s[2].z + s[3].z); ps[3] = (s[0].w + s[1].w) + (s[2].w + s[3].w);
+  pq[0] = (ss[0].x + ss[1].x) + (ss[2].x + ss[3].x); pq[1] = (ss[0].y + ss[1].y) + (ss[2].y + ss[3].y);
+  pq[2] = (ss[0].z + ss[1].z) + (ss[2].z + ss[3].z); pq[3] = (ss[0].w + ss[1].w) + (ss[2].w + ss[3].w);
   __syncthreads();
   if (threadIdx.x < 32) {
     const int g = threadIdx.x, cpg = C / 32;
@@ -51,21 +87,33 @@ __global__ void gn_stats_kernel(const float* __restrict__ src0, const float* __r
 }
 
 struct GnApplyArgs {
-  const float* src0; const float* src1;
+  const void* src0; const float* src1;
   int H, W, C0, C1;
   const float* gamma; const float* beta; const float* film; long film_stride;
-  int silu, resample, chunks;
+  int silu, resample, chunks, ppb, PLa;
   const double* partial;
   op_t* out; op_t* raw_out; float* pool_out;
 };
 
+template <bool kHalfIn>
 __device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, int c, float (&v)[8]) {
-  const int HW = a.H * a.W;
-  const float* p = (c < a.C0) ? a.src0 + (static_cast<long>(n) * HW + pix) * a.C0 + c
-                              : a.src1 + (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
-  const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 hi = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  const long HW = static_cast<long>(a.H) * a.W;
+  if (c < a.C0) {
+    const long off = (static_cast<long>(n) * HW + pix) * a.C0 + c;
+    if (kHalfIn) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(static_cast<const op_t*>(a.src0) + off));
+      const float2 p0 = unpack_op2(r.x), p1 = unpack_op2(r.y), p2 = unpack_op2(r.z), p3 = unpack_op2(r.w);
+      v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+      return;
+    }
+    const float* p = static_cast<const float*>(a.src0) + off;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  } else {
+    const float* p = a.src1 + (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  }
 }
 __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
   uint4 o = make_uint4(pack_op2(y[0], y[1]), pack_op2(y[2], y[3]), pack_op2(y[4], y[5]), pack_op2(y[6], y[7]));
@@ -73,7 +121,10 @@ __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
 }
 
 // Pass 2: normalise + affine (+FiLM) (+SiLU), write op_t NHWC, optionally pooled / upsampled.
-__global__ void gn_apply_kernel(const GnApplyArgs a) {
+// Thread = (8-channel slice cg, pixel lane): the folded per-channel scale/offset live in
+// registers for the whole block; the block walks `ppb` pixels.
+template <bool kHalfIn>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
@@ -93,74 +144,90 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
   }
   __syncthreads();
-  const int Ho = a.resample == 1 ? a.H >> 1 : a.H, Wo = a.resample == 1 ? a.W >> 1 : a.W;
-  const long items = static_cast<long>(Ho) * Wo * C8;  // iterate over input pixels (pooled: output pixels)
-  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (idx >= items) return;
-  const int cg = idx % C8;
-  const int pix = idx / C8;
+  const int cg = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int c = cg * 8;
-  float sc[8], sh[8];
+  // y = ((v - mean) rstd gamma + beta) (1 + scale) + shift  ==  v * ka + kb
+  float ka[8], kb[8];
+  {
+    const float* f = a.film ? a.film + static_cast<long>(n) * a.film_stride : nullptr;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c + j) / cpg;
-    const float ga = __ldg(a.gamma + c + j) * s_rstd[g];
-    sc[j] = ga;
-    sh[j] = __ldg(a.beta + c + j) - s_mean[g] * ga;
-  }
-  float fs[8], fb[8];
-  const bool film = a.film != nullptr;
-  if (film) {
-    const float* f = a.film + static_cast<long>(n) * a.film_stride;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { fs[j] = 1.0f + __ldg(f + c + j); fb[j] = __ldg(f + C + c + j); }
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      const float ga = __ldg(a.gamma + c + j) * s_rstd[g];
+      const float be = __ldg(a.beta + c + j) - s_mean[g] * ga;
+      const float fs = f ? 1.0f + __ldg(f + c + j) : 1.0f;
+      const float fb = f ? __ldg(f + C + c + j) : 0.0f;
+      ka[j] = ga * fs;
+      kb[j] = be * fs + fb;
+    }
   }
   auto xform = [&](const float (&v)[8], float (&y)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = v[j] * sc[j] + sh[j];
-      if (film) t = t * fs[j] + fb[j];
+      const float t = v[j] * ka[j] + kb[j];
       y[j] = a.silu ? silu(t) : t;
     }
   };
-  float v[8], y[8];
+  const int Ho = a.resample == 1 ? a.H >> 1 : a.H, Wo = a.resample == 1 ? a.W >> 1 : a.W;
+  const int n_iter = Ho * Wo;  // pooled: output pixels; otherwise input pixels
+  const int p_begin = blockIdx.x * a.ppb;
+  const int p_end = min(p_begin + a.ppb, n_iter);
   if (a.resample == 0) {
-    gn_load8(a, n, pix, c, v);
-    xform(v, y);
-    store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y);
-    if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v);
+    int pix = p_begin + lane;
+    for (; pix + a.PLa < p_end; pix += 2 * a.PLa) {  // two pixels in flight
+      float v0[8], v1[8], y0[8], y1[8];
+      gn_load8<kHalfIn>(a, n, pix, c, v0);
+      gn_load8<kHalfIn>(a, n, pix + a.PLa, c, v1);
+      xform(v0, y0);
+      xform(v1, y1);
+      store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y0);
+      store8_op(a.out + (static_cast<long>(n) * HW + pix + a.PLa) * C + c, y1);
+      if (a.raw_out) {
+        store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v0);
+        store8_op(a.raw_out + (static_cast<long>(n) * HW + pix + a.PLa) * C + c, v1);
+      }
+    }
+    for (; pix < p_end; pix += a.PLa) {
+      float v[8], y[8];
+      gn_load8<kHalfIn>(a, n, pix, c, v);
+      xform(v, y);
+      store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y);
+      if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v);
+    }
   } else if (a.resample == 1) {
-    const int yo = pix / Wo, xo = pix - yo * Wo;
-    float acc[8], racc[8];
+    for (int pix = p_begin + lane; pix < p_end; pix += a.PLa) {
+      const int yo = pix / Wo, xo = pix - yo * Wo;
+      float v[4][8], y[8], acc[8], racc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j] = 0.f; racc[j] = 0.f; }
+      for (int k = 0; k < 4; ++k) gn_load8<kHalfIn>(a, n, (2 * yo + (k >> 1)) * a.W + 2 * xo + (k & 1), c, v[k]);
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+      for (int j = 0; j < 8; ++j) { acc[j] = 0.f; racc[j] = 0.f; }
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        gn_load8(a, n, (2 * yo + dy) * a.W + 2 * xo + dx, c, v);
-        xform(v, y);
+      for (int k = 0; k < 4; ++k) {
+        xform(v[k], y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[j] += y[j]; racc[j] += v[j]; }
+        for (int j = 0; j < 8; ++j) { acc[j] += y[j]; racc[j] += v[k][j]; }
       }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j] *= 0.25f; racc[j] *= 0.25f; }
-    const long o = (static_cast<long>(n) * Ho * Wo + pix) * C + c;
-    store8_op(a.out + o, acc);
-    if (a.pool_out) {
-      *reinterpret_cast<float4*>(a.pool_out + o) = make_float4(racc[0], racc[1], racc[2], racc[3]);
-      *reinterpret_cast<float4*>(a.pool_out + o + 4) = make_float4(racc[4], racc[5], racc[6], racc[7]);
+      for (int j = 0; j < 8; ++j) { acc[j] *= 0.25f; racc[j] *= 0.25f; }
+      const long o = (static_cast<long>(n) * n_iter + pix) * C + c;
+      store8_op(a.out + o, acc);
+      if (a.pool_out) {
+        *reinterpret_cast<float4*>(a.pool_out + o) = make_float4(racc[0], racc[1], racc[2], racc[3]);
+        *reinterpret_cast<float4*>(a.pool_out + o + 4) = make_float4(racc[4], racc[5], racc[6], racc[7]);
+      }
     }
   } else {
-    gn_load8(a, n, pix, c, v);
-    xform(v, y);
-    const int yi = pix / a.W, xi = pix - yi * a.W;
     const int W2 = a.W * 2;
+    for (int pix = p_begin + lane; pix < p_end; pix += a.PLa) {
+      float v[8], y[8];
+      gn_load8<kHalfIn>(a, n, pix, c, v);
+      xform(v, y);
+      const int yi = pix / a.W, xi = pix - yi * a.W;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx)
-        store8_op(a.out + ((static_cast<long>(n) * a.H * 2 + 2 * yi + dy) * W2 + 2 * xi + dx) * C + c, y);
+      for (int k = 0; k < 4; ++k)
+        store8_op(a.out + ((static_cast<long>(n) * a.H * 2 + 2 * yi + (k >> 1)) * W2 + 2 * xi + (k & 1)) * C + c, y);
+    }
   }
 }
 
@@ -178,13 +245,25 @@ int gn_chunks_for(int B, int HW, int C) {
 int gn_launch(const GnDesc& d, cudaStream_t s) {
   const int C = d.C0 + d.C1, HW = d.H * d.W;
   if (C % 32 || C > 1024 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;
+  if (d.src0_is_op && d.C1) return 1;
   const int C4 = C / 4;
   const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
-  gn_stats_kernel<<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+  if (d.src0_is_op)
+    gn_stats_kernel<true><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+  else
+    gn_stats_kernel<false><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+  const int C8 = C / 8;
+  const int PLa = 256 / C8 > 0 ? 256 / C8 : 1;
+  const int n_iter = d.resample == 1 ? HW / 4 : HW;
+  // pixels per block: >= 8 per thread when the grid stays large enough to fill the chip
+  int ppb = PLa * 8;
+  while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 4 * kNumSMs) ppb >>= 1;
+  if (ppb > n_iter) ppb = n_iter;
   GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
-                d.silu, d.resample, d.chunks, d.partial, d.out, d.raw_out, d.pool_out};
-  const long items = (d.resample == 1 ? static_cast<long>(HW) / 4 : static_cast<long>(HW)) * (C / 8);
-  gn_apply_kernel<<<dim3(static_cast<unsigned>((items + 255) / 256), d.B), 256, 0, s>>>(a);
+                d.silu, d.resample, d.chunks, ppb, PLa, d.partial, d.out, d.raw_out, d.pool_out};
+  const dim3 grid((n_iter + ppb - 1) / ppb, d.B);
+  if (d.src0_is_op) gn_apply_kernel<true><<<grid, C8 * PLa, 0, s>>>(a);
+  else gn_apply_kernel<false><<<grid, C8 * PLa, 0, s>>>(a);
   return SGDM_LAUNCH_OK();
 }
 
