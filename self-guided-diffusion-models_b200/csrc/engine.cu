@@ -626,10 +626,15 @@ struct Builder {
     if (dry) return;
     const double el = static_cast<double>(Bp) * d.H * d.W * (d.C0 + d.C1);
     const double out_el = d.resample == 1 ? el / 4 : d.resample == 2 ? el * 4 : el;
+    const double in_b = d.src0_is_op ? 2 : 4;
     push([d](cudaStream_t s) {
-      g_launches += 2;
-      return gn_launch(d, s);
-    }, "groupnorm", 0, el * (d.src0_is_op ? 2 : 4) * 2 + out_el * 2 + (d.raw_out ? el * 2 : 0) + (d.pool_out ? out_el * 4 : 0));
+      ++g_launches;
+      return gn_stats_launch(d, s);
+    }, "gn_stats", 0, el * in_b);
+    push([d](cudaStream_t s) {
+      ++g_launches;
+      return gn_apply_launch(d, s);
+    }, "gn_apply", 0, el * in_b + out_el * 2 + (d.raw_out ? el * 2 : 0) + (d.pool_out ? out_el * 4 : 0));
   }
 
   // ResBlock._forward (openaimodel.py:300-320)

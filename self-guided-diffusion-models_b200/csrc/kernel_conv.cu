@@ -140,15 +140,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int m_base = m_tile * kTileM + quarter * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * block_n;
+      // fp32 path: lane = (row group lane>>3, column quad lane&7).  The residual rows this lane
+      // will need are known before the accumulator is ready: their loads are issued one 32-column
+      // chunk ahead (and the first chunk before waiting on the MMA), so that ~32 KB of residual
+      // reads per SM are in flight instead of one dependent 16-byte load per lane.
+      const int cq4 = (lane & 7) * 4;
+      const bool use_res = p.res_mode != 0 && p.out_f32 != nullptr;
+      int rrow[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int m = m_base + 4 * k + (lane >> 3);
+        int r = -1;
+        if (use_res && m < p.M_total) {
+          r = m;
+          if (p.res_mode == 2) {
+            const int img = m / p.HW, pix = m - img * p.HW;
+            const int y = pix / p.Wout, x = pix - y * p.Wout;
+            r = (img * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+          }
+        }
+        rrow[k] = r;
+      }
+      float4 rcur[8], rnext[8];
+      auto load_res = [&](int c0, float4 (&r)[8]) {
+        const int col = n_tile * block_n + c0 + cq4;
+        const bool ok = c0 + cq4 < block_n && col < p.N_total;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && rrow[k] >= 0) r[k] = __ldg(reinterpret_cast<const float4*>(p.res + static_cast<long>(rrow[k]) * p.N_total + col));
+        }
+      };
+      if (use_res) load_res(0, rcur);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
       for (int c0 = 0; c0 < block_n; c0 += 32) {
         uint32_t v[32];
         const int nc = min(32, block_n - c0);
         if (nc == 32) tmem_ld_32x32(taddr + c0, v);
         else tmem_ld_32x16(taddr + c0, v);
+        if (use_res && c0 + 32 < block_n) load_res(c0 + 32, rnext);
         tmem_ld_wait();
         const int col0 = n_tile * block_n + c0;
         if (p.out_nchw != nullptr) {  // final conv: lanes = adjacent pixels -> already coalesced
@@ -176,29 +209,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         __syncwarp();
         if (p.out_f32) {
           // 8 lanes per row (float4 each), 4 rows per instruction
-          const int cq = (lane & 7) * 4;
-          const int col = col0 + cq;
-          const bool col_ok = cq < nc && col < p.N_total;
+          const int col = col0 + cq4;
+          const bool col_ok = cq4 < nc && col < p.N_total;
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (col_ok && p.bias) b = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int rr = 0; rr < 32; rr += 4) {
-            const int rl = rr + (lane >> 3);
+          for (int k = 0; k < 8; ++k) {
+            const int rl = 4 * k + (lane >> 3);
             const int m = m_base + rl;
             if (!col_ok || m >= p.M_total) continue;
-            float4 a = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+            float4 a = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq4);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            if (p.res_mode) {
-              long rrow = m;
-              if (p.res_mode == 2) {
-                const int img = m / p.HW, pix = m - img * p.HW;
-                const int y = pix / p.Wout, x = pix - y * p.Wout;
-                rrow = (static_cast<long>(img) * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
-              }
-              const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + rrow * p.N_total + col));
-              a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-            }
+            if (use_res) { a.x += rcur[k].x; a.y += rcur[k].y; a.z += rcur[k].z; a.w += rcur[k].w; }
             *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
+          }
+          if (use_res) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
           }
         } else {
           // 16-bit output: 4 lanes per row (8 columns = 16 bytes each), 8 rows per instruction

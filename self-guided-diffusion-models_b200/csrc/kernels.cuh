@@ -27,7 +27,9 @@ struct GnDesc {
   float* pool_out = nullptr;     // optional fp32 avg-pooled raw input (residual of a down ResBlock)
 };
 int gn_chunks_for(int B, int HW, int C);
-int gn_launch(const GnDesc& d, cudaStream_t s);
+int gn_launch(const GnDesc& d, cudaStream_t s);        // stats + apply
+int gn_stats_launch(const GnDesc& d, cudaStream_t s);  // pass 1 only
+int gn_apply_launch(const GnDesc& d, cudaStream_t s);  // pass 2 only
 
 // ---- LayerNorm over channels (Attention_LR, crossattetion_lr.py:36-43) -------------------
 // mode 0: out_op = LN(x)*gamma+beta ; mode 1: out_f32 = res + LN(x)*gamma+beta

@@ -86,6 +86,61 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
   }
 }
 
+// 16-bit source variant: thread = (8-channel column, pixel lane), 16-byte loads.
+__global__ void __launch_bounds__(256) gn_stats_op_kernel(const op_t* __restrict__ src, int HW, int C, int chunks, int PL,
+                                                          double* __restrict__ partial) {
+  __shared__ float s_sum[2048];
+  __shared__ float s_sq[2048];
+  const int C8 = C >> 3;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int q = threadIdx.x % C8, pl = threadIdx.x / C8;
+  const int ppc = HW / chunks;
+  const int c = q * 8;
+  const op_t* base = src + static_cast<long>(n) * HW * C + c;
+  float s[2][8], ss[2][8];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[u][j] = 0.f; ss[u][j] = 0.f; }
+  auto acc8 = [&](const uint4& r, float (&a)[8], float (&b)[8]) {
+    const float2 p0 = unpack_op2(r.x), p1 = unpack_op2(r.y), p2 = unpack_op2(r.z), p3 = unpack_op2(r.w);
+    const float v[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] += v[j]; b[j] += v[j] * v[j]; }
+  };
+  const int px_end = (chunk + 1) * ppc;
+  int px = chunk * ppc + pl;
+  for (; px + 3 * PL < px_end; px += 4 * PL) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(px + u * PL) * C));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc8(r[u], s[u & 1], ss[u & 1]);
+  }
+  for (; px < px_end; px += PL) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long>(px) * C));
+    acc8(r, s[0], ss[0]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_sum[pl * C + c + j] = s[0][j] + s[1][j];
+    s_sq[pl * C + c + j] = ss[0][j] + ss[1][j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x, cpg = C / 32;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < PL; ++l)
+      for (int k = 0; k < cpg; ++k) {
+        a += static_cast<double>(s_sum[l * C + g * cpg + k]);
+        b += static_cast<double>(s_sq[l * C + g * cpg + k]);
+      }
+    double* out = partial + ((static_cast<long>(n) * chunks + chunk) * 32 + g) * 2;
+    out[0] = a;
+    out[1] = b;
+  }
+}
+
 struct GnApplyArgs {
   const void* src0; const float* src1;
   int H, W, C0, C1;
@@ -242,16 +297,32 @@ int gn_chunks_for(int B, int HW, int C) {
   return chunks;
 }
 
-int gn_launch(const GnDesc& d, cudaStream_t s) {
+static int gn_check(const GnDesc& d) {
   const int C = d.C0 + d.C1, HW = d.H * d.W;
   if (C % 32 || C > 1024 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;
   if (d.src0_is_op && d.C1) return 1;
-  const int C4 = C / 4;
-  const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
-  if (d.src0_is_op)
-    gn_stats_kernel<true><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
-  else
+  return 0;
+}
+
+int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
+  if (gn_check(d)) return 1;
+  const int C = d.C0 + d.C1, HW = d.H * d.W;
+  if (d.src0_is_op) {
+    const int C8 = C / 8;
+    const int PL = 256 / C8 > 0 ? 256 / C8 : 1;
+    gn_stats_op_kernel<<<dim3(d.chunks, d.B), C8 * PL, 0, s>>>(static_cast<const op_t*>(d.src0), HW, C, d.chunks, PL,
+                                                             d.partial);
+  } else {
+    const int C4 = C / 4;
+    const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
     gn_stats_kernel<false><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+  }
+  return SGDM_LAUNCH_OK();
+}
+
+int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
+  if (gn_check(d)) return 1;
+  const int C = d.C0 + d.C1, HW = d.H * d.W;
   const int C8 = C / 8;
   const int PLa = 256 / C8 > 0 ? 256 / C8 : 1;
   const int n_iter = d.resample == 1 ? HW / 4 : HW;
@@ -266,6 +337,8 @@ int gn_launch(const GnDesc& d, cudaStream_t s) {
   else gn_apply_kernel<false><<<grid, C8 * PLa, 0, s>>>(a);
   return SGDM_LAUNCH_OK();
 }
+
+int gn_launch(const GnDesc& d, cudaStream_t s) { return gn_stats_launch(d, s) || gn_apply_launch(d, s); }
 
 // =========================================================================== LayerNorm
 // One warp per row of C channels (C % 128 == 0, C <= 1024); two-pass in registers.
