@@ -5,9 +5,9 @@
 // (crossattetion_lr.py:88-137: multi-query, ONE shared k/v head, keys = [16 context |
 // 1 null | T self], q scaled by d^-1/2) — SURVEY.md §2.3 rows K6/K7.
 //
-// One CTA = 64 queries of one (sample, head); 4 warps x 16 query rows.  K and V of the
+// One CTA = 128 queries of one (sample, head); 8 warps x 16 query rows.  K and V of the
 // sample (T_kv <= 320 rows incl. the extra context/null rows) are staged once in shared
-// memory; S = QK^T and O = PV run on mma.sync m16n8k16 (16-bit operands, fp32 accumulate);
+// memory with 16-byte cp.async; S = QK^T and O = PV run on mma.sync m16n8k16 (16-bit operands, fp32 accumulate);
 // the softmax is computed in fp32 over key chunks of 64 with running max / sum.
 // Attention is ~1 % of the UNet FLOPs.
 #include "attn.cuh"
@@ -36,43 +36,62 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
                : "r"(smem_u32(p)));
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+constexpr int kAttnQ = 128;       // queries per CTA
+constexpr int kAttnThreads = 256;  // 8 warps x 16 query rows
+
 template <int D>
-__global__ void __launch_bounds__(128) attn_kernel(const AttnDesc a, int tkv_pad) {
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, int tkv_pad) {
   constexpr int LD = D + 8;  // padded row: conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_attn[];
   op_t* sK = reinterpret_cast<op_t*>(smem_attn);
   op_t* sV = sK + static_cast<long>(tkv_pad) * LD;
   op_t* sQ = sV + static_cast<long>(tkv_pad) * LD;
-  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tkv = a.n_extra + a.T;
   constexpr int CPR = D / 8;  // 16-byte chunks per row
 
-  // ---- stage K, V (extra rows first, then the T self rows) and the Q tile
-  for (int i = threadIdx.x; i < tkv_pad * CPR; i += 128) {
+  // ---- stage K, V (extra rows first, then the T self rows) and the Q tile: 16-byte cp.async,
+  //      zero-fill for the padding rows
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < tkv_pad * CPR; i += kAttnThreads) {
     const int row = i / CPR, ch = i - row * CPR;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    op_t* dk = sK + row * LD + ch * 8;
+    op_t* dv = sV + row * LD + ch * 8;
     if (row < a.n_extra) {
       const long o = (static_cast<long>(n) * a.n_extra + row) * D + ch * 8;
-      kv = *reinterpret_cast<const uint4*>(a.k_extra + o);
-      vv = *reinterpret_cast<const uint4*>(a.v_extra + o);
+      cp_async16(dk, a.k_extra + o);
+      cp_async16(dv, a.v_extra + o);
     } else if (row < Tkv) {
       const long tok = static_cast<long>(n) * a.T + (row - a.n_extra);
-      kv = *reinterpret_cast<const uint4*>(a.k + tok * a.k_row_stride + h * a.k_head_stride + ch * 8);
-      vv = *reinterpret_cast<const uint4*>(a.v + tok * a.v_row_stride + h * a.v_head_stride + ch * 8);
+      cp_async16(dk, a.k + tok * a.k_row_stride + h * a.k_head_stride + ch * 8);
+      cp_async16(dv, a.v + tok * a.v_row_stride + h * a.v_head_stride + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(dk) = zero4;
+      *reinterpret_cast<uint4*>(dv) = zero4;
     }
-    *reinterpret_cast<uint4*>(sK + row * LD + ch * 8) = kv;
-    *reinterpret_cast<uint4*>(sV + row * LD + ch * 8) = vv;
   }
-  for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
+  for (int i = threadIdx.x; i < kAttnQ * CPR; i += kAttnThreads) {
     const int row = i / CPR, ch = i - row * CPR;
-    uint4 qv = make_uint4(0, 0, 0, 0);
+    op_t* dq = sQ + row * LD + ch * 8;
     if (q0 + row < a.T)
-      qv = *reinterpret_cast<const uint4*>(a.q + (static_cast<long>(n) * a.T + q0 + row) * a.q_row_stride +
-                                           h * a.q_head_stride + ch * 8);
-    *reinterpret_cast<uint4*>(sQ + row * LD + ch * 8) = qv;
+      cp_async16(dq, a.q + (static_cast<long>(n) * a.T + q0 + row) * a.q_row_stride + h * a.q_head_stride + ch * 8);
+    else
+      *reinterpret_cast<uint4*>(dq) = zero4;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (q0 + warp * 16 >= a.T) return;  // this warp's 16 query rows are all padding
 
   // ---- Q fragments (A operand, 16 x D per warp)
   uint32_t qf[D / 16][4];
@@ -119,15 +138,15 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnDesc a, int tkv_pad
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+    const float c0 = fast_exp2(m0 - mx0), c1 = fast_exp2(m1 - mx1);
     m0 = mx0;
     m1 = mx1;
     float rs0 = 0.f, rs1 = 0.f;
     uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - m0), p1 = exp2f(s[nt][1] - m0);
-      const float p2 = exp2f(s[nt][2] - m1), p3 = exp2f(s[nt][3] - m1);
+      const float p0 = fast_exp2(s[nt][0] - m0), p1 = fast_exp2(s[nt][1] - m0);
+      const float p2 = fast_exp2(s[nt][2] - m1), p3 = fast_exp2(s[nt][3] - m1);
       rs0 += p0 + p1;
       rs1 += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_op2(p0, p1);
@@ -173,9 +192,9 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
   const int tkv_pad = (Tkv + 63) / 64 * 64;
   if (a.D != 32 && a.D != 64) return 1;
   const int LD = a.D + 8;
-  const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + 64) * LD * sizeof(op_t);
+  const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + kAttnQ) * LD * sizeof(op_t);
   if (smem > 200 * 1024) return 1;
-  const dim3 grid((a.T + 63) / 64, a.heads, a.B);
+  const dim3 grid((a.T + kAttnQ - 1) / kAttnQ, a.heads, a.B);
   static size_t max_set[2] = {0, 0};  // opt-in dynamic smem limit, raised on demand
   if (a.D == 64) {
     if (smem > max_set[0]) {
@@ -184,7 +203,7 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
         return 1;
       max_set[0] = smem;
     }
-    attn_kernel<64><<<grid, 128, smem, s>>>(a, tkv_pad);
+    attn_kernel<64><<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
   } else {
     if (smem > max_set[1]) {
       if (cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -192,7 +211,7 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
         return 1;
       max_set[1] = smem;
     }
-    attn_kernel<32><<<grid, 128, smem, s>>>(a, tkv_pad);
+    attn_kernel<32><<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

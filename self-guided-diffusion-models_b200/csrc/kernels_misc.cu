@@ -229,17 +229,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   const int p_end = min(p_begin + a.ppb, n_iter);
   if (a.resample == 0) {
     int pix = p_begin + lane;
-    for (; pix + a.PLa < p_end; pix += 2 * a.PLa) {  // two pixels in flight
-      float v0[8], v1[8], y0[8], y1[8];
-      gn_load8<kHalfIn>(a, n, pix, c, v0);
-      gn_load8<kHalfIn>(a, n, pix + a.PLa, c, v1);
-      xform(v0, y0);
-      xform(v1, y1);
-      store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y0);
-      store8_op(a.out + (static_cast<long>(n) * HW + pix + a.PLa) * C + c, y1);
-      if (a.raw_out) {
-        store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v0);
-        store8_op(a.raw_out + (static_cast<long>(n) * HW + pix + a.PLa) * C + c, v1);
+    for (; pix + 3 * a.PLa < p_end; pix += 4 * a.PLa) {  // four pixels (8 x 16-byte loads) in flight
+      float v[4][8], y[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gn_load8<kHalfIn>(a, n, pix + u * a.PLa, c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xform(v[u], y);
+        store8_op(a.out + (static_cast<long>(n) * HW + pix + u * a.PLa) * C + c, y);
+        if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix + u * a.PLa) * C + c, v[u]);
       }
     }
     for (; pix < p_end; pix += a.PLa) {
