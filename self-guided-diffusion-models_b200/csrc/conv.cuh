@@ -35,6 +35,10 @@ struct ConvDesc {
   op_t* out_op = nullptr;       // NHWC op_t
   float* out_nchw = nullptr;    // NCHW fp32 [B,Cout,Hout,Wout] (final conv, Cout = 3)
   int block_n = 128;            // 16 or a multiple of 32, <= 256; Npad = roundup(Cout, block_n)
+  // Cout == 128 only: compute D^T = W * X^T, i.e. the 128 output channels are the MMA M dimension and a
+  // tile of 256 PIXELS is the MMA N dimension.  An M128xN128 SS-MMA needs 128 B/clk of shared-memory
+  // reads (the port limit, ~50 % tensor rate); M128xN256 needs 96 B/clk and runs at full rate.
+  int swap_ab = 0;
 };
 
 struct alignas(64) ConvKernelParams {
@@ -45,6 +49,7 @@ struct alignas(64) ConvKernelParams {
   int stride, pad, ks, taps;
   int kc1, kc2;
   int N_total, block_n, n_tiles, m_tiles;
+  int swap_ab, tile_px;  // tile_px: pixels per tile (128, or 256 when swap_ab)
   const float* bias;
   const float* res;
   int res_mode;
@@ -67,5 +72,11 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream);
 int conv_launch_naive(const ConvDesc& d, cudaStream_t stream);
 
 inline int conv_npad(int cout, int block_n) { return (cout + block_n - 1) / block_n * block_n; }
+// policy used by the engine and by block_n = 0 in sgdm_k_conv
+inline bool conv_can_swap(const ConvDesc& d) {
+  const int HW = d.Hout * d.Wout;
+  return d.Cout == 128 && d.out_nchw == nullptr && !(d.res && d.res_mode == 2) && d.Wout <= 256 &&
+         (256 % d.Wout) == 0 && ((HW % 256) == 0 || (256 % HW) == 0);
+}
 
 }  // namespace sgdm

@@ -600,6 +600,7 @@ struct Builder {
   void conv(ConvDesc d, int real_cin = 0) {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
+    d.swap_ab = conv_can_swap(d) ? 1 : 0;
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
     char msg[256];
@@ -1163,6 +1164,7 @@ int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, 
   d.ks = ks; d.stride = stride; d.pad = ks == 3 ? 1 : 0; d.Hout = Hout; d.Wout = Wout; d.Cout = Cout;
   d.bias = bias; d.res = res; d.res_mode = res_mode; d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
   d.out_nchw = out_nchw; d.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
+  d.swap_ab = (block_n <= 0 && conv_can_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
   ++g_launches;
   if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const int block_n = p.block_n;
   // two accumulator stages of block_n fp32 columns each; allocation must be a power of 2 >= 32
+  const uint32_t acc_cols = p.swap_ab ? 256u : static_cast<uint32_t>(block_n);  // fp32 columns per accumulator
   uint32_t ncols = 32;
-  while (ncols < 2u * block_n) ncols <<= 1;
+  while (ncols < 2u * acc_cols) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -75,28 +76,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx_bytes = kABytes + block_n * 128;
+      // swap_ab: the activation tile (256 pixels, 32 KB) lives in the big slot and is the MMA B operand,
+      // the weight tile (128 x 64, 16 KB) in the small slot is the A operand.
+      const uint32_t tx_bytes = p.swap_ab ? (kABytes + kBBytesMax) : (kABytes + block_n * 128);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
-        const int p0 = m_tile * kTileM;
+        const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          uint8_t* act_dst = p.swap_ab ? sB + stage * kBBytesMax : sA + stage * kABytes;
+          uint8_t* wgt_dst = p.swap_ab ? sA + stage * kABytes : sB + stage * kBBytesMax;
           if (kb < p.taps * p.kc1) {
             const int tap = kb / p.kc1;
             const int cc = kb - tap * p.kc1;
             const int r = tap / p.ks;
             const int s = tap - r * p.ks;
-            tma_load_4d(&p.tmA, &full[stage], sA + stage * kABytes, cc * 64, s - p.pad,
-                        y0 * p.stride + r - p.pad, img);
+            tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
           } else {
             const int cc = kb - p.taps * p.kc1;
-            tma_load_4d(&p.tmA2, &full[stage], sA + stage * kABytes, cc * 64, 0, y0, img);
+            tma_load_4d(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
           }
-          tma_load_2d(&p.tmB, &full[stage], sB + stage * kBBytesMax, kb * 64, n_tile * block_n);
+          tma_load_2d(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -104,13 +108,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = umma_idesc(kTileM, block_n);
+      const uint32_t idesc = umma_idesc(kTileM, p.swap_ab ? 256 : block_n);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * block_n;
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -140,6 +144,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      if (p.swap_ab) {
+        // D^T tile: TMEM lane = output channel, column = pixel.  For a fixed pixel the 32 lanes of the
+        // warp hold 32 consecutive channels -> every scalar load/store instruction is one full
+        // 128-byte (fp32) row segment; no staging needed.  Residual values are prefetched one
+        // 32-pixel chunk ahead.
+        const int ch = quarter * 32 + lane;
+        const float bias_c = p.bias ? p.bias[ch] : 0.f;
+        const long p0 = static_cast<long>(m_tile) * p.tile_px;
+        const uint32_t taddr_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
+        const bool use_res_s = p.res_mode == 1;
+        float rc[32], rn[32];
+        auto load_res_s = [&](int c0, float (&r)[32]) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long px = p0 + c0 + j;
+            r[j] = px < p.M_total ? __ldg(p.res + px * p.N_total + ch) : 0.f;
+          }
+        };
+        if (use_res_s) load_res_s(0, rc);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.tile_px; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr_s + c0, v);
+          if (use_res_s && c0 + 32 < p.tile_px) load_res_s(c0 + 32, rn);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long px = p0 + c0 + j;
+            if (px >= p.M_total) break;
+            float a = __uint_as_float(v[j]) + bias_c;
+            if (use_res_s) a += rc[j];
+            if (p.out_f32) p.out_f32[px * p.N_total + ch] = a;
+            else p.out_op[px * p.N_total + ch] = to_op(a);
+          }
+          if (use_res_s) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rc[j] = rn[j];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+      }
       const int m_base = m_tile * kTileM + quarter * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * block_n;
       // fp32 path: lane = (row group lane>>3, column quad lane&7).  The residual rows this lane
@@ -314,16 +363,22 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.Cin % 64 || (d.in2 && d.C2 % 64)) return fail("channel counts must be multiples of 64");
   if (!(d.ks == 1 || d.ks == 3) || !(d.stride == 1 || d.stride == 2)) return fail("unsupported ks/stride");
   if (d.block_n != 16 && (d.block_n % 32 || d.block_n > 256 || d.block_n <= 0)) return fail("bad block_n");
-  if (d.Wout > 128 || (128 % d.Wout) != 0) return fail("Wout must divide 128");
   const int HW = d.Hout * d.Wout;
-  if (!((HW % 128) == 0 || (128 % HW) == 0)) return fail("Hout*Wout must divide or be a multiple of 128");
+  if (!d.swap_ab) {
+    if (d.Wout > 128 || (128 % d.Wout) != 0) return fail("Wout must divide 128");
+    if (!((HW % 128) == 0 || (128 % HW) == 0)) return fail("Hout*Wout must divide or be a multiple of 128");
+  } else if (d.block_n != 128) {
+    return fail("swap_ab uses block_n == 128 (all output channels in one tile)");
+  }
   if (d.out_nchw == nullptr && (d.Cout % 8)) return fail("Cout % 8 != 0 needs the NCHW epilogue");
   if ((d.out_f32 != nullptr) + (d.out_op != nullptr) + (d.out_nchw != nullptr) != 1) return fail("exactly one output");
   if (d.out_op && d.res && d.res_mode == 2) return fail("res_mode 2 needs the fp32 output");
   if (d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
+  if (d.swap_ab && !conv_can_swap(d)) return fail("swap_ab needs Cout == 128, no NCHW / upsampled-residual epilogue");
+  const int tile_px = d.swap_ab ? 256 : kTileM;
   const int bw = d.Wout;
-  const int bh = min(d.Hout, 128 / bw);
-  const int bn = 128 / (bw * bh);
+  const int bh = min(d.Hout, tile_px / bw);
+  const int bn = tile_px / (bw * bh);
   if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, bh, bn, d.stride, err, errlen)) return 1;
   if (d.in2) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
@@ -357,7 +412,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.N_total = d.Cout;
   p.block_n = d.block_n;
   p.n_tiles = npad / d.block_n;
-  p.m_tiles = (p.M_total + kTileM - 1) / kTileM;
+  p.swap_ab = d.swap_ab;
+  p.tile_px = tile_px;
+  p.m_tiles = (p.M_total + tile_px - 1) / tile_px;
   p.bias = d.bias;
   p.res = d.res;
   p.res_mode = d.res ? d.res_mode : 0;

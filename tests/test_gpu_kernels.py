@@ -96,6 +96,10 @@ CONV_CASES = [
     (5, 64, 64, 64, 128, 3, 1, 0, 1, "f32", "160 tiles > 148 CTAs: second tile on some CTAs"),
     (40, 32, 32, 128, 256, 3, 1, 128, 0, "f32", "320 tiles x N=256: persistent loop, both TMEM stages, phase flips"),
     (37, 16, 16, 512, 512, 1, 1, 0, 1, "f32", "74 m-tiles x 2 n-tiles"),
+    (3, 64, 64, 384, 128, 3, 1, 0, 0, "op", "Cout=128: 384->128 at 64x64, 16-bit out (swap-AB candidate)"),
+    (3, 8, 8, 128, 128, 3, 1, 0, 1, "f32", "Cout=128 at 8x8: 256-pixel tile spans 4 images, ragged"),
+    (40, 32, 32, 128, 128, 3, 2, 0, 0, "f32", "Cout=128 stride 2, 320 tiles"),
+    (2, 32, 32, 256, 128, 3, 1, 384, 0, "f32", "Cout=128 with fused 1x1 skip"),
 ]
 
 
@@ -128,13 +132,16 @@ def test_conv_tcgen05_vs_torch(L, case):
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    for naive in (1, 0):
-        got = run_conv(L, x, wp, bn, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
+    modes = [("naive", bn, 1), ("tcgen05", bn, 0)]
+    if Cout == 128 and out != "nchw" and res_mode != 2:
+        modes.append(("tcgen05 swap-AB (block_n=0: engine policy)", 0, 0))
+    for label, bn_arg, naive in modes:
+        got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
         got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
-        assert torch.isfinite(got).all(), f"non-finite output ({'naive' if naive else 'tcgen05'})"
+        assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)
-        print(f"[conv {note}] {'naive ' if naive else 'tcgen05'} rel_l2={e:.3e}")
-        assert e < (2e-3 if out == "op" else 2e-5), f"{'naive' if naive else 'tcgen05'} conv mismatch {e}"
+        print(f"[conv {note}] {label} rel_l2={e:.3e}")
+        assert e < (2e-3 if out == "op" else 2e-5), f"{label} conv mismatch {e}"
 
 
 def test_conv_rejects_bad_shapes(L):
