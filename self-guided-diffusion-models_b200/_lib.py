@@ -66,8 +66,12 @@ PROTOTYPES = {
     "sgdm_launch_count": (_i64, []),
     "sgdm_debug_set_naive_conv": (_i, [_i]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
+    "sgdm_k_conv_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
+                                _vp, _i]),
     "sgdm_k_pack_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "sgdm_k_groupnorm": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "sgdm_k_groupnorm_fused": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp,
+                                     _vp]),
     "sgdm_k_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i]),
     "sgdm_k_attention": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _f]),
     "sgdm_k_linear_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),

@@ -39,6 +39,14 @@ struct ConvDesc {
   // tile of 256 PIXELS is the MMA N dimension.  An M128xN128 SS-MMA needs 128 B/clk of shared-memory
   // reads (the port limit, ~50 % tensor rate); M128xN256 needs 96 B/clk and runs at full rate.
   int swap_ab = 0;
+  // Optional GroupNorm partial statistics of the FINAL output values (after bias / residual, before the
+  // 16-bit rounding): stats[(row / 32) * (Cout / stat_gran) + channel / stat_gran] = {sum, sum of squares}
+  // over that 32-row block and `stat_gran` (2 or 4) adjacent channels.  Rows are output pixels in NHWC
+  // order, so with Hout*Wout % 32 == 0 every block lies inside one sample and any GroupNorm whose groups
+  // are unions of such channel granules (also across a channel concat) is finalised from these sums
+  // without re-reading the tensor (gn_finalize_kernel).  Buffer: ceil(M/32) * Cout/stat_gran float2.
+  float2* stats = nullptr;
+  int stat_gran = 4;
 };
 
 struct alignas(64) ConvKernelParams {
@@ -56,6 +64,8 @@ struct alignas(64) ConvKernelParams {
   float* out_f32;
   op_t* out_op;
   float* out_nchw;
+  float2* stats;
+  int stat_gran;
 };
 
 struct ConvLaunch {

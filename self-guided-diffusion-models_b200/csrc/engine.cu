@@ -84,6 +84,7 @@ struct Layer {
 struct Act {
   float* p = nullptr;
   int C = 0, H = 0, W = 0;
+  float2* stats = nullptr;  // GroupNorm partial sums emitted by the producing conv (ConvDesc::stats), or null
 };
 
 struct OpMeta {
@@ -591,6 +592,14 @@ struct Builder {
     stream_off += bytes;
     return p;
   }
+  // GroupNorm statistics ride on the producing conv's epilogue whenever 32-row blocks stay inside a sample
+  int stat_gran() const { return e->mc % 128 == 0 ? 4 : 2; }
+  static bool stats_ok(int H, int W) { return (H * W) % 32 == 0; }
+  size_t stats_elems(size_t rows, int C) const { return (rows + 31) / 32 * (C / stat_gran()); }
+  float2* stats_alloc(size_t rows, int C, int H, int W) {
+    if (!stats_ok(H, W)) return nullptr;
+    return reinterpret_cast<float2*>(stream_alloc(2 * stats_elems(rows, C)));
+  }
   void push(Op op, const char* kind = "misc", double flops = 0, double bytes = 0) {
     if (dry) return;
     plan->ops.push_back(std::move(op));
@@ -601,6 +610,7 @@ struct Builder {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
     d.swap_ab = conv_can_swap(d) ? 1 : 0;
+    d.stat_gran = stat_gran();
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
     char msg[256];
@@ -624,14 +634,25 @@ struct Builder {
     d.B = Bp;
     d.chunks = gn_chunks_for(Bp, d.H * d.W, d.C0 + d.C1);
     d.partial = static_cast<double*>(scratch("gn_partial", static_cast<size_t>(Bp) * 16 * 32 * 2 * sizeof(double)));
+    d.final = static_cast<float2*>(scratch("gn_final", static_cast<size_t>(Bp) * 32 * sizeof(float2)));
+    d.stat_gran = stat_gran();
     if (dry) return;
+    const bool fused = d.stats0 != nullptr && (d.C1 == 0 || d.stats1 != nullptr);
+    if (!fused) { d.stats0 = nullptr; d.stats1 = nullptr; }
     const double el = static_cast<double>(Bp) * d.H * d.W * (d.C0 + d.C1);
     const double out_el = d.resample == 1 ? el / 4 : d.resample == 2 ? el * 4 : el;
     const double in_b = d.src0_is_op ? 2 : 4;
-    push([d](cudaStream_t s) {
-      ++g_launches;
-      return gn_stats_launch(d, s);
-    }, "gn_stats", 0, el * in_b);
+    if (fused) {
+      push([d](cudaStream_t s) {
+        ++g_launches;
+        return gn_finalize_launch(d, s);
+      }, "gn_stats", 0, el / 32 / d.stat_gran * 8);
+    } else {
+      push([d](cudaStream_t s) {
+        ++g_launches;
+        return gn_stats_launch(d, s);
+      }, "gn_stats", 0, el * in_b);
+    }
     push([d](cudaStream_t s) {
       ++g_launches;
       return gn_apply_launch(d, s);
@@ -650,25 +671,30 @@ struct Builder {
     g.src0 = a.p; g.src1 = b.p; g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
     g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
     g.out = g1; g.raw_out = raw; g.pool_out = pooled;
+    g.stats0 = a.stats; g.stats1 = b.stats;
     gn(g);
     // h1 only feeds the second GroupNorm: kept in the 16-bit operand type (halves its HBM traffic;
     // measured cost on eps: rel-L2 1.65e-3 -> 1.96e-3, DESIGN.md "operand precision")
     op_t* h1 = static_cast<op_t*>(scratch("h1", px_out * r.cout * sizeof(op_t)));
+    float2* h1_stats = static_cast<float2*>(scratch("h1_stats", stats_elems(px_out, r.cout) * sizeof(float2)));
+    if (!stats_ok(Ho, Wo)) h1_stats = nullptr;
     ConvDesc c1;
     c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
-    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_op = h1;
+    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_op = h1; c1.stats = h1_stats;
     conv(c1);
     op_t* g2 = static_cast<op_t*>(scratch("gn_out", px_out * r.cout * sizeof(op_t)));
     GnDesc gg;
     gg.src0 = h1; gg.src0_is_op = 1; gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
     gg.film = dry ? nullptr : emb_out + r.emb_off; gg.film_stride = e->NE; gg.silu = 1; gg.out = g2;
+    gg.stats0 = h1_stats;
     gn(gg);
     Act o;
     o.C = r.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(px_out * r.cout);
+    o.stats = stats_alloc(px_out, r.cout, Ho, Wo);
     ConvDesc c2;
     c2.in = g2; c2.Hin = Ho; c2.Win = Wo; c2.Cin = r.cout; c2.w = r.w2; c2.ks = 3; c2.stride = 1; c2.pad = 1;
-    c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p;
+    c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p; c2.stats = o.stats;
     if (r.skip) {
       c2.in2 = raw; c2.C2 = C; c2.bias = r.bfused;
     } else {
@@ -687,6 +713,7 @@ struct Builder {
     op_t* g = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
     GnDesc gd;
     gd.src0 = a.p; gd.H = a.H; gd.W = a.W; gd.C0 = C; gd.gamma = w.norm_w; gd.beta = w.norm_b; gd.silu = 0; gd.out = g;
+    gd.stats0 = a.stats;
     gn(gd);
     op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * 3 * C * sizeof(op_t)));
     ConvDesc c1;
@@ -706,9 +733,11 @@ struct Builder {
     }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * T * dh, static_cast<double>(rows) * 4 * C * 2);
     Act o = a;
     o.p = stream_alloc(rows * C);
+    o.stats = stats_alloc(rows, C, a.H, a.W);
     ConvDesc c2;
     c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = C; c2.w = w.wproj; c2.ks = 1; c2.stride = 1; c2.pad = 0;
     c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.bias = w.bproj; c2.res = a.p; c2.res_mode = 1; c2.out_f32 = o.p;
+    c2.stats = o.stats;
     conv(c2);
     return o;
   }
@@ -762,6 +791,7 @@ struct Builder {
     conv(c2);
     Act o = a;
     o.p = stream_alloc(rows * C);
+    o.stats = nullptr;  // produced by the LayerNorm kernel: consumers run the standalone statistics pass
     {
       const float* x = a.p;
       const float *g = w.out_g, *b = w.out_b;
@@ -790,9 +820,10 @@ struct Builder {
     Act o;
     o.C = cw.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(static_cast<size_t>(Bp) * Ho * Wo * cw.cout);
+    o.stats = stats_alloc(static_cast<size_t>(Bp) * Ho * Wo, cw.cout, Ho, Wo);
     ConvDesc c;
     c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
-    c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
+    c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p; c.stats = o.stats;
     conv(c);
     return o;
   }
@@ -892,9 +923,10 @@ struct Builder {
       const ConvW& cw = e->convs[e->in_blocks[0][0].idx];
       h.C = cw.cout; h.H = H; h.W = W;
       h.p = stream_alloc(px * cw.cout);
+      h.stats = stats_alloc(px, cw.cout, H, W);
       ConvDesc d;
       d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
-      d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
+      d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p; d.stats = h.stats;
       conv(d, cw.cin);
       hs.push_back(h);
     }
@@ -913,6 +945,7 @@ struct Builder {
     op_t* g = static_cast<op_t*>(scratch("gn_out", px * h.C * sizeof(op_t)));
     GnDesc gd;
     gd.src0 = h.p; gd.H = H; gd.W = W; gd.C0 = h.C; gd.gamma = e->out_gn_w; gd.beta = e->out_gn_b; gd.silu = 1; gd.out = g;
+    gd.stats0 = h.stats;
     gn(gd);
     ConvDesc d;
     d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
@@ -1158,7 +1191,15 @@ int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, 
                 const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
                 const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
                 int naive) {
+  return sgdm_k_conv_stats(stream, in, B, Hin, Win, Cin, in2, C2, w, ks, stride, Hout, Wout, Cout, bias, res, res_mode,
+                           out_f32, out_op, out_nchw, block_n, naive, nullptr, 4);
+}
+int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int Cin, const void* in2, int C2,
+                      const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
+                      const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
+                      int naive, float* stats, int stat_gran) {
   ConvDesc d;
+  d.stats = reinterpret_cast<float2*>(stats); d.stat_gran = stat_gran;
   d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = Hin; d.Win = Win; d.Cin = Cin;
   d.in2 = static_cast<const op_t*>(in2); d.C2 = C2; d.w = static_cast<const op_t*>(w);
   d.ks = ks; d.stride = stride; d.pad = ks == 3 ? 1 : 0; d.Hout = Hout; d.Wout = Wout; d.Cout = Cout;
@@ -1185,14 +1226,25 @@ int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Ci
 int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W, int C0,
                      int C1, const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
                      int resample, void* out_op, void* raw_out_op, float* pool_out) {
+  return sgdm_k_groupnorm_fused(stream, src0, src0_is_op, src1, B, H, W, C0, C1, gamma, beta, film, film_stride, silu,
+                                resample, nullptr, nullptr, 4, out_op, raw_out_op, pool_out);
+}
+int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W,
+                           int C0, int C1, const float* gamma, const float* beta, const float* film,
+                           int64_t film_stride, int silu, int resample, const float* stats0, const float* stats1,
+                           int stat_gran, void* out_op, void* raw_out_op, float* pool_out) {
   GnDesc d;
+  d.stats0 = reinterpret_cast<const float2*>(stats0); d.stats1 = reinterpret_cast<const float2*>(stats1);
+  d.stat_gran = stat_gran;
   d.src0 = src0; d.src0_is_op = src0_is_op; d.src1 = src1; d.B = B; d.H = H; d.W = W; d.C0 = C0; d.C1 = C1; d.gamma = gamma; d.beta = beta;
   d.film = film; d.film_stride = film_stride; d.silu = silu; d.resample = resample;
   d.out = static_cast<op_t*>(out_op); d.raw_out = static_cast<op_t*>(raw_out_op); d.pool_out = pool_out;
   d.chunks = gn_chunks_for(B, H * W, C0 + C1);
   double* partial = nullptr;
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * d.chunks * 64 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&partial),
+                      static_cast<size_t>(B) * d.chunks * 64 * sizeof(double) + static_cast<size_t>(B) * 32 * sizeof(float2)));
   d.partial = partial;
+  d.final = reinterpret_cast<float2*>(partial + static_cast<size_t>(B) * d.chunks * 64);
   g_launches += 2;
   const int rc = gn_launch(d, static_cast<cudaStream_t>(stream));
   cudaStreamSynchronize(static_cast<cudaStream_t>(stream));  // test entry point only: frees its scratch

@@ -133,74 +133,37 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
-    // Each warp owns 32 accumulator rows (its TMEM lane quarter).  A 32x32 fp32 sub-tile is read
-    // from TMEM (thread = row), transposed through a private smem staging tile, and written
-    // back with thread = (row group, column quad) so that every global load / store instruction
-    // of the warp touches whole 128-byte row segments (bias, residual and output alike).
+    // Each warp owns one TMEM lane quarter and walks its part of the accumulator in 32x32 fp32
+    // chunks.  A chunk is read from TMEM, put into a private smem staging tile as [pixel][channel]
+    // (normal mode: thread = pixel row, 8 x 16-byte stores; swap-AB: thread = channel, 32 scalar
+    // stores), and written back with thread = (row group, column quad) so that every global load /
+    // store instruction of the warp touches whole 128-byte row segments (bias, residual and output
+    // alike).  The same pass optionally emits GroupNorm partial statistics of the FINAL values:
+    // per (32-row block, `stat_gran` channels) sum and sum of squares (see conv.cuh).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     float* stg = stg_all + (warp - 2) * 32 * kStgLd;
+    const int rg = lane >> 3, cq4 = (lane & 7) * 4;  // fp32 path: 8 lanes per row (float4 each), 4 rows per instruction
+    const int rl8 = lane >> 2, cq8 = (lane & 3) * 8;  // 16-bit path: 4 lanes per row (8 columns each), 8 rows per instruction
+    const bool use_res = p.res_mode != 0 && p.out_f32 != nullptr;
+    const int n_chunks = p.swap_ab ? p.tile_px / 32 : (block_n + 31) / 32;
+    const int sg_shift = p.stat_gran == 4 ? 2 : 1;
+    const int stat_ld = p.N_total >> sg_shift;  // stat entries per 32-row block
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      if (p.swap_ab) {
-        // D^T tile: TMEM lane = output channel, column = pixel.  For a fixed pixel the 32 lanes of the
-        // warp hold 32 consecutive channels -> every scalar load/store instruction is one full
-        // 128-byte (fp32) row segment; no staging needed.  Residual values are prefetched one
-        // 32-pixel chunk ahead.
-        const int ch = quarter * 32 + lane;
-        const float bias_c = p.bias ? p.bias[ch] : 0.f;
-        const long p0 = static_cast<long>(m_tile) * p.tile_px;
-        const uint32_t taddr_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
-        const bool use_res_s = p.res_mode == 1;
-        float rc[32], rn[32];
-        auto load_res_s = [&](int c0, float (&r)[32]) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long px = p0 + c0 + j;
-            r[j] = px < p.M_total ? __ldg(p.res + px * p.N_total + ch) : 0.f;
-          }
-        };
-        if (use_res_s) load_res_s(0, rc);
-        mbar_wait(&tfull[acc], acc_phase);
-        tc_fence_after();
-        for (int c0 = 0; c0 < p.tile_px; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr_s + c0, v);
-          if (use_res_s && c0 + 32 < p.tile_px) load_res_s(c0 + 32, rn);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long px = p0 + c0 + j;
-            if (px >= p.M_total) break;
-            float a = __uint_as_float(v[j]) + bias_c;
-            if (use_res_s) a += rc[j];
-            if (p.out_f32) p.out_f32[px * p.N_total + ch] = a;
-            else p.out_op[px * p.N_total + ch] = to_op(a);
-          }
-          if (use_res_s) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) rc[j] = rn[j];
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        continue;
-      }
-      const int m_base = m_tile * kTileM + quarter * 32;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * block_n;
-      // fp32 path: lane = (row group lane>>3, column quad lane&7).  The residual rows this lane
-      // will need are known before the accumulator is ready: their loads are issued one 32-column
-      // chunk ahead (and the first chunk before waiting on the MMA), so that ~32 KB of residual
-      // reads per SM are in flight instead of one dependent 16-byte load per lane.
-      const int cq4 = (lane & 7) * 4;
-      const bool use_res = p.res_mode != 0 && p.out_f32 != nullptr;
+      // chunk i covers rows [row0(i), +32) x columns [col0(i), +nc(i)) of the output matrix
+      const int tile_row0 = p.swap_ab ? m_tile * p.tile_px : m_tile * kTileM + quarter * 32;
+      const int tile_col0 = p.swap_ab ? quarter * 32 : n_tile * block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
+      // Residual rows are known before the accumulator is ready: their loads are issued one chunk
+      // ahead (the first before waiting on the MMA), so that ~32 KB of residual reads per SM are in
+      // flight instead of one dependent 16-byte load per lane.
       int rrow[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int m = m_base + 4 * k + (lane >> 3);
+        const int m = tile_row0 + 4 * k + rg;
         int r = -1;
         if (use_res && m < p.M_total) {
           r = m;
@@ -213,28 +176,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         rrow[k] = r;
       }
       float4 rcur[8], rnext[8];
-      auto load_res = [&](int c0, float4 (&r)[8]) {
-        const int col = n_tile * block_n + c0 + cq4;
-        const bool ok = c0 + cq4 < block_n && col < p.N_total;
+      auto load_res = [&](int i, float4 (&r)[8]) {
+        const int nc = p.swap_ab ? 32 : min(32, block_n - 32 * i);
+        const int col = tile_col0 + (p.swap_ab ? 0 : 32 * i) + cq4;
+        const bool ok = cq4 < nc && col < p.N_total;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          int rr = rrow[k];
+          if (p.swap_ab) {  // rows advance with the chunk (res_mode 1 only)
+            rr = tile_row0 + 32 * i + 4 * k + rg;
+            if (rr >= p.M_total) rr = -1;
+          }
           r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && rrow[k] >= 0) r[k] = __ldg(reinterpret_cast<const float4*>(p.res + static_cast<long>(rrow[k]) * p.N_total + col));
+          if (ok && rr >= 0) r[k] = __ldg(reinterpret_cast<const float4*>(p.res + static_cast<long>(rr) * p.N_total + col));
         }
       };
       if (use_res) load_res(0, rcur);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
+      for (int i = 0; i < n_chunks; ++i) {
         uint32_t v[32];
-        const int nc = min(32, block_n - c0);
-        if (nc == 32) tmem_ld_32x32(taddr + c0, v);
-        else tmem_ld_32x16(taddr + c0, v);
-        if (use_res && c0 + 32 < block_n) load_res(c0 + 32, rnext);
+        const int nc = p.swap_ab ? 32 : min(32, block_n - 32 * i);
+        const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
+        const int col0 = p.swap_ab ? tile_col0 : tile_col0 + 32 * i;
+        if (nc == 32) tmem_ld_32x32(taddr + 32 * i, v);
+        else tmem_ld_32x16(taddr + 32 * i, v);
+        if (use_res && i + 1 < n_chunks) load_res(i + 1, rnext);
         tmem_ld_wait();
-        const int col0 = n_tile * block_n + c0;
         if (p.out_nchw != nullptr) {  // final conv: lanes = adjacent pixels -> already coalesced
-          const int m = m_base + lane;
+          const int m = row0 + lane;
           if (m < p.M_total) {
             const int img = m / p.HW, pix = m - img * p.HW;
 #pragma unroll
@@ -249,38 +219,60 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           continue;
         }
-        float4* srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
+        if (!p.swap_ab) {
+          float4* srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (4 * j < nc)
-            srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nc)
+              srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[j * kStgLd + lane] = __uint_as_float(v[j]);
+        }
         __syncwarp();
+        // pair sums for the GroupNorm statistics: sg/qg[u] covers columns {2u, 2u+1} of this lane's slice
+        float sg[4] = {0.f, 0.f, 0.f, 0.f}, qg[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.out_f32) {
-          // 8 lanes per row (float4 each), 4 rows per instruction
           const int col = col0 + cq4;
           const bool col_ok = cq4 < nc && col < p.N_total;
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (col_ok && p.bias) b = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const int rl = 4 * k + (lane >> 3);
-            const int m = m_base + rl;
+            const int rl = 4 * k + rg;
+            const int m = row0 + rl;
             if (!col_ok || m >= p.M_total) continue;
             float4 a = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq4);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
             if (use_res) { a.x += rcur[k].x; a.y += rcur[k].y; a.z += rcur[k].z; a.w += rcur[k].w; }
             *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
+            sg[0] += a.x + a.y; qg[0] += a.x * a.x + a.y * a.y;
+            sg[1] += a.z + a.w; qg[1] += a.z * a.z + a.w * a.w;
           }
           if (use_res) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
           }
+          if (p.stats) {
+            if (p.stat_gran == 4) { sg[0] += sg[1]; qg[0] += qg[1]; }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
+                qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
+              }
+            }
+            if (rg == 0 && col_ok && row0 < p.M_total) {
+              float2* dst = p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift);
+              if (p.stat_gran == 4) dst[0] = make_float2(sg[0], qg[0]);
+              else *reinterpret_cast<float4*>(dst) = make_float4(sg[0], qg[0], sg[1], qg[1]);
+            }
+          }
         } else {
-          // 16-bit output: 4 lanes per row (8 columns = 16 bytes each), 8 rows per instruction
-          const int cq = (lane & 3) * 8;
-          const int col = col0 + cq;
-          const bool col_ok = cq < nc && col < p.N_total;
+          const int col = col0 + cq8;
+          const bool col_ok = cq8 < nc && col < p.N_total;
           float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
           if (col_ok && p.bias) {
             b0 = *reinterpret_cast<const float4*>(p.bias + col);
@@ -288,11 +280,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
 #pragma unroll
           for (int rr = 0; rr < 32; rr += 8) {
-            const int rl = rr + (lane >> 2);
-            const int m = m_base + rl;
+            const int rl = rr + rl8;
+            const int m = row0 + rl;
             if (!col_ok || m >= p.M_total) continue;
-            float4 a0 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
-            float4 a1 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq + 4);
+            float4 a0 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq8);
+            float4 a1 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq8 + 4);
             a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
             a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
             if (p.res_mode == 1) {
@@ -303,6 +295,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
             const uint4 h = make_uint4(pack_op2(a0.x, a0.y), pack_op2(a0.z, a0.w), pack_op2(a1.x, a1.y), pack_op2(a1.z, a1.w));
             *reinterpret_cast<uint4*>(p.out_op + static_cast<long>(m) * p.N_total + col) = h;
+            sg[0] += a0.x + a0.y; qg[0] += a0.x * a0.x + a0.y * a0.y;
+            sg[1] += a0.z + a0.w; qg[1] += a0.z * a0.z + a0.w * a0.w;
+            sg[2] += a1.x + a1.y; qg[2] += a1.x * a1.x + a1.y * a1.y;
+            sg[3] += a1.z + a1.w; qg[3] += a1.z * a1.z + a1.w * a1.w;
+          }
+          if (p.stats) {
+            if (p.stat_gran == 4) {
+              sg[0] += sg[1]; qg[0] += qg[1];
+              sg[1] = sg[2] + sg[3]; qg[1] = qg[2] + qg[3];
+            }
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (u < 2 || p.stat_gran != 4) {
+                  sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
+                  qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
+                }
+              }
+            }
+            if (rl8 == 0 && col_ok && row0 < p.M_total) {
+              float4* dst = reinterpret_cast<float4*>(p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift));
+              dst[0] = make_float4(sg[0], qg[0], sg[1], qg[1]);
+              if (p.stat_gran != 4) dst[1] = make_float4(sg[2], qg[2], sg[3], qg[3]);
+            }
           }
         }
         __syncwarp();
@@ -375,6 +392,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.out_op && d.res && d.res_mode == 2) return fail("res_mode 2 needs the fp32 output");
   if (d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
   if (d.swap_ab && !conv_can_swap(d)) return fail("swap_ab needs Cout == 128, no NCHW / upsampled-residual epilogue");
+  if (d.stats && (d.out_nchw || (d.Cout % 8) || (d.stat_gran != 2 && d.stat_gran != 4)))
+    return fail("stats need an NHWC output, Cout % 8 == 0 and stat_gran in {2, 4}");
   const int tile_px = d.swap_ab ? 256 : kTileM;
   const int bw = d.Wout;
   const int bh = min(d.Hout, tile_px / bw);
@@ -421,6 +440,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.out_f32 = d.out_f32;
   p.out_op = d.out_op;
   p.out_nchw = d.out_nchw;
+  p.stats = d.stats;
+  p.stat_gran = d.stat_gran;
   const int total = p.m_tiles * p.n_tiles;
   out->grid = total < kNumSMs ? total : kNumSMs;
   static bool attr_set = false;

@@ -25,9 +25,17 @@ struct GnDesc {
   op_t* out = nullptr;           // NHWC op_t [B, H', W', C]
   op_t* raw_out = nullptr;       // optional op_t copy of the un-normalised concat input (for the 1x1 skip conv)
   float* pool_out = nullptr;     // optional fp32 avg-pooled raw input (residual of a down ResBlock)
+  // Statistics emitted by the producing conv's epilogue (ConvDesc::stats, conv.cuh).  When stats0 is set
+  // (and stats1 whenever C1 > 0) the standalone statistics pass over the tensor is skipped: a tiny
+  // finalise kernel reduces the partial sums into `final` = {mean, rstd} per (sample, group).
+  const float2* stats0 = nullptr;
+  const float2* stats1 = nullptr;
+  int stat_gran = 4;
+  float2* final = nullptr;       // scratch [B][32]
 };
 int gn_chunks_for(int B, int HW, int C);
-int gn_launch(const GnDesc& d, cudaStream_t s);        // stats + apply
+int gn_launch(const GnDesc& d, cudaStream_t s);        // stats (or finalise) + apply
+int gn_finalize_launch(const GnDesc& d, cudaStream_t s);  // fused-statistics path: partial sums -> {mean, rstd}
 int gn_stats_launch(const GnDesc& d, cudaStream_t s);  // pass 1 only
 int gn_apply_launch(const GnDesc& d, cudaStream_t s);  // pass 2 only
 

@@ -147,8 +147,42 @@ struct GnApplyArgs {
   const float* gamma; const float* beta; const float* film; long film_stride;
   int silu, resample, chunks, ppb, PLa;
   const double* partial;
+  const float2* final;
   op_t* out; op_t* raw_out; float* pool_out;
 };
+
+// Fused-statistics path: reduce the conv epilogue's partial sums (per 32-row block and channel
+// granule, see ConvDesc::stats) to {mean, rstd} per (sample, group).  One warp per group; the
+// summation order depends on the sample's shape only (batch-invariant bits), accumulation in double.
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restrict__ st0, int C0,
+                                                           const float2* __restrict__ st1, int C1, int HW,
+                                                           int gran, float2* __restrict__ out) {
+  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = C0 + C1, cpg = C / 32, epg = cpg / gran, rbs = HW >> 5;
+  const int e0 = C0 / gran, e1 = C1 / gran;
+  const int total = rbs * epg;
+  double s = 0.0, q = 0.0;
+  for (int e = lane; e < total; e += 32) {
+    const int rb = e / epg, j = e - rb * epg;
+    const int cgi = g * epg + j;
+    const long row = static_cast<long>(n) * rbs + rb;
+    const float2 v = cgi < e0 ? __ldg(st0 + row * e0 + cgi) : __ldg(st1 + row * e1 + (cgi - e0));
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    out[n * 32 + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + 1e-5)));
+  }
+}
 
 template <bool kHalfIn>
 __device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, int c, float (&v)[8]) {
@@ -184,7 +218,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
-  if (threadIdx.x < 32) {
+  if (a.final) {
+    if (threadIdx.x < 32) {
+      const float2 mr = a.final[n * 32 + threadIdx.x];
+      s_mean[threadIdx.x] = mr.x;
+      s_rstd[threadIdx.x] = mr.y;
+    }
+  } else if (threadIdx.x < 32) {
     double s = 0.0, q = 0.0;
     for (int k = 0; k < a.chunks; ++k) {
       const double* pp = a.partial + ((static_cast<long>(n) * a.chunks + k) * 32 + threadIdx.x) * 2;
@@ -229,6 +269,25 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   const int p_end = min(p_begin + a.ppb, n_iter);
   if (a.resample == 0) {
     int pix = p_begin + lane;
+    if (kHalfIn) {
+      // 16-bit source (C1 == 0): eight pixels = 8 x 16-byte loads in flight per thread, kept packed
+      const op_t* src = static_cast<const op_t*>(a.src0) + static_cast<long>(n) * HW * C + c;
+      for (; pix + 7 * a.PLa < p_end; pix += 8 * a.PLa) {
+        uint4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long>(pix + u * a.PLa) * C));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float2 p0 = unpack_op2(r[u].x), p1 = unpack_op2(r[u].y), p2 = unpack_op2(r[u].z), p3 = unpack_op2(r[u].w);
+          const float v[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+          float y[8];
+          xform(v, y);
+          const long o = (static_cast<long>(n) * HW + pix + u * a.PLa) * C + c;
+          store8_op(a.out + o, y);
+          if (a.raw_out) *reinterpret_cast<uint4*>(a.raw_out + o) = r[u];
+        }
+      }
+    }
     for (; pix + 3 * a.PLa < p_end; pix += 4 * a.PLa) {  // four pixels (8 x 16-byte loads) in flight
       float v[4][8], y[8];
 #pragma unroll
@@ -302,6 +361,17 @@ static int gn_check(const GnDesc& d) {
   return 0;
 }
 
+static bool gn_fused(const GnDesc& d) { return d.stats0 != nullptr && (d.C1 == 0 || d.stats1 != nullptr); }
+
+int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
+  const int C = d.C0 + d.C1, HW = d.H * d.W;
+  if (gn_check(d) || !gn_fused(d) || d.final == nullptr || (HW % 32) || (d.stat_gran != 2 && d.stat_gran != 4) ||
+      ((C / 32) % d.stat_gran) || (d.C0 % d.stat_gran) || (d.C1 % d.stat_gran))
+    return 1;
+  gn_finalize_kernel<<<d.B, 1024, 0, s>>>(d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, d.final);
+  return SGDM_LAUNCH_OK();
+}
+
 int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
   if (gn_check(d)) return 1;
   const int C = d.C0 + d.C1, HW = d.H * d.W;
@@ -325,18 +395,21 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
   const int PLa = 256 / C8 > 0 ? 256 / C8 : 1;
   const int n_iter = d.resample == 1 ? HW / 4 : HW;
   // pixels per block: >= 8 per thread when the grid stays large enough to fill the chip
-  int ppb = PLa * 8;
+  int ppb = PLa * (d.src0_is_op ? 16 : 8);
   while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 4 * kNumSMs) ppb >>= 1;
   if (ppb > n_iter) ppb = n_iter;
   GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
-                d.silu, d.resample, d.chunks, ppb, PLa, d.partial, d.out, d.raw_out, d.pool_out};
+                d.silu, d.resample, d.chunks, ppb, PLa, d.partial, gn_fused(d) ? d.final : nullptr, d.out, d.raw_out,
+                d.pool_out};
   const dim3 grid((n_iter + ppb - 1) / ppb, d.B);
   if (d.src0_is_op) gn_apply_kernel<true><<<grid, C8 * PLa, 0, s>>>(a);
   else gn_apply_kernel<false><<<grid, C8 * PLa, 0, s>>>(a);
   return SGDM_LAUNCH_OK();
 }
 
-int gn_launch(const GnDesc& d, cudaStream_t s) { return gn_stats_launch(d, s) || gn_apply_launch(d, s); }
+int gn_launch(const GnDesc& d, cudaStream_t s) {
+  return (gn_fused(d) ? gn_finalize_launch(d, s) : gn_stats_launch(d, s)) || gn_apply_launch(d, s);
+}
 
 // =========================================================================== LayerNorm
 // One warp per row of C channels (C % 128 == 0, C <= 1024); two-pass in registers.

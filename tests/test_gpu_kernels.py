@@ -144,6 +144,93 @@ def test_conv_tcgen05_vs_torch(L, case):
         assert e < (2e-3 if out == "op" else 2e-5), f"{label} conv mismatch {e}"
 
 
+STATS_CASES = [
+    # (B, H, W, Cin, Cout, ks, res_mode, out, block_n, gran, note)
+    (3, 16, 16, 64, 256, 3, 1, "f32", 256, 4, "fp32 out + residual, N=256, gran 4"),
+    (3, 16, 16, 64, 256, 3, 0, "op", 256, 2, "16-bit out, gran 2"),
+    (2, 32, 32, 128, 128, 3, 1, "f32", 0, 4, "swap-AB fp32 out + residual"),
+    (3, 32, 32, 128, 128, 3, 0, "op", 0, 4, "swap-AB 16-bit out (h1), ragged tile"),
+    (2, 32, 32, 128, 128, 3, 0, "op", 0, 2, "swap-AB 16-bit out, gran 2"),
+    (5, 8, 8, 128, 64, 3, 0, "f32", 64, 2, "N=64, 8x8 images (two row blocks per sample)"),
+    (2, 16, 16, 512, 512, 1, 1, "f32", 256, 4, "1x1 proj + residual, two n-tiles"),
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES, ids=[c[-1] for c in STATS_CASES])
+def test_conv_epilogue_groupnorm_stats(L, case):
+    """The conv epilogue's GroupNorm partial sums equal sums over the tensor it wrote."""
+    B, H, W, Cin, Cout, ks, res_mode, out, bn, gran, note = case
+    g = torch.Generator(device="cuda").manual_seed(abs(hash(note)) % 2**31)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    w = torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * ks * ks)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g) if res_mode else None
+    wp, bn_auto = pack_weight(L, w, None, bn or None)
+    M = B * H * W
+    nblk = (M + 31) // 32
+    stats = torch.full((nblk, Cout // gran, 2), float("nan"), device="cuda")
+    o32 = torch.full((B, H, W, Cout), float("nan"), device="cuda") if out == "f32" else None
+    oop = torch.zeros((B, H, W, Cout), dtype=L._op, device="cuda") if out == "op" else None
+    ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res), res_mode,
+                              P(o32), P(oop), None, bn, 0, P(stats), gran))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=1 if ks == 3 else 0)
+    if res_mode:
+        ref = ref + res.permute(0, 3, 1, 2)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, Cout)
+    got = (o32 if o32 is not None else oop).float().reshape(M, Cout)
+    assert relerr(got, ref) < (2e-3 if out == "op" else 2e-5)
+    pad = nblk * 32 - M
+    refp = torch.cat([ref, torch.zeros(pad, Cout, device="cuda")]) if pad else ref
+    blk = refp.double().reshape(nblk, 32, Cout // gran, gran)
+    want = torch.stack([blk.sum((1, 3)), (blk * blk).sum((1, 3))], -1)
+    assert torch.isfinite(stats).all()
+    e = relerr(stats, want)
+    print(f"[conv stats {note}] rel_l2={e:.3e}")
+    assert e < 1e-5
+
+
+def torch_partial_stats(t, gran):
+    """[B,H,W,C] fp32 -> the conv-epilogue statistics layout [rows/32, C/gran, 2]."""
+    C = t.shape[-1]
+    blk = t.double().reshape(-1, 32, C // gran, gran)
+    return torch.stack([blk.sum((1, 3)), (blk * blk).sum((1, 3))], -1).float().contiguous()
+
+
+FUSED_GN_CASES = [
+    # (B, H, W, C0, C1, gran, half_in, note)
+    (3, 16, 16, 128, 0, 4, False, "C=128 gran 4"),
+    (2, 8, 8, 256, 128, 4, False, "concat 256+128: 12 ch/group straddles the sources"),
+    (2, 16, 16, 128, 64, 2, False, "concat 128+64 = 192 (6 ch/group), gran 2"),
+    (2, 8, 8, 64, 0, 2, True, "C=64 (2 ch/group), 16-bit source"),
+    (1, 64, 64, 128, 0, 4, True, "64x64 16-bit source (deep-unroll path)"),
+    (2, 16, 16, 512, 512, 4, False, "concat 1024"),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_GN_CASES, ids=[c[-1] for c in FUSED_GN_CASES])
+def test_groupnorm_from_epilogue_stats(L, case):
+    B, H, W, C0, C1, gran, half_in, note = case
+    C = C0 + C1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(B, H, W, C0, device="cuda", generator=g) * 2 + 0.5
+    b = torch.randn(B, H, W, C1, device="cuda", generator=g) * 0.5 - 1 if C1 else None
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    st0 = torch_partial_stats(a, gran)  # statistics of the unrounded values, as the producing conv emits them
+    st1 = torch_partial_stats(b, gran) if C1 else None
+    src = a.to(L._op) if half_in else a
+    out = torch.zeros(B, H, W, C, dtype=L._op, device="cuda")
+    ck(L, L.sgdm_k_groupnorm_fused(S(), P(src), 1 if half_in else 0, P(b), B, H, W, C0, C1, P(gamma), P(beta), None, 0,
+                                   1, 0, P(st0), P(st1), gran, P(out), None, None))
+    torch.cuda.synchronize()
+    x = torch.cat([a, b], -1) if C1 else a
+    ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    e = relerr(out.float().permute(0, 3, 1, 2), ref)
+    print(f"[gn fused stats {note}] rel_l2={e:.3e}")
+    assert e < 1e-3
+
+
 def test_conv_rejects_bad_shapes(L):
     x = torch.zeros(1, 16, 16, 48, dtype=L._op, device="cuda")
     w = torch.zeros(64, 9 * 48, dtype=L._op, device="cuda")
