@@ -123,6 +123,9 @@ int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double
 int64_t sgdm_launch_count(void);
 /* bring-up switch: 1 routes every conv through the CUDA-core checker kernel (tests only) */
 int sgdm_debug_set_naive_conv(int on);
+/* CTA-pair (tcgen05 cta_group::2) conv mode for plans / single-kernel calls created afterwards:
+ * -1 = library policy (default), 0 = never, 1 = whenever the shape allows (tests, A/B timing) */
+int sgdm_debug_set_conv_pair(int mode);
 
 /* ---- single-kernel entry points (unit parity tests). 16-bit tensors are `op` = fp16 (or bf16). ---- */
 /* conv / GEMM: in [B,Hin,Win,Cin] op NHWC; in2 optional [B,Hout,Wout,C2]; w packed [Npad][ks*ks*Cin + C2] op */

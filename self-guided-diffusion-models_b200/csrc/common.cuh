@@ -195,6 +195,69 @@ __device__ __forceinline__ uint32_t umma_idesc(uint32_t m, uint32_t n) {
   return (1u << 4) | (SGDM_UMMA_FMT << 7) | (SGDM_UMMA_FMT << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC issue one M=256 MMA -------------
+// The shared::cluster address of a CTA's own shared memory carries the CTA rank in bit 24; clearing
+// it addresses the same offset in the even ("leader") CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are
+// counted on the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* d, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* d, uint64_t* bar, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on `bar` (same offset) in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA's smem]
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -47,6 +47,8 @@ struct ConvDesc {
   // without re-reading the tensor (gn_finalize_kernel).  Buffer: ceil(M/32) * Cout/stat_gran float2.
   float2* stats = nullptr;
   int stat_gran = 4;
+  // CTA-pair mode (tcgen05 cta_group::2, M = 256 over two CTAs): -1 = policy (conv_use_pair), 0 = off, 1 = on
+  int pair = -1;
 };
 
 struct alignas(64) ConvKernelParams {
@@ -71,6 +73,7 @@ struct alignas(64) ConvKernelParams {
 struct ConvLaunch {
   ConvKernelParams p;
   int grid = 0;
+  int pair = 0;
   ConvDesc desc;  // kept for the naive checker path
 };
 
@@ -87,6 +90,15 @@ inline bool conv_can_swap(const ConvDesc& d) {
   const int HW = d.Hout * d.Wout;
   return d.Cout == 128 && d.out_nchw == nullptr && !(d.res && d.res_mode == 2) && d.Wout <= 256 &&
          (256 % d.Wout) == 0 && ((HW % 256) == 0 || (256 % HW) == 0);
+}
+
+// CTA pairs need two m-tiles to share a weight tile of >= 64 output channels (each CTA stages block_n/2 rows).
+inline bool conv_pair_ok(const ConvDesc& d) { return !d.swap_ab && d.block_n >= 64 && (d.block_n % 32) == 0; }
+inline bool conv_use_pair(const ConvDesc& d) {
+  if (d.pair == 0 || !conv_pair_ok(d)) return false;
+  if (d.pair == 1) return true;
+  const long m_tiles = (static_cast<long>(d.B) * d.Hout * d.Wout + 127) / 128;
+  return m_tiles >= 2;
 }
 
 }  // namespace sgdm

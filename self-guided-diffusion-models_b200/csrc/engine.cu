@@ -26,6 +26,7 @@ using namespace sgdm;
 static thread_local char g_err[1024] = "";
 static int64_t g_launches = 0;
 static int g_naive_conv = 0;
+static int g_conv_pair = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -611,6 +612,7 @@ struct Builder {
     d.block_n = pick_block_n(d.Cout);
     d.swap_ab = conv_can_swap(d) ? 1 : 0;
     d.stat_gran = stat_gran();
+    d.pair = g_conv_pair;
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
     char msg[256];
@@ -1054,6 +1056,10 @@ int sgdm_debug_set_naive_conv(int on) {
   g_naive_conv = on;
   return 0;
 }
+int sgdm_debug_set_conv_pair(int mode) {
+  g_conv_pair = mode;
+  return 0;
+}
 
 int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   if (!cfg || !out) return fail("null argument");
@@ -1206,6 +1212,7 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.bias = bias; d.res = res; d.res_mode = res_mode; d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
   d.out_nchw = out_nchw; d.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
   d.swap_ab = (block_n <= 0 && conv_can_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
+  d.pair = g_conv_pair;
   ++g_launches;
   if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

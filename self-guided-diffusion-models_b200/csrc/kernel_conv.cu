@@ -25,6 +25,11 @@ constexpr int kStgBytes = 4 * 32 * kStgLd * 4;      // one 32x32 fp32 sub-tile p
 constexpr int kConvSmem = 1024 + kStages * (kABytes + kBBytesMax) + kBarBytes + kStgBytes;
 constexpr int kConvThreads = 192;
 
+// kCtas == 2: CTA-pair mode.  The two CTAs of a cluster own adjacent 128-row m-tiles of one 256-row MMA
+// (tcgen05 cta_group::2): each loads its own A tile and HALF of the B (weight) tile, the leader CTA
+// issues the MMAs for both and the accumulator rows land in each CTA's own TMEM.  Per CTA this halves
+// the weight bytes pulled through L2 -> SM and the shared-memory reads per MMA.
+template <int kCtas>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -56,21 +61,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], 4 * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, ncols);
-    tmem_relinquish();
+    if (kCtas == 2) { tmem_alloc_pair(tmem_slot, ncols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, ncols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int KB = p.taps * p.kc1 + p.kc2;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int cta_rank = kCtas == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  // work items: (m_tile, n_tile), or (pair of adjacent m_tiles, n_tile) per 2-CTA cluster
+  const int total_tiles = (kCtas == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int tile_begin = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -78,16 +87,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t stage = 0, phase = 0;
       // swap_ab: the activation tile (256 pixels, 32 KB) lives in the big slot and is the MMA B operand,
       // the weight tile (128 x 64, 16 KB) in the small slot is the A operand.
-      const uint32_t tx_bytes = p.swap_ab ? (kABytes + kBBytesMax) : (kABytes + block_n * 128);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t tx_bytes = p.swap_ab ? (kABytes + kBBytesMax) : (kCtas * kABytes + block_n * 128);  // of the whole pair in pair mode
+      const int b_rows = block_n / kCtas;  // weight rows this CTA loads
+      for (int tile = tile_begin; tile < total_tiles; tile += tile_step) {
+        const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
+        const int n_tile = tile % p.n_tiles;
         const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
           uint8_t* act_dst = p.swap_ab ? sB + stage * kBBytesMax : sA + stage * kABytes;
           uint8_t* wgt_dst = p.swap_ab ? sA + stage * kABytes : sB + stage * kBBytesMax;
           if (kb < p.taps * p.kc1) {
@@ -95,22 +105,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const int cc = kb - tap * p.kc1;
             const int r = tap / p.ks;
             const int s = tap - r * p.ks;
-            tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
+            if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
+            else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
           } else {
             const int cc = kb - p.taps * p.kc1;
-            tma_load_4d(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
+            if (kCtas == 2) tma_load_4d_pair(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
+            else tma_load_4d(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
           }
-          tma_load_2d(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n);
+          if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n + cta_rank * b_rows);
+          else tma_load_2d(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = umma_idesc(kTileM, p.swap_ab ? 256 : block_n);
+    if (lane == 0 && cta_rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (the leader CTA in pair mode)
+      const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -122,11 +135,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t b_addr = smem_u32(sB + stage * kBBytesMax);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            if (kCtas == 2)
+              umma_f16_pair(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);            // frees the smem stage when these MMAs retire
-          if (kb == KB - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          // frees the smem stage (in both CTAs) when these MMAs retire; accumulator complete -> epilogue(s)
+          if (kCtas == 2) {
+            umma_commit_pair(&empty[stage]);
+            if (kb == KB - 1) umma_commit_pair(&tfull[acc]);
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb == KB - 1) umma_commit(&tfull[acc]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -149,9 +172,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int sg_shift = p.stat_gran == 4 ? 2 : 1;
     const int stat_ld = p.N_total >> sg_shift;  // stat entries per 32-row block
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+    for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+      const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
+      const int n_tile = tile % p.n_tiles;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       // chunk i covers rows [row0(i), +32) x columns [col0(i), +nc(i)) of the output matrix
       const int tile_row0 = p.swap_ab ? m_tile * p.tile_px : m_tile * kTileM + quarter * 32;
@@ -326,12 +349,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_leader(&tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  __syncwarp();
+  if (kCtas == 2) {
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the peer can still touch it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, ncols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -395,6 +427,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.stats && (d.out_nchw || (d.Cout % 8) || (d.stat_gran != 2 && d.stat_gran != 4)))
     return fail("stats need an NHWC output, Cout % 8 == 0 and stat_gran in {2, 4}");
   const int tile_px = d.swap_ab ? 256 : kTileM;
+  const bool pair = conv_use_pair(d);
   const int bw = d.Wout;
   const int bh = min(d.Hout, tile_px / bw);
   const int bn = tile_px / (bw * bh);
@@ -408,7 +441,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     auto fn = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)d.block_n};
+    cuuint32_t box[2] = {64, (cuuint32_t)(d.block_n / (pair ? 2 : 1))};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&p.tmB, SGDM_TMA_DTYPE, 2, const_cast<op_t*>(d.w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -442,11 +475,19 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.out_nchw = d.out_nchw;
   p.stats = d.stats;
   p.stat_gran = d.stat_gran;
-  const int total = p.m_tiles * p.n_tiles;
-  out->grid = total < kNumSMs ? total : kNumSMs;
+  out->pair = pair ? 1 : 0;
+  if (pair) {
+    const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
+    out->grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
+  } else {
+    const int total = p.m_tiles * p.n_tiles;
+    out->grid = total < kNumSMs ? total : kNumSMs;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
@@ -454,7 +495,22 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 }
 
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
-  conv_gemm_kernel<<<l.grid, kConvThreads, kConvSmem, stream>>>(l.p);
+  if (l.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(l.grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = kConvSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, l.p) == cudaSuccess ? 0 : 1;
+  }
+  conv_gemm_kernel<1><<<l.grid, kConvThreads, kConvSmem, stream>>>(l.p);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

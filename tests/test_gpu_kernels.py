@@ -132,11 +132,17 @@ def test_conv_tcgen05_vs_torch(L, case):
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    modes = [("naive", bn, 1), ("tcgen05", bn, 0)]
+    modes = [("naive", bn, 1, 0), ("tcgen05 1-CTA", bn, 0, 0)]
+    if bn >= 64:
+        modes.append(("tcgen05 CTA pair (cta_group::2)", bn, 0, 1))
     if Cout == 128 and out != "nchw" and res_mode != 2:
-        modes.append(("tcgen05 swap-AB (block_n=0: engine policy)", 0, 0))
-    for label, bn_arg, naive in modes:
-        got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
+        modes.append(("tcgen05 swap-AB (block_n=0: engine policy)", 0, 0, -1))
+    for label, bn_arg, naive, pair in modes:
+        L.sgdm_debug_set_conv_pair(pair)
+        try:
+            got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
+        finally:
+            L.sgdm_debug_set_conv_pair(-1)
         got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
         assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)
@@ -171,8 +177,12 @@ def test_conv_epilogue_groupnorm_stats(L, case):
     stats = torch.full((nblk, Cout // gran, 2), float("nan"), device="cuda")
     o32 = torch.full((B, H, W, Cout), float("nan"), device="cuda") if out == "f32" else None
     oop = torch.zeros((B, H, W, Cout), dtype=L._op, device="cuda") if out == "op" else None
-    ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res), res_mode,
-                              P(o32), P(oop), None, bn, 0, P(stats), gran))
+    L.sgdm_debug_set_conv_pair(1 if B % 2 else 0)  # odd-batch cases run as CTA pairs, the others as single CTAs
+    try:
+        ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res), res_mode,
+                                  P(o32), P(oop), None, bn, 0, P(stats), gran))
+    finally:
+        L.sgdm_debug_set_conv_pair(-1)
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=1 if ks == 3 else 0)
     if res_mode:
