@@ -126,6 +126,9 @@ int sgdm_debug_set_naive_conv(int on);
 /* CTA-pair (tcgen05 cta_group::2) conv mode for plans / single-kernel calls created afterwards:
  * -1 = library policy (default), 0 = never, 1 = whenever the shape allows (tests, A/B timing) */
 int sgdm_debug_set_conv_pair(int mode);
+/* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array
+ * of 16 int64 (NULL = off); slot meaning in csrc/kernel_conv.cu */
+int sgdm_debug_set_conv_timing(void* device_counters16);
 
 /* ---- single-kernel entry points (unit parity tests). 16-bit tensors are `op` = fp16 (or bf16). ---- */
 /* conv / GEMM: in [B,Hin,Win,Cin] op NHWC; in2 optional [B,Hout,Wout,C2]; w packed [Npad][ks*ks*Cin + C2] op */

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "sgdm_launch_count": (_i64, []),
     "sgdm_debug_set_naive_conv": (_i, [_i]),
     "sgdm_debug_set_conv_pair": (_i, [_i]),
+    "sgdm_debug_set_conv_timing": (_i, [_vp]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
     "sgdm_k_conv_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
                                 _vp, _i]),

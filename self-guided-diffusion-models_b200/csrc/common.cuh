@@ -124,6 +124,11 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* d, uint64_t* bar,
       : "memory");
 }
 
+// bulk prefetch of [p, p + bytes) into L2 (16-byte aligned, bytes % 16 == 0); no destination registers
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- tcgen05 / TMEM -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

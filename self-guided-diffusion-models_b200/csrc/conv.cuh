@@ -49,31 +49,36 @@ struct ConvDesc {
   int stat_gran = 4;
   // CTA-pair mode (tcgen05 cta_group::2, M = 256 over two CTAs): -1 = policy (conv_use_pair), 0 = off, 1 = on
   int pair = -1;
+  long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
 };
 
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA;
   CUtensorMap tmA2;
   CUtensorMap tmB;
+  CUtensorMap tmOut;  // output matrix [M_total, Cout]: 32-row x 128-byte tiles (TMA store)
+  CUtensorMap tmRes;  // residual matrix (res_mode 1): same tiling (TMA load)
   int M_total, HW, Wout, Hout;
   int stride, pad, ks, taps;
   int kc1, kc2;
   int N_total, block_n, n_tiles, m_tiles;
   int swap_ab, tile_px;  // tile_px: pixels per tile (128, or 256 when swap_ab)
+  int n_stages, b_bytes, b_tx;  // K-block ring: stage = 16 KB (M operand) + b_bytes; b_tx = bytes TMA delivers to the B slot
+  int epi_mode, epi_bufs;       // 0 NCHW direct | 1 fp32 NHWC | 2 16-bit NHWC; staging buffers per epilogue warp
   const float* bias;
   const float* res;
   int res_mode;
-  float* out_f32;
-  op_t* out_op;
   float* out_nchw;
   float2* stats;
   int stat_gran;
+  long long* timing;
 };
 
 struct ConvLaunch {
   ConvKernelParams p;
   int grid = 0;
   int pair = 0;
+  int smem = 0;
   ConvDesc desc;  // kept for the naive checker path
 };
 

@@ -7,6 +7,7 @@
 // list on the caller's stream (no allocation, no host sync, no Python in the loop).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -26,6 +27,7 @@ using namespace sgdm;
 static thread_local char g_err[1024] = "";
 static int64_t g_launches = 0;
 static int g_naive_conv = 0;
+static long long* g_conv_timing = nullptr;
 static int g_conv_pair = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
 
 static int fail(const char* fmt, ...) {
@@ -610,7 +612,7 @@ struct Builder {
   void conv(ConvDesc d, int real_cin = 0) {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
-    d.swap_ab = conv_can_swap(d) ? 1 : 0;
+    d.swap_ab = (conv_can_swap(d) && !getenv("SGDM_NO_SWAP")) ? 1 : 0;
     d.stat_gran = stat_gran();
     d.pair = g_conv_pair;
     if (dry) return;
@@ -1060,6 +1062,10 @@ int sgdm_debug_set_conv_pair(int mode) {
   g_conv_pair = mode;
   return 0;
 }
+int sgdm_debug_set_conv_timing(void* device_counters16) {
+  g_conv_timing = static_cast<long long*>(device_counters16);
+  return 0;
+}
 
 int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   if (!cfg || !out) return fail("null argument");
@@ -1213,6 +1219,7 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.out_nchw = out_nchw; d.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
   d.swap_ab = (block_n <= 0 && conv_can_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
   d.pair = g_conv_pair;
+  d.timing = g_conv_timing;
   ++g_launches;
   if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

@@ -1,11 +1,15 @@
 // tcgen05 + TMA implicit-GEMM convolution (see conv.cuh).
 //
 // CTA = 192 threads, persistent over (m_tile, n_tile) work items, 1 CTA / SM:
-//   warp 0 (one lane)  TMA producer : 4-stage ring of {A 128x64, B block_n x 64} tiles
-//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per stage,
-//                                     accumulating in one of two TMEM accumulator stages
-//   warps 2..5         epilogue     : tcgen05.ld -> +bias (+residual) -> global store,
+//   warp 0 (one lane)  TMA producer : ring of {A 128x64, B rows x 64} K-block stages (as many as fit)
+//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (K16) per stage into one of two TMEM
+//                                     accumulator stages
+//   warps 2..5         epilogue     : tcgen05.ld -> +bias (+residual) -> swizzled smem tile -> TMA store,
 //                                     overlapping the next tile's MMAs
+// Three geometries share the code:
+//   normal   D[128 px, block_n ch]            one CTA
+//   pair     D[2 x 128 px, block_n ch]        tcgen05 cta_group::2 over a 2-CTA cluster (M = 256)
+//   swap-AB  D^T[128 ch, 256 px] (Cout = 128) weights are the M operand, a 256-pixel tile the N operand
 // Roofline: tensor pipe.  FLOPs per launch = 2 * M_total * Cout * Ktot.
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -15,39 +19,114 @@
 
 namespace sgdm {
 
-constexpr int kStages = 4;
 constexpr int kTileM = 128;
-constexpr int kABytes = kTileM * 64 * 2;   // 16 KB
-constexpr int kBBytesMax = 256 * 64 * 2;   // 32 KB
-constexpr int kBarBytes = 256;
-constexpr int kStgLd = 36;                          // staging row stride in floats (32 + 4: conflict-free)
-constexpr int kStgBytes = 4 * 32 * kStgLd * 4;      // one 32x32 fp32 sub-tile per epilogue warp
-constexpr int kConvSmem = 1024 + kStages * (kABytes + kBBytesMax) + kBarBytes + kStgBytes;
+constexpr int kMaxStages = 8;
+constexpr int kABytes = kTileM * 64 * 2;  // 16 KB: the M-side operand tile of one K block
 constexpr int kConvThreads = 192;
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
+constexpr int kBarBytes = 512;
+constexpr int kBiasBytes = 2 * 256 * 4;  // bias of the tile's columns, double-buffered by tile parity
+constexpr int kEpiBuf = 4096;            // one epilogue staging buffer: 32 rows x 128 B
+constexpr int kMaxEpiBufs = 6;
+
+// ---- shared-window accessors (explicit state space: the 1024-byte alignment of the dynamic smem base
+//      goes through an integer and the compiler would otherwise emit generic LD/ST) -------------------
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, op_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<unsigned short*>(&v)));
+}
+// TMA tile store smem -> global (bulk async-group of the issuing thread) and tile load with mbarrier
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* d, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(d)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// pull one tile of a tensor map into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* d, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(d)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(const CUtensorMap* d, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 
 // kCtas == 2: CTA-pair mode.  The two CTAs of a cluster own adjacent 128-row m-tiles of one 256-row MMA
 // (tcgen05 cta_group::2): each loads its own A tile and HALF of the B (weight) tile, the leader CTA
 // issues the MMAs for both and the accumulator rows land in each CTA's own TMEM.  Per CTA this halves
 // the weight bytes pulled through L2 -> SM and the shared-memory reads per MMA.
+// Optional cycle accounting of the epilogue warps (ConvDesc::timing != nullptr; bring-up / tuning only):
+// slots 0 wait-for-accumulator | 1 wait-for-staging-buffer (TMA store drained) | 2 wait-for-residual |
+// 3 TMEM load | 4 bias/residual/stage | 5 statistics | 6 fence + TMA store issue | 7 chunks | 8 MMA-issuer
+// stalls on smem stages | 9 MMA-issuer stalls on the accumulator | 10 producer stalls on free stages
+#define SGDM_T0() long long t_prev_ = p.timing ? clock64() : 0
+#define SGDM_T(slot)                                   \
+  do {                                                 \
+    if (p.timing) {                                    \
+      const long long t_now_ = clock64();              \
+      t_acc_[slot] += t_now_ - t_prev_;                \
+      t_prev_ = t_now_;                                \
+    }                                                  \
+  } while (0)
+
 template <int kCtas>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytesMax));
-  uint64_t* full = bars;             // [kStages] TMA -> MMA
-  uint64_t* empty = bars + kStages;  // [kStages] MMA -> TMA
-  uint64_t* tfull = bars + 2 * kStages;       // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* stg_all = reinterpret_cast<float*>(smem + kStages * (kABytes + kBBytesMax) + kBarBytes);
+  // No static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked), which the
+  // 128-byte swizzle of the TMA / UMMA tiles needs.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // [ring: n_stages x (A | B)] [epilogue staging: 4 warps x epi_bufs x 4 KB] [bias: 2 x 1 KB] [barriers]
+  const int stage_bytes = kABytes + p.b_bytes;
+  uint8_t* ring = smem;
+  uint8_t* after_ring = smem + p.n_stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring + 4 * p.epi_bufs * kEpiBuf + kBiasBytes);
+  uint64_t* full = bars;                         // [kMaxStages] TMA -> MMA
+  uint64_t* empty = bars + kMaxStages;           // [kMaxStages] MMA -> TMA
+  uint64_t* tfull = bars + 2 * kMaxStages;       // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2] epilogue -> MMA
+  uint64_t* rbars = bars + 2 * kMaxStages + 4;   // [4 warps][kMaxEpiBufs] residual tile landed
+  uint64_t* bfree = bars + 2 * kMaxStages + 4 + 4 * kMaxEpiBufs;  // [2] all epilogue warps are done with a bias buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 4 * kMaxEpiBufs);
+  const uint32_t epi_all = smem_u32(after_ring);
+  const uint32_t sbias_all = epi_all + 4 * p.epi_bufs * kEpiBuf;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int block_n = p.block_n;
-  // two accumulator stages of block_n fp32 columns each; allocation must be a power of 2 >= 32
-  const uint32_t acc_cols = p.swap_ab ? 256u : static_cast<uint32_t>(block_n);  // fp32 columns per accumulator
+  const int n_stages = p.n_stages;
+  // two accumulator stages of acc_cols fp32 columns each; allocation must be a power of 2 >= 32
+  const uint32_t acc_cols = p.swap_ab ? 256u : static_cast<uint32_t>(block_n);
   uint32_t ncols = 32;
   while (ncols < 2u * acc_cols) ncols <<= 1;
 
@@ -55,7 +134,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (p.kc2) tma_prefetch_desc(&p.tmA2);
-    for (int i = 0; i < kStages; ++i) {
+    if (p.epi_mode != 0) tma_prefetch_desc(&p.tmOut);
+    if (p.res_mode == 1) tma_prefetch_desc(&p.tmRes);
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -63,6 +144,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4 * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
+    for (int i = 0; i < 4 * kMaxEpiBufs; ++i) mbar_init(&rbars[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bfree[i], 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -85,10 +168,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
-      // swap_ab: the activation tile (256 pixels, 32 KB) lives in the big slot and is the MMA B operand,
-      // the weight tile (128 x 64, 16 KB) in the small slot is the A operand.
-      const uint32_t tx_bytes = p.swap_ab ? (kABytes + kBBytesMax) : (kCtas * kABytes + block_n * 128);  // of the whole pair in pair mode
-      const int b_rows = block_n / kCtas;  // weight rows this CTA loads
+      long long t_prod = 0;
+      // swap_ab: the weight tile (128 x 64) is the MMA A operand, the activation tile (256 pixels) the B operand
+      const uint32_t tx_bytes = kCtas * (kABytes + p.b_tx);  // of the whole pair in pair mode
+      const int b_rows = block_n / kCtas;                    // weight rows this CTA loads
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
         const int n_tile = tile % p.n_tiles;
@@ -96,10 +179,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
         for (int kb = 0; kb < KB; ++kb) {
+          const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
+          if (p.timing) t_prod += clock64() - tw0;
           if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          uint8_t* act_dst = p.swap_ab ? sB + stage * kBBytesMax : sA + stage * kABytes;
-          uint8_t* wgt_dst = p.swap_ab ? sA + stage * kABytes : sB + stage * kBBytesMax;
+          uint8_t* sa = ring + stage * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          uint8_t* act_dst = p.swap_ab ? sb : sa;
+          uint8_t* wgt_dst = p.swap_ab ? sa : sb;
           if (kb < p.taps * p.kc1) {
             const int tap = kb / p.kc1;
             const int cc = kb - tap * p.kc1;
@@ -114,25 +201,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n + cta_rank * b_rows);
           else tma_load_2d(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.timing) atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + 10, static_cast<unsigned long long>(t_prod));
     }
   } else if (warp == 1) {
     if (lane == 0 && cta_rank == 0) {
       // ------------------------------------------------------------ MMA issuer (the leader CTA in pair mode)
       const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
       uint32_t stage = 0, phase = 0, it = 0;
+      long long t_full = 0, t_acc = 0;
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const long long ta0 = p.timing ? clock64() : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
+        if (p.timing) t_acc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int kb = 0; kb < KB; ++kb) {
+          const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (p.timing) t_full += clock64() - tw0;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * kBBytesMax);
+          const uint32_t a_addr = smem_u32(ring + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (kCtas == 2)
@@ -150,209 +243,358 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             umma_commit(&empty[stage]);
             if (kb == KB - 1) umma_commit(&tfull[acc]);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
+      }
+      if (p.timing) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + 8, static_cast<unsigned long long>(t_full));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + 9, static_cast<unsigned long long>(t_acc));
       }
     }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..5)
-    // Each warp owns one TMEM lane quarter and walks its part of the accumulator in 32x32 fp32
-    // chunks.  A chunk is read from TMEM, put into a private smem staging tile as [pixel][channel]
-    // (normal mode: thread = pixel row, 8 x 16-byte stores; swap-AB: thread = channel, 32 scalar
-    // stores), and written back with thread = (row group, column quad) so that every global load /
-    // store instruction of the warp touches whole 128-byte row segments (bias, residual and output
-    // alike).  The same pass optionally emits GroupNorm partial statistics of the FINAL values:
-    // per (32-row block, `stat_gran` channels) sum and sum of squares (see conv.cuh).
+    // Each warp owns one TMEM lane quarter and walks its part of the accumulator in chunks of 32 rows x
+    // 128 output bytes (32 fp32 or 64 16-bit columns).  A chunk goes TMEM -> registers (thread = row, or
+    // thread = channel in swap-AB mode) -> +bias (+residual) -> a 128-byte-swizzled smem tile -> one TMA
+    // tile store.  The residual tile is TMA-LOADED into that same smem tile two chunks ahead and added in
+    // place, so the loop contains no global load, no bounds check (TMA clips / zero-fills) and no address
+    // arithmetic per row.  GroupNorm partial statistics of the final values (ConvDesc::stats) are read back
+    // from the staged tile: per (32-row block, stat_gran channels) sum and sum of squares.
+    const int wq = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = stg_all + (warp - 2) * 32 * kStgLd;
-    const int rg = lane >> 3, cq4 = (lane & 7) * 4;  // fp32 path: 8 lanes per row (float4 each), 4 rows per instruction
-    const int rl8 = lane >> 2, cq8 = (lane & 3) * 8;  // 16-bit path: 4 lanes per row (8 columns each), 8 rows per instruction
-    const bool use_res = p.res_mode != 0 && p.out_f32 != nullptr;
-    const int n_chunks = p.swap_ab ? p.tile_px / 32 : (block_n + 31) / 32;
+    const uint32_t ebuf0 = epi_all + wq * p.epi_bufs * kEpiBuf;
+    uint64_t* rbar = rbars + wq * kMaxEpiBufs;
+    const uint32_t NB = p.epi_bufs;         // staging buffers per warp (2 without a residual, else 4..6)
+    const bool tma_res = p.res_mode == 1;   // residual tile TMA-loaded INTO the staging buffer, added in place
+    const bool tma_res2 = p.res_mode == 2;  // nearest-2x upsampled source: 16 source rows into a side slot
     const int sg_shift = p.stat_gran == 4 ? 2 : 1;
     const int stat_ld = p.N_total >> sg_shift;  // stat entries per 32-row block
-    uint32_t it = 0;
-    for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
-      const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
-      const int n_tile = tile % p.n_tiles;
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      // chunk i covers rows [row0(i), +32) x columns [col0(i), +nc(i)) of the output matrix
-      const int tile_row0 = p.swap_ab ? m_tile * p.tile_px : m_tile * kTileM + quarter * 32;
-      const int tile_col0 = p.swap_ab ? quarter * 32 : n_tile * block_n;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
-      // Residual rows are known before the accumulator is ready: their loads are issued one chunk
-      // ahead (the first before waiting on the MMA), so that ~32 KB of residual reads per SM are in
-      // flight instead of one dependent 16-byte load per lane.
-      int rrow[8];
+    const int x7 = lane & 7;
+    const int rg = lane >> 3, cc = lane & 7;  // read-back layout: row group, 16-byte chunk
+    // chunks per tile, columns per chunk
+    const int cpc = (p.epi_mode == 2 && !p.swap_ab) ? 64 : 32;
+    const int n_chunks = p.swap_ab ? p.tile_px / 32 : (block_n + cpc - 1) / cpc;
+
+    if (p.epi_mode == 0) {
+      // final conv (Cout = 3 padded to N = 16), NCHW fp32 output: lanes = adjacent pixels -> coalesced already
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+        const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
+        const int n_tile = tile % p.n_tiles;
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
+        float bias_r[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int m = tile_row0 + 4 * k + rg;
-        int r = -1;
-        if (use_res && m < p.M_total) {
-          r = m;
-          if (p.res_mode == 2) {
-            const int img = m / p.HW, pix = m - img * p.HW;
-            const int y = pix / p.Wout, x = pix - y * p.Wout;
-            r = (img * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+        for (int j = 0; j < 16; ++j) {
+          const int col = n_tile * block_n + j;
+          bias_r[j] = (p.bias != nullptr && col < p.N_total) ? __ldg(p.bias + col) : 0.f;
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x16(taddr, v);
+        tmem_ld_wait();
+        const int m = m_tile * kTileM + quarter * 32 + lane;
+        if (m < p.M_total) {
+          const int img = m / p.HW, pix = m - img * p.HW;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n_tile * block_n + j;
+            if (col < p.N_total)
+              p.out_nchw[(static_cast<long>(img) * p.N_total + col) * p.HW + pix] = __uint_as_float(v[j]) + bias_r[j];
           }
         }
-        rrow[k] = r;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_leader(&tempty[acc]);
+          else mbar_arrive(&tempty[acc]);
+        }
       }
-      float4 rcur[8], rnext[8];
-      auto load_res = [&](int i, float4 (&r)[8]) {
-        const int nc = p.swap_ab ? 32 : min(32, block_n - 32 * i);
-        const int col = tile_col0 + (p.swap_ab ? 0 : 32 * i) + cq4;
-        const bool ok = cq4 < nc && col < p.N_total;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          int rr = rrow[k];
-          if (p.swap_ab) {  // rows advance with the chunk (res_mode 1 only)
-            rr = tile_row0 + 32 * i + 4 * k + rg;
-            if (rr >= p.M_total) rr = -1;
-          }
-          r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && rr >= 0) r[k] = __ldg(reinterpret_cast<const float4*>(p.res + static_cast<long>(rr) * p.N_total + col));
+    } else {
+      // coordinates of chunk i of a tile: rows [row0, +32) x columns [col0, +cpc) of the output matrix
+      auto chunk_coords = [&](int tile, int i, int& row0, int& col0) {
+        const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
+        const int n_tile = tile % p.n_tiles;
+        if (p.swap_ab) {
+          row0 = m_tile * p.tile_px + 32 * i;
+          col0 = quarter * 32;
+        } else {
+          row0 = m_tile * kTileM + quarter * 32;
+          col0 = n_tile * block_n + cpc * i;
         }
       };
-      if (use_res) load_res(0, rcur);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      for (int i = 0; i < n_chunks; ++i) {
-        uint32_t v[32];
-        const int nc = p.swap_ab ? 32 : min(32, block_n - 32 * i);
-        const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
-        const int col0 = p.swap_ab ? tile_col0 : tile_col0 + 32 * i;
-        if (nc == 32) tmem_ld_32x32(taddr + 32 * i, v);
-        else tmem_ld_32x16(taddr + 32 * i, v);
-        if (use_res && i + 1 < n_chunks) load_res(i + 1, rnext);
-        tmem_ld_wait();
-        if (p.out_nchw != nullptr) {  // final conv: lanes = adjacent pixels -> already coalesced
-          const int m = row0 + lane;
-          if (m < p.M_total) {
-            const int img = m / p.HW, pix = m - img * p.HW;
+      // row of the nearest-2x upsampled residual source that output row m reads (res_mode 2)
+      auto src_row = [&](int m) {
+        const int img = m / p.HW, pix = m - img * p.HW;
+        const int y = pix / p.Wout, x = pix - y * p.Wout;
+        return (img * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+      };
+      // residual prefetch cursor: runs NB-2 chunks ahead of the processing cursor (in-flight residual bytes
+      // per SM = 4 warps x (NB-2) x 4 KB must cover HBM latency x the residual read rate).  NB slots per warp:
+      // res_mode 1: the 4 KB staging buffers themselves; res_mode 2: 2 KB slots behind two staging buffers.
+      int pre_tile = tile_begin, pre_i = 0;
+      uint32_t g = 0, gp = 0;  // chunks processed / residual tiles requested
+      auto res_slot_addr = [&](uint32_t slot) { return tma_res ? ebuf0 + slot * kEpiBuf : ebuf0 + 2 * kEpiBuf + slot * 2048; };
+      auto issue_res = [&]() {
+        if (pre_tile >= total_tiles) return;
+        if (lane == 0) {
+          int r0, c0;
+          chunk_coords(pre_tile, pre_i, r0, c0);
+          const uint32_t slot = gp % NB;
+          mbar_arrive_expect_tx(&rbar[slot], tma_res ? kEpiBuf : 2048);
+          tma_load_2d_a(&p.tmRes, smem_u32(&rbar[slot]), res_slot_addr(slot), c0, tma_res ? r0 : src_row(r0));
+        }
+        ++gp;
+        if (++pre_i == n_chunks) { pre_i = 0; pre_tile += tile_step; }
+      };
+      if (tma_res || tma_res2)
+        for (uint32_t k = 0; k + 2 < NB; ++k) issue_res();
+
+      uint32_t it = 0;
+      long long t_acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
+        int tile_row0, tile_col0;
+        chunk_coords(tile, 0, tile_row0, tile_col0);
+        // bias of this tile's columns -> smem, before the wait on the MMA.  The four warps write identical
+        // values into the buffer of this tile's parity, once every warp has left the tile that used it last
+        // (a warp may run up to two tiles ahead of another).  swap-AB: the warp's own 32 channels.
+        const uint32_t sbias = sbias_all + acc * 1024 + (p.swap_ab ? quarter * 128 : 0);
+        mbar_wait(&bfree[acc], acc_phase ^ 1);
+        {
+          const int ncol = p.swap_ab ? 32 : block_n;
+          for (int c = lane; c < ncol; c += 32)
+            sts32(sbias + c * 4, (p.bias != nullptr && tile_col0 + c < p.N_total) ? __ldg(p.bias + tile_col0 + c) : 0.f);
+          __syncwarp();
+        }
+        // res_mode 2: which of the 16 staged source rows this thread's output row reads (the rows a 32-row
+        // chunk needs are contiguous in the source, starting at the source row of the chunk's first row)
+        int s_r = 0;
+        if (tma_res2) {
+          s_r = src_row(min(tile_row0 + lane, p.M_total - 1)) - src_row(min(tile_row0, p.M_total - 1));
+          s_r = max(0, min(s_r, 15));
+        }
+        const float bias_ch = p.swap_ab ? lds32(sbias + lane * 4) : 0.f;
+        SGDM_T0();
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        SGDM_T(0);
+        for (int i = 0; i < n_chunks; ++i, ++g) {
+          const uint32_t b = tma_res ? (g % NB) : (g & 1);
+          const uint32_t baddr = ebuf0 + b * kEpiBuf;
+          const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
+          const int col0 = p.swap_ab ? tile_col0 : tile_col0 + cpc * i;
+          // the buffer written next (by the residual load for chunk g+NB-2, or by this chunk when there is
+          // no residual) was last read by the TMA store of chunk g-2: all but the newest store must be done
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          SGDM_T(1);
+          if (tma_res || tma_res2) {
+            issue_res();
+            mbar_wait(&rbar[g % NB], (g / NB) & 1);
+          }
+          SGDM_T(2);
+          // All shared-memory loads of a phase are issued back to back before their first use (the accessors
+          // are volatile asm: the compiler keeps their order, so a load placed after a store would wait for it).
+          float sg[4] = {0.f, 0.f, 0.f, 0.f}, qg[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.swap_ab) {
+            // thread = output channel, registers = 32 consecutive pixels
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + 32 * i, v);
+            float val[32];
+            if (p.epi_mode == 1) {
+              const uint32_t lane_off = (lane & 3) << 2;
+              const uint32_t lane_chunk = lane >> 2;
+              float rr[32];
+              if (tma_res) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (j < nc && col < p.N_total) {
-                float a = __uint_as_float(v[j]);
-                if (p.bias) a += p.bias[col];
-                p.out_nchw[(static_cast<long>(img) * p.N_total + col) * p.HW + pix] = a;
+                for (int j = 0; j < 32; ++j) rr[j] = lds32(baddr + j * 128 + (((lane_chunk ^ (j & 7)) << 4) | lane_off));
+              }
+              tmem_ld_wait();
+              SGDM_T(3);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                val[j] = __uint_as_float(v[j]) + bias_ch;
+                if (tma_res) val[j] += rr[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sts32(baddr + j * 128 + (((lane_chunk ^ (j & 7)) << 4) | lane_off), val[j]);
+            } else {
+              tmem_ld_wait();
+              SGDM_T(3);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const op_t h = to_op(__uint_as_float(v[j]) + bias_ch);
+                sts16(baddr + j * 64 + lane * 2, h);
+                val[j] = from_op(h);
               }
             }
-          }
-          continue;
-        }
-        if (!p.swap_ab) {
-          float4* srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
+            SGDM_T(4);
+            if (p.stats) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (4 * j < nc)
-              srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[j * kStgLd + lane] = __uint_as_float(v[j]);
-        }
-        __syncwarp();
-        // pair sums for the GroupNorm statistics: sg/qg[u] covers columns {2u, 2u+1} of this lane's slice
-        float sg[4] = {0.f, 0.f, 0.f, 0.f}, qg[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.out_f32) {
-          const int col = col0 + cq4;
-          const bool col_ok = cq4 < nc && col < p.N_total;
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col_ok && p.bias) b = *reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rl = 4 * k + rg;
-            const int m = row0 + rl;
-            if (!col_ok || m >= p.M_total) continue;
-            float4 a = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq4);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            if (use_res) { a.x += rcur[k].x; a.y += rcur[k].y; a.z += rcur[k].z; a.w += rcur[k].w; }
-            *reinterpret_cast<float4*>(p.out_f32 + static_cast<long>(m) * p.N_total + col) = a;
-            sg[0] += a.x + a.y; qg[0] += a.x * a.x + a.y * a.y;
-            sg[1] += a.z + a.w; qg[1] += a.z * a.z + a.w * a.w;
-          }
-          if (use_res) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
-          }
-          if (p.stats) {
-            if (p.stat_gran == 4) { sg[0] += sg[1]; qg[0] += qg[1]; }
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
-                qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
+              for (int j = 0; j < 32; ++j) {
+                s4[j & 3] += val[j];
+                q4[j & 3] += val[j] * val[j];
               }
+              sg[0] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              qg[0] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+              sg[0] += __shfl_xor_sync(0xffffffffu, sg[0], 1);
+              qg[0] += __shfl_xor_sync(0xffffffffu, qg[0], 1);
+              if (p.stat_gran == 4) {
+                sg[0] += __shfl_xor_sync(0xffffffffu, sg[0], 2);
+                qg[0] += __shfl_xor_sync(0xffffffffu, qg[0], 2);
+              }
+              const int ch = col0 + lane;
+              if ((lane & (p.stat_gran - 1)) == 0 && row0 < p.M_total)
+                p.stats[static_cast<long>(row0 >> 5) * stat_ld + (ch >> sg_shift)] = make_float2(sg[0], qg[0]);
             }
-            if (rg == 0 && col_ok && row0 < p.M_total) {
-              float2* dst = p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift);
-              if (p.stat_gran == 4) dst[0] = make_float2(sg[0], qg[0]);
-              else *reinterpret_cast<float4*>(dst) = make_float4(sg[0], qg[0], sg[1], qg[1]);
-            }
-          }
-        } else {
-          const int col = col0 + cq8;
-          const bool col_ok = cq8 < nc && col < p.N_total;
-          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-          if (col_ok && p.bias) {
-            b0 = *reinterpret_cast<const float4*>(p.bias + col);
-            b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-          }
+          } else if (p.epi_mode == 1) {
+            // thread = output row, registers = 32 consecutive channels (8 x 16-byte chunks, XOR-swizzled)
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + 32 * i, v);
+            const uint32_t rowaddr = baddr + lane * 128;
+            float4 bb[8], rr[8];
 #pragma unroll
-          for (int rr = 0; rr < 32; rr += 8) {
-            const int rl = rr + rl8;
-            const int m = row0 + rl;
-            if (!col_ok || m >= p.M_total) continue;
-            float4 a0 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq8);
-            float4 a1 = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq8 + 4);
-            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
-            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
-            if (p.res_mode == 1) {
-              const float* rp = p.res + static_cast<long>(m) * p.N_total + col;
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-              a0.x += r0.x; a0.y += r0.y; a0.z += r0.z; a0.w += r0.w;
-              a1.x += r1.x; a1.y += r1.y; a1.z += r1.z; a1.w += r1.w;
-            }
-            const uint4 h = make_uint4(pack_op2(a0.x, a0.y), pack_op2(a0.z, a0.w), pack_op2(a1.x, a1.y), pack_op2(a1.z, a1.w));
-            *reinterpret_cast<uint4*>(p.out_op + static_cast<long>(m) * p.N_total + col) = h;
-            sg[0] += a0.x + a0.y; qg[0] += a0.x * a0.x + a0.y * a0.y;
-            sg[1] += a0.z + a0.w; qg[1] += a0.z * a0.z + a0.w * a0.w;
-            sg[2] += a1.x + a1.y; qg[2] += a1.x * a1.x + a1.y * a1.y;
-            sg[3] += a1.z + a1.w; qg[3] += a1.z * a1.z + a1.w * a1.w;
-          }
-          if (p.stats) {
-            if (p.stat_gran == 4) {
-              sg[0] += sg[1]; qg[0] += qg[1];
-              sg[1] = sg[2] + sg[3]; qg[1] = qg[2] + qg[3];
-            }
+            for (int c = 0; c < 8; ++c) bb[c] = lds128(sbias + (32 * i + 4 * c) * 4);
+            if (tma_res) {
 #pragma unroll
-            for (int o = 4; o <= 16; o <<= 1) {
+              for (int c = 0; c < 8; ++c) rr[c] = lds128(rowaddr + ((c ^ x7) << 4));
+            } else if (tma_res2) {
+              const uint32_t ra = res_slot_addr(g % NB) + s_r * 128;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (u < 2 || p.stat_gran != 4) {
+              for (int c = 0; c < 8; ++c) rr[c] = lds128(ra + ((c ^ (s_r & 7)) << 4));
+            }
+            tmem_ld_wait();
+            SGDM_T(3);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 a = make_float4(__uint_as_float(v[4 * c]) + bb[c].x, __uint_as_float(v[4 * c + 1]) + bb[c].y,
+                                     __uint_as_float(v[4 * c + 2]) + bb[c].z, __uint_as_float(v[4 * c + 3]) + bb[c].w);
+              if (tma_res || tma_res2) { a.x += rr[c].x; a.y += rr[c].y; a.z += rr[c].z; a.w += rr[c].w; }
+              sts128(rowaddr + ((c ^ x7) << 4), a);
+            }
+            SGDM_T(4);
+            if (p.stats) {
+              __syncwarp();
+              float4 a[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int row = 4 * k + rg;
+                a[k] = lds128(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                sg[0] += a[k].x + a[k].y; qg[0] += a[k].x * a[k].x + a[k].y * a[k].y;
+                sg[1] += a[k].z + a[k].w; qg[1] += a[k].z * a[k].z + a[k].w * a[k].w;
+              }
+              if (p.stat_gran == 4) { sg[0] += sg[1]; qg[0] += qg[1]; }
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
                   sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
                   qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
                 }
               }
+              const int col = col0 + 4 * cc;
+              if (rg == 0 && col < p.N_total && row0 < p.M_total) {
+                float2* dst = p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift);
+                if (p.stat_gran == 4) dst[0] = make_float2(sg[0], qg[0]);
+                else *reinterpret_cast<float4*>(dst) = make_float4(sg[0], qg[0], sg[1], qg[1]);
+              }
             }
-            if (rl8 == 0 && col_ok && row0 < p.M_total) {
-              float4* dst = reinterpret_cast<float4*>(p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift));
-              dst[0] = make_float4(sg[0], qg[0], sg[1], qg[1]);
-              if (p.stat_gran != 4) dst[1] = make_float4(sg[2], qg[2], sg[3], qg[3]);
+          } else {
+            // 16-bit output: thread = output row, 64 consecutive channels = 8 x 16-byte chunks of 8
+            const uint32_t rowaddr = baddr + lane * 128;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(taddr + 64 * i, v0);
+            tmem_ld_32x32(taddr + 64 * i + 32, v1);
+#pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              float4 bb[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) bb[c] = lds128(sbias + (64 * i + 32 * hsel + 4 * c) * 4);
+              if (hsel == 0) {
+                tmem_ld_wait();
+                SGDM_T(3);
+              }
+              const uint32_t(&v)[32] = hsel == 0 ? v0 : v1;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 b0 = bb[2 * c], b1 = bb[2 * c + 1];
+                const uint4 h = make_uint4(
+                    pack_op2(__uint_as_float(v[8 * c]) + b0.x, __uint_as_float(v[8 * c + 1]) + b0.y),
+                    pack_op2(__uint_as_float(v[8 * c + 2]) + b0.z, __uint_as_float(v[8 * c + 3]) + b0.w),
+                    pack_op2(__uint_as_float(v[8 * c + 4]) + b1.x, __uint_as_float(v[8 * c + 5]) + b1.y),
+                    pack_op2(__uint_as_float(v[8 * c + 6]) + b1.z, __uint_as_float(v[8 * c + 7]) + b1.w));
+                sts128u(rowaddr + (((4 * hsel + c) ^ x7) << 4), h);
+              }
+            }
+            SGDM_T(4);
+            if (p.stats) {
+              __syncwarp();
+              uint4 hh[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int row = 4 * k + rg;
+                hh[k] = lds128u(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float2 p0 = unpack_op2(hh[k].x), p1 = unpack_op2(hh[k].y), p2 = unpack_op2(hh[k].z), p3 = unpack_op2(hh[k].w);
+                sg[0] += p0.x + p0.y; qg[0] += p0.x * p0.x + p0.y * p0.y;
+                sg[1] += p1.x + p1.y; qg[1] += p1.x * p1.x + p1.y * p1.y;
+                sg[2] += p2.x + p2.y; qg[2] += p2.x * p2.x + p2.y * p2.y;
+                sg[3] += p3.x + p3.y; qg[3] += p3.x * p3.x + p3.y * p3.y;
+              }
+              if (p.stat_gran == 4) {
+                sg[0] += sg[1]; qg[0] += qg[1];
+                sg[1] = sg[2] + sg[3]; qg[1] = qg[2] + qg[3];
+              }
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (u < 2 || p.stat_gran != 4) {
+                    sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
+                    qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
+                  }
+                }
+              }
+              const int col = col0 + 8 * cc;
+              if (rg == 0 && col < p.N_total && row0 < p.M_total) {
+                float4* dst = reinterpret_cast<float4*>(p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift));
+                dst[0] = make_float4(sg[0], qg[0], sg[1], qg[1]);
+                if (p.stat_gran != 4) dst[1] = make_float4(sg[2], qg[2], sg[3], qg[3]);
+              }
             }
           }
+          SGDM_T(5);
+          // generic-proxy writes -> visible to the async proxy, then one lane stores the tile
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, baddr, col0, row0);
+            bulk_commit();
+          }
+          SGDM_T(6);
+          t_acc_[7] += 1;
         }
+        tc_fence_before();
         __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_leader(&tempty[acc]);
+          else mbar_arrive(&tempty[acc]);
+          mbar_arrive(&bfree[acc]);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kCtas == 2) mbar_arrive_leader(&tempty[acc]);
-        else mbar_arrive(&tempty[acc]);
-      }
+      if (lane == 0) bulk_wait_all();  // the staging smem must outlive the last stores
+      if (p.timing && lane == 0)
+        for (int k = 0; k < 8; ++k)
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + k, static_cast<unsigned long long>(t_acc_[k]));
     }
   }
   tc_fence_before();
@@ -404,6 +646,27 @@ static int encode_nhwc(CUtensorMap* tm, const op_t* base, int B, int H, int W, i
   return 0;
 }
 
+// row-major [rows, cols] matrix, box = box_rows rows x box_cols columns (128 bytes when `swizzle` is on)
+static int encode_matrix(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, bool swizzle,
+                         char* err, int errlen, int box_rows = 32) {
+  auto fn = get_encode_fn();
+  if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return 1; }
+  const int es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : SGDM_TMA_DTYPE, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled(matrix %ld x %d, es %d, box %d) failed: %d", rows, cols, es, box_cols, (int)r);
+    return 1;
+  }
+  return 0;
+}
+
 int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   memset(&out->p, 0, sizeof(out->p));
   out->desc = d;
@@ -420,9 +683,13 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     return fail("swap_ab uses block_n == 128 (all output channels in one tile)");
   }
   if (d.out_nchw == nullptr && (d.Cout % 8)) return fail("Cout % 8 != 0 needs the NCHW epilogue");
+  if (d.out_nchw != nullptr && d.block_n != 16) return fail("the NCHW epilogue is the block_n == 16 (Cout <= 16) path");
+  if (d.out_nchw == nullptr && d.block_n == 16) return fail("block_n == 16 needs the NCHW epilogue");
   if ((d.out_f32 != nullptr) + (d.out_op != nullptr) + (d.out_nchw != nullptr) != 1) return fail("exactly one output");
-  if (d.out_op && d.res && d.res_mode == 2) return fail("res_mode 2 needs the fp32 output");
-  if (d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
+  if (d.out_op && d.res) return fail("a residual needs the fp32 output");
+  if (d.out_nchw && d.res) return fail("the NCHW epilogue has no residual");
+  if (d.out_op && !d.swap_ab && (d.block_n % 64)) return fail("16-bit output needs block_n % 64 == 0");
+  if (d.res && d.res_mode == 2 && ((d.Hout | d.Wout) & 1)) return fail("res_mode 2 needs even output size");
   if (d.swap_ab && !conv_can_swap(d)) return fail("swap_ab needs Cout == 128, no NCHW / upsampled-residual epilogue");
   if (d.stats && (d.out_nchw || (d.Cout % 8) || (d.stat_gran != 2 && d.stat_gran != 4)))
     return fail("stats need an NHWC output, Cout % 8 == 0 and stat_gran in {2, 4}");
@@ -437,11 +704,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
   const int npad = conv_npad(d.Cout, d.block_n);
+  const int b_rows = d.block_n / (pair ? 2 : 1);  // weight rows per CTA and stage
   {
     auto fn = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(d.block_n / (pair ? 2 : 1))};
+    cuuint32_t box[2] = {64, (cuuint32_t)b_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&p.tmB, SGDM_TMA_DTYPE, 2, const_cast<op_t*>(d.w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -470,11 +738,49 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.bias = d.bias;
   p.res = d.res;
   p.res_mode = d.res ? d.res_mode : 0;
-  p.out_f32 = d.out_f32;
-  p.out_op = d.out_op;
   p.out_nchw = d.out_nchw;
   p.stats = d.stats;
   p.stat_gran = d.stat_gran;
+  p.timing = d.timing;
+  // epilogue: output / residual tile maps
+  p.epi_mode = d.out_nchw ? 0 : d.out_f32 ? 1 : 2;
+  if (p.epi_mode == 1) {
+    if (encode_matrix(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
+    if (p.res_mode == 1 && encode_matrix(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
+    if (p.res_mode == 2 &&
+        encode_matrix(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, true, err,
+                      errlen, 16))
+      return 1;
+  } else if (p.epi_mode == 2) {
+    // swap-AB: a warp owns 32 channels = 64-byte rows (dense); normal: 64 channels = 128-byte swizzled rows
+    if (encode_matrix(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, !d.swap_ab, err, errlen)) return 1;
+  }
+  // shared memory: as many K-block stages as fit beside the epilogue staging
+  p.b_tx = d.swap_ab ? 256 * 128 : b_rows * 128;  // bytes the TMA delivers into the B slot
+  p.b_bytes = (p.b_tx + 1023) / 1024 * 1024;      // slot size (1024-byte aligned for the 128B swizzle)
+  const int stage_bytes = kABytes + p.b_bytes;
+  // without a residual: 2 staging buffers per warp.  With one: keep >= 4 K-block stages (>= 3 of the 48 KB ones)
+  // and give the rest to the residual ring (res_mode 2 uses 2 KB slots inside two extra buffers: 4 total).
+  p.epi_bufs = p.epi_mode == 0 ? 0 : 2;
+  int n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * p.epi_bufs * kEpiBuf) / stage_bytes;
+  if (p.res_mode == 2) {
+    p.epi_bufs = 4;
+    n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * p.epi_bufs * kEpiBuf) / stage_bytes;
+  } else if (p.res_mode == 1) {
+    const int min_stages = stage_bytes > 32768 ? 3 : 4;
+    n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * 4 * kEpiBuf) / stage_bytes;
+    if (n_stages > min_stages && n_stages * stage_bytes + 4 * kMaxEpiBufs * kEpiBuf > kSmemLimit - kBarBytes - kBiasBytes)
+      n_stages = n_stages - 1 >= min_stages ? n_stages - 1 : n_stages;
+    if (n_stages > kMaxStages) n_stages = kMaxStages;
+    p.epi_bufs = (kSmemLimit - kBarBytes - kBiasBytes - n_stages * stage_bytes) / (4 * kEpiBuf);
+    if (p.epi_bufs > kMaxEpiBufs) p.epi_bufs = kMaxEpiBufs;
+    if (p.epi_bufs < 3) return fail("shared memory budget: no room for the residual ring");
+  }
+  const int fixed = kBarBytes + kBiasBytes + 4 * p.epi_bufs * kEpiBuf;
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
+  p.n_stages = n_stages;
+  out->smem = fixed + n_stages * (kABytes + p.b_bytes);
   out->pair = pair ? 1 : 0;
   if (pair) {
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
@@ -485,9 +791,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem);
+      e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
@@ -499,7 +805,7 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(l.grid);
     cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = kConvSmem;
+    cfg.dynamicSmemBytes = l.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -510,7 +816,7 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, l.p) == cudaSuccess ? 0 : 1;
   }
-  conv_gemm_kernel<1><<<l.grid, kConvThreads, kConvSmem, stream>>>(l.p);
+  conv_gemm_kernel<1><<<l.grid, kConvThreads, l.smem, stream>>>(l.p);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
