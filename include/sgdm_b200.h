@@ -126,9 +126,14 @@ int sgdm_debug_set_naive_conv(int on);
 /* CTA-pair (tcgen05 cta_group::2) conv mode for plans / single-kernel calls created afterwards:
  * -1 = library policy (default), 0 = never, 1 = whenever the shape allows (tests, A/B timing) */
 int sgdm_debug_set_conv_pair(int mode);
+/* halo mode of 3x3 stride-1 convs (one staged activation tile shared by the three vertical taps), same values */
+int sgdm_debug_set_conv_halo(int mode);
 /* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array
  * of 16 int64 (NULL = off); slot meaning in csrc/kernel_conv.cu */
 int sgdm_debug_set_conv_timing(void* device_counters16);
+/* tuning aid for single-kernel conv calls: cap the K-block ring depth (0 = no cap); flags 1 / 2 stop
+ * re-loading the activation / weight operand after the first ring fill (timing experiments, WRONG results) */
+int sgdm_debug_set_conv_knobs(int max_stages, int flags);
 
 /* ---- single-kernel entry points (unit parity tests). 16-bit tensors are `op` = fp16 (or bf16). ---- */
 /* conv / GEMM: in [B,Hin,Win,Cin] op NHWC; in2 optional [B,Hout,Wout,C2]; w packed [Npad][ks*ks*Cin + C2] op */

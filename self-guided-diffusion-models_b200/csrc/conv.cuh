@@ -49,7 +49,11 @@ struct ConvDesc {
   int stat_gran = 4;
   // CTA-pair mode (tcgen05 cta_group::2, M = 256 over two CTAs): -1 = policy (conv_use_pair), 0 = off, 1 = on
   int pair = -1;
+  // halo mode (one activation load per horizontal tap, shared by the three vertical taps): -1 policy, 0 off, 1 on
+  int halo = -1;
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
+  int debug_stages = 0;         // tuning only: cap the K-block ring depth
+  int debug_flags = 0;          // tuning only: 1 = stop re-loading the activation operand, 2 = the weight operand (WRONG results)
 };
 
 struct alignas(64) ConvKernelParams {
@@ -63,7 +67,10 @@ struct alignas(64) ConvKernelParams {
   int kc1, kc2;
   int N_total, block_n, n_tiles, m_tiles;
   int swap_ab, tile_px;  // tile_px: pixels per tile (128, or 256 when swap_ab)
-  int n_stages, b_bytes, b_tx;  // K-block ring: stage = 16 KB (M operand) + b_bytes; b_tx = bytes TMA delivers to the B slot
+  // K-block ring: stage = [activation slot: act_bytes][tps weight slots: wgt_bytes each]; *_tx = bytes TMA delivers
+  int n_stages, act_bytes, act_tx, act_tx_halo, wgt_bytes, wgt_tx;
+  int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
+  int tps2;                       // K blocks of the fused 1x1-skip source per stage (3 in halo mode, else 1)
   int epi_mode, epi_bufs;       // 0 NCHW direct | 1 fp32 NHWC | 2 16-bit NHWC; staging buffers per epilogue warp
   const float* bias;
   const float* res;
@@ -72,6 +79,7 @@ struct alignas(64) ConvKernelParams {
   float2* stats;
   int stat_gran;
   long long* timing;
+  int debug;
 };
 
 struct ConvLaunch {

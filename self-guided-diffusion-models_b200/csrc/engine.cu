@@ -28,7 +28,9 @@ static thread_local char g_err[1024] = "";
 static int64_t g_launches = 0;
 static int g_naive_conv = 0;
 static long long* g_conv_timing = nullptr;
-static int g_conv_pair = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
+static int g_conv_dbg_stages = 0, g_conv_dbg_flags = 0;
+static int g_conv_pair = -1;
+static int g_conv_halo = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -615,6 +617,11 @@ struct Builder {
     d.swap_ab = (conv_can_swap(d) && !getenv("SGDM_NO_SWAP")) ? 1 : 0;
     d.stat_gran = stat_gran();
     d.pair = g_conv_pair;
+    d.halo = g_conv_halo;
+    // A/B switches for whole-step timing (same process image, same box): SGDM_CONV_HALO / SGDM_CONV_PAIR = 0 | 1
+    if (const char* ev = getenv("SGDM_CONV_HALO")) d.halo = atoi(ev) ? -1 : 0;
+    if (const char* ev = getenv("SGDM_CONV_PAIR")) d.pair = atoi(ev) ? -1 : 0;
+    if (d.in2 && d.swap_ab && getenv("SGDM_CONV_HALO_SKIP") != nullptr) d.halo = 0;  // A/B: swap-AB skip blocks take a whole halo stage each
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
     char msg[256];
@@ -1062,6 +1069,15 @@ int sgdm_debug_set_conv_pair(int mode) {
   g_conv_pair = mode;
   return 0;
 }
+int sgdm_debug_set_conv_halo(int mode) {
+  g_conv_halo = mode;
+  return 0;
+}
+int sgdm_debug_set_conv_knobs(int max_stages, int flags) {
+  g_conv_dbg_stages = max_stages;
+  g_conv_dbg_flags = flags;
+  return 0;
+}
 int sgdm_debug_set_conv_timing(void* device_counters16) {
   g_conv_timing = static_cast<long long*>(device_counters16);
   return 0;
@@ -1220,6 +1236,9 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.swap_ab = (block_n <= 0 && conv_can_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
   d.pair = g_conv_pair;
   d.timing = g_conv_timing;
+  d.halo = g_conv_halo;
+  d.debug_stages = g_conv_dbg_stages;
+  d.debug_flags = g_conv_dbg_flags;
   ++g_launches;
   if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

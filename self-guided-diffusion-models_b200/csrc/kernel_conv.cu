@@ -10,6 +10,10 @@
 //   normal   D[128 px, block_n ch]            one CTA
 //   pair     D[2 x 128 px, block_n ch]        tcgen05 cta_group::2 over a 2-CTA cluster (M = 256)
 //   swap-AB  D^T[128 ch, 256 px] (Cout = 128) weights are the M operand, a 256-pixel tile the N operand
+// Halo mode (3x3, stride 1, tiles of whole image rows): one stage holds the activation rows y0-1 .. y0+bh
+// of ONE horizontal tap and 64 channels, plus the three weight tiles of the vertical taps; the three MMA
+// groups read that one tile at row offsets 0 / W / 2W (whole 1024-byte swizzle atoms), so every activation
+// row is pulled through L2 -> SM once per horizontal tap instead of once per tap.
 // Roofline: tensor pipe.  FLOPs per launch = 2 * M_total * Cout * Ktot.
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // [ring: n_stages x (A | B)] [epilogue staging: 4 warps x epi_bufs x 4 KB] [bias: 2 x 1 KB] [barriers]
-  const int stage_bytes = kABytes + p.b_bytes;
+  const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;  // [activation slot][tps weight slots]
   uint8_t* ring = smem;
   uint8_t* after_ring = smem + p.n_stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring + 4 * p.epi_bufs * kEpiBuf + kBiasBytes);
@@ -158,7 +162,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int KB = p.taps * p.kc1 + p.kc2;
   const int cta_rank = kCtas == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   // work items: (m_tile, n_tile), or (pair of adjacent m_tiles, n_tile) per 2-CTA cluster
   const int total_tiles = (kCtas == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
@@ -169,38 +172,59 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       long long t_prod = 0;
-      // swap_ab: the weight tile (128 x 64) is the MMA A operand, the activation tile (256 pixels) the B operand
-      const uint32_t tx_bytes = kCtas * (kABytes + p.b_tx);  // of the whole pair in pair mode
-      const int b_rows = block_n / kCtas;                    // weight rows this CTA loads
+      uint32_t fill = 0;
+      const int b_rows = block_n / kCtas;  // weight rows this CTA loads
+      const int n_main = (p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
         const int n_tile = tile % p.n_tiles;
         const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int q = 0; q < n_st; ++q) {
           const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (p.timing) t_prod += clock64() - tw0;
-          if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          uint8_t* sa = ring + stage * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          uint8_t* act_dst = p.swap_ab ? sb : sa;
-          uint8_t* wgt_dst = p.swap_ab ? sa : sb;
-          if (kb < p.taps * p.kc1) {
-            const int tap = kb / p.kc1;
-            const int cc = kb - tap * p.kc1;
-            const int r = tap / p.ks;
-            const int s = tap - r * p.ks;
-            if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
-            else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s - p.pad, y0 * p.stride + r - p.pad, img);
+          const bool skip_a = (p.debug & 1) && fill >= static_cast<uint32_t>(n_stages);  // tuning only: stale smem
+          const bool skip_b = (p.debug & 2) && fill >= static_cast<uint32_t>(n_stages);
+          ++fill;
+          const bool main_st = q < n_main;
+          // a stage of the fused 1x1-skip source holds up to tps2 plain (tile, weight) K blocks
+          const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
+          const uint32_t act_tx = (main_st && p.halo) ? p.act_tx_halo : (main_st ? p.act_tx : ntap * p.act_tx);
+          if (cta_rank == 0)
+            mbar_arrive_expect_tx(&full[stage], kCtas * ((skip_a ? 0u : act_tx) + (skip_b ? 0u : ntap * p.wgt_tx)));
+          uint8_t* act_dst = ring + stage * stage_bytes;
+          uint8_t* wgt_dst = act_dst + p.act_bytes;
+          int cc, kb0;
+          if (main_st) {
+            const int tap = q / p.kc1;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
+            cc = q - tap * p.kc1;
+            const int r = p.halo ? 0 : tap / p.ks;
+            const int s_tap = p.halo ? tap : tap - r * p.ks;
+            kb0 = p.halo ? s_tap * p.kc1 + cc : q;
+            if (!skip_a) {
+              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+            }
           } else {
-            const int cc = kb - p.taps * p.kc1;
-            if (kCtas == 2) tma_load_4d_pair(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
-            else tma_load_4d(&p.tmA2, &full[stage], act_dst, cc * 64, 0, y0, img);
+            cc = (q - n_main) * p.tps2;
+            kb0 = p.taps * p.kc1 + cc;
+            if (!skip_a) {
+              for (int t = 0; t < ntap; ++t) {
+                if (kCtas == 2) tma_load_4d_pair(&p.tmA2, &full[stage], act_dst + t * p.act_tx, (cc + t) * 64, 0, y0, img);
+                else tma_load_4d(&p.tmA2, &full[stage], act_dst + t * p.act_tx, (cc + t) * 64, 0, y0, img);
+              }
+            }
           }
-          if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n + cta_rank * b_rows);
-          else tma_load_2d(&p.tmB, &full[stage], wgt_dst, kb * 64, n_tile * block_n);
+          if (!skip_b) {
+            for (int t = 0; t < ntap; ++t) {
+              // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
+              const int kb = kb0 + (main_st ? t * p.ks * p.kc1 : t);
+              if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n + cta_rank * b_rows);
+              else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n);
+            }
+          }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
       }
@@ -212,6 +236,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
       uint32_t stage = 0, phase = 0, it = 0;
       long long t_full = 0, t_acc = 0;
+      const int n_main = (p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const long long ta0 = p.timing ? clock64() : 0;
@@ -219,29 +244,38 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (p.timing) t_acc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int q = 0; q < n_st; ++q) {
           const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&full[stage], phase);
           if (p.timing) t_full += clock64() - tw0;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const bool main_st = q < n_main;
+          const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
+          const uint32_t act_addr = smem_u32(ring + stage * stage_bytes);
+          const uint32_t wgt_addr = act_addr + p.act_bytes;
+          for (int t = 0; t < ntap; ++t) {
+            // halo: vertical tap t reads the staged rows starting t image rows further down
+            const uint32_t act_t = act_addr + (main_st ? (p.halo ? t * p.halo_row_bytes : 0) : t * p.act_tx);
+            const uint32_t wgt_t = wgt_addr + t * p.wgt_bytes;
+            const uint32_t a_addr = p.swap_ab ? wgt_t : act_t;  // M-side operand
+            const uint32_t b_addr = p.swap_ab ? act_t : wgt_t;  // N-side operand
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kCtas == 2)
-              umma_f16_pair(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (kCtas == 2)
+                umma_f16_pair(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                              (q | t | k) != 0 ? 1u : 0u);
+              else
+                umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                         (q | t | k) != 0 ? 1u : 0u);
+            }
           }
           // frees the smem stage (in both CTAs) when these MMAs retire; accumulator complete -> epilogue(s)
           if (kCtas == 2) {
             umma_commit_pair(&empty[stage]);
-            if (kb == KB - 1) umma_commit_pair(&tfull[acc]);
+            if (q == n_st - 1) umma_commit_pair(&tfull[acc]);
           } else {
             umma_commit(&empty[stage]);
-            if (kb == KB - 1) umma_commit(&tfull[acc]);
+            if (q == n_st - 1) umma_commit(&tfull[acc]);
           }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
@@ -698,13 +732,55 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const int bw = d.Wout;
   const int bh = min(d.Hout, tile_px / bw);
   const int bn = tile_px / (bw * bh);
-  if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, bh, bn, d.stride, err, errlen)) return 1;
+  // halo mode: 3x3 stride 1, tiles made of whole rows of one image, row pitch = whole swizzle atoms
+  bool halo = d.halo != 0 && d.ks == 3 && d.stride == 1 && bn == 1 && bw * bh == tile_px && (HW % tile_px) == 0 &&
+              (d.Wout % 8) == 0 && bh + 2 <= 256;
+  if (d.halo == 1 && !halo) return fail("halo mode needs a 3x3 stride-1 conv whose tiles are whole rows of one image");
+  const int b_rows = d.block_n / (pair ? 2 : 1);  // weight rows per CTA and stage slot
+  p.wgt_tx = d.swap_ab ? kABytes : b_rows * 128;
+  p.wgt_bytes = (p.wgt_tx + 1023) / 1024 * 1024;
+  p.act_tx = tile_px * 128;
+  p.epi_mode = d.out_nchw ? 0 : d.out_f32 ? 1 : 2;
+  p.res_mode = d.res ? d.res_mode : 0;
+  const int budget = kSmemLimit - kBarBytes - kBiasBytes;
+  // staging buffers per epilogue warp: 2 without a residual; res_mode 1 adds the in-place residual ring (>= 3,
+  // up to 6: in-flight residual bytes per SM must cover HBM latency); res_mode 2 uses four 2 KB slots in two more
+  const int min_bufs = p.epi_mode == 0 ? 0 : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
+  int n_stages = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    p.halo = halo ? 1 : 0;
+    p.tps = halo ? 3 : 1;
+    p.act_tx_halo = (bh + 2) * bw * 128;
+    p.act_bytes = halo ? p.act_tx_halo : p.act_tx;
+    p.halo_row_bytes = bw * 128;
+    // halo stages have three weight slots: let the fused 1x1-skip K blocks use them three at a time as well
+    // (needs room for three plain activation tiles in the activation slot)
+    p.tps2 = (halo && d.in2 && !d.swap_ab) ? 3 : 1;
+    if (p.tps2 == 3 && p.act_bytes < 3 * p.act_tx) p.act_bytes = 3 * p.act_tx;
+    const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;
+    const int min_stages = halo ? 2 : (stage_bytes > 32768 ? 3 : 4);
+    n_stages = (budget - 4 * min_bufs * kEpiBuf) / stage_bytes;
+    if (n_stages > kMaxStages) n_stages = kMaxStages;
+    if (n_stages < min_stages && halo && d.halo != 1) { halo = false; continue; }  // policy: fall back to per-tap stages
+    if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
+    p.epi_bufs = min_bufs;
+    if (p.res_mode == 1) {
+      // trade ring depth beyond the minimum for a deeper residual ring
+      while (n_stages > min_stages && (budget - n_stages * stage_bytes) / (4 * kEpiBuf) < kMaxEpiBufs) --n_stages;
+      p.epi_bufs = (budget - n_stages * stage_bytes) / (4 * kEpiBuf);
+      if (p.epi_bufs > kMaxEpiBufs) p.epi_bufs = kMaxEpiBufs;
+    }
+    break;
+  }
+  if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
+  p.n_stages = n_stages;
+  out->smem = kBarBytes + kBiasBytes + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
+  if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen)) return 1;
   if (d.in2) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
   }
   const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
   const int npad = conv_npad(d.Cout, d.block_n);
-  const int b_rows = d.block_n / (pair ? 2 : 1);  // weight rows per CTA and stage
   {
     auto fn = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
@@ -737,13 +813,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.m_tiles = (p.M_total + tile_px - 1) / tile_px;
   p.bias = d.bias;
   p.res = d.res;
-  p.res_mode = d.res ? d.res_mode : 0;
   p.out_nchw = d.out_nchw;
   p.stats = d.stats;
   p.stat_gran = d.stat_gran;
   p.timing = d.timing;
+  p.debug = d.debug_flags;
   // epilogue: output / residual tile maps
-  p.epi_mode = d.out_nchw ? 0 : d.out_f32 ? 1 : 2;
   if (p.epi_mode == 1) {
     if (encode_matrix(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
     if (p.res_mode == 1 && encode_matrix(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
@@ -756,31 +831,6 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (encode_matrix(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, !d.swap_ab, err, errlen)) return 1;
   }
   // shared memory: as many K-block stages as fit beside the epilogue staging
-  p.b_tx = d.swap_ab ? 256 * 128 : b_rows * 128;  // bytes the TMA delivers into the B slot
-  p.b_bytes = (p.b_tx + 1023) / 1024 * 1024;      // slot size (1024-byte aligned for the 128B swizzle)
-  const int stage_bytes = kABytes + p.b_bytes;
-  // without a residual: 2 staging buffers per warp.  With one: keep >= 4 K-block stages (>= 3 of the 48 KB ones)
-  // and give the rest to the residual ring (res_mode 2 uses 2 KB slots inside two extra buffers: 4 total).
-  p.epi_bufs = p.epi_mode == 0 ? 0 : 2;
-  int n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * p.epi_bufs * kEpiBuf) / stage_bytes;
-  if (p.res_mode == 2) {
-    p.epi_bufs = 4;
-    n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * p.epi_bufs * kEpiBuf) / stage_bytes;
-  } else if (p.res_mode == 1) {
-    const int min_stages = stage_bytes > 32768 ? 3 : 4;
-    n_stages = (kSmemLimit - kBarBytes - kBiasBytes - 4 * 4 * kEpiBuf) / stage_bytes;
-    if (n_stages > min_stages && n_stages * stage_bytes + 4 * kMaxEpiBufs * kEpiBuf > kSmemLimit - kBarBytes - kBiasBytes)
-      n_stages = n_stages - 1 >= min_stages ? n_stages - 1 : n_stages;
-    if (n_stages > kMaxStages) n_stages = kMaxStages;
-    p.epi_bufs = (kSmemLimit - kBarBytes - kBiasBytes - n_stages * stage_bytes) / (4 * kEpiBuf);
-    if (p.epi_bufs > kMaxEpiBufs) p.epi_bufs = kMaxEpiBufs;
-    if (p.epi_bufs < 3) return fail("shared memory budget: no room for the residual ring");
-  }
-  const int fixed = kBarBytes + kBiasBytes + 4 * p.epi_bufs * kEpiBuf;
-  if (n_stages > kMaxStages) n_stages = kMaxStages;
-  if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
-  p.n_stages = n_stages;
-  out->smem = fixed + n_stages * (kABytes + p.b_bytes);
   out->pair = pair ? 1 : 0;
   if (pair) {
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;

@@ -395,8 +395,9 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
   const int PLa = 256 / C8 > 0 ? 256 / C8 : 1;
   const int n_iter = d.resample == 1 ? HW / 4 : HW;
   // pixels per block: >= 8 per thread when the grid stays large enough to fill the chip
-  int ppb = PLa * (d.src0_is_op ? 16 : 8);
-  while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 4 * kNumSMs) ppb >>= 1;
+  // the per-block prologue (group statistics, folded scale / offset per channel) is amortised over ppb pixels
+  int ppb = PLa * (d.src0_is_op ? 64 : 32);
+  while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 8 * kNumSMs) ppb >>= 1;
   if (ppb > n_iter) ppb = n_iter;
   GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
                 d.silu, d.resample, d.chunks, ppb, PLa, d.partial, gn_fused(d) ? d.final : nullptr, d.out, d.raw_out,

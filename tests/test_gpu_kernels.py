@@ -100,6 +100,9 @@ CONV_CASES = [
     (3, 8, 8, 128, 128, 3, 1, 0, 1, "f32", "Cout=128 at 8x8: 256-pixel tile spans 4 images, ragged"),
     (40, 32, 32, 128, 128, 3, 2, 0, 0, "f32", "Cout=128 stride 2, 320 tiles"),
     (2, 32, 32, 256, 128, 3, 1, 384, 0, "f32", "Cout=128 with fused 1x1 skip"),
+    (5, 16, 16, 256, 256, 3, 1, 0, 1, "f32", "halo candidate: 256->256 at 16x16, residual, odd batch"),
+    (3, 32, 32, 192, 256, 3, 1, 0, 0, "op", "halo candidate: Cin=192 at 32x32, 16-bit out"),
+    (2, 64, 64, 128, 512, 3, 1, 0, 1, "f32", "halo candidate: 64x64 (2-row tiles), two n-tiles, residual"),
 ]
 
 
@@ -132,17 +135,28 @@ def test_conv_tcgen05_vs_torch(L, case):
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    modes = [("naive", bn, 1, 0), ("tcgen05 1-CTA", bn, 0, 0)]
+    # (label, block_n argument, naive, CTA-pair mode, halo mode); -1 = the library's policy
+    modes = [("naive", bn, 1, 0, 0), ("tcgen05 1-CTA", bn, 0, 0, 0)]
     if bn >= 64:
-        modes.append(("tcgen05 CTA pair (cta_group::2)", bn, 0, 1))
+        modes.append(("tcgen05 CTA pair (cta_group::2)", bn, 0, 1, 0))
     if Cout == 128 and out != "nchw" and res_mode != 2:
-        modes.append(("tcgen05 swap-AB (block_n=0: engine policy)", 0, 0, -1))
-    for label, bn_arg, naive, pair in modes:
+        modes.append(("tcgen05 swap-AB (block_n=0: engine policy)", 0, 0, -1, 0))
+    if ks == 3 and stride == 1 and (H * W) % 128 == 0 and W % 8 == 0:
+        modes.append(("tcgen05 halo (3 vertical taps share one staged tile), policy pair/swap", 0 if Cout == 128 and out != "nchw" and res_mode != 2 else bn, 0, -1, 1))
+        modes.append(("tcgen05 halo, 1-CTA", bn, 0, 0, 1))
+    for label, bn_arg, naive, pair, halo in modes:
         L.sgdm_debug_set_conv_pair(pair)
+        L.sgdm_debug_set_conv_halo(halo)
         try:
             got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
+        except AssertionError as e:
+            if halo == 1 and ("halo mode needs" in str(e) or "shared memory budget" in str(e)):
+                print(f"[conv {note}] {label}: not applicable ({e})")
+                continue
+            raise
         finally:
             L.sgdm_debug_set_conv_pair(-1)
+            L.sgdm_debug_set_conv_halo(-1)
         got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
         assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)

@@ -1,4 +1,5 @@
 python -c "import __graft_entry__ as g; g.build()" | tail -1
-timeout 900 python -m pytest tests/test_gpu_kernels.py -k "conv or stats" -q -p no:cacheprovider 2>&1 | tail -3
-python tools/bench_conv.py "proj 512->512 1x1 @16 B512" "conv 128->128 3x3 @64 B512" "first 64->128 3x3 @64 B512" 2>&1 | tee gpurun_out/bench_conv.log | grep -E "stats=1|res=0 stats=0" 
-NCU=0 bash tools/gpu_round.sh
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -p no:cacheprovider 2>&1 | tail -3
+for cfg in "SGDM_CONV_HALO=1" "SGDM_CONV_HALO=1 SGDM_CONV_HALO_SKIP=1" "SGDM_CONV_HALO=1"; do
+  echo "== $cfg"; env $cfg python bench.py --no-cpu-baseline --dump-ops gpurun_out/ops_$(echo $cfg | tr ' =' '__').json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['clocks'], {k:v['ms'] for k,v in d['roofline']['families'].items()})"
+done

@@ -20,7 +20,7 @@ def pack(w, bn):
     assert L.sgdm_k_pack_weight(S(), P(w.contiguous()), P(dst), Co, Ci, ks, Ci, ktot, 0) == 0
     return dst
 
-def run(name, B, H, Cin, Cout, ks, out, res, stats, pair, iters=10):
+def run(name, B, H, Cin, Cout, ks, out, res, stats, pair, iters=10, halo=-1):
     bn = next(b for b in (256, 128, 64, 32) if Cout % b == 0)
     x = torch.randn(B, H, H, Cin, device="cuda").to(OP)
     w = torch.randn(Cout, Cin, ks, ks, device="cuda") / math.sqrt(Cin * ks * ks)
@@ -31,6 +31,7 @@ def run(name, B, H, Cin, Cout, ks, out, res, stats, pair, iters=10):
     oop = torch.empty(B, H, H, Cout, dtype=OP, device="cuda") if out == "op" else None
     st = torch.empty((B * H * H + 31) // 32, Cout // 4, 2, device="cuda") if stats else None
     L.sgdm_debug_set_conv_pair(pair)
+    L.sgdm_debug_set_conv_halo(halo)
     def go():
         rc = L.sgdm_k_conv_stats(S(), P(x), B, H, H, Cin, None, 0, P(wp), ks, 1, H, H, Cout, P(bias), P(r), 1 if res else 0,
                                  P(o32), P(oop), None, 0, 0, P(st), 4)
@@ -52,7 +53,8 @@ def run(name, B, H, Cin, Cout, ks, out, res, stats, pair, iters=10):
     fl = 2.0 * B * H * H * Cout * Cin * ks * ks
     by = x.numel() * 2 + B * H * H * Cout * ((4 if out == "f32" else 2) + (4 if res else 0))
     L.sgdm_debug_set_conv_pair(-1)
-    print(f"{name:34s} out={out:3s} res={int(res)} stats={int(stats)} pair={pair:2d}  {ms:7.3f} ms  {fl/ms/1e9:7.0f} TFLOP/s  {by/ms/1e6:6.0f} GB/s | clk/chunk: {epi} | mma_wait_smem={t[8]/1e6:.1f}M mma_wait_acc={t[9]/1e6:.1f}M prod_wait={t[10]/1e6:.1f}M", flush=True)
+    L.sgdm_debug_set_conv_halo(-1)
+    print(f"halo={halo:2d} {name:34s} out={out:3s} res={int(res)} stats={int(stats)} pair={pair:2d}  {ms:7.3f} ms  {fl/ms/1e9:7.0f} TFLOP/s  {by/ms/1e6:6.0f} GB/s | clk/chunk: {epi} | mma_wait_smem={t[8]/1e6:.1f}M mma_wait_acc={t[9]/1e6:.1f}M prod_wait={t[10]/1e6:.1f}M", flush=True)
 
 SHAPES = {
     "proj 512->512 1x1 @16 B512": (512, 16, 512, 512, 1),
@@ -62,6 +64,28 @@ SHAPES = {
     "conv 512->512 3x3 @16 B512": (512, 16, 512, 512, 3),
     "first 64->128 3x3 @64 B512": (512, 64, 64, 128, 3),
 }
+if os.environ.get("KNOBS"):
+    # mainloop experiments: ring depth and operand-reload knobs on one big layer
+    name = os.environ.get("KNOB_SHAPE", "conv 512->512 3x3 @16 B512")
+    B, H, Cin, Cout, ks = SHAPES[name]
+    for stages, flags in ((0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 1), (0, 2), (0, 3)):
+        L.sgdm_debug_set_conv_knobs(stages, flags)
+        for pair in ((-1,) if Cout == 128 else (0, 1)):
+            print(f"stages<={stages} flags={flags}", end="  ")
+            run(name, B, H, Cin, Cout, ks, "op", False, False, pair)
+    L.sgdm_debug_set_conv_knobs(0, 0)
+    sys.exit(0)
+if os.environ.get("HALO"):
+    SHAPES["last 128->3 3x3 @64 B512"] = (512, 64, 128, 3, 3)
+    for name in ("conv 512->512 3x3 @16 B512", "conv 256->256 3x3 @32 B512", "conv 128->128 3x3 @64 B512", "first 64->128 3x3 @64 B512"):
+        B, H, Cin, Cout, ks = SHAPES[name]
+        for out, res, stats in (("op", False, True), ("f32", True, True)):
+            for halo in (0, 1):
+                try:
+                    run(name, B, H, Cin, Cout, ks, out, res, stats, -1, halo=halo)
+                except AssertionError as e:
+                    print(f"halo={halo} {name} out={out} res={int(res)}: {e}")
+    sys.exit(0)
 sel = sys.argv[1:] or list(SHAPES)
 for name in sel:
     B, H, Cin, Cout, ks = SHAPES[name]
