@@ -141,23 +141,26 @@ int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, 
                 const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
                 const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
                 int naive);
-/* same, additionally emitting GroupNorm partial statistics of the final output values:
- * stats[(row/32) * (Cout/stat_gran) + c/stat_gran] = {sum, sum of squares} (float2) over 32 output rows
- * (NHWC pixels) x stat_gran (2 or 4) channels; buffer of ceil(B*Hout*Wout/32) * Cout/stat_gran float2. */
+/* same, with the optional extras of the engine's fused layers:
+ *  - stats: GroupNorm partial statistics of the final output values,
+ *    stats[(row/32) * (Cout/stat_gran) + c/stat_gran] = {sum, sum of squares} (float2) over 32 output rows
+ *    (NHWC pixels) x stat_gran (2 or 4) channels; buffer of ceil(B*Hout*Wout/32) * Cout/stat_gran float2
+ *  - out_op2 (with out_f32): a second NHWC tensor holding the same values rounded to the 16-bit operand type
+ *  - in2b / C2b: the 1x1 skip source is the channel concat [in2 (C2) | in2b (C2b)] of two tensors */
 int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int Cin, const void* in2, int C2,
                       const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
                       const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
-                      int naive, float* stats, int stat_gran);
+                      int naive, float* stats, int stat_gran, void* out_op2, const void* in2b, int C2b);
 /* packs a torch conv weight [Cout,Cin,ks,ks] fp32 into dst[co][k_off + tap*cin_pad + ci] (row length ktot) */
 int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad,
                        int ktot, int k_off);
-/* src0: fp32 NHWC, or op NHWC when src0_is_op (then src1 must be NULL) */
-int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W, int C0,
+/* src0 / src1: fp32 NHWC, or both op NHWC when src0_is_op (a 16-bit concat needs sgdm_k_groupnorm_fused) */
+int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const void* src1, int B, int H, int W, int C0,
                      int C1, const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
                      int resample, void* out_op, void* raw_out_op, float* pool_out);
 /* same, with the statistics taken from conv-epilogue partial sums (sgdm_k_conv_stats) of the producer(s)
  * of src0 / src1 instead of a pass over the tensor; requires H*W % 32 == 0. */
-int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W,
+int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const void* src1, int B, int H, int W,
                            int C0, int C1, const float* gamma, const float* beta, const float* film,
                            int64_t film_stride, int silu, int resample, const float* stats0, const float* stats1,
                            int stat_gran, void* out_op, void* raw_out_op, float* pool_out);

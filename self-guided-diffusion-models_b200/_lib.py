@@ -71,7 +71,7 @@ PROTOTYPES = {
     "sgdm_debug_set_conv_knobs": (_i, [_i, _i]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
     "sgdm_k_conv_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
-                                _vp, _i]),
+                                _vp, _i, _vp, _vp, _i]),
     "sgdm_k_pack_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "sgdm_k_groupnorm": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "sgdm_k_groupnorm_fused": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp,

@@ -23,6 +23,9 @@ struct ConvDesc {
   // optional 1x1 skip source at OUTPUT resolution: NHWC op_t [B, Hout, Wout, C2], C2 % 64 == 0
   const op_t* in2 = nullptr;
   int C2 = 0;
+  // ... which may itself be a channel concat [in2 (C2) | in2b (C2b)] of two tensors
+  const op_t* in2b = nullptr;
+  int C2b = 0;
   // packed weights: op_t [Npad][Ktot], Ktot = ks*ks*Cin + C2, K order = (tap, cin) then skip cin
   const op_t* w = nullptr;
   int ks = 3, stride = 1, pad = 1;
@@ -34,6 +37,7 @@ struct ConvDesc {
   float* out_f32 = nullptr;     // NHWC fp32 [B,Hout,Wout,Cout]
   op_t* out_op = nullptr;       // NHWC op_t
   float* out_nchw = nullptr;    // NCHW fp32 [B,Cout,Hout,Wout] (final conv, Cout = 3)
+  op_t* out_op2 = nullptr;      // with out_f32: the same values rounded to op_t as a second NHWC tensor (GroupNorm input copy)
   int block_n = 128;            // 16 or a multiple of 32, <= 256; Npad = roundup(Cout, block_n)
   // Cout == 128 only: compute D^T = W * X^T, i.e. the 128 output channels are the MMA M dimension and a
   // tile of 256 PIXELS is the MMA N dimension.  An M128xN128 SS-MMA needs 128 B/clk of shared-memory
@@ -59,12 +63,14 @@ struct ConvDesc {
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA;
   CUtensorMap tmA2;
+  CUtensorMap tmA2b;
   CUtensorMap tmB;
   CUtensorMap tmOut;  // output matrix [M_total, Cout]: 32-row x 128-byte tiles (TMA store)
   CUtensorMap tmRes;  // residual matrix (res_mode 1): same tiling (TMA load)
+  CUtensorMap tmOut2; // optional 16-bit copy of the fp32 output: 32-row x 64-byte tiles
   int M_total, HW, Wout, Hout;
   int stride, pad, ks, taps;
-  int kc1, kc2;
+  int kc1, kc2, kc2a;  // 64-channel chunks: main source; skip source(s) in total; of the first skip tensor
   int N_total, block_n, n_tiles, m_tiles;
   int swap_ab, tile_px;  // tile_px: pixels per tile (128, or 256 when swap_ab)
   // K-block ring: stage = [activation slot: act_bytes][tps weight slots: wgt_bytes each]; *_tx = bytes TMA delivers
@@ -72,6 +78,7 @@ struct alignas(64) ConvKernelParams {
   int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
   int tps2;                       // K blocks of the fused 1x1-skip source per stage (3 in halo mode, else 1)
   int epi_mode, epi_bufs;       // 0 NCHW direct | 1 fp32 NHWC | 2 16-bit NHWC; staging buffers per epilogue warp
+  int out2;                     // epi_mode 1: also store the 16-bit copy
   const float* bias;
   const float* res;
   int res_mode;

@@ -90,6 +90,9 @@ struct Act {
   float* p = nullptr;
   int C = 0, H = 0, W = 0;
   float2* stats = nullptr;  // GroupNorm partial sums emitted by the producing conv (ConvDesc::stats), or null
+  op_t* p16 = nullptr;      // the same tensor rounded to the 16-bit operand type (ConvDesc::out_op2): what the
+                            // consuming GroupNorms and fused 1x1 skip convs read instead of the fp32 tensor
+  bool has_stats = false, has16 = false;  // valid in the sizing (dry) pass too, where the pointers are null
 };
 
 struct OpMeta {
@@ -605,6 +608,18 @@ struct Builder {
     if (!stats_ok(H, W)) return nullptr;
     return reinterpret_cast<float2*>(stream_alloc(2 * stats_elems(rows, C)));
   }
+  // Optional (SGDM_GN16=1): 16-bit GroupNorm-input copies written by the producing conv's epilogue next to the
+  // fp32 tensor.  Measured on B200 (config 2, batch 256): gn_apply 9.7 -> 8.3 ms, but the epilogue-bound convs
+  // lose about as much and eps rel-L2 rises 1.9e-3 -> 2.2e-3 (DDIM-10 PSNR 43.7 -> 41.3 dB): off by default.
+  bool use16 = getenv("SGDM_GN16") != nullptr && atoi(getenv("SGDM_GN16")) != 0;
+  void attach_outputs(Act& o, size_t rows, ConvDesc& c, bool allow16 = true) {
+    o.has_stats = stats_ok(o.H, o.W);
+    o.stats = stats_alloc(rows, o.C, o.H, o.W);
+    o.has16 = use16 && o.has_stats && allow16;
+    o.p16 = o.has16 ? reinterpret_cast<op_t*>(stream_alloc((rows * o.C + 1) / 2)) : nullptr;
+    c.stats = o.stats;
+    c.out_op2 = o.p16;
+  }
   void push(Op op, const char* kind = "misc", double flops = 0, double bytes = 0) {
     if (dry) return;
     plan->ops.push_back(std::move(op));
@@ -631,11 +646,12 @@ struct Builder {
       return;
     }
     const double M = static_cast<double>(Bp) * d.Hout * d.Wout;
-    const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin) + (d.in2 ? d.C2 : 0);
+    const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin) + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
     const double flops = 2.0 * M * d.Cout * k_real;
     const double in_px = static_cast<double>(Bp) * d.Hin * d.Win;
-    const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * d.C2 * 2 : 0) +
-                         M * d.Cout * ((d.out_f32 || d.out_nchw) ? 4 : 2) + (d.res ? M * d.Cout * 4 / (d.res_mode == 2 ? 4 : 1) : 0);
+    const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * (d.C2 + (d.in2b ? d.C2b : 0)) * 2 : 0) +
+                         M * d.Cout * ((d.out_f32 || d.out_nchw) ? 4 : 2) + (d.out_op2 ? M * d.Cout * 2 : 0) +
+                         (d.res ? M * d.Cout * 4 / (d.res_mode == 2 ? 4 : 1) : 0);
     push([l](cudaStream_t s) {
       ++g_launches;
       return g_naive_conv ? conv_launch_naive(l->desc, s) : conv_launch(*l, s);
@@ -676,10 +692,16 @@ struct Builder {
     const int Ho = r.down ? H / 2 : r.up ? H * 2 : H, Wo = r.down ? W / 2 : r.up ? W * 2 : W;
     const size_t px_in = static_cast<size_t>(Bp) * H * W, px_out = static_cast<size_t>(Bp) * Ho * Wo;
     op_t* g1 = static_cast<op_t*>(scratch("gn_out", px_out * C * sizeof(op_t)));
-    op_t* raw = r.skip ? static_cast<op_t*>(scratch("raw_op", px_in * C * sizeof(op_t))) : nullptr;
+    // 16-bit input copies (with producer statistics) for every source: the GroupNorm reads 2 B instead of 4 B
+    // per element and the fused 1x1 skip conv reads the copies directly (no raw concat copy).  A down block
+    // pools its fp32 input for the residual, so it keeps the fp32 path.
+    const bool in16 = a.has16 && a.has_stats && (b.C == 0 || (b.has16 && b.has_stats)) && !r.down;
+    op_t* raw = (r.skip && !in16) ? static_cast<op_t*>(scratch("raw_op", px_in * C * sizeof(op_t))) : nullptr;
     float* pooled = r.down ? static_cast<float*>(scratch("pooled", px_out * C * sizeof(float))) : nullptr;
     GnDesc g;
-    g.src0 = a.p; g.src1 = b.p; g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
+    g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
+    if (in16) { g.src0 = a.p16; g.src1 = b.p16; g.src0_is_op = 1; }
+    else { g.src0 = a.p; g.src1 = b.p; }
     g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
     g.out = g1; g.raw_out = raw; g.pool_out = pooled;
     g.stats0 = a.stats; g.stats1 = b.stats;
@@ -702,12 +724,15 @@ struct Builder {
     Act o;
     o.C = r.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(px_out * r.cout);
-    o.stats = stats_alloc(px_out, r.cout, Ho, Wo);
     ConvDesc c2;
     c2.in = g2; c2.Hin = Ho; c2.Win = Wo; c2.Cin = r.cout; c2.w = r.w2; c2.ks = 3; c2.stride = 1; c2.pad = 1;
-    c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p; c2.stats = o.stats;
+    c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p;
+    // (an upsampled-residual epilogue needs its shared memory for the residual slots: no 16-bit copy there)
+    attach_outputs(o, px_out, c2, !(r.up && !r.skip));
     if (r.skip) {
-      c2.in2 = raw; c2.C2 = C; c2.bias = r.bfused;
+      c2.bias = r.bfused;
+      if (in16) { c2.in2 = a.p16; c2.C2 = a.C; c2.in2b = b.C ? b.p16 : nullptr; c2.C2b = b.C; }
+      else { c2.in2 = raw; c2.C2 = C; }
     } else {
       c2.bias = r.bfused;
       c2.res = r.down ? pooled : a.p;
@@ -723,7 +748,9 @@ struct Builder {
     const size_t rows = static_cast<size_t>(Bp) * T;
     op_t* g = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
     GnDesc gd;
-    gd.src0 = a.p; gd.H = a.H; gd.W = a.W; gd.C0 = C; gd.gamma = w.norm_w; gd.beta = w.norm_b; gd.silu = 0; gd.out = g;
+    gd.H = a.H; gd.W = a.W; gd.C0 = C; gd.gamma = w.norm_w; gd.beta = w.norm_b; gd.silu = 0; gd.out = g;
+    if (a.has16 && a.has_stats) { gd.src0 = a.p16; gd.src0_is_op = 1; }
+    else gd.src0 = a.p;
     gd.stats0 = a.stats;
     gn(gd);
     op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * 3 * C * sizeof(op_t)));
@@ -744,11 +771,10 @@ struct Builder {
     }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * T * dh, static_cast<double>(rows) * 4 * C * 2);
     Act o = a;
     o.p = stream_alloc(rows * C);
-    o.stats = stats_alloc(rows, C, a.H, a.W);
     ConvDesc c2;
     c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = C; c2.w = w.wproj; c2.ks = 1; c2.stride = 1; c2.pad = 0;
     c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.bias = w.bproj; c2.res = a.p; c2.res_mode = 1; c2.out_f32 = o.p;
-    c2.stats = o.stats;
+    attach_outputs(o, rows, c2);
     conv(c2);
     return o;
   }
@@ -803,6 +829,7 @@ struct Builder {
     Act o = a;
     o.p = stream_alloc(rows * C);
     o.stats = nullptr;  // produced by the LayerNorm kernel: consumers run the standalone statistics pass
+    o.p16 = nullptr; o.has_stats = false; o.has16 = false;
     {
       const float* x = a.p;
       const float *g = w.out_g, *b = w.out_b;
@@ -831,10 +858,10 @@ struct Builder {
     Act o;
     o.C = cw.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(static_cast<size_t>(Bp) * Ho * Wo * cw.cout);
-    o.stats = stats_alloc(static_cast<size_t>(Bp) * Ho * Wo, cw.cout, Ho, Wo);
     ConvDesc c;
     c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
-    c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p; c.stats = o.stats;
+    c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
+    attach_outputs(o, static_cast<size_t>(Bp) * Ho * Wo, c);
     conv(c);
     return o;
   }
@@ -934,10 +961,10 @@ struct Builder {
       const ConvW& cw = e->convs[e->in_blocks[0][0].idx];
       h.C = cw.cout; h.H = H; h.W = W;
       h.p = stream_alloc(px * cw.cout);
-      h.stats = stats_alloc(px, cw.cout, H, W);
       ConvDesc d;
       d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
-      d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p; d.stats = h.stats;
+      d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
+      attach_outputs(h, px, d);
       conv(d, cw.cin);
       hs.push_back(h);
     }
@@ -955,7 +982,9 @@ struct Builder {
     // out = GN + SiLU + conv3x3 -> eps NCHW (openaimodel.py:830-835,956)
     op_t* g = static_cast<op_t*>(scratch("gn_out", px * h.C * sizeof(op_t)));
     GnDesc gd;
-    gd.src0 = h.p; gd.H = H; gd.W = W; gd.C0 = h.C; gd.gamma = e->out_gn_w; gd.beta = e->out_gn_b; gd.silu = 1; gd.out = g;
+    gd.H = H; gd.W = W; gd.C0 = h.C; gd.gamma = e->out_gn_w; gd.beta = e->out_gn_b; gd.silu = 1; gd.out = g;
+    if (h.has16 && h.has_stats) { gd.src0 = h.p16; gd.src0_is_op = 1; }
+    else gd.src0 = h.p;
     gd.stats0 = h.stats;
     gn(gd);
     ConvDesc d;
@@ -1220,14 +1249,15 @@ int sgdm_k_conv(void* stream, const void* in, int B, int Hin, int Win, int Cin, 
                 const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
                 int naive) {
   return sgdm_k_conv_stats(stream, in, B, Hin, Win, Cin, in2, C2, w, ks, stride, Hout, Wout, Cout, bias, res, res_mode,
-                           out_f32, out_op, out_nchw, block_n, naive, nullptr, 4);
+                           out_f32, out_op, out_nchw, block_n, naive, nullptr, 4, nullptr, nullptr, 0);
 }
 int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int Cin, const void* in2, int C2,
                       const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
                       const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
-                      int naive, float* stats, int stat_gran) {
+                      int naive, float* stats, int stat_gran, void* out_op2, const void* in2b, int C2b) {
   ConvDesc d;
   d.stats = reinterpret_cast<float2*>(stats); d.stat_gran = stat_gran;
+  d.out_op2 = static_cast<op_t*>(out_op2); d.in2b = static_cast<const op_t*>(in2b); d.C2b = C2b;
   d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = Hin; d.Win = Win; d.Cin = Cin;
   d.in2 = static_cast<const op_t*>(in2); d.C2 = C2; d.w = static_cast<const op_t*>(w);
   d.ks = ks; d.stride = stride; d.pad = ks == 3 ? 1 : 0; d.Hout = Hout; d.Wout = Wout; d.Cout = Cout;
@@ -1256,13 +1286,13 @@ int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Ci
              ? fail("pack launch failed")
              : 0;
 }
-int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W, int C0,
+int sgdm_k_groupnorm(void* stream, const void* src0, int src0_is_op, const void* src1, int B, int H, int W, int C0,
                      int C1, const float* gamma, const float* beta, const float* film, int64_t film_stride, int silu,
                      int resample, void* out_op, void* raw_out_op, float* pool_out) {
   return sgdm_k_groupnorm_fused(stream, src0, src0_is_op, src1, B, H, W, C0, C1, gamma, beta, film, film_stride, silu,
                                 resample, nullptr, nullptr, 4, out_op, raw_out_op, pool_out);
 }
-int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const float* src1, int B, int H, int W,
+int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const void* src1, int B, int H, int W,
                            int C0, int C1, const float* gamma, const float* beta, const float* film,
                            int64_t film_stride, int silu, int resample, const float* stats0, const float* stats1,
                            int stat_gran, void* out_op, void* raw_out_op, float* pool_out) {

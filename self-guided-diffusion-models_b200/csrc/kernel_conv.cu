@@ -32,6 +32,7 @@ constexpr int kBarBytes = 512;
 constexpr int kBiasBytes = 2 * 256 * 4;  // bias of the tile's columns, double-buffered by tile parity
 constexpr int kEpiBuf = 4096;            // one epilogue staging buffer: 32 rows x 128 B
 constexpr int kMaxEpiBufs = 6;
+constexpr int kEpi2Bytes = 4 * 2 * 2048;  // staging of the optional 16-bit copy: 32 rows x 64 B, double-buffered per warp
 
 // ---- shared-window accessors (explicit state space: the 1024-byte alignment of the dynamic smem base
 //      goes through an integer and the compiler would otherwise emit generic LD/ST) -------------------
@@ -110,11 +111,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   // 128-byte swizzle of the TMA / UMMA tiles needs.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  // [ring: n_stages x (A | B)] [epilogue staging: 4 warps x epi_bufs x 4 KB] [bias: 2 x 1 KB] [barriers]
+  // [ring: n_stages x (act | weights)] [epilogue staging: 4 warps x epi_bufs x 4 KB]
+  // [16-bit copy staging: 4 warps x 2 x 2 KB, only with a second output] [bias: 2 x 1 KB] [barriers]
   const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;  // [activation slot][tps weight slots]
   uint8_t* ring = smem;
   uint8_t* after_ring = smem + p.n_stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring + 4 * p.epi_bufs * kEpiBuf + kBiasBytes);
+  const int epi2_bytes = p.out2 ? kEpi2Bytes : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring + 4 * p.epi_bufs * kEpiBuf + epi2_bytes + kBiasBytes);
   uint64_t* full = bars;                         // [kMaxStages] TMA -> MMA
   uint64_t* empty = bars + kMaxStages;           // [kMaxStages] MMA -> TMA
   uint64_t* tfull = bars + 2 * kMaxStages;       // [2] MMA -> epilogue
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* bfree = bars + 2 * kMaxStages + 4 + 4 * kMaxEpiBufs;  // [2] all epilogue warps are done with a bias buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 4 * kMaxEpiBufs);
   const uint32_t epi_all = smem_u32(after_ring);
-  const uint32_t sbias_all = epi_all + 4 * p.epi_bufs * kEpiBuf;
+  const uint32_t epi2_all = epi_all + 4 * p.epi_bufs * kEpiBuf;
+  const uint32_t sbias_all = epi2_all + epi2_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,7 +142,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (p.kc2) tma_prefetch_desc(&p.tmA2);
+    if (p.kc2 > p.kc2a) tma_prefetch_desc(&p.tmA2b);
     if (p.epi_mode != 0) tma_prefetch_desc(&p.tmOut);
+    if (p.out2) tma_prefetch_desc(&p.tmOut2);
     if (p.res_mode == 1) tma_prefetch_desc(&p.tmRes);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
@@ -212,8 +218,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             kb0 = p.taps * p.kc1 + cc;
             if (!skip_a) {
               for (int t = 0; t < ntap; ++t) {
-                if (kCtas == 2) tma_load_4d_pair(&p.tmA2, &full[stage], act_dst + t * p.act_tx, (cc + t) * 64, 0, y0, img);
-                else tma_load_4d(&p.tmA2, &full[stage], act_dst + t * p.act_tx, (cc + t) * 64, 0, y0, img);
+                // the skip source may be a channel concat of two tensors: [kc2a chunks of tmA2 | rest of tmA2b]
+                const CUtensorMap* tm2 = (cc + t) < p.kc2a ? &p.tmA2 : &p.tmA2b;
+                const int c2 = (cc + t) < p.kc2a ? (cc + t) : (cc + t) - p.kc2a;
+                if (kCtas == 2) tma_load_4d_pair(tm2, &full[stage], act_dst + t * p.act_tx, c2 * 64, 0, y0, img);
+                else tma_load_4d(tm2, &full[stage], act_dst + t * p.act_tx, c2 * 64, 0, y0, img);
               }
             }
           }
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int i = 0; i < n_chunks; ++i, ++g) {
           const uint32_t b = tma_res ? (g % NB) : (g & 1);
           const uint32_t baddr = ebuf0 + b * kEpiBuf;
+          const uint32_t b2addr = epi2_all + (wq * 2 + (g & 1)) * 2048;  // 16-bit copy tile (second output)
           const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
           const int col0 = p.swap_ab ? tile_col0 : tile_col0 + cpc * i;
           // the buffer written next (by the residual load for chunk g+NB-2, or by this chunk when there is
@@ -455,6 +465,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) sts32(baddr + j * 128 + (((lane_chunk ^ (j & 7)) << 4) | lane_off), val[j]);
+              if (p.out2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sts16(b2addr + j * 64 + lane * 2, to_op(val[j]));
+              }
             } else {
               tmem_ld_wait();
               SGDM_T(3);
@@ -509,6 +523,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                                      __uint_as_float(v[4 * c + 2]) + bb[c].z, __uint_as_float(v[4 * c + 3]) + bb[c].w);
               if (tma_res || tma_res2) { a.x += rr[c].x; a.y += rr[c].y; a.z += rr[c].z; a.w += rr[c].w; }
               sts128(rowaddr + ((c ^ x7) << 4), a);
+              bb[c] = a;  // kept for the 16-bit copy
+            }
+            if (p.out2) {
+              // 32 rows x 64 B, 64-byte swizzle: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+              const uint32_t row2 = b2addr + lane * 64;
+              const uint32_t x3 = (lane >> 1) & 3;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 lo = bb[2 * j], hi = bb[2 * j + 1];
+                sts128u(row2 + ((j ^ x3) << 4),
+                        make_uint4(pack_op2(lo.x, lo.y), pack_op2(lo.z, lo.w), pack_op2(hi.x, hi.y), pack_op2(hi.z, hi.w)));
+              }
             }
             SGDM_T(4);
             if (p.stats) {
@@ -612,6 +638,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.tmOut, baddr, col0, row0);
+            if (p.out2) tma_store_2d(&p.tmOut2, b2addr, col0, row0);  // same bulk group: one wait covers both
             bulk_commit();
           }
           SGDM_T(6);
@@ -680,8 +707,8 @@ static int encode_nhwc(CUtensorMap* tm, const op_t* base, int B, int H, int W, i
   return 0;
 }
 
-// row-major [rows, cols] matrix, box = box_rows rows x box_cols columns (128 bytes when `swizzle` is on)
-static int encode_matrix(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, bool swizzle,
+// row-major [rows, cols] matrix, box = box_rows rows x box_cols columns; swizzle = 0 | 64 | 128 (= the box row bytes)
+static int encode_matrix(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, int swizzle,
                          char* err, int errlen, int box_rows = 32) {
   auto fn = get_encode_fn();
   if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return 1; }
@@ -692,7 +719,8 @@ static int encode_matrix(CUtensorMap* tm, const void* base, bool f32, long rows,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : SGDM_TMA_DTYPE, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled(matrix %ld x %d, es %d, box %d) failed: %d", rows, cols, es, box_cols, (int)r);
@@ -706,7 +734,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   out->desc = d;
   ConvKernelParams& p = out->p;
   auto fail = [&](const char* msg) { snprintf(err, errlen, "conv_prepare: %s", msg); return 1; };
-  if (d.Cin % 64 || (d.in2 && d.C2 % 64)) return fail("channel counts must be multiples of 64");
+  if (d.Cin % 64 || (d.in2 && d.C2 % 64) || (d.in2b && (d.C2b % 64 || !d.in2)))
+    return fail("channel counts must be multiples of 64");
   if (!(d.ks == 1 || d.ks == 3) || !(d.stride == 1 || d.stride == 2)) return fail("unsupported ks/stride");
   if (d.block_n != 16 && (d.block_n % 32 || d.block_n > 256 || d.block_n <= 0)) return fail("bad block_n");
   const int HW = d.Hout * d.Wout;
@@ -742,12 +771,15 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.act_tx = tile_px * 128;
   p.epi_mode = d.out_nchw ? 0 : d.out_f32 ? 1 : 2;
   p.res_mode = d.res ? d.res_mode : 0;
-  const int budget = kSmemLimit - kBarBytes - kBiasBytes;
+  if (d.out_op2 && !d.out_f32) return fail("the 16-bit copy (out_op2) accompanies the fp32 output");
+  p.out2 = d.out_op2 ? 1 : 0;
+  const int budget = kSmemLimit - kBarBytes - kBiasBytes - (p.out2 ? kEpi2Bytes : 0);
   // staging buffers per epilogue warp: 2 without a residual; res_mode 1 adds the in-place residual ring (>= 3,
   // up to 6: in-flight residual bytes per SM must cover HBM latency); res_mode 2 uses four 2 KB slots in two more
   const int min_bufs = p.epi_mode == 0 ? 0 : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
   int n_stages = 0;
-  for (int pass = 0; pass < 2; ++pass) {
+  bool pack_skip = true;  // three skip-source K blocks per halo stage (needs a 48 KB activation slot)
+  for (int pass = 0; pass < 3; ++pass) {
     p.halo = halo ? 1 : 0;
     p.tps = halo ? 3 : 1;
     p.act_tx_halo = (bh + 2) * bw * 128;
@@ -755,13 +787,14 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     p.halo_row_bytes = bw * 128;
     // halo stages have three weight slots: let the fused 1x1-skip K blocks use them three at a time as well
     // (needs room for three plain activation tiles in the activation slot)
-    p.tps2 = (halo && d.in2 && !d.swap_ab) ? 3 : 1;
+    p.tps2 = (halo && d.in2 && !d.swap_ab && pack_skip) ? 3 : 1;
     if (p.tps2 == 3 && p.act_bytes < 3 * p.act_tx) p.act_bytes = 3 * p.act_tx;
     const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;
     const int min_stages = halo ? 2 : (stage_bytes > 32768 ? 3 : 4);
     n_stages = (budget - 4 * min_bufs * kEpiBuf) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
-    if (n_stages < min_stages && halo && d.halo != 1) { halo = false; continue; }  // policy: fall back to per-tap stages
+    if (n_stages < min_stages && p.tps2 == 3) { pack_skip = false; continue; }     // first give up the skip packing,
+    if (n_stages < min_stages && halo && d.halo != 1) { halo = false; continue; }  // then fall back to per-tap stages
     if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
@@ -774,12 +807,13 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
-  out->smem = kBarBytes + kBiasBytes + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
+  out->smem = kSmemLimit - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
   if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen)) return 1;
   if (d.in2) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
+    if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen)) return 1;
   }
-  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
+  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
   const int npad = conv_npad(d.Cout, d.block_n);
   {
     auto fn = get_encode_fn();
@@ -804,7 +838,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.ks = d.ks;
   p.taps = d.ks * d.ks;
   p.kc1 = d.Cin / 64;
-  p.kc2 = d.in2 ? d.C2 / 64 : 0;
+  p.kc2a = d.in2 ? d.C2 / 64 : 0;
+  p.kc2 = p.kc2a + (d.in2 && d.in2b ? d.C2b / 64 : 0);
   p.N_total = d.Cout;
   p.block_n = d.block_n;
   p.n_tiles = npad / d.block_n;
@@ -820,15 +855,17 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.debug = d.debug_flags;
   // epilogue: output / residual tile maps
   if (p.epi_mode == 1) {
-    if (encode_matrix(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
-    if (p.res_mode == 1 && encode_matrix(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, true, err, errlen)) return 1;
+    if (encode_matrix(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
+    if (p.res_mode == 1 && encode_matrix(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
     if (p.res_mode == 2 &&
-        encode_matrix(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, true, err,
+        encode_matrix(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, 128, err,
                       errlen, 16))
       return 1;
+    // second output: the same values rounded to the 16-bit operand type (32 channels = 64-byte rows)
+    if (d.out_op2 && encode_matrix(&p.tmOut2, d.out_op2, false, p.M_total, d.Cout, 32, d.swap_ab ? 0 : 64, err, errlen)) return 1;
   } else if (p.epi_mode == 2) {
     // swap-AB: a warp owns 32 channels = 64-byte rows (dense); normal: 64 channels = 128-byte swizzled rows
-    if (encode_matrix(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, !d.swap_ab, err, errlen)) return 1;
+    if (encode_matrix(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, d.swap_ab ? 0 : 128, err, errlen)) return 1;
   }
   // shared memory: as many K-block stages as fit beside the epilogue staging
   out->pair = pair ? 1 : 0;
@@ -879,7 +916,7 @@ __global__ void conv_naive_kernel(ConvDesc d, int npad) {
   const long m = idx / d.Cout;
   const int HW = d.Hout * d.Wout;
   const int img = m / HW, pix = m % HW, y = pix / d.Wout, x = pix % d.Wout;
-  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 : 0);
+  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
   const op_t* wrow = d.w + static_cast<long>(col) * Ktot;
   float acc = 0.f;
   for (int r = 0; r < d.ks; ++r)
@@ -894,12 +931,17 @@ __global__ void conv_naive_kernel(ConvDesc d, int npad) {
     const op_t* a = d.in2 + m * d.C2;
     const op_t* w = wrow + d.ks * d.ks * d.Cin;
     for (int c = 0; c < d.C2; ++c) acc += from_op(a[c]) * from_op(w[c]);
+    if (d.in2b) {
+      const op_t* a2 = d.in2b + m * d.C2b;
+      for (int c = 0; c < d.C2b; ++c) acc += from_op(a2[c]) * from_op(w[d.C2 + c]);
+    }
   }
   if (d.bias) acc += d.bias[col];
   if (d.res && d.res_mode == 1) acc += d.res[m * d.Cout + col];
   if (d.res && d.res_mode == 2)
     acc += d.res[((static_cast<long>(img) * (d.Hout / 2) + y / 2) * (d.Wout / 2) + x / 2) * d.Cout + col];
   if (d.out_f32) d.out_f32[m * d.Cout + col] = acc;
+  if (d.out_op2) d.out_op2[m * d.Cout + col] = to_op(acc);
   if (d.out_op) d.out_op[m * d.Cout + col] = to_op(acc);
   if (d.out_nchw) d.out_nchw[(static_cast<long>(img) * d.Cout + col) * HW + pix] = acc;
 }

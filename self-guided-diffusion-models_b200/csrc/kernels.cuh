@@ -10,9 +10,9 @@ namespace sgdm {
 // `out_norm(h) * (1 + scale) + shift` (openaimodel.py:312-316), avg_pool2d / nearest
 // upsample of up/down ResBlocks (:253-258,301-306), skip concat th.cat([h, hs.pop()], 1) (:950).
 struct GnDesc {
-  const void* src0 = nullptr;   // NHWC [B, H, W, C0]: fp32, or op_t when src0_is_op (then C1 must be 0)
-  int src0_is_op = 0;
-  const float* src1 = nullptr;  // optional second concat source [B, H, W, C1]
+  const void* src0 = nullptr;   // NHWC [B, H, W, C0]: fp32, or op_t when src0_is_op
+  int src0_is_op = 0;           // applies to BOTH sources; a 16-bit concat (C1 > 0) needs producer statistics (stats0/1)
+  const void* src1 = nullptr;   // optional second concat source [B, H, W, C1]
   int B = 0, H = 0, W = 0, C0 = 0, C1 = 0;
   const float* gamma = nullptr;  // [C0+C1]
   const float* beta = nullptr;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) gn_stats_op_kernel(const op_t* __restrict
 }
 
 struct GnApplyArgs {
-  const void* src0; const float* src1;
+  const void* src0; const void* src1;
   int H, W, C0, C1;
   const float* gamma; const float* beta; const float* film; long film_stride;
   int silu, resample, chunks, ppb, PLa;
@@ -199,7 +199,14 @@ __device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, i
     const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
   } else {
-    const float* p = a.src1 + (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
+    const long off = (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
+    if (kHalfIn) {  // both concat sources are 16-bit
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(static_cast<const op_t*>(a.src1) + off));
+      const float2 p0 = unpack_op2(r.x), p1 = unpack_op2(r.y), p2 = unpack_op2(r.z), p3 = unpack_op2(r.w);
+      v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
+      return;
+    }
+    const float* p = static_cast<const float*>(a.src1) + off;
     const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
   }
@@ -270,12 +277,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   if (a.resample == 0) {
     int pix = p_begin + lane;
     if (kHalfIn) {
-      // 16-bit source (C1 == 0): eight pixels = 8 x 16-byte loads in flight per thread, kept packed
-      const op_t* src = static_cast<const op_t*>(a.src0) + static_cast<long>(n) * HW * C + c;
+      // 16-bit source(s): eight pixels = 8 x 16-byte loads in flight per thread, kept packed.  A thread's
+      // 8-channel slice lies in exactly one of the two concat sources.
+      const bool first = c < a.C0;
+      const long cs = first ? a.C0 : a.C1;
+      const op_t* src = (first ? static_cast<const op_t*>(a.src0) + c : static_cast<const op_t*>(a.src1) + (c - a.C0)) +
+                        static_cast<long>(n) * HW * cs;
       for (; pix + 7 * a.PLa < p_end; pix += 8 * a.PLa) {
         uint4 r[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long>(pix + u * a.PLa) * C));
+        for (int u = 0; u < 8; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long>(pix + u * a.PLa) * cs));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const float2 p0 = unpack_op2(r[u].x), p1 = unpack_op2(r[u].y), p2 = unpack_op2(r[u].z), p3 = unpack_op2(r[u].w);
@@ -357,7 +368,6 @@ int gn_chunks_for(int B, int HW, int C) {
 static int gn_check(const GnDesc& d) {
   const int C = d.C0 + d.C1, HW = d.H * d.W;
   if (C % 32 || C > 1024 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;
-  if (d.src0_is_op && d.C1) return 1;
   return 0;
 }
 
@@ -373,7 +383,7 @@ int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
 }
 
 int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
-  if (gn_check(d)) return 1;
+  if (gn_check(d) || (d.src0_is_op && d.C1)) return 1;  // a 16-bit concat only comes with producer statistics
   const int C = d.C0 + d.C1, HW = d.H * d.W;
   if (d.src0_is_op) {
     const int C8 = C / 8;
@@ -383,7 +393,8 @@ int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
   } else {
     const int C4 = C / 4;
     const int PL = 256 / C4 > 0 ? 256 / C4 : 1;
-    gn_stats_kernel<false><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, d.src1, HW, d.C0, d.C1, d.chunks, PL, d.partial);
+    gn_stats_kernel<false><<<dim3(d.chunks, d.B), C4 * PL, 0, s>>>(d.src0, static_cast<const float*>(d.src1), HW, d.C0, d.C1,
+                                                                   d.chunks, PL, d.partial);
   }
   return SGDM_LAUNCH_OK();
 }

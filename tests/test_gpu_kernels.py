@@ -191,10 +191,11 @@ def test_conv_epilogue_groupnorm_stats(L, case):
     stats = torch.full((nblk, Cout // gran, 2), float("nan"), device="cuda")
     o32 = torch.full((B, H, W, Cout), float("nan"), device="cuda") if out == "f32" else None
     oop = torch.zeros((B, H, W, Cout), dtype=L._op, device="cuda") if out == "op" else None
+    copy16 = torch.zeros((B, H, W, Cout), dtype=L._op, device="cuda") if out == "f32" else None  # second output
     L.sgdm_debug_set_conv_pair(1 if B % 2 else 0)  # odd-batch cases run as CTA pairs, the others as single CTAs
     try:
         ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res), res_mode,
-                                  P(o32), P(oop), None, bn, 0, P(stats), gran))
+                                  P(o32), P(oop), None, bn, 0, P(stats), gran, P(copy16), None, 0))
     finally:
         L.sgdm_debug_set_conv_pair(-1)
     torch.cuda.synchronize()
@@ -204,6 +205,8 @@ def test_conv_epilogue_groupnorm_stats(L, case):
     ref = ref.permute(0, 2, 3, 1).reshape(M, Cout)
     got = (o32 if o32 is not None else oop).float().reshape(M, Cout)
     assert relerr(got, ref) < (2e-3 if out == "op" else 2e-5)
+    if copy16 is not None:  # the 16-bit copy is exactly the rounded fp32 output
+        assert torch.equal(copy16.reshape(M, Cout), o32.reshape(M, Cout).to(L._op))
     # the statistics describe the values the kernel WROTE (for a 16-bit output: the rounded values)
     pad = nblk * 32 - M
     gotp = torch.cat([got, torch.zeros(pad, Cout, device="cuda")]) if pad else got
@@ -213,6 +216,33 @@ def test_conv_epilogue_groupnorm_stats(L, case):
     e = relerr(stats, want)
     print(f"[conv stats {note}] rel_l2={e:.3e}")
     assert e < 1e-5
+
+
+def test_conv_skip_source_from_two_tensors(L):
+    """Fused 1x1 skip whose source is the channel concat of two 16-bit tensors (never materialised)."""
+    B, H, W, Cin, Cout, Ca, Cb = 3, 16, 16, 128, 256, 192, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    sa = torch.randn(B, H, W, Ca, device="cuda", generator=g).to(L._op)
+    sb = torch.randn(B, H, W, Cb, device="cuda", generator=g).to(L._op)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(Cin * 9)
+    ws = torch.randn(Cout, Ca + Cb, 1, 1, device="cuda", generator=g) / math.sqrt(Ca + Cb)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    wp, bn = pack_weight(L, w, ws)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=1)
+    ref = ref + F.conv2d(torch.cat([sa, sb], -1).float().permute(0, 3, 1, 2), ws.to(L._op).float())
+    for halo in (0, 1):
+        o32 = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+        L.sgdm_debug_set_conv_halo(halo)
+        try:
+            ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, P(sa), Ca, P(wp), 3, 1, H, W, Cout, P(bias), None, 0,
+                                      P(o32), None, None, bn, 0, None, 4, None, P(sb), Cb))
+        finally:
+            L.sgdm_debug_set_conv_halo(-1)
+        torch.cuda.synchronize()
+        e = relerr(o32.permute(0, 3, 1, 2), ref)
+        print(f"[conv skip source = concat of two tensors, halo={halo}] rel_l2={e:.3e}")
+        assert e < 2e-5
 
 
 def torch_partial_stats(t, gran):
@@ -230,6 +260,8 @@ FUSED_GN_CASES = [
     (2, 8, 8, 64, 0, 2, True, "C=64 (2 ch/group), 16-bit source"),
     (1, 64, 64, 128, 0, 4, True, "64x64 16-bit source (deep-unroll path)"),
     (2, 16, 16, 512, 512, 4, False, "concat 1024"),
+    (2, 16, 16, 256, 128, 4, True, "16-bit concat 256+128 (both sources are epilogue copies)"),
+    (3, 8, 8, 128, 64, 2, True, "16-bit concat 192, gran 2"),
 ]
 
 
@@ -245,11 +277,13 @@ def test_groupnorm_from_epilogue_stats(L, case):
     st0 = torch_partial_stats(a, gran)  # statistics of the unrounded values, as the producing conv emits them
     st1 = torch_partial_stats(b, gran) if C1 else None
     src = a.to(L._op) if half_in else a
+    if half_in and C1:
+        b = b.to(L._op)
     out = torch.zeros(B, H, W, C, dtype=L._op, device="cuda")
     ck(L, L.sgdm_k_groupnorm_fused(S(), P(src), 1 if half_in else 0, P(b), B, H, W, C0, C1, P(gamma), P(beta), None, 0,
                                    1, 0, P(st0), P(st1), gran, P(out), None, None))
     torch.cuda.synchronize()
-    x = torch.cat([a, b], -1) if C1 else a
+    x = torch.cat([a, b.float()], -1) if C1 else a
     ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
     e = relerr(out.float().permute(0, 3, 1, 2), ref)
     print(f"[gn fused stats {note}] rel_l2={e:.3e}")
