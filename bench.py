@@ -43,6 +43,33 @@ CFG = dict(kind="unet_fast", image_size=64, in_channels=3, out_channels=3, model
            condition_method="label", layout_dim=0, context_dim=None, cond_token_num=0, scale_type="imagen")
 
 
+def ncu_conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch, from the committed `ncu --set full`
+    capture of one step (profiles/*ncu_conv_gemm*.csv, written by tools/ncu_summary.py); None if absent."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_conv_gemm*.csv")))
+    if not files:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        hdr = rows[0]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot, n = 0.0, 0
+        for r in rows[1:]:
+            b = 0.0
+            for name in ("dram_read", "dram_write"):
+                j = next(i for i, h in enumerate(hdr) if h.startswith(name))
+                u = hdr[j].split("[")[-1].rstrip("]")
+                b += float(r[j]) * unit.get(u, 1.0)
+            tot += b
+            n += 1
+        return (tot / n if n else None), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -176,7 +203,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sgdm_b200", choices=["sgdm_b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline steps (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-launch profile of one step to this JSON file")
@@ -371,8 +398,11 @@ def main():
                     conv[q] += fam[k_][q]
         total_ms = sum(f["ms"] for f in fam.values())
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        traffic, traffic_src = ncu_conv_traffic()
         roof = dict(bound="tensor", kernel="conv_gemm_kernel (tcgen05 implicit GEMM: conv3x3 + 1x1/linear GEMMs)",
-                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None,
+                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic,
+                    traffic_unit="bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step)",
+                    traffic_source=traffic_src, algorithmic_bytes_per_launch=(fam.get("conv3x3", {}).get("bytes", 0.0) + fam.get("gemm1x1", {}).get("bytes", 0.0)) / max(conv["launches"], 1),
                     peak_source=pk["src"], launches_per_step=conv["launches"],
                     avg_launch_ms=conv["ms"] / max(conv["launches"], 1),
                     flops_per_step=conv["flops"], share_of_step=conv["ms"] / total_ms if total_ms else None,
@@ -384,7 +414,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cs = args.cpu_steps or 8
+        cs = args.cpu_steps or 30  # ~10-30 s of host work at batch 4
         r = cpu_reference_arm(cs, 1, args.cpu_batch)
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                    ms_per_step_at_sample_batch=r["ms_per_step"])

@@ -89,6 +89,12 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u);
 
+/* Two-stream mode of sgdm_forward_guided (default: environment SGDM_SPLIT_STREAMS, else off): the conditional
+ * and the unconditional rows run as two plans on `stream` and on an engine-owned side stream (forked / joined
+ * with events, no host synchronisation), so that HBM-bound kernels of one half overlap tensor-bound kernels of
+ * the other.  Same values as the single-plan mode.  Switching drops the cached plans. */
+int sgdm_set_split_streams(sgdm_handle h, int on);
+
 /* eps = (1-w) eps_u + w eps_c (imagen) | (1+w) eps_c - w eps_u (cfg); w scalar (a double, like the
  * Python number the reference multiplies with: 1-w is formed in double, then rounded to fp32), or
  * per sample when w_per_sample != NULL ([B] fp32 device; 1-w is then an fp32 op). */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "sgdm_set_timestep_freqs": (_i, [_vp, _vp, _i]),
     "sgdm_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgdm_forward_guided": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "sgdm_set_split_streams": (_i, [_vp, _i]),
     "sgdm_mix": (_i, [_vp, _vp, _vp, _d, _vp, _i, _vp, _i, _i64]),
     "sgdm_ddim_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64]),
     "sgdm_ddpm_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64]),

@@ -55,6 +55,7 @@ struct ConvDesc {
   int pair = -1;
   // halo mode (one activation load per horizontal tap, shared by the three vertical taps): -1 policy, 0 off, 1 on
   int halo = -1;
+  int smem_reserve = 0;         // shared-memory bytes to leave free per SM (two-stream mode: co-resident GroupNorm CTAs)
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
   int debug_stages = 0;         // tuning only: cap the K-block ring depth
   int debug_flags = 0;          // tuning only: 1 = stop re-loading the activation operand, 2 = the weight operand (WRONG results)

@@ -143,11 +143,20 @@ struct sgdm_engine {
   int* ci_map_first = nullptr;
   std::vector<void*> owned;
   bool device_ready = false;
-  std::map<int, std::unique_ptr<Plan>> plans;
+  std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + variant
+  // Two-stream mode of the guided forward: the conditional and the unconditional half run as two independent
+  // plans on two streams, so that the HBM-bound kernels of one half (GroupNorm, attention) overlap the
+  // tensor-bound conv kernels of the other half on the same SMs.
+  bool split_streams = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profiling = false;
   Plan* last_profiled = nullptr;
 
   ~sgdm_engine() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     plans.clear();
     for (void* p : owned) cudaFree(p);
   }
@@ -612,6 +621,7 @@ struct Builder {
   // fp32 tensor.  Measured on B200 (config 2, batch 256): gn_apply 9.7 -> 8.3 ms, but the epilogue-bound convs
   // lose about as much and eps rel-L2 rises 1.9e-3 -> 2.2e-3 (DDIM-10 PSNR 43.7 -> 41.3 dB): off by default.
   bool use16 = getenv("SGDM_GN16") != nullptr && atoi(getenv("SGDM_GN16")) != 0;
+  int smem_reserve = 0;
   void attach_outputs(Act& o, size_t rows, ConvDesc& c, bool allow16 = true) {
     o.has_stats = stats_ok(o.H, o.W);
     o.stats = stats_alloc(rows, o.C, o.H, o.W);
@@ -633,6 +643,7 @@ struct Builder {
     d.stat_gran = stat_gran();
     d.pair = g_conv_pair;
     d.halo = g_conv_halo;
+    d.smem_reserve = smem_reserve;
     // A/B switches for whole-step timing (same process image, same box): SGDM_CONV_HALO / SGDM_CONV_PAIR = 0 | 1
     if (const char* ev = getenv("SGDM_CONV_HALO")) d.halo = atoi(ev) ? -1 : 0;
     if (const char* ev = getenv("SGDM_CONV_PAIR")) d.pair = atoi(ev) ? -1 : 0;
@@ -994,18 +1005,19 @@ struct Builder {
   }
 };
 
-int get_plan(sgdm_engine* e, int Bp, Plan** out) {
-  auto it = e->plans.find(Bp);
+int get_plan(sgdm_engine* e, int Bp, Plan** out, int variant = 0) {
+  auto it = e->plans.find(2 * Bp + variant);
   if (it != e->plans.end()) {
     *out = it->second.get();
     return 0;
   }
   // keep at most 3 plans alive (workspace is large)
-  while (e->plans.size() >= 3) e->plans.erase(e->plans.begin());
+  while (e->plans.size() >= 4) e->plans.erase(e->plans.begin());
   std::unique_ptr<Plan> plan(new Plan());
   plan->Bp = Bp;
   Builder b;
   b.e = e; b.plan = plan.get(); b.Bp = Bp;
+  b.smem_reserve = e->split_streams ? 4096 : 0;
   b.dry = true;
   b.build();
   size_t total = b.stream_bytes;
@@ -1026,7 +1038,7 @@ int get_plan(sgdm_engine* e, int Bp, Plan** out) {
   b.build();
   if (b.err) return 1;
   *out = plan.get();
-  e->plans[Bp] = std::move(plan);
+  e->plans[2 * Bp + variant] = std::move(plan);
   return 0;
 }
 
@@ -1075,6 +1087,48 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
   return 0;
 }
 
+// Guided forward in two-stream mode: plan A = the B conditional rows on the caller's stream, plan B = the B
+// unconditional rows on the engine's side stream; their launches are issued alternately so both queues stay
+// full.  GroupNorm is per sample and the conv / attention kernels are batch-invariant, so the values are the
+// ones of the single 2B-row plan (tests/test_gpu_e2e.py checks bit equality).
+int run_forward_split(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t, const float* cond,
+                      const float* layout, int B, Plan** plan_c, Plan** plan_u) {
+  if (!e->device_ready) return fail("no parameters loaded");
+  for (auto& p : e->params)
+    if (!p.loaded) return fail("parameter %s was never loaded", p.name.c_str());
+  if (e->cfg.cond_dim > 0 && cond == nullptr) return fail("cond is required (cond_dim=%d)", e->cfg.cond_dim);
+  if (e->cfg.layout_dim > 0 && layout == nullptr) return fail("layout is required (layout_dim=%d)", e->cfg.layout_dim);
+  if (!e->side) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  Plan *pa = nullptr, *pb = nullptr;
+  if (get_plan(e, B, &pa, 0) || get_plan(e, B, &pb, 1)) return 1;
+  CUDA_TRY(cudaEventRecord(e->ev_fork, s));  // the inputs (and the previous step's consumers of eps) are on s
+  CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  CUDA_TRY(cudaMemsetAsync(pa->drop, 0, B, s));
+  CUDA_TRY(cudaMemsetAsync(pb->drop, 1, B, e->side));
+  PrepDesc pda = pa->prep, pdb = pb->prep;
+  pda.x = pdb.x = x; pda.t = pdb.t = reinterpret_cast<const long long*>(t);
+  pda.cond = pdb.cond = cond; pda.layout = pdb.layout = layout; pda.B = pdb.B = B;
+  g_launches += 4;
+  if (prep_launch(pda, s) || prep_launch(pdb, e->side)) return fail("prep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const size_t n = pa->ops.size();
+  if (pb->ops.size() != n) return fail("internal: plan variants differ");
+  for (size_t i = 0; i < n; ++i) {
+    if (pa->ops[i](s) || pb->ops[i](e->side)) {
+      cudaError_t ce = cudaGetLastError();
+      return fail("launch %zu (%s) of %zu failed: %s", i, pa->meta[i].kind, n, cudaGetErrorString(ce));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e->ev_join, e->side));
+  CUDA_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+  *plan_c = pa;
+  *plan_u = pb;
+  return 0;
+}
+
 }  // namespace
 
 // ======================================================================================= C ABI
@@ -1116,6 +1170,7 @@ int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   if (!cfg || !out) return fail("null argument");
   std::unique_ptr<sgdm_engine> e(new sgdm_engine());
   e->cfg = *cfg;
+  if (const char* ev = getenv("SGDM_SPLIT_STREAMS")) e->split_streams = atoi(ev) != 0;
   if (build_topology(e.get())) return 1;
   *out = e.release();
   return 0;
@@ -1187,8 +1242,21 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
   CUDA_TRY(cudaMemcpyAsync(eps_out, plan->eps, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
+int sgdm_set_split_streams(sgdm_handle h, int on) {
+  if (!h) return fail("null handle");
+  if ((on != 0) != h->split_streams) h->plans.clear();  // plans are laid out for one mode
+  h->split_streams = on != 0;
+  return 0;
+}
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u) {
+  if (h->split_streams && !h->profiling) {
+    Plan *pc = nullptr, *pu = nullptr;
+    if (run_forward_split(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, B, &pc, &pu)) return 1;
+    *eps_c = pc->eps;
+    *eps_u = pu->eps;
+    return 0;
+  }
   Plan* plan = nullptr;
   if (run_forward(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, nullptr, B, 2 * B, &plan)) return 1;
   const size_t n = static_cast<size_t>(B) * h->cfg.out_channels * h->cfg.image_size * h->cfg.image_size;

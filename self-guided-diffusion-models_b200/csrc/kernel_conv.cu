@@ -443,50 +443,61 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           // All shared-memory loads of a phase are issued back to back before their first use (the accessors
           // are volatile asm: the compiler keeps their order, so a load placed after a store would wait for it).
           float sg[4] = {0.f, 0.f, 0.f, 0.f}, qg[4] = {0.f, 0.f, 0.f, 0.f};
+          // (each chunk is walked in two 16-column halves: halves the live registers of the accumulator /
+          //  bias / residual values, which is what bounds the register count of the whole kernel)
           if (p.swap_ab) {
-            // thread = output channel, registers = 32 consecutive pixels
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + 32 * i, v);
-            float val[32];
-            if (p.epi_mode == 1) {
-              const uint32_t lane_off = (lane & 3) << 2;
-              const uint32_t lane_chunk = lane >> 2;
-              float rr[32];
-              if (tma_res) {
+            // thread = output channel, registers = 16 consecutive pixels per half
+            float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t lane_off = (lane & 3) << 2;
+            const uint32_t lane_chunk = lane >> 2;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rr[j] = lds32(baddr + j * 128 + (((lane_chunk ^ (j & 7)) << 4) | lane_off));
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t v[32];
+              tmem_ld_32x16(taddr + 32 * i + 16 * hf, v);
+              float val[16];
+              if (p.epi_mode == 1) {
+                float rr[16];
+                if (tma_res) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const int px = 16 * hf + j;
+                    rr[j] = lds32(baddr + px * 128 + (((lane_chunk ^ (px & 7)) << 4) | lane_off));
+                  }
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  val[j] = __uint_as_float(v[j]) + bias_ch;
+                  if (tma_res) val[j] += rr[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int px = 16 * hf + j;
+                  sts32(baddr + px * 128 + (((lane_chunk ^ (px & 7)) << 4) | lane_off), val[j]);
+                }
+                if (p.out2) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) sts16(b2addr + (16 * hf + j) * 64 + lane * 2, to_op(val[j]));
+                }
+              } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const op_t h = to_op(__uint_as_float(v[j]) + bias_ch);
+                  sts16(baddr + (16 * hf + j) * 64 + lane * 2, h);
+                  val[j] = from_op(h);
+                }
               }
-              tmem_ld_wait();
-              SGDM_T(3);
+              if (p.stats) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                val[j] = __uint_as_float(v[j]) + bias_ch;
-                if (tma_res) val[j] += rr[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sts32(baddr + j * 128 + (((lane_chunk ^ (j & 7)) << 4) | lane_off), val[j]);
-              if (p.out2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sts16(b2addr + j * 64 + lane * 2, to_op(val[j]));
-              }
-            } else {
-              tmem_ld_wait();
-              SGDM_T(3);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const op_t h = to_op(__uint_as_float(v[j]) + bias_ch);
-                sts16(baddr + j * 64 + lane * 2, h);
-                val[j] = from_op(h);
+                for (int j = 0; j < 16; ++j) {
+                  s4[j & 3] += val[j];
+                  q4[j & 3] += val[j] * val[j];
+                }
               }
             }
             SGDM_T(4);
             if (p.stats) {
-              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                s4[j & 3] += val[j];
-                q4[j & 3] += val[j] * val[j];
-              }
               sg[0] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
               qg[0] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
               sg[0] += __shfl_xor_sync(0xffffffffu, sg[0], 1);
@@ -500,55 +511,59 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 p.stats[static_cast<long>(row0 >> 5) * stat_ld + (ch >> sg_shift)] = make_float2(sg[0], qg[0]);
             }
           } else if (p.epi_mode == 1) {
-            // thread = output row, registers = 32 consecutive channels (8 x 16-byte chunks, XOR-swizzled)
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + 32 * i, v);
+            // thread = output row, 32 consecutive channels = 8 x 16-byte chunks (XOR-swizzled), 4 per half
             const uint32_t rowaddr = baddr + lane * 128;
-            float4 bb[8], rr[8];
+            const uint32_t row2 = b2addr + lane * 64;  // 16-bit copy: 64-byte rows, chunk j at j ^ ((row >> 1) & 3)
+            const uint32_t x3 = (lane >> 1) & 3;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) bb[c] = lds128(sbias + (32 * i + 4 * c) * 4);
-            if (tma_res) {
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t v[32];
+              tmem_ld_32x16(taddr + 32 * i + 16 * hf, v);
+              float4 bb[4], rr[4];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) rr[c] = lds128(rowaddr + ((c ^ x7) << 4));
-            } else if (tma_res2) {
-              const uint32_t ra = res_slot_addr(g % NB) + s_r * 128;
+              for (int c = 0; c < 4; ++c) bb[c] = lds128(sbias + (32 * i + 16 * hf + 4 * c) * 4);
+              if (tma_res) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) rr[c] = lds128(ra + ((c ^ (s_r & 7)) << 4));
-            }
-            tmem_ld_wait();
-            SGDM_T(3);
+                for (int c = 0; c < 4; ++c) rr[c] = lds128(rowaddr + (((4 * hf + c) ^ x7) << 4));
+              } else if (tma_res2) {
+                const uint32_t ra = res_slot_addr(g % NB) + s_r * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float4 a = make_float4(__uint_as_float(v[4 * c]) + bb[c].x, __uint_as_float(v[4 * c + 1]) + bb[c].y,
-                                     __uint_as_float(v[4 * c + 2]) + bb[c].z, __uint_as_float(v[4 * c + 3]) + bb[c].w);
-              if (tma_res || tma_res2) { a.x += rr[c].x; a.y += rr[c].y; a.z += rr[c].z; a.w += rr[c].w; }
-              sts128(rowaddr + ((c ^ x7) << 4), a);
-              bb[c] = a;  // kept for the 16-bit copy
-            }
-            if (p.out2) {
-              // 32 rows x 64 B, 64-byte swizzle: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
-              const uint32_t row2 = b2addr + lane * 64;
-              const uint32_t x3 = (lane >> 1) & 3;
+                for (int c = 0; c < 4; ++c) rr[c] = lds128(ra + (((4 * hf + c) ^ (s_r & 7)) << 4));
+              }
+              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 lo = bb[2 * j], hi = bb[2 * j + 1];
-                sts128u(row2 + ((j ^ x3) << 4),
-                        make_uint4(pack_op2(lo.x, lo.y), pack_op2(lo.z, lo.w), pack_op2(hi.x, hi.y), pack_op2(hi.z, hi.w)));
+              for (int c = 0; c < 4; ++c) {
+                float4 a = make_float4(__uint_as_float(v[4 * c]) + bb[c].x, __uint_as_float(v[4 * c + 1]) + bb[c].y,
+                                       __uint_as_float(v[4 * c + 2]) + bb[c].z, __uint_as_float(v[4 * c + 3]) + bb[c].w);
+                if (tma_res || tma_res2) { a.x += rr[c].x; a.y += rr[c].y; a.z += rr[c].z; a.w += rr[c].w; }
+                sts128(rowaddr + (((4 * hf + c) ^ x7) << 4), a);
+                bb[c] = a;  // kept for the 16-bit copy
+              }
+              if (p.out2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const float4 lo = bb[2 * j], hi = bb[2 * j + 1];
+                  sts128u(row2 + (((2 * hf + j) ^ x3) << 4),
+                          make_uint4(pack_op2(lo.x, lo.y), pack_op2(lo.z, lo.w), pack_op2(hi.x, hi.y), pack_op2(hi.z, hi.w)));
+                }
               }
             }
             SGDM_T(4);
             if (p.stats) {
               __syncwarp();
-              float4 a[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int row = 4 * k + rg;
-                a[k] = lds128(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
-              }
+              for (int kh = 0; kh < 2; ++kh) {
+                float4 a[4];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                sg[0] += a[k].x + a[k].y; qg[0] += a[k].x * a[k].x + a[k].y * a[k].y;
-                sg[1] += a[k].z + a[k].w; qg[1] += a[k].z * a[k].z + a[k].w * a[k].w;
+                for (int k = 0; k < 4; ++k) {
+                  const int row = 4 * (4 * kh + k) + rg;
+                  a[k] = lds128(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  sg[0] += a[k].x + a[k].y; qg[0] += a[k].x * a[k].x + a[k].y * a[k].y;
+                  sg[1] += a[k].z + a[k].w; qg[1] += a[k].z * a[k].z + a[k].w * a[k].w;
+                }
               }
               if (p.stat_gran == 4) { sg[0] += sg[1]; qg[0] += qg[1]; }
 #pragma unroll
@@ -567,48 +582,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
             }
           } else {
-            // 16-bit output: thread = output row, 64 consecutive channels = 8 x 16-byte chunks of 8
+            // 16-bit output: thread = output row, 64 consecutive channels = 8 x 16-byte chunks of 8, 2 per quarter
             const uint32_t rowaddr = baddr + lane * 128;
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(taddr + 64 * i, v0);
-            tmem_ld_32x32(taddr + 64 * i + 32, v1);
 #pragma unroll
-            for (int hsel = 0; hsel < 2; ++hsel) {
-              float4 bb[8];
+            for (int qt = 0; qt < 4; ++qt) {
+              uint32_t v[32];
+              tmem_ld_32x16(taddr + 64 * i + 16 * qt, v);
+              float4 bb[4];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) bb[c] = lds128(sbias + (64 * i + 32 * hsel + 4 * c) * 4);
-              if (hsel == 0) {
-                tmem_ld_wait();
-                SGDM_T(3);
-              }
-              const uint32_t(&v)[32] = hsel == 0 ? v0 : v1;
+              for (int c = 0; c < 4; ++c) bb[c] = lds128(sbias + (64 * i + 16 * qt + 4 * c) * 4);
+              tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
+              for (int c = 0; c < 2; ++c) {
                 const float4 b0 = bb[2 * c], b1 = bb[2 * c + 1];
                 const uint4 h = make_uint4(
                     pack_op2(__uint_as_float(v[8 * c]) + b0.x, __uint_as_float(v[8 * c + 1]) + b0.y),
                     pack_op2(__uint_as_float(v[8 * c + 2]) + b0.z, __uint_as_float(v[8 * c + 3]) + b0.w),
                     pack_op2(__uint_as_float(v[8 * c + 4]) + b1.x, __uint_as_float(v[8 * c + 5]) + b1.y),
                     pack_op2(__uint_as_float(v[8 * c + 6]) + b1.z, __uint_as_float(v[8 * c + 7]) + b1.w));
-                sts128u(rowaddr + (((4 * hsel + c) ^ x7) << 4), h);
+                sts128u(rowaddr + (((2 * qt + c) ^ x7) << 4), h);
               }
             }
             SGDM_T(4);
             if (p.stats) {
               __syncwarp();
-              uint4 hh[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int row = 4 * k + rg;
-                hh[k] = lds128u(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
-              }
+              for (int kh = 0; kh < 2; ++kh) {
+                uint4 hh[4];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float2 p0 = unpack_op2(hh[k].x), p1 = unpack_op2(hh[k].y), p2 = unpack_op2(hh[k].z), p3 = unpack_op2(hh[k].w);
-                sg[0] += p0.x + p0.y; qg[0] += p0.x * p0.x + p0.y * p0.y;
-                sg[1] += p1.x + p1.y; qg[1] += p1.x * p1.x + p1.y * p1.y;
-                sg[2] += p2.x + p2.y; qg[2] += p2.x * p2.x + p2.y * p2.y;
-                sg[3] += p3.x + p3.y; qg[3] += p3.x * p3.x + p3.y * p3.y;
+                for (int k = 0; k < 4; ++k) {
+                  const int row = 4 * (4 * kh + k) + rg;
+                  hh[k] = lds128u(baddr + row * 128 + ((cc ^ (row & 7)) << 4));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 p0 = unpack_op2(hh[k].x), p1 = unpack_op2(hh[k].y), p2 = unpack_op2(hh[k].z), p3 = unpack_op2(hh[k].w);
+                  sg[0] += p0.x + p0.y; qg[0] += p0.x * p0.x + p0.y * p0.y;
+                  sg[1] += p1.x + p1.y; qg[1] += p1.x * p1.x + p1.y * p1.y;
+                  sg[2] += p2.x + p2.y; qg[2] += p2.x * p2.x + p2.y * p2.y;
+                  sg[3] += p3.x + p3.y; qg[3] += p3.x * p3.x + p3.y * p3.y;
+                }
               }
               if (p.stat_gran == 4) {
                 sg[0] += sg[1]; qg[0] += qg[1];
@@ -773,7 +786,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.res_mode = d.res ? d.res_mode : 0;
   if (d.out_op2 && !d.out_f32) return fail("the 16-bit copy (out_op2) accompanies the fp32 output");
   p.out2 = d.out_op2 ? 1 : 0;
-  const int budget = kSmemLimit - kBarBytes - kBiasBytes - (p.out2 ? kEpi2Bytes : 0);
+  // smem_reserve: bytes left free on the SM so that small CTAs of a concurrent stream (GroupNorm) can co-reside
+  const int smem_cap = kSmemLimit - (d.smem_reserve > 0 ? d.smem_reserve : 0);
+  const int budget = smem_cap - kBarBytes - kBiasBytes - (p.out2 ? kEpi2Bytes : 0);
   // staging buffers per epilogue warp: 2 without a residual; res_mode 1 adds the in-place residual ring (>= 3,
   // up to 6: in-flight residual bytes per SM must cover HBM latency); res_mode 2 uses four 2 KB slots in two more
   const int min_bufs = p.epi_mode == 0 ? 0 : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
@@ -807,7 +822,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
-  out->smem = kSmemLimit - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
+  out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
   if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen)) return 1;
   if (d.in2) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;

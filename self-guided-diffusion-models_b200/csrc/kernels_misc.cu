@@ -219,8 +219,8 @@ __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
 // Pass 2: normalise + affine (+FiLM) (+SiLU), write op_t NHWC, optionally pooled / upsampled.
 // Thread = (8-channel slice cg, pixel lane): the folded per-channel scale/offset live in
 // registers for the whole block; the block walks `ppb` pixels.
-template <bool kHalfIn>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
+template <bool kHalfIn, int kResample>
+__global__ void __launch_bounds__(256, kResample == 0 ? 4 : 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
       y[j] = a.silu ? silu(t) : t;
     }
   };
-  const int Ho = a.resample == 1 ? a.H >> 1 : a.H, Wo = a.resample == 1 ? a.W >> 1 : a.W;
+  const int Ho = kResample == 1 ? a.H >> 1 : a.H, Wo = kResample == 1 ? a.W >> 1 : a.W;
   const int n_iter = Ho * Wo;  // pooled: output pixels; otherwise input pixels
   const int p_begin = blockIdx.x * a.ppb;
   const int p_end = min(p_begin + a.ppb, n_iter);
-  if (a.resample == 0) {
+  if (kResample == 0) {
     int pix = p_begin + lane;
     if (kHalfIn) {
       // 16-bit source(s): eight pixels = 8 x 16-byte loads in flight per thread, kept packed.  A thread's
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
       store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y);
       if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v);
     }
-  } else if (a.resample == 1) {
+  } else if (kResample == 1) {
     for (int pix = p_begin + lane; pix < p_end; pix += a.PLa) {
       const int yo = pix / Wo, xo = pix - yo * Wo;
       float v[4][8], y[8], acc[8], racc[8];
@@ -414,8 +414,16 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
                 d.silu, d.resample, d.chunks, ppb, PLa, d.partial, gn_fused(d) ? d.final : nullptr, d.out, d.raw_out,
                 d.pool_out};
   const dim3 grid((n_iter + ppb - 1) / ppb, d.B);
-  if (d.src0_is_op) gn_apply_kernel<true><<<grid, C8 * PLa, 0, s>>>(a);
-  else gn_apply_kernel<false><<<grid, C8 * PLa, 0, s>>>(a);
+  const int threads = C8 * PLa;
+  if (d.src0_is_op) {
+    if (d.resample == 0) gn_apply_kernel<true, 0><<<grid, threads, 0, s>>>(a);
+    else if (d.resample == 1) gn_apply_kernel<true, 1><<<grid, threads, 0, s>>>(a);
+    else gn_apply_kernel<true, 2><<<grid, threads, 0, s>>>(a);
+  } else {
+    if (d.resample == 0) gn_apply_kernel<false, 0><<<grid, threads, 0, s>>>(a);
+    else if (d.resample == 1) gn_apply_kernel<false, 1><<<grid, threads, 0, s>>>(a);
+    else gn_apply_kernel<false, 2><<<grid, threads, 0, s>>>(a);
+  }
   return SGDM_LAUNCH_OK();
 }
 
