@@ -74,6 +74,28 @@ def test_unet_eps_vs_reference_golden(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["unet_fast_label_tiny", "unetca_stego_tiny"])
+def test_two_stream_guided_forward_is_bit_identical(name):
+    """sgdm_set_split_streams: cond / uncond halves as two plans on two streams give the same bits."""
+    need_gpu()
+    from sgdm_b200 import _lib
+
+    meta, a = load_unet_case(name)
+    m = cuda_model(meta)
+    kw = dev(kwargs_from_arrays(a))
+    x, t = a["x"].cuda(), a["t"].cuda()
+    one = m.forward_with_cond_scale(x, t, meta["cond_scale"], **kw).clone()
+    _lib.check(_lib.lib().sgdm_set_split_streams(m._h, 1))
+    try:
+        two = m.forward_with_cond_scale(x, t, meta["cond_scale"], **kw).clone()
+        again = m.forward_with_cond_scale(x, t, meta["cond_scale"], **kw).clone()  # side stream re-used
+    finally:
+        _lib.check(_lib.lib().sgdm_set_split_streams(m._h, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(one, two) and torch.equal(two, again)
+
+
+@pytest.mark.gpu
 def test_unetca_float_one_is_doubled_path():
     need_gpu()
     meta, a = load_unet_case("unetca_clusterlayout_tiny")

@@ -1,5 +1,5 @@
 python -c "import __graft_entry__ as g; g.build()" | tail -1
-timeout 900 python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovider 2>&1 | tail -3
-for cfg in "SGDM_GN16=0" "SGDM_GN16=1" "SGDM_GN16=0" "SGDM_GN16=1"; do
-  echo "== $cfg"; env $cfg python bench.py --no-cpu-baseline --dump-ops gpurun_out/ops_$(echo $cfg | tr ' =' '__').json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['clocks'], {k:v['ms'] for k,v in d['roofline']['families'].items()})"
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovider 2>&1 | tail -2
+for cfg in "SGDM_SPLIT_STREAMS=0" "SGDM_SPLIT_STREAMS=1" "SGDM_SPLIT_STREAMS=0" "SGDM_SPLIT_STREAMS=1"; do
+  echo "== $cfg"; env $cfg python bench.py --no-cpu-baseline | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'], {k:v['ms'] for k,v in d['roofline']['families'].items()})"
 done
