@@ -162,8 +162,12 @@ def cpu_reference_arm(steps, warmup, batch, threads=None):
     from sgdm_b200 import synthetic
     from test_host_mirror import build_model
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: set the count explicitly)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     cores = torch.get_num_threads()
     torch.manual_seed(0)
     m = build_model(CFG)

@@ -152,30 +152,46 @@ struct GnApplyArgs {
 };
 
 // Fused-statistics path: reduce the conv epilogue's partial sums (per 32-row block and channel
-// granule, see ConvDesc::stats) to {mean, rstd} per (sample, group).  One warp per group; the
-// summation order depends on the sample's shape only (batch-invariant bits), accumulation in double.
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float2* __restrict__ st0, int C0,
-                                                           const float2* __restrict__ st1, int C1, int HW,
-                                                           int gran, float2* __restrict__ out) {
-  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// granule, see ConvDesc::stats) to {mean, rstd} per (sample, group).  One block per sample, one thread
+// per channel granule walking the sample's row blocks (consecutive threads read consecutive float2:
+// coalesced), double accumulation, then the granules of a group are added in order.  The summation
+// order depends on the sample's shape only (batch-invariant bits).
+__global__ void __launch_bounds__(512) gn_finalize_kernel(const float2* __restrict__ st0, int C0,
+                                                          const float2* __restrict__ st1, int C1, int HW,
+                                                          int gran, int RL, float2* __restrict__ out) {
+  __shared__ double s_s[512], s_q[512];
+  const int n = blockIdx.x;
   const int C = C0 + C1, cpg = C / 32, epg = cpg / gran, rbs = HW >> 5;
-  const int e0 = C0 / gran, e1 = C1 / gran;
-  const int total = rbs * epg;
-  double s = 0.0, q = 0.0;
-  for (int e = lane; e < total; e += 32) {
-    const int rb = e / epg, j = e - rb * epg;
-    const int cgi = g * epg + j;
-    const long row = static_cast<long>(n) * rbs + rb;
-    const float2 v = cgi < e0 ? __ldg(st0 + row * e0 + cgi) : __ldg(st1 + row * e1 + (cgi - e0));
-    s += static_cast<double>(v.x);
-    q += static_cast<double>(v.y);
-  }
+  const int e0 = C0 / gran, e1 = C1 / gran, ne = e0 + e1;  // granules: ne * RL <= 512 threads
+  // thread = (row-block lane rl, granule cg): consecutive threads read consecutive float2 of one row block
+  const int cg = threadIdx.x % ne, rl = threadIdx.x / ne;
+  {
+    const bool first = cg < e0;
+    const float2* p = first ? st0 + static_cast<long>(n) * rbs * e0 + cg : st1 + static_cast<long>(n) * rbs * e1 + (cg - e0);
+    const long ld = first ? e0 : e1;
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+    int rb = rl;
+    for (; rb + 3 * RL < rbs; rb += 4 * RL) {
+      float2 v[4];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (rb + u * RL) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s[u] += static_cast<double>(v[u].x); q[u] += static_cast<double>(v[u].y); }
+    }
+    for (; rb < rbs; rb += RL) {
+      const float2 v = __ldg(p + rb * ld);
+      s[0] += static_cast<double>(v.x);
+      q[0] += static_cast<double>(v.y);
+    }
+    s_s[rl * ne + cg] = (s[0] + s[1]) + (s[2] + s[3]);
+    s_q[rl * ne + cg] = (q[0] + q[1]) + (q[2] + q[3]);
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int l = 0; l < RL; ++l)
+      for (int j = 0; j < epg; ++j) { s += s_s[l * ne + g * epg + j]; q += s_q[l * ne + g * epg + j]; }
     const double cnt = static_cast<double>(HW) * cpg;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -378,7 +394,11 @@ int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
   if (gn_check(d) || !gn_fused(d) || d.final == nullptr || (HW % 32) || (d.stat_gran != 2 && d.stat_gran != 4) ||
       ((C / 32) % d.stat_gran) || (d.C0 % d.stat_gran) || (d.C1 % d.stat_gran))
     return 1;
-  gn_finalize_kernel<<<d.B, 1024, 0, s>>>(d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, d.final);
+  // RL row-block lanes per granule (a power of two, fixed by the sample's shape -> batch-invariant summation order)
+  const int ne = C / d.stat_gran, rbs = HW / 32;
+  int RL = 1;
+  while (RL * 2 * ne <= 512 && RL * 2 <= rbs && RL < 16) RL *= 2;
+  gn_finalize_kernel<<<d.B, ne * RL, 0, s>>>(d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, RL, d.final);
   return SGDM_LAUNCH_OK();
 }
 
