@@ -132,6 +132,8 @@ int sgdm_debug_set_naive_conv(int on);
 /* CTA-pair (tcgen05 cta_group::2) conv mode for plans / single-kernel calls created afterwards:
  * -1 = library policy (default), 0 = never, 1 = whenever the shape allows (tests, A/B timing) */
 int sgdm_debug_set_conv_pair(int mode);
+/* tcgen05 self-attention kernel (T = 256, head dim 64): -1 = whenever applicable (default), 0 = mma.sync kernel */
+int sgdm_debug_set_attn_tc(int mode);
 /* halo mode of 3x3 stride-1 convs (one staged activation tile shared by the three vertical taps), same values */
 int sgdm_debug_set_conv_halo(int mode);
 /* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array

@@ -14,7 +14,11 @@ struct AttnDesc {
   op_t* out = nullptr; long o_row_stride = 0;  // out[(n*T + r) * o_row_stride + head*D + d]
   int B = 0, T = 0, heads = 0, D = 0;
   float scale = 1.f;  // logits = scale * <q, k>
+  int use_tc = -1;    // tcgen05 kernel (kernel_attn_tc.cu): -1 = whenever applicable, 0 = never (mma.sync kernel)
 };
 int attn_launch(const AttnDesc& a, cudaStream_t s);
+// tcgen05 / TMEM self-attention for T = 256, D = 64 with q, k, v as column blocks of one packed matrix
+bool attn_tc_applicable(const AttnDesc& a);
+int attn_tc_launch(const AttnDesc& a, cudaStream_t s);
 
 }  // namespace sgdm

@@ -98,6 +98,11 @@ struct ConvLaunch {
   ConvDesc desc;  // kept for the naive checker path
 };
 
+// Tiled tensor map of a row-major [rows, cols] matrix (fp32 or op_t), box = box_rows x box_cols,
+// swizzle = 0 | 64 | 128 (= the box row bytes).  Returns 0 on success.
+int encode_matrix_map(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, int swizzle,
+                      char* err, int errlen, int box_rows = 32);
+
 // Builds the TMA descriptors and launch geometry.  Returns 0 on success; on failure
 // writes a message into err (size errlen).
 int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen);

@@ -30,7 +30,8 @@ static int g_naive_conv = 0;
 static long long* g_conv_timing = nullptr;
 static int g_conv_dbg_stages = 0, g_conv_dbg_flags = 0;
 static int g_conv_pair = -1;
-static int g_conv_halo = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
+static int g_conv_halo = -1;
+static int g_attn_tc = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -776,6 +777,7 @@ struct Builder {
     ad.v = dry ? nullptr : qkv + 2 * dh; ad.v_row_stride = 3 * C; ad.v_head_stride = 3 * dh;
     ad.out = att; ad.o_row_stride = C; ad.B = Bp; ad.T = T; ad.heads = e->heads; ad.D = dh;
     ad.scale = 1.0f / sqrtf(static_cast<float>(dh));  // (ch^-1/4 on q) * (ch^-1/4 on k)
+    ad.use_tc = getenv("SGDM_ATTN_TC") ? (atoi(getenv("SGDM_ATTN_TC")) ? -1 : 0) : g_attn_tc;
     push([ad](cudaStream_t s) {
       ++g_launches;
       return attn_launch(ad, s);
@@ -1152,6 +1154,10 @@ int sgdm_debug_set_conv_pair(int mode) {
   g_conv_pair = mode;
   return 0;
 }
+int sgdm_debug_set_attn_tc(int mode) {
+  g_attn_tc = mode;
+  return 0;
+}
 int sgdm_debug_set_conv_halo(int mode) {
   g_conv_halo = mode;
   return 0;
@@ -1401,6 +1407,7 @@ int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_he
   a.k_extra = static_cast<const op_t*>(k_extra); a.v_extra = static_cast<const op_t*>(v_extra); a.n_extra = n_extra;
   a.out = static_cast<op_t*>(out); a.o_row_stride = o_row_stride; a.B = B; a.T = T; a.heads = heads; a.D = D;
   a.scale = scale;
+  a.use_tc = g_attn_tc;
   ++g_launches;
   return attn_launch(a, static_cast<cudaStream_t>(stream))
              ? fail("attention launch: %s", cudaGetErrorString(cudaGetLastError()))

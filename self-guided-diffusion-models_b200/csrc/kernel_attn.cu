@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
 }
 
 int attn_launch(const AttnDesc& a, cudaStream_t s) {
+  if (a.use_tc != 0 && attn_tc_applicable(a)) return attn_tc_launch(a, s);
   const int Tkv = a.n_extra + a.T;
   const int tkv_pad = (Tkv + 63) / 64 * 64;
   if (a.D != 32 && a.D != 64) return 1;

@@ -721,8 +721,8 @@ static int encode_nhwc(CUtensorMap* tm, const op_t* base, int B, int H, int W, i
 }
 
 // row-major [rows, cols] matrix, box = box_rows rows x box_cols columns; swizzle = 0 | 64 | 128 (= the box row bytes)
-static int encode_matrix(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, int swizzle,
-                         char* err, int errlen, int box_rows = 32) {
+int encode_matrix_map(CUtensorMap* tm, const void* base, bool f32, long rows, int cols, int box_cols, int swizzle,
+                      char* err, int errlen, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return 1; }
   const int es = f32 ? 4 : 2;
@@ -870,17 +870,17 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.debug = d.debug_flags;
   // epilogue: output / residual tile maps
   if (p.epi_mode == 1) {
-    if (encode_matrix(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
-    if (p.res_mode == 1 && encode_matrix(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
+    if (encode_matrix_map(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
+    if (p.res_mode == 1 && encode_matrix_map(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
     if (p.res_mode == 2 &&
-        encode_matrix(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, 128, err,
+        encode_matrix_map(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, 128, err,
                       errlen, 16))
       return 1;
     // second output: the same values rounded to the 16-bit operand type (32 channels = 64-byte rows)
-    if (d.out_op2 && encode_matrix(&p.tmOut2, d.out_op2, false, p.M_total, d.Cout, 32, d.swap_ab ? 0 : 64, err, errlen)) return 1;
+    if (d.out_op2 && encode_matrix_map(&p.tmOut2, d.out_op2, false, p.M_total, d.Cout, 32, d.swap_ab ? 0 : 64, err, errlen)) return 1;
   } else if (p.epi_mode == 2) {
     // swap-AB: a warp owns 32 channels = 64-byte rows (dense); normal: 64 channels = 128-byte swizzled rows
-    if (encode_matrix(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, d.swap_ab ? 0 : 128, err, errlen)) return 1;
+    if (encode_matrix_map(&p.tmOut, d.out_op, false, p.M_total, d.Cout, d.swap_ab ? 32 : 64, d.swap_ab ? 0 : 128, err, errlen)) return 1;
   }
   // shared memory: as many K-block stages as fit beside the epilogue staging
   out->pair = pair ? 1 : 0;

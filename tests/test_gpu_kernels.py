@@ -358,6 +358,7 @@ def test_groupnorm(L, case):
 ATTN_CASES = [
     # (B, T, heads, D, n_extra, mqa, note)
     (2, 256, 8, 64, 0, False, "legacy qkv layout, T=256 d=64 (cfg2)"),
+    (40, 256, 8, 64, 0, False, "legacy, T=256 d=64, 320 (sample, head) pairs > 148 CTAs (tcgen05 ring reuse)"),
     (3, 64, 8, 32, 0, False, "legacy, T=64 d=32 (cfg1)"),
     (2, 16, 8, 32, 0, False, "T=16 < one query tile"),
     (2, 256, 8, 64, 17, True, "multi-query + 17 context/null keys (Attention_LR)"),
@@ -374,10 +375,18 @@ def test_attention(L, case):
     if not mqa:
         qkv = torch.randn(B, T, 3 * C, device="cuda", generator=g).to(L._op)
         out = torch.zeros(B, T, C, dtype=L._op, device="cuda")
-        ck(L, L.sgdm_k_attention(S(), qkv.data_ptr(), 3 * C, 3 * D, qkv.data_ptr() + 2 * D, 3 * C, 3 * D,
-                                 qkv.data_ptr() + 4 * D, 3 * C, 3 * D, None, None, 0, P(out), C, B, T, H, D,
-                                 1 / math.sqrt(D)))
-        torch.cuda.synchronize()
+        outs = {}
+        for mode in (0, -1):  # mma.sync kernel, then the tcgen05 kernel where it applies (T = 256, D = 64)
+            L.sgdm_debug_set_attn_tc(mode)
+            try:
+                out.zero_()
+                ck(L, L.sgdm_k_attention(S(), qkv.data_ptr(), 3 * C, 3 * D, qkv.data_ptr() + 2 * D, 3 * C, 3 * D,
+                                         qkv.data_ptr() + 4 * D, 3 * C, 3 * D, None, None, 0, P(out), C, B, T, H, D,
+                                         1 / math.sqrt(D)))
+                torch.cuda.synchronize()
+                outs[mode] = out.clone()
+            finally:
+                L.sgdm_debug_set_attn_tc(-1)
         # QKVAttentionLegacy on [N, H*3*D, T]
         x = qkv.float().permute(0, 2, 1)
         q, k, v = x.reshape(B * H, 3 * D, T).split(D, dim=1)
@@ -399,6 +408,10 @@ def test_attention(L, case):
         v = torch.cat([vx.float(), buf[..., C + D:].float()], 1)
         attn = torch.einsum("bhid,bjd->bhij", q, k).softmax(-1)
         ref = torch.einsum("bhij,bjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(B, T, C)
+    if not mqa:
+        e0 = relerr(outs[0].float(), ref)
+        print(f"[attn {note}] mma.sync kernel rel_l2={e0:.3e}")
+        assert e0 < 3e-3
     e = relerr(out.float(), ref)
     print(f"[attn {note}] rel_l2={e:.3e}")
     assert torch.isfinite(out.float()).all()
