@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
           tc_fence_after();
           store_o(0);
         }
-        // pass 2: exponentials (log2 domain), row sum, P as 16-bit K-major operand.  (Double-buffering the TMEM
-        // loads in registers was measured slower: 255 registers, spills.)
+        // pass 2: exponentials (log2 domain), row sum, P as 16-bit K-major operand.  (Measured slower: double-
+        // buffering the TMEM loads in registers, and 64-column loads — both end at 255 registers with spills.)
         float l = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
