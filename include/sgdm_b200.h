@@ -112,6 +112,24 @@ int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, double 
 int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out /* may be NULL */, int B, int64_t per_sample);
+/* The same updates with the optional sampling_kwargs extras (either pointer may be NULL):
+ *   dyn_s     [B] per-sample dynamic threshold from sgdm_dyn_threshold (dtp < 1): pred_x0 <- clamp(x0,-s,s)/s
+ *             replaces the clamp to [-1,1] (clip_x0_minus_one_to_one, diffusion_utils/util.py:70-82)
+ *   noise_mul [B, per_sample] F.dropout factor {0, 1/(1-p)} multiplied onto the scaled noise (noise_dropout > 0,
+ *             ddpm_sampler.py:184-185, ddim_plms_sampler.py:388-389); drawn by the host like the noise itself */
+int sgdm_ddim_step_ex(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                      int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                      float* x_out, float* x0_out, float* eps_out, int B, int64_t per_sample, const float* dyn_s,
+                      const float* noise_mul);
+int sgdm_ddpm_step_ex(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                      int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                      float* x_out, float* x0_out, int B, int64_t per_sample, const float* dyn_s,
+                      const float* noise_mul);
+/* Dynamic thresholding, phase 1: s_out[b] = max(quantile(|pred_x0[b]|, dtp), 1) (torch.quantile, 'linear') for the
+ * update described by the same eps / coef6 (kind 0 = DDPM coefficients, 1 = DDIM); scratch_x0 [B, per_sample]. */
+int sgdm_dyn_threshold(void* stream, int kind, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                       int scale_type, const float* coef6, const float* x, double dtp, float* scratch_x0, float* s_out, int B,
+                       int64_t per_sample);
 /* PLMS multistep eps combination (ddim_plms_sampler.py:432-459): out = (sum_k coefs[k]*terms[k]) / div,
  * n_terms <= 4; `terms` and `coefs` are HOST arrays (of device pointers / floats). */
 int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const float* coefs, float div, float* out,
@@ -181,6 +199,8 @@ int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_he
 int sgdm_k_linear_f32(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
                       float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate);
 int sgdm_k_cast(void* stream, const float* src, void* dst_op, int B, int H, int W, int C, int up2);
+/* s_out[b] = max(quantile(|v[b, 0:n]|, q), 1), torch.quantile 'linear' (diffusion_utils/util.py:74-77) */
+int sgdm_k_quantile_abs(void* stream, const float* v, int B, int64_t n, double q, float* s_out);
 
 #ifdef __cplusplus
 }

@@ -61,8 +61,9 @@ def ddpm_sample(eps_fn, tape, tables, sampling_kwargs):
         mean = _ext(tables["posterior_mean_coef1"], t, x) * x0 + _ext(tables["posterior_mean_coef2"], t, x) * x
         logvar = _ext(tables["posterior_log_variance_clipped"], t, x)
         noise = tape["noise"][k] * temperature[i]
+        if sampling_kwargs["noise_dropout"] > 0:  # F.dropout(noise, p) (ddpm_sampler.py:184-185), factor from the tape
+            noise = noise * tape["dropout_mul"][k]
         k += 1
-        assert sampling_kwargs["noise_dropout"] == 0, "oracle: noise_dropout draws are not on the tape"
         nonzero = (1 - (t == 0).float()).reshape(b, *((1,) * (x.dim() - 1)))
         x = mean + nonzero * (0.5 * logvar).exp() * noise
         if i in logs:
@@ -72,7 +73,7 @@ def ddpm_sample(eps_fn, tape, tables, sampling_kwargs):
     return x, out
 
 
-def _ddim_update(x, e_t, dt, index, noise, sampling_kwargs):
+def _ddim_update(x, e_t, dt, index, noise, sampling_kwargs, dropout_mul=None):
     """p_sample_ddim / p_sample_plms arithmetic (ddim_plms_sampler.py:360-391,493-525)."""
     a_t = torch.full_like(x, dt["alphas"][index])
     a_prev = torch.full_like(x, dt["alphas_prev"][index])
@@ -82,7 +83,8 @@ def _ddim_update(x, e_t, dt, index, noise, sampling_kwargs):
     x0 = clip_x0(x0, sampling_kwargs["clip_denoised"], sampling_kwargs["dtp"])
     dir_xt = (1.0 - a_prev - sigma_t**2).sqrt() * e_t
     nz = sigma_t * noise * sampling_kwargs["temperature"]
-    assert sampling_kwargs["noise_dropout"] == 0
+    if sampling_kwargs["noise_dropout"] > 0:  # F.dropout(noise, p) (ddim_plms_sampler.py:388-389), factor from the tape
+        nz = nz * dropout_mul
     return a_prev.sqrt() * x0 + dir_xt + nz, x0
 
 
@@ -99,7 +101,8 @@ def ddim_sample(eps_fn, tape, alphas_cumprod, num_ddpm, sampling_kwargs):
         index = total - i - 1
         t = torch.full((b,), int(step), dtype=torch.long)
         e_t = eps_fn(x, t)
-        x, x0 = _ddim_update(x, e_t, dt, index, tape["noise"][i], sampling_kwargs)
+        x, x0 = _ddim_update(x, e_t, dt, index, tape["noise"][i], sampling_kwargs,
+                             tape["dropout_mul"][i] if "dropout_mul" in tape else None)
         if index in logs:
             out["x_inter"].append(x.unsqueeze(0))
             out["pred_x0"].append(x0.unsqueeze(0))
@@ -128,7 +131,8 @@ def plms_sample(eps_fn, tape, alphas_cumprod, num_ddpm, sampling_kwargs):
         t_next = torch.full((b,), int(time_range[min(i + 1, len(time_range) - 1)]), dtype=torch.long)
         e_t = eps_fn(x, t)
         if len(old) == 0:
-            x_prev, _ = _ddim_update(x, e_t, dt, index, tape["noise"][k], kw)
+            x_prev, _ = _ddim_update(x, e_t, dt, index, tape["noise"][k], kw,
+                                     tape["dropout_mul"][k] if "dropout_mul" in tape else None)
             k += 1
             e_next = eps_fn(x_prev, t_next)
             e_p = (e_t + e_next) / 2
@@ -138,7 +142,8 @@ def plms_sample(eps_fn, tape, alphas_cumprod, num_ddpm, sampling_kwargs):
             e_p = (23 * e_t - 16 * old[-1] + 5 * old[-2]) / 12
         else:
             e_p = (55 * e_t - 59 * old[-1] + 37 * old[-2] - 9 * old[-3]) / 24
-        x, x0 = _ddim_update(x, e_p, dt, index, tape["noise"][k], kw)
+        x, x0 = _ddim_update(x, e_p, dt, index, tape["noise"][k], kw,
+                             tape["dropout_mul"][k] if "dropout_mul" in tape else None)
         k += 1
         old.append(e_t)
         if len(old) >= 4:

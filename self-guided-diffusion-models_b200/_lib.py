@@ -59,6 +59,9 @@ PROTOTYPES = {
     "sgdm_mix": (_i, [_vp, _vp, _vp, _d, _vp, _i, _vp, _i, _i64]),
     "sgdm_ddim_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64]),
     "sgdm_ddpm_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64]),
+    "sgdm_ddim_step_ex": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "sgdm_ddpm_step_ex": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "sgdm_dyn_threshold": (_i, [_vp, _i, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _vp, _d, _vp, _vp, _i, _i64]),
     "sgdm_lincomb": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_f), _f, _vp, _i64]),
     "sgdm_to_uint8": (_i, [_vp, _vp, _vp, _i64]),
     "sgdm_set_profiling": (_i, [_vp, _i]),
@@ -82,6 +85,7 @@ PROTOTYPES = {
     "sgdm_k_attention": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _f]),
     "sgdm_k_linear_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),
     "sgdm_k_cast": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "sgdm_k_quantile_abs": (_i, [_vp, _vp, _i, _i64, _d, _vp]),
 }
 
 _lib = None

@@ -1285,12 +1285,43 @@ int sgdm_mix(void* stream, const float* eps_c, const float* eps_u, double w, con
     return fail("mix launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
+// dtp < 1: s_out[b] = max(quantile(|pred_x0[b]|, dtp), 1) for the update that follows (same eps / coefficients)
+int sgdm_dyn_threshold(void* stream, int kind, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                       int scale_type, const float* coef6, const float* x, double dtp, float* scratch_x0, float* s_out, int B,
+                       int64_t per_sample) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StepExtras ex;
+  ex.x0_raw = scratch_x0;
+  const MixDesc m = make_mix(eps_c, eps_u, w, w_per_sample, scale_type);
+  g_launches += 2;
+  int rc;
+  if (kind == 0) {
+    DdpmCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], 0};
+    rc = ddpm_step_launch(m, c, ex, x, nullptr, nullptr, nullptr, B, per_sample, st);
+  } else {
+    DdimCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], 0};
+    rc = ddim_step_launch(m, c, ex, x, nullptr, nullptr, nullptr, nullptr, B, per_sample, st);
+  }
+  if (rc || quantile_abs_launch(scratch_x0, B, per_sample, static_cast<float>(dtp), s_out, st))
+    return fail("dynamic-threshold launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
 int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out, float* eps_out, int B, int64_t per_sample) {
+  return sgdm_ddim_step_ex(stream, eps_c, eps_u, w, w_per_sample, scale_type, coef6, clip_denoised, x, noise, x_out,
+                           x0_out, eps_out, B, per_sample, nullptr, nullptr);
+}
+int sgdm_ddim_step_ex(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                      int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                      float* x_out, float* x0_out, float* eps_out, int B, int64_t per_sample, const float* dyn_s,
+                      const float* noise_mul) {
   DdimCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};
+  StepExtras ex;
+  ex.dyn_s = dyn_s;
+  ex.noise_mul = noise_mul;
   ++g_launches;
-  if (ddim_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, x, noise, x_out, x0_out, eps_out, B,
+  if (ddim_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, ex, x, noise, x_out, x0_out, eps_out, B,
                        per_sample, static_cast<cudaStream_t>(stream)))
     return fail("ddim step launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
@@ -1298,9 +1329,19 @@ int sgdm_ddim_step(void* stream, const float* eps_c, const float* eps_u, double 
 int sgdm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
                    int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
                    float* x_out, float* x0_out, int B, int64_t per_sample) {
+  return sgdm_ddpm_step_ex(stream, eps_c, eps_u, w, w_per_sample, scale_type, coef6, clip_denoised, x, noise, x_out,
+                           x0_out, B, per_sample, nullptr, nullptr);
+}
+int sgdm_ddpm_step_ex(void* stream, const float* eps_c, const float* eps_u, double w, const float* w_per_sample,
+                      int scale_type, const float* coef6, int clip_denoised, const float* x, const float* noise,
+                      float* x_out, float* x0_out, int B, int64_t per_sample, const float* dyn_s,
+                      const float* noise_mul) {
   DdpmCoef c{coef6[0], coef6[1], coef6[2], coef6[3], coef6[4], coef6[5], clip_denoised};
+  StepExtras ex;
+  ex.dyn_s = dyn_s;
+  ex.noise_mul = noise_mul;
   ++g_launches;
-  if (ddpm_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, x, noise, x_out, x0_out, B,
+  if (ddpm_step_launch(make_mix(eps_c, eps_u, w, w_per_sample, scale_type), c, ex, x, noise, x_out, x0_out, B,
                        per_sample, static_cast<cudaStream_t>(stream)))
     return fail("ddpm step launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
@@ -1425,6 +1466,13 @@ int sgdm_k_cast(void* stream, const float* src, void* dst_op, int B, int H, int 
   ++g_launches;
   return cast_launch(src, static_cast<op_t*>(dst_op), B, H, W, C, up2, static_cast<cudaStream_t>(stream))
              ? fail("cast launch failed")
+             : 0;
+}
+int sgdm_k_quantile_abs(void* stream, const float* v, int B, int64_t n, double q, float* s_out) {
+  if (B <= 0 || n <= 0 || !(q >= 0.0 && q <= 1.0)) return fail("quantile_abs: B=%d n=%lld q=%g", B, (long long)n, q);
+  ++g_launches;
+  return quantile_abs_launch(v, B, n, static_cast<float>(q), s_out, static_cast<cudaStream_t>(stream))
+             ? fail("quantile launch failed")
              : 0;
 }
 

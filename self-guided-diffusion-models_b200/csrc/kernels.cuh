@@ -107,15 +107,23 @@ int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStr
 //   sqrt_one_minus_at = ddim_sqrt_one_minus_alphas[i]; sqrt_at = fp32 sqrt(ddim_alphas[i]);
 //   sqrt_a_prev = fp32 sqrt(fp32(ddim_alphas_prev[i])); dir_coef = fp32 sqrt(1 - a_prev - sigma^2)
 struct DdimCoef { float sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_t, temperature; int clip; };
+// Optional extras of both update kernels (all null = the plain update):
+struct StepExtras {
+  float* x0_raw = nullptr;           // write ONLY the unclipped pred_x0 here (phase 1 of dynamic thresholding)
+  const float* dyn_s = nullptr;      // [B] dynamic threshold s: x0 <- clamp(x0, -s, s) / s instead of the [-1, 1] clamp
+  const float* noise_mul = nullptr;  // per-element F.dropout factor {0, 1/(1-p)} on the scaled noise
+};
+// s[b] = max(quantile(|x0[b]|, q), 1): torch.quantile 'linear' (clip_x0_minus_one_to_one, diffusion_utils/util.py:70-82)
+int quantile_abs_launch(const float* x0, int B, long n, float q, float* s_out, cudaStream_t s);
 // p_sample_ddim arithmetic (ddim_plms_sampler.py:360-391) fused with the mix.
-int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const float* x, const float* noise, float* x_out,
-                     float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s);
+int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const StepExtras& ex, const float* x, const float* noise,
+                     float* x_out, float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s);
 
 // nonzero_sigma = (t != 0) * exp(0.5 * posterior_log_variance_clipped[t]) (fp32, host-computed)
 struct DdpmCoef { float sqrt_recip, sqrt_recipm1, coef1, coef2, nonzero_sigma, temperature; int clip; };
 // p_mean_variance + p_sample arithmetic (ddpm_sampler.py:154-192) fused with the mix.
-int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const float* x, const float* noise, float* x_out,
-                     float* x0_out, int B, long per_sample, cudaStream_t s);
+int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const StepExtras& ex, const float* x, const float* noise,
+                     float* x_out, float* x0_out, int B, long per_sample, cudaStream_t s);
 
 // ((x+1)*127.5).clamp(0,255).to(uint8)  (diffusion_utils/util.py:99-100)
 int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s);

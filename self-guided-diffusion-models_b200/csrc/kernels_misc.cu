@@ -725,53 +725,130 @@ int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStr
   return SGDM_LAUNCH_OK();
 }
 
-__global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const float* __restrict__ x,
+// Optional extras of the update kernels (sampling_kwargs dtp < 1 / noise_dropout > 0):
+//   x0_raw   phase 1 of dynamic thresholding: only the UNCLIPPED pred_x0 is written (then quantile_abs_kernel)
+//   dyn_s    [B] per-sample threshold s = max(quantile(|x0|, dtp), 1): x0 <- clamp(x0, -s, s) / s, replacing the
+//            clamp to [-1, 1] (clip_x0_minus_one_to_one, diffusion_utils/util.py:70-82)
+//   noise_mul per-element F.dropout factor {0, 1/(1-p)} applied to the scaled noise last, like F.dropout does
+__device__ __forceinline__ float clip_x0_dev(float x0, int clip, const float* dyn_s, int b) {
+  if (dyn_s) {
+    const float s = dyn_s[b];
+    return __fdiv_rn(fminf(fmaxf(x0, -s), s), s);
+  }
+  return clip ? fminf(fmaxf(x0, -1.0f), 1.0f) : x0;
+}
+
+__global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const StepExtras ex, const float* __restrict__ x,
                                  const float* __restrict__ noise, float* __restrict__ x_out,
                                  float* __restrict__ x0_out, float* __restrict__ eps_out, long per_sample,
                                  long total) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
+  const int b = static_cast<int>(i / per_sample);
   float w, ow;
-  mix_coeffs(m, static_cast<int>(i / per_sample), w, ow);
+  mix_coeffs(m, b, w, ow);
   const float e = mix1(m, m.eps_c[i], m.eps_u ? m.eps_u[i] : 0.f, w, ow);
   // pred_x0 = (x - sqrt(1-a_t) e) / sqrt(a_t)
   float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(c.sqrt_one_minus_at, e)), c.sqrt_at);
-  if (c.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  if (ex.x0_raw) { ex.x0_raw[i] = x0; return; }
+  x0 = clip_x0_dev(x0, c.clip, ex.dyn_s, b);
   const float dir = __fmul_rn(c.dir_coef, e);                              // sqrt(1 - a_prev - sigma^2) e
-  const float nz = __fmul_rn(__fmul_rn(c.sigma_t, noise[i]), c.temperature);  // sigma * noise * temperature
+  float nz = __fmul_rn(__fmul_rn(c.sigma_t, noise[i]), c.temperature);     // sigma * noise * temperature
+  if (ex.noise_mul) nz = __fmul_rn(nz, ex.noise_mul[i]);
   x_out[i] = __fadd_rn(__fadd_rn(__fmul_rn(c.sqrt_a_prev, x0), dir), nz);
   if (x0_out) x0_out[i] = x0;
   if (eps_out) eps_out[i] = e;
 }
-int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const float* x, const float* noise, float* x_out,
-                     float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s) {
+int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const StepExtras& ex, const float* x, const float* noise,
+                     float* x_out, float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
-  ddim_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, x, noise, x_out, x0_out, eps_out,
+  ddim_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, ex, x, noise, x_out, x0_out, eps_out,
                                                                              per_sample, total);
   return SGDM_LAUNCH_OK();
 }
 
-__global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const float* __restrict__ x,
+__global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const StepExtras ex, const float* __restrict__ x,
                                  const float* __restrict__ noise, float* __restrict__ x_out,
                                  float* __restrict__ x0_out, long per_sample, long total) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
+  const int b = static_cast<int>(i / per_sample);
   float w, ow;
-  mix_coeffs(m, static_cast<int>(i / per_sample), w, ow);
+  mix_coeffs(m, b, w, ow);
   const float e = mix1(m, m.eps_c[i], m.eps_u ? m.eps_u[i] : 0.f, w, ow);
   const float xi = x[i];
   float x0 = __fsub_rn(__fmul_rn(c.sqrt_recip, xi), __fmul_rn(c.sqrt_recipm1, e));
-  if (c.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  if (ex.x0_raw) { ex.x0_raw[i] = x0; return; }
+  x0 = clip_x0_dev(x0, c.clip, ex.dyn_s, b);
   const float mean = __fadd_rn(__fmul_rn(c.coef1, x0), __fmul_rn(c.coef2, xi));
-  const float nz = __fmul_rn(noise[i], c.temperature);
+  float nz = __fmul_rn(noise[i], c.temperature);
+  if (ex.noise_mul) nz = __fmul_rn(nz, ex.noise_mul[i]);
   x_out[i] = __fadd_rn(mean, __fmul_rn(c.nonzero_sigma, nz));  // nonzero_mask * exp(0.5 logvar) * noise
   if (x0_out) x0_out[i] = x0;
 }
-int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const float* x, const float* noise, float* x_out,
-                     float* x0_out, int B, long per_sample, cudaStream_t s) {
+int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const StepExtras& ex, const float* x, const float* noise,
+                     float* x_out, float* x0_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
-  ddpm_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, x, noise, x_out, x0_out,
+  ddpm_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, ex, x, noise, x_out, x0_out,
                                                                              per_sample, total);
+  return SGDM_LAUNCH_OK();
+}
+
+// s[b] = max(quantile(|x0[b, :]|, q), 1) with torch.quantile's default 'linear' interpolation
+// (diffusion_utils/util.py:74-77).  One block per sample; the two order statistics around rank q (n-1) are
+// found EXACTLY by a 4-pass most-significant-byte radix select on the bit patterns of |x| (non-negative
+// floats order like their bits), then interpolated with torch's two-branch lerp.
+__global__ void __launch_bounds__(256) quantile_abs_kernel(const float* __restrict__ x0, long n, float q,
+                                                           float* __restrict__ s_out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh_prefix, sh_rank;
+  const float* v = x0 + blockIdx.x * n;
+  const float ranks = __fmul_rn(q, static_cast<float>(n - 1));  // q * (n - 1) in fp32, like torch
+  const float below = floorf(ranks);
+  const float wgt = __fsub_rn(ranks, below);
+  const long r_lo = static_cast<long>(below), r_hi = static_cast<long>(ceilf(ranks));
+  float val[2];
+  for (int which = 0; which < 2; ++which) {
+    if (which == 1 && r_hi == r_lo) { val[1] = val[0]; break; }
+    unsigned int prefix = 0, mask = 0;
+    unsigned int rank = static_cast<unsigned int>(which == 0 ? r_lo : r_hi);  // 0-based rank among the n values
+    for (int pass = 3; pass >= 0; --pass) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned int u = __float_as_uint(fabsf(v[i]));
+        if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned int cum = 0;
+        int bin = 0;
+        for (; bin < 255; ++bin) {
+          if (cum + hist[bin] > rank) break;
+          cum += hist[bin];
+        }
+        sh_prefix = prefix | (static_cast<unsigned int>(bin) << (8 * pass));
+        sh_rank = rank - cum;
+      }
+      __syncthreads();
+      prefix = sh_prefix;
+      rank = sh_rank;
+      mask |= 0xFFu << (8 * pass);
+      __syncthreads();
+    }
+    val[which] = __uint_as_float(prefix);
+  }
+  if (threadIdx.x == 0) {
+    const float a = val[0], b = val[1];
+    const float d = __fsub_rn(b, a);
+    // at::lerp as ATen evaluates it on CPU (vectorised) and CUDA (contracted): one fused multiply-add,
+    // weight < 0.5 ? fma(w, b - a, a) : fma(w - 1, b - a, b)   [checked against torch.quantile bit for bit]
+    const float r = wgt < 0.5f ? __fmaf_rn(wgt, d, a) : __fmaf_rn(__fsub_rn(wgt, 1.0f), d, b);
+    s_out[blockIdx.x] = fmaxf(r, 1.0f);
+  }
+}
+int quantile_abs_launch(const float* x0, int B, long n, float q, float* s_out, cudaStream_t s) {
+  quantile_abs_kernel<<<B, 256, 0, s>>>(x0, n, q, s_out);
   return SGDM_LAUNCH_OK();
 }
 

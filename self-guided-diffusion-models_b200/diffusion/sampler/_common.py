@@ -128,11 +128,44 @@ def coef6(*vals):
     return (C.c_float * 6)(*[float(v) for v in vals])
 
 
+class StepExtras:
+    """The optional parts of an update (sampling_kwargs `dtp` < 1, `noise_dropout` > 0) as device pointers
+    for sgdm_ddpm_step_ex / sgdm_ddim_step_ex.
+
+    dtp < 1 (clip_x0_minus_one_to_one, diffusion_utils/util.py:70-82): sgdm_dyn_threshold runs the first half of
+    the same update (unclipped pred_x0 into a scratch tensor) and a per-sample quantile kernel; the update then
+    clamps to [-s, s] and divides by s.  noise_dropout (ddpm_sampler.py:184-185, ddim_plms_sampler.py:388-389):
+    the F.dropout factor {0, 1/(1-p)} is drawn by the host exactly where the reference draws it (after the
+    step's noise) and multiplied onto the scaled noise inside the kernel."""
+
+    def __init__(self, sampling_kwargs, like, noise_source=None, noise_dropout=None):
+        self.dtp = float(sampling_kwargs.get("dtp", 1))
+        p = sampling_kwargs.get("noise_dropout", 0) if noise_dropout is None else noise_dropout
+        self.p = float(p)
+        self.noise = noise_source
+        self.scratch = torch.empty_like(like) if self.dtp < 1.0 else None
+        self.s = torch.empty((like.shape[0],), device=like.device, dtype=torch.float32) if self.dtp < 1.0 else None
+        self._mul = None
+
+    def pointers(self, stream, kind, eps, coefs, x, B, per_sample):
+        """-> (dyn_s pointer or None, noise_mul pointer or None) for the update that follows"""
+        dyn = None
+        if self.dtp < 1.0:
+            pc, pu, w, w_ptr, st = eps
+            _lib.check(_lib.lib().sgdm_dyn_threshold(stream, kind, pc, pu, w, w_ptr, st, coefs, x.data_ptr(), self.dtp,
+                                                     self.scratch.data_ptr(), self.s.data_ptr(), B, per_sample))
+            dyn = self.s.data_ptr()
+        mul = None
+        if self.p > 0.0:
+            if self.noise is not None:
+                self._mul = self.noise.dropout_mul(self.p)
+            else:
+                self._mul = torch.nn.functional.dropout(torch.ones_like(x), p=self.p)
+            mul = self._mul.data_ptr()
+        return dyn, mul
+
+
 def check_supported(sampling_kwargs):
-    if sampling_kwargs.get("dtp", 1) < 1.0:
-        raise NotImplementedError("dynamic thresholding (dtp < 1) is not built into the fused update yet")
-    if sampling_kwargs.get("noise_dropout", 0) > 0.0:
-        raise NotImplementedError("noise_dropout > 0 is not built into the fused update yet")
     vis = sampling_kwargs.get("vis", None)
     for flag in ("condscale", "interp", "chainvis", "scoremix_vis"):
         if vis is not None and hasattr(vis, flag) and getattr(vis, flag):
@@ -160,3 +193,10 @@ class NoiseSource:
             self.k += 1
             return n
         return torch.randn(self.shape, device=self.device)
+
+    def dropout_mul(self, p):
+        """The F.dropout factor {0, 1/(1-p)} belonging to the noise returned by the last next(): from the tape
+        (`dropout_mul`, parity runs) or drawn here — F.dropout's draw depends on the shape only."""
+        if self.tape is not None and "dropout_mul" in self.tape:
+            return self.tape["dropout_mul"][self.k - 1].to(self.device, torch.float32).contiguous()
+        return torch.nn.functional.dropout(torch.ones(self.shape, device=self.device), p=p)

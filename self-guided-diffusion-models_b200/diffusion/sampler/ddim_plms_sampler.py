@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ._common import (GuidedEps, NoiseSource, check_supported, coef6, log_indices, make_ddim_sampling_parameters,
+from ._common import (GuidedEps, NoiseSource, StepExtras, check_supported, coef6, log_indices, make_ddim_sampling_parameters,
                       make_ddim_timesteps)
 
 
@@ -61,6 +61,7 @@ class DDIMSampler(object):
             raise _lib.SgdmError(f"sampler device is {device}: sgdm_b200 has no CPU path")
         noise = NoiseSource(shape, device, noise_tape)
         img = noise.x_T().contiguous()
+        self._extras = StepExtras(sampling_kwargs, img, noise)
         return device, noise, img
 
     def _step(self, stream, eps, index, clip, temperature, img, nz, nxt, x0, B, per_sample, eps_out=None):
@@ -68,8 +69,9 @@ class DDIMSampler(object):
         k = self._coefs
         c = coef6(k["s1m"][index], k["sqrt_at"][index], k["sqrt_a_prev"][index], k["dir"][index], k["sigma"][index],
                   temperature)
-        _lib.check(_lib.lib().sgdm_ddim_step(stream, pc, pu, w, w_ptr, st, c, clip, img.data_ptr(), nz.data_ptr(),
-                                             nxt.data_ptr(), _lib.ptr(x0), _lib.ptr(eps_out), B, per_sample))
+        dyn, mul = self._extras.pointers(stream, 1, eps, c, img, B, per_sample)
+        _lib.check(_lib.lib().sgdm_ddim_step_ex(stream, pc, pu, w, w_ptr, st, c, clip, img.data_ptr(), nz.data_ptr(),
+                                                nxt.data_ptr(), _lib.ptr(x0), _lib.ptr(eps_out), B, per_sample, dyn, mul))
 
     @torch.no_grad()
     def ddim_sampling(self, shape, sampling_kwargs, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,

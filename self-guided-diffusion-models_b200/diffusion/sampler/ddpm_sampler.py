@@ -13,7 +13,7 @@ from torch import nn
 
 from ... import _lib
 from ...diffusion_utils import dict2obj
-from ._common import GuidedEps, NoiseSource, check_supported, coef6, log_indices, make_beta_schedule
+from ._common import GuidedEps, NoiseSource, StepExtras, check_supported, coef6, log_indices, make_beta_schedule
 
 
 class Schedule_DDPM(nn.Module):
@@ -65,8 +65,8 @@ class Schedule_DDPM(nn.Module):
         `t` must be batch-uniform (it always is while sampling); pass `index` = that timestep to
         avoid reading it back from the device.  `noise` is an optional host-supplied draw."""
         check_supported(sampling_kwargs)
-        if noise_dropout > 0.0 or repeat_noise:
-            raise NotImplementedError("noise_dropout / repeat_noise")
+        if repeat_noise:
+            raise NotImplementedError("repeat_noise")
         i = int(t[0]) if index is None else int(index)
         device = x.device
         if not hasattr(self, "_step_tab") or self._step_tab[0] is not self.posterior_log_variance_clipped:
@@ -84,9 +84,12 @@ class Schedule_DDPM(nn.Module):
         c = coef6(tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i],
                   tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
                   tab["sigma"][i] if i != 0 else 0.0, temperature)
-        _lib.check(_lib.lib().sgdm_ddpm_step(_lib.current_stream(device), pc, pu, w, w_ptr, st, c,
-                                             1 if sampling_kwargs["clip_denoised"] else 0, x.data_ptr(), nz.data_ptr(),
-                                             out.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel()))
+        stream = _lib.current_stream(device)
+        extras = StepExtras(sampling_kwargs, x, noise_dropout=noise_dropout)
+        dyn, mul = extras.pointers(stream, 0, (pc, pu, w, w_ptr, st), c, x, x.shape[0], x[0].numel())
+        _lib.check(_lib.lib().sgdm_ddpm_step_ex(stream, pc, pu, w, w_ptr, st, c,
+                                                1 if sampling_kwargs["clip_denoised"] else 0, x.data_ptr(), nz.data_ptr(),
+                                                out.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel(), dyn, mul))
         return out, x0, None
 
     @torch.no_grad()
@@ -118,6 +121,7 @@ class Schedule_DDPM(nn.Module):
         eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device)
         clip = 1 if sampling_kwargs["clip_denoised"] else 0
         per_sample = img[0].numel()
+        extras = StepExtras(sampling_kwargs, img, noise)
         out = dict(pred_x0=[], x_inter=[])
         for i in reversed(range(0, timesteps)):
             ts = torch.full((B,), i, device=device, dtype=torch.long)
@@ -127,8 +131,9 @@ class Schedule_DDPM(nn.Module):
             c = coef6(tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i],
                       tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
                       sigma[i] if i != 0 else 0.0, temperature[i])
-            _lib.check(lib.sgdm_ddpm_step(stream, pc, pu, w, w_ptr, st, c, clip, img.data_ptr(), nz.data_ptr(),
-                                          nxt.data_ptr(), _lib.ptr(x0), B, per_sample))
+            dyn, mul = extras.pointers(stream, 0, (pc, pu, w, w_ptr, st), c, img, B, per_sample)
+            _lib.check(lib.sgdm_ddpm_step_ex(stream, pc, pu, w, w_ptr, st, c, clip, img.data_ptr(), nz.data_ptr(),
+                                             nxt.data_ptr(), _lib.ptr(x0), B, per_sample, dyn, mul))
             img, nxt = nxt, img
             if i in logs:
                 out["pred_x0"].append(x0.unsqueeze(0))

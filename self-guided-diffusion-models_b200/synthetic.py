@@ -52,11 +52,17 @@ def synthetic_state_dict(named_shapes, seed=0):
     return {n: synthetic_tensor(n, s, seed) for n, s in named_shapes}
 
 
-def noise_tape(shape, n_draws, seed=1234):
+def noise_tape(shape, n_draws, seed=1234, noise_dropout=0.0):
+    """Host-supplied randomness of one trajectory: x_T, the per-step noise and (noise_dropout > 0) the
+    F.dropout factor {0, 1/(1-p)} of every step, drawn after the noise so shorter tapes are prefixes."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     x_T = torch.randn(shape, generator=g)
     noise = torch.randn((n_draws, *shape), generator=g)
-    return {"x_T": x_T, "noise": noise}
+    tape = {"x_T": x_T, "noise": noise}
+    if noise_dropout > 0.0:
+        keep = torch.rand((n_draws, *shape), generator=g) >= noise_dropout
+        tape["dropout_mul"] = keep.float() * torch.ones(()).div(1.0 - noise_dropout)
+    return tape
 
 
 def synthetic_batch(condition_method, batch, cond_dim, image_size, layout_dim=0, seed=4321):

@@ -223,6 +223,11 @@ def gen_sampling(model, cfg, batch):
         "ddim10_eta1": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=1.0)),
         "native10": ("native", 10, dict(num_timesteps=10, ddim_eta=0.0)),
         "plms10": ("plms", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
+        # dynamic thresholding (the reference's own torch.quantile) and noise dropout; F.dropout's
+        # random factor is replaced by the tape's `dropout_mul` exactly like torch.randn by the noise
+        "ddim10_dtp": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=1.0, dtp=0.9)),
+        "native10_dtp_dropout": ("native", 10, dict(num_timesteps=10, dtp=0.95, noise_dropout=0.25)),
+        "ddim10_eta1_dropout": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=1.0, noise_dropout=0.25)),
     }
     for rname, (method, T, over) in runs.items():
         ld = ref_ddpm.LatentDiffusion(**diffusion_kwargs(T))
@@ -233,15 +238,23 @@ def gen_sampling(model, cfg, batch):
         skw.update(over)
         kw = prepare_denoise_fn_kwargs_4sampling(FakeModule(cfg), dict(data), skw, cond_scale=2.0)
         n_draws = 11 if method == "plms" else 10
-        tape = synthetic.noise_tape(shape, n_draws, seed=1234)
-        real_randn = torch.randn
+        tape = synthetic.noise_tape(shape, n_draws, seed=1234, noise_dropout=skw["noise_dropout"])
+        real_randn, real_dropout = torch.randn, torch.nn.functional.dropout
         torch.randn = Tape(tape)
+        if skw["noise_dropout"] > 0:  # the factor belonging to the noise drawn last
+            def taped_dropout(x, p=0.5, training=True, inplace=False):
+                if not training:  # the UNet's nn.Dropout modules in eval mode
+                    return x
+                assert p == skw["noise_dropout"]
+                return x * tape["dropout_mul"][torch.randn.k - 2]
+
+            torch.nn.functional.dropout = taped_dropout
         try:
             samples, inter = ld.p_sample_loop(method, shape, skw, denoise_sample_fn_kwargs=kw,
                                               condition_kwargs=dict(cond_scale=2.0, condition_method="label"))
             used = torch.randn.k
         finally:
-            torch.randn = real_randn
+            torch.randn, torch.nn.functional.dropout = real_randn, real_dropout
         assert used == 1 + n_draws, (rname, used)
         arrays[f"{rname}_samples"] = samples.numpy()
         arrays[f"{rname}_pred_x0"] = inter["pred_x0"].numpy()

@@ -165,7 +165,8 @@ def _ld(T, device="cuda"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("run", ["ddim10_eta0", "ddim10_eta1", "native10", "plms10"])
+@pytest.mark.parametrize("run", ["ddim10_eta0", "ddim10_eta1", "native10", "plms10", "ddim10_dtp", "native10_dtp_dropout",
+                                 "ddim10_eta1_dropout"])
 def test_sampling_vs_reference_golden(run):
     need_gpu()
     from sgdm_b200 import synthetic
@@ -181,7 +182,8 @@ def test_sampling_vs_reference_golden(run):
                temperature=1.0, noise_dropout=0, random_sample_condition=False, return_inter_dict=False,
                disable_tqdm=True)
     skw.update(over)
-    tape = synthetic.noise_tape((B, 3, H, H), 11 if method == "plms" else 10, seed=meta["tape_seed"])
+    tape = synthetic.noise_tape((B, 3, H, H), 11 if method == "plms" else 10, seed=meta["tape_seed"],
+                                noise_dropout=skw["noise_dropout"])
     kw = dict(cond=torch.from_numpy(g["data_label"]).cuda(), cond_scale=meta["cond_scale"])
     samples, inter = ld.p_sample_loop(method, (B, 3, H, H), skw, denoise_sample_fn_kwargs=kw,
                                       condition_kwargs=dict(cond_scale=2.0), noise_tape=tape)

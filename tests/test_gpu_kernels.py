@@ -528,6 +528,58 @@ def test_sampler_update_kernels_bit_exact(L):
         torch.cuda.synchronize()
         assert torch.equal(x0o.cpu(), x0)
         assert torch.equal(xo.cpu(), ref)
+    # sampling_kwargs extras: dynamic thresholding and noise dropout inside the fused updates
+    mul = (torch.rand(shape, generator=g) >= 0.25).float() * torch.ones(()).div(0.75)
+    muld = mul.cuda()
+    s_dev = torch.empty(B, device="cuda")
+    scratch = torch.empty_like(xd)
+    big = x * torch.tensor([0.5, 1.0, 2.0, 4.0]).view(B, 1, 1, 1)  # samples below and above the s > 1 regime
+    bigd = big.cuda()
+    for dtp in (0.9, 0.995, 0.37):
+        w = 2.0
+        e = (1 - w) * eu + w * ec
+        kw = dict(clip_denoised=True, dtp=dtp, temperature=0.7, noise_dropout=0.25)
+        dt = osched.ddim_tables(tab["alphas_cumprod"], 10, 1000, 1.0)
+        index = 4
+        ref_x, ref_x0 = osamp._ddim_update(big, e, dt, index, nz, kw, mul)
+        z = torch.zeros(())
+        a_t = torch.full_like(z, dt["alphas"][index]); a_p = torch.full_like(z, dt["alphas_prev"][index])
+        sg = torch.full_like(z, dt["sigmas"][index]); s1 = torch.full_like(z, dt["sqrt_one_minus_alphas"][index])
+        coef = (C.c_float * 6)(s1.item(), a_t.sqrt().item(), a_p.sqrt().item(), (1.0 - a_p - sg**2).sqrt().item(),
+                               sg.item(), 0.7)
+        ck(L, L.sgdm_dyn_threshold(S(), 1, P(ecd), P(eud), w, None, 0, coef, P(bigd), dtp, P(scratch), P(s_dev), B, per))
+        raw = (big - s1 * e) / a_t.sqrt()
+        s_ref = torch.quantile(raw.flatten(1).abs(), dtp, dim=-1).clamp(min=1.0)
+        assert torch.equal(scratch.cpu(), raw), "unclipped pred_x0 not bit-exact"
+        assert torch.equal(s_dev.cpu(), s_ref), "dynamic threshold differs from torch.quantile"
+        assert torch.equal(s_dev, torch.quantile(scratch.flatten(1).abs(), dtp, dim=-1).clamp(min=1.0)), "vs CUDA torch.quantile"
+        xo, x0o = torch.empty_like(xd), torch.empty_like(xd)
+        ck(L, L.sgdm_ddim_step_ex(S(), P(ecd), P(eud), w, None, 0, coef, 1, P(bigd), P(nzd), P(xo), P(x0o), None, B, per,
+                                  P(s_dev), P(muld)))
+        assert torch.equal(x0o.cpu(), ref_x0), "dynamically thresholded pred_x0 not bit-exact"
+        assert torch.equal(xo.cpu(), ref_x), "x_prev with dtp + noise dropout not bit-exact"
+        # DDPM flavour of the same
+        i = 500
+        t = torch.full((B,), i, dtype=torch.long)
+        x0 = osamp._ext(tab["sqrt_recip_alphas_cumprod"], t, x) * big - osamp._ext(tab["sqrt_recipm1_alphas_cumprod"], t, x) * e
+        x0 = osamp.clip_x0(x0, True, dtp)
+        mean = osamp._ext(tab["posterior_mean_coef1"], t, x) * x0 + osamp._ext(tab["posterior_mean_coef2"], t, x) * big
+        logvar = osamp._ext(tab["posterior_log_variance_clipped"], t, x)
+        ref = mean + (0.5 * logvar).exp() * ((nz * 0.7) * mul)
+        sig = (0.5 * tab["posterior_log_variance_clipped"]).exp()
+        coef = (C.c_float * 6)(tab["sqrt_recip_alphas_cumprod"][i].item(), tab["sqrt_recipm1_alphas_cumprod"][i].item(),
+                               tab["posterior_mean_coef1"][i].item(), tab["posterior_mean_coef2"][i].item(), sig[i].item(), 0.7)
+        ck(L, L.sgdm_dyn_threshold(S(), 0, P(ecd), P(eud), w, None, 0, coef, P(bigd), dtp, P(scratch), P(s_dev), B, per))
+        ck(L, L.sgdm_ddpm_step_ex(S(), P(ecd), P(eud), w, None, 0, coef, 1, P(bigd), P(nzd), P(xo), P(x0o), B, per,
+                                  P(s_dev), P(muld)))
+        assert torch.equal(x0o.cpu(), x0) and torch.equal(xo.cpu(), ref), "DDPM update with dtp + noise dropout"
+    # quantile kernel alone: ties, constants, exact-rank q, odd lengths
+    for n, q in ((1, 0.5), (2, 0.5), (777, 0.25), (12288, 0.9), (12288, 1.0 - 2**-20), (1001, 0.5)):
+        v = (torch.randn(3, n, generator=g) * 2).round() / 2 if n > 2 else torch.randn(3, n, generator=g) * 3
+        vd = v.cuda()
+        so = torch.empty(3, device="cuda")
+        ck(L, L.sgdm_k_quantile_abs(S(), P(vd), 3, n, q, P(so)))
+        assert torch.equal(so.cpu(), torch.quantile(v.abs(), q, dim=-1).clamp(min=1.0)), (n, q)
     # per-sample tensor cond_scale and the 'cfg' scale type
     wt = torch.linspace(0.5, 3.0, B)
     out = torch.empty_like(xd)

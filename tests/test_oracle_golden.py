@@ -104,7 +104,8 @@ def test_ddim_timesteps_quirks():
     assert list(osched.ddim_timesteps(10, 1000)) == [1, 101, 201, 301, 401, 501, 601, 701, 801, 901]
 
 
-@pytest.mark.parametrize("run", ["ddim10_eta0", "ddim10_eta1", "native10", "plms10"])
+@pytest.mark.parametrize("run", ["ddim10_eta0", "ddim10_eta1", "native10", "plms10", "ddim10_dtp", "native10_dtp_dropout",
+                                 "ddim10_eta1_dropout"])
 def test_sampling_matches_reference(run):
     meta, g = load_npz("sampling_tiny.npz")
     umeta, _ = load_unet_case(meta["unet_case"])
@@ -116,7 +117,7 @@ def test_sampling_matches_reference(run):
     skw = dict(ddim_eta=0.0, log_num_per_prog=10, clip_denoised=True, dtp=1, temperature=1.0, noise_dropout=0)
     skw.update(over)
     tape = synthetic.noise_tape((B, 3, cfg["image_size"], cfg["image_size"]), 11 if method == "plms" else 10,
-                                seed=meta["tape_seed"])
+                                seed=meta["tape_seed"], noise_dropout=skw["noise_dropout"])
     eps_fn = lambda x, t: ounet.forward_with_cond_scale(sd, cfg, x, t, meta["cond_scale"], cond=cond)
     with torch.no_grad():
         u8, inter, x = osamp.p_sample_loop(method, eps_fn, tape, dict(num_timesteps=T), skw)
