@@ -177,6 +177,11 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
                       const void* w, int ks, int stride, int Hout, int Wout, int Cout, const float* bias,
                       const float* res, int res_mode, float* out_f32, void* out_op, float* out_nchw, int block_n,
                       int naive, float* stats, int stat_gran, void* out_op2, const void* in2b, int C2b);
+/* the output head (3x3, stride 1, pad 1, 3 * Cout <= 16, NCHW fp32 result) with the horizontal taps folded into the
+ * GEMM's N dimension (openaimodel.py:830-835: the conv of self.out): w is the torch weight [Cout,Cin,3,3] fp32,
+ * w_scratch 16 * 3 * Cin op elements for its packed form; needs tiles of whole image rows (W | 128, H*W % 128 == 0) */
+int sgdm_k_conv_head_hfold(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
+                           const float* bias, float* out_nchw, int Cout);
 /* packs a torch conv weight [Cout,Cin,ks,ks] fp32 into dst[co][k_off + tap*cin_pad + ci] (row length ktot) */
 int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad,
                        int ktot, int k_off);

@@ -55,6 +55,14 @@ struct ConvDesc {
   int pair = -1;
   // halo mode (one activation load per horizontal tap, shared by the three vertical taps): -1 policy, 0 off, 1 on
   int halo = -1;
+  // Horizontal-tap folding for the output head (3x3, stride 1, 3 * Cout <= 16, NCHW epilogue, halo geometry):
+  // the GEMM computes, per pixel p and horizontal tap s, the partial sums P[p, s * Cout + co] = sum over
+  // (vertical tap r, channel c) of in(y + r - 1, x, c) * w[co, c, r, s] — one staged activation tile (rows
+  // y0-1 .. y0+bh, NO horizontal shift) serves all nine taps — and the epilogue adds the three shifted
+  // partials: out(y, x) = P[(y, x-1), s=0] + P[(y, x), s=1] + P[(y, x+1), s=2].  Activation bytes through
+  // L2 -> SM drop 3x against halo mode, the MMA count 3x.  `w` is then packed [16][3 * Cin]:
+  // row s * Cout + co, column r * Cin + c (pack_conv_weight_hfold_launch).
+  int hfold = 0;
   int smem_reserve = 0;         // shared-memory bytes to leave free per SM (two-stream mode: co-resident GroupNorm CTAs)
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
   int debug_stages = 0;         // tuning only: cap the K-block ring depth
@@ -77,6 +85,7 @@ struct alignas(64) ConvKernelParams {
   // K-block ring: stage = [activation slot: act_bytes][tps weight slots: wgt_bytes each]; *_tx = bytes TMA delivers
   int n_stages, act_bytes, act_tx, act_tx_halo, wgt_bytes, wgt_tx;
   int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
+  int hfold;                      // horizontal taps folded into the N dimension (output head)
   int tps2;                       // K blocks of the fused 1x1-skip source per stage (3 in halo mode, else 1)
   int epi_mode, epi_bufs;       // 0 NCHW direct | 1 fp32 NHWC | 2 16-bit NHWC; staging buffers per epilogue warp
   int out2;                     // epi_mode 1: also store the 16-bit copy

@@ -80,6 +80,7 @@ struct ConvW {
   int cin = 0, cin_pad = 0, cout = 0;
   op_t* w = nullptr;
   float* b = nullptr;
+  op_t* w_hfold = nullptr;  // output head only: the [16][3 * cin_pad] packing of ConvDesc::hfold
 };
 enum LayerKind { L_CONV_IN, L_RES, L_ATTN, L_DOWN, L_UP };
 struct Layer {
@@ -571,7 +572,18 @@ int setup_device(sgdm_engine* e) {
     const int ktot = 9 * cw.cin_pad;
     if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
     if (bind_f32(e, "out.2.bias", &cw.b)) return 1;
-    if (bind_loader(e, "out.2.weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0))) return 1;
+    // both packings of the head's weights (36 KB each): which one a plan uses depends on the image geometry
+    if (3 * cw.cout <= 16 && dalloc(e, &cw.w_hfold, static_cast<size_t>(16) * 3 * cw.cin_pad)) return 1;
+    auto std_pack = pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0);
+    op_t* wh = cw.w_hfold;
+    const int co = cw.cout, ci = cw.cin, cp = cw.cin_pad;
+    if (bind_loader(e, "out.2.weight", [=](const float* src, cudaStream_t st) {
+          if (std_pack(src, st)) return 1;
+          if (!wh) return 0;
+          ++g_launches;
+          return pack_conv_weight_hfold_launch(src, wh, co, ci, cp, st);
+        }))
+      return 1;
   }
   if (dalloc(e, &e->freqs, e->mc / 2 + 1)) return 1;
   e->device_ready = true;
@@ -648,6 +660,7 @@ struct Builder {
     // A/B switches for whole-step timing (same process image, same box): SGDM_CONV_HALO / SGDM_CONV_PAIR = 0 | 1
     if (const char* ev = getenv("SGDM_CONV_HALO")) d.halo = atoi(ev) ? -1 : 0;
     if (const char* ev = getenv("SGDM_CONV_PAIR")) d.pair = atoi(ev) ? -1 : 0;
+    if (d.hfold) { d.halo = 1; d.pair = 0; }
     if (d.in2 && d.swap_ab && getenv("SGDM_CONV_HALO_SKIP") != nullptr) d.halo = 0;  // A/B: swap-AB skip blocks take a whole halo stage each
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
@@ -1003,6 +1016,12 @@ struct Builder {
     ConvDesc d;
     d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
     d.Hout = H; d.Wout = W; d.Cout = c.out_channels; d.bias = e->conv_out.b; d.out_nchw = eps;
+    // horizontal-tap folding (ConvDesc::hfold) whenever the head's tiles are whole image rows; SGDM_CONV_HFOLD=0: A/B
+    const bool fold_env = !(getenv("SGDM_CONV_HFOLD") && atoi(getenv("SGDM_CONV_HFOLD")) == 0);
+    if (fold_env && e->conv_out.w_hfold && W <= 128 && (128 % W) == 0 && (W % 8) == 0 && ((H * W) % 128) == 0) {
+      d.hfold = 1;
+      d.w = e->conv_out.w_hfold;
+    }
     conv(d);
   }
 };
@@ -1391,6 +1410,24 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   if (conv_prepare(d, &l, msg, sizeof(msg))) return fail("%s", msg);
   if (conv_launch(l, static_cast<cudaStream_t>(stream)))
     return fail("conv launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+int sgdm_k_conv_head_hfold(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
+                           const float* bias, float* out_nchw, int Cout) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (3 * Cout > 16 || Cin % 64) return fail("conv_head_hfold: 3 * Cout <= 16 and Cin %% 64 == 0 required");
+  g_launches += 3;
+  if (cudaMemsetAsync(w_scratch, 0, static_cast<size_t>(16) * 3 * Cin * sizeof(op_t), st) != cudaSuccess ||
+      pack_conv_weight_hfold_launch(w, static_cast<op_t*>(w_scratch), Cout, Cin, Cin, st))
+    return fail("hfold weight pack failed");
+  ConvDesc d;
+  d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = H; d.Win = W; d.Cin = Cin; d.w = static_cast<const op_t*>(w_scratch);
+  d.ks = 3; d.stride = 1; d.pad = 1; d.Hout = H; d.Wout = W; d.Cout = Cout; d.bias = bias; d.out_nchw = out_nchw;
+  d.block_n = 16; d.hfold = 1; d.halo = 1; d.pair = 0;
+  ConvLaunch l;
+  char msg[256];
+  if (conv_prepare(d, &l, msg, sizeof(msg))) return fail("%s", msg);
+  if (conv_launch(l, st)) return fail("conv launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
 int sgdm_k_pack_weight(void* stream, const float* w, void* dst, int Cout, int Cin, int ks, int cin_pad, int ktot,

@@ -15,6 +15,7 @@
 // pair, the MMAs need ~2 k: FLOPs per launch = 4 * B * heads * T * T * D.
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "attn.cuh"
 #include "conv.cuh"
@@ -220,6 +221,219 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Second generation: TWO softmax warpgroups, one per query tile, running concurrently (10 warps).
+//   warp 0 (one lane)  TMA producer: Q|K (64 KB) and V (32 KB) of the next pair as soon as the MMAs that read
+//                                    them have retired (Q, K: after both S MMAs; V: after both PV MMAs)
+//   warp 1 (one lane)  MMA issuer  : an event loop over the two query tiles; per tile strictly S_j, PV_j, S_j, ...
+//   warps 2..5 / 6..9  softmax of query tile 0 / 1: thread = query row, exact two-pass softmax from TMEM, P_j
+//                                    into its OWN 64 KB operand buffer, O_j read back, scaled, stored
+// The first generation ran the two tiles back to back on four warps and spent most of a pair waiting on the
+// TMEM-load round trips of one warp per scheduler; with a warp of each group on every scheduler the round trips
+// of one tile hide behind the arithmetic of the other, and S / PV of one tile overlap the softmax of the other.
+// Shared memory: Q | K | V | P_0 | P_1 = 224 KB (single Q/K/V stage: the loads of the next pair are issued a whole
+// softmax ahead of their first use, so a second stage would buy nothing).
+constexpr int kTc2Threads = 320;
+constexpr int kTc2P = 4 * 16384;  // P_j: four K-major [128 x 64] blocks
+constexpr int kTc2Smem = 3 * kTcTile + 2 * kTc2P + 256;
+
+__global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTcTile + 2 * kTc2P);
+  uint64_t* qk_full = bars;        // TMA -> MMA
+  uint64_t* v_full = bars + 1;     // TMA -> MMA
+  uint64_t* qk_free = bars + 2;    // both S MMAs of a pair retired -> TMA
+  uint64_t* v_free = bars + 3;     // both PV MMAs of a pair retired -> TMA
+  uint64_t* s_ready = bars + 4;    // [2] S_j complete -> softmax group j
+  uint64_t* p_ready = bars + 6;    // [2] P_j staged (4 warps) -> MMA
+  uint64_t* o_ready = bars + 8;    // [2] O_j complete -> softmax group j
+  uint64_t* tfree = bars + 10;     // [2] O_j read out of TMEM (4 warps) -> MMA (S_j of the next pair)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(qk_free, 1);
+    mbar_init(v_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&tfree[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_my = blockIdx.x < p.pairs ? (p.pairs - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_my; ++it) {
+        const int pair = blockIdx.x + it * gridDim.x;
+        const int n = pair / p.heads, h = pair - n * p.heads;
+        const uint32_t ph = it & 1;
+        mbar_wait(qk_free, ph ^ 1);
+        mbar_arrive_expect_tx(qk_full, 2 * kTcTile);
+        tma_load_2d(&p.tm, qk_full, smem, p.q_col + h * p.head_stride, n * kTcT);
+        tma_load_2d(&p.tm, qk_full, smem + kTcTile, p.k_col + h * p.head_stride, n * kTcT);
+        mbar_wait(v_free, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, kTcTile);
+        tma_load_2d(&p.tm, v_full, smem + 2 * kTcTile, p.v_col + h * p.head_stride, n * kTcT);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(128, 256);
+      const uint32_t idesc_o = umma_idesc(128, 64) | (1u << 16);  // B operand (V) is MN-major
+      const uint32_t sbase = smem_u32(smem);
+      // per query tile: index of the next pair and whether its S has been issued (then PV is next)
+      int it_j[2] = {0, 0};
+      bool s_done[2] = {false, false};
+      uint32_t idle = 0;
+      while (it_j[0] < n_my || it_j[1] < n_my) {
+        bool progressed = false;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (it_j[j] >= n_my) continue;
+          const uint32_t ph = it_j[j] & 1;
+          if (!s_done[j]) {
+            // S_j = Q_j K^T: needs this pair's Q, K and the TMEM columns of tile j (O_j of the previous pair drained)
+            if (!mbar_try_wait(qk_full, ph) || !mbar_try_wait(&tfree[j], ph ^ 1)) continue;
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + j * 256, umma_smem_desc(sbase + j * 16384 + k * 32),
+                       umma_smem_desc(sbase + kTcTile + k * 32), idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_ready[j]);
+            s_done[j] = true;
+            // Q and K may be overwritten once the S MMAs of BOTH tiles of this pair have retired
+            if (s_done[j ^ 1] ? it_j[j ^ 1] == it_j[j] : it_j[j ^ 1] > it_j[j]) umma_commit(qk_free);
+            progressed = true;
+          } else {
+            // O_j = P_j V: P_j staged by the softmax group (which has then also finished reading S_j)
+            if (!mbar_try_wait(&p_ready[j], ph) || !mbar_try_wait(v_full, ph)) continue;
+            tc_fence_after();
+            const uint32_t pbase = sbase + 3 * kTcTile + j * kTc2P;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+              umma_f16(tmem_base + j * 256, umma_smem_desc(pbase + (kk >> 2) * 16384 + (kk & 3) * 32),
+                       umma_smem_desc(sbase + 2 * kTcTile + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
+            umma_commit(&o_ready[j]);
+            s_done[j] = false;
+            ++it_j[j];
+            // V may be overwritten once the PV MMAs of both tiles of this pair have retired
+            if (it_j[j ^ 1] >= it_j[j]) umma_commit(v_free);
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 27)) __trap();  // bounded like mbar_wait: a protocol bug must not hang the GPU
+      }
+    }
+  } else {
+    const int j = warp >= 6 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * 256;
+    const uint32_t x7 = r & 7;
+    const uint32_t pbase = smem_u32(smem) + 3 * kTcTile + j * kTc2P + r * 128;
+    for (int it = 0; it < n_my; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
+      const uint32_t ph = it & 1;
+      const int n = pair / p.heads, h = pair - n * p.heads;
+      mbar_wait(&s_ready[j], ph);
+      tc_fence_after();
+      // Both passes keep the TMEM load of the next 32 columns in flight while the current 32 are processed
+      // (two register buffers; tcgen05.wait::ld waits for everything outstanding, hence the issue order).
+      // pass 1: row maximum over the 256 keys, four independent chains
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 32 * (c + 1), vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(va[i]));
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 32 * ((c + 2) & 7), va);  // after the last chunk: chunk 0 again, for pass 2
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(vb[i]));
+      }
+      const float mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      // pass 2: exponentials (log2 domain), row sum, P as the 16-bit K-major operand
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial row sums
+      auto exp_chunk = [&](const uint32_t(&v)[32], int c) {
+        const uint32_t blk = pbase + (c >> 1) * 16384;  // K block of 64 keys
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = ex2f(__uint_as_float(v[8 * q + i]) * p.scale_log2 - mb);
+            l4[i & 3] += e[i];
+          }
+          const uint32_t ci = (c & 1) * 4 + q;  // 16-byte chunk (8 keys) inside the 128-byte row
+          sts128u_(blk + ((ci ^ x7) << 4), make_uint4(pack_op2(e[0], e[1]), pack_op2(e[2], e[3]), pack_op2(e[4], e[5]),
+                                                      pack_op2(e[6], e[7])));
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + 32 * (c + 1), vb);
+        exp_chunk(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) tmem_ld_32x32(taddr + 32 * (c + 2), va);
+        exp_chunk(vb, c + 1);
+      }
+      const float inv_l = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[j]);
+      mbar_wait(&o_ready[j], ph);
+      tc_fence_after();
+      {
+        // O_j row -> * 1/l -> 64 x 16-bit = 128 B of the output row
+        op_t* dst = p.out + (static_cast<long>(n) * kTcT + j * 128 + r) * p.o_row_stride + h * kTcD;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tfree[j]);  // the values are in registers: tile j's TMEM columns are free
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t(&v)[32] = half == 0 ? v0 : v1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 o = make_uint4(pack_op2(__uint_as_float(v[8 * c]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
+                                       pack_op2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
+                                       pack_op2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
+                                       pack_op2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(dst + 32 * half + 8 * c) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // The tcgen05 path covers the UNet's self-attention shape; everything else stays on the mma.sync kernel.
 bool attn_tc_applicable(const AttnDesc& a) {
   if (a.T != kTcT || a.D != kTcD || a.n_extra != 0) return false;
@@ -248,11 +462,16 @@ int attn_tc_launch(const AttnDesc& a, cudaStream_t s) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess)
+      return 1;
     attr_set = true;
   }
   const int grid = p.pairs < kNumSMs ? p.pairs : kNumSMs;
-  attn_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(p);
+  // SGDM_ATTN_TC_GEN = 1 selects the first-generation kernel (one softmax warpgroup, two-stage Q/K/V ring): A/B switch
+  static const int gen = getenv("SGDM_ATTN_TC_GEN") ? atoi(getenv("SGDM_ATTN_TC_GEN")) : 2;
+  if (gen == 1) attn_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(p);
+  else attn_tc2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -17,6 +17,7 @@
 // Roofline: tensor pipe.  FLOPs per launch = 2 * M_total * Cout * Ktot.
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv.cuh"
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       long long t_prod = 0;
       uint32_t fill = 0;
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
-      const int n_main = (p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
+      const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
         const int n_tile = tile % p.n_tiles;
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const int tap = q / p.kc1;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
             cc = q - tap * p.kc1;
             const int r = p.halo ? 0 : tap / p.ks;
-            const int s_tap = p.halo ? tap : tap - r * p.ks;
-            kb0 = p.halo ? s_tap * p.kc1 + cc : q;
+            const int s_tap = p.hfold ? p.pad : p.halo ? tap : tap - r * p.ks;  // hfold: no horizontal shift
+            kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q;
             if (!skip_a) {
               if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
               else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
@@ -229,7 +230,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (!skip_b) {
             for (int t = 0; t < ntap; ++t) {
               // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
-              const int kb = kb0 + (main_st ? t * p.ks * p.kc1 : t);
+              // (hfold: the packed K axis is (vertical tap, channel) only)
+              const int kb = kb0 + (main_st ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
               if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n + cta_rank * b_rows);
               else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n);
             }
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
       uint32_t stage = 0, phase = 0, it = 0;
       long long t_full = 0, t_acc = 0;
-      const int n_main = (p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
+      const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const long long ta0 = p.timing ? clock64() : 0;
@@ -338,7 +340,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         tmem_ld_32x16(taddr, v);
         tmem_ld_wait();
         const int m = m_tile * kTileM + quarter * 32 + lane;
-        if (m < p.M_total) {
+        if (p.hfold) {
+          // v[s * Cout + co] = partial sum of horizontal tap s at THIS pixel; out(x) = P[x-1][s=0] + P[x][s=1] +
+          // P[x+1][s=2].  Tiles are whole image rows, so both neighbours live in this tile (or are padding).
+          // Exchange through shared memory, double-buffered by tile parity: one named barrier per tile.
+          const int nco = p.N_total, row = quarter * 32 + lane;
+          const uint32_t xb = epi_all + (it & 1) * (kTileM * 60);  // [128 pixels][15 floats]: odd stride, no conflicts
+#pragma unroll
+          for (int j = 0; j < 15; ++j) sts32(xb + (row * 15 + j) * 4, __uint_as_float(v[j]));
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int x = m % p.Wout;
+          const int img = m / p.HW, pix = m - img * p.HW;
+          for (int co = 0; co < nco; ++co) {
+            float o = lds32(xb + (row * 15 + nco + co) * 4) + (p.bias ? __ldg(p.bias + co) : 0.f);
+            if (x > 0) o += lds32(xb + ((row - 1) * 15 + co) * 4);
+            if (x < p.Wout - 1) o += lds32(xb + ((row + 1) * 15 + 2 * nco + co) * 4);
+            p.out_nchw[(static_cast<long>(img) * nco + co) * p.HW + pix] = o;
+          }
+        } else if (m < p.M_total) {
           const int img = m / p.HW, pix = m - img * p.HW;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -425,14 +444,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         tc_fence_after();
         SGDM_T(0);
         for (int i = 0; i < n_chunks; ++i, ++g) {
-          const uint32_t b = tma_res ? (g % NB) : (g & 1);
+          const uint32_t b = tma_res2 ? (g & 1) : (g % NB);
           const uint32_t baddr = ebuf0 + b * kEpiBuf;
           const uint32_t b2addr = epi2_all + (wq * 2 + (g & 1)) * 2048;  // 16-bit copy tile (second output)
           const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
           const int col0 = p.swap_ab ? tile_col0 : tile_col0 + cpc * i;
           // the buffer written next (by the residual load for chunk g+NB-2, or by this chunk when there is
           // no residual) was last read by the TMA store of chunk g-2: all but the newest store must be done
-          if (lane == 0) bulk_wait_read<1>();
+          // (without a residual all NB buffers rotate as store sources: the store of chunk g-NB must be done)
+          if (lane == 0) {
+            if (tma_res || tma_res2 || NB == 2 || p.out2) bulk_wait_read<1>();  // (the 16-bit copy staging is 2 deep)
+            else if (NB == 3) bulk_wait_read<2>();
+            else bulk_wait_read<3>();
+          }
           __syncwarp();
           SGDM_T(1);
           if (tma_res || tma_res2) {
@@ -778,6 +802,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   bool halo = d.halo != 0 && d.ks == 3 && d.stride == 1 && bn == 1 && bw * bh == tile_px && (HW % tile_px) == 0 &&
               (d.Wout % 8) == 0 && bh + 2 <= 256;
   if (d.halo == 1 && !halo) return fail("halo mode needs a 3x3 stride-1 conv whose tiles are whole rows of one image");
+  if (d.hfold && (!halo || !d.out_nchw || 3 * d.Cout > 16 || d.in2 || d.swap_ab || pair))
+    return fail("hfold needs the NCHW head (3 * Cout <= 16) in halo geometry, one CTA per tile");
   const int b_rows = d.block_n / (pair ? 2 : 1);  // weight rows per CTA and stage slot
   p.wgt_tx = d.swap_ab ? kABytes : b_rows * 128;
   p.wgt_bytes = (p.wgt_tx + 1023) / 1024 * 1024;
@@ -791,7 +817,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const int budget = smem_cap - kBarBytes - kBiasBytes - (p.out2 ? kEpi2Bytes : 0);
   // staging buffers per epilogue warp: 2 without a residual; res_mode 1 adds the in-place residual ring (>= 3,
   // up to 6: in-flight residual bytes per SM must cover HBM latency); res_mode 2 uses four 2 KB slots in two more
-  const int min_bufs = p.epi_mode == 0 ? 0 : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
+  // (the NCHW head needs no staging; with hfold its pixel-exchange buffers, 2 x 4.5 KB, live in that region)
+  const int min_bufs = p.epi_mode == 0 ? (d.hfold ? 1 : 0) : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
   int n_stages = 0;
   bool pack_skip = true;  // three skip-source K blocks per halo stage (needs a 48 KB activation slot)
   for (int pass = 0; pass < 3; ++pass) {
@@ -809,7 +836,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     n_stages = (budget - 4 * min_bufs * kEpiBuf) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
     if (n_stages < min_stages && p.tps2 == 3) { pack_skip = false; continue; }     // first give up the skip packing,
-    if (n_stages < min_stages && halo && d.halo != 1) { halo = false; continue; }  // then fall back to per-tap stages
+    if (n_stages < min_stages && halo && d.halo != 1 && !d.hfold) { halo = false; continue; }  // then fall back to per-tap stages
     if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
@@ -820,6 +847,14 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     }
     break;
   }
+  // Without a residual the staging buffers only rotate as TMA-store sources: two suffice, up to two more are
+  // taken from shared memory the K-block ring left over (never from the ring itself: measured, reserving them
+  // up front costs halo-mode stages and 3.5 ms per step).  A/B knob: SGDM_EPI_BUFS_EXTRA=0 keeps two.
+  static const bool extra_bufs = !(getenv("SGDM_EPI_BUFS_EXTRA") && atoi(getenv("SGDM_EPI_BUFS_EXTRA")) == 0);
+  if (extra_bufs && p.epi_mode != 0 && p.res_mode == 0) {
+    const int left = budget - n_stages * (p.act_bytes + p.tps * p.wgt_bytes) - 4 * min_bufs * kEpiBuf;
+    p.epi_bufs = min(4, min_bufs + left / (4 * kEpiBuf));
+  }
   if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
   out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
@@ -828,7 +863,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
     if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen)) return 1;
   }
-  const int Ktot = d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
+  const int Ktot = d.hfold ? d.ks * d.Cin : d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
   const int npad = conv_npad(d.Cout, d.block_n);
   {
     auto fn = get_encode_fn();
@@ -859,6 +894,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.block_n = d.block_n;
   p.n_tiles = npad / d.block_n;
   p.swap_ab = d.swap_ab;
+  p.hfold = d.hfold;
   p.tile_px = tile_px;
   p.m_tiles = (p.M_total + tile_px - 1) / tile_px;
   p.bias = d.bias;

@@ -134,6 +134,7 @@ int lincomb_launch(const float* const* a, const float* c, int n_terms, float div
 // ---- weight packing --------------------------------------------------------------------------
 // torch conv weight fp32 [Cout, Cin, ks, ks] -> op_t dst[co][k_off + (r*ks+s)*cin_pad + ci] (row length ktot);
 // channels ci >= Cin (padding) are left untouched (buffers are zero-initialised).
+int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s);
 int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
                             const int* ci_map, cudaStream_t s);
 int add_bias_launch(const float* a, const float* b, float* out, int n, cudaStream_t s);

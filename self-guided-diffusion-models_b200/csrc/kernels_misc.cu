@@ -1,6 +1,8 @@
 // HBM-bound kernels: GroupNorm(+FiLM+SiLU+resample), LayerNorm, casts, the fp32 prologue
 // (timestep embedding, null substitution, small MLPs), the fused guidance-mix + sampler
 // update, uint8 conversion and weight packing.  See kernels.cuh for the reference lines.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace sgdm {
@@ -227,6 +229,10 @@ __device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, i
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
   }
 }
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
 __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
   uint4 o = make_uint4(pack_op2(y[0], y[1]), pack_op2(y[2], y[3]), pack_op2(y[4], y[5]), pack_op2(y[6], y[7]));
   *reinterpret_cast<uint4*>(dst) = o;
@@ -267,16 +273,20 @@ __global__ void __launch_bounds__(256, kResample == 0 ? 4 : 3) gn_apply_kernel(c
   // y = ((v - mean) rstd gamma + beta) (1 + scale) + shift  ==  v * ka + kb
   float ka[8], kb[8];
   {
+    // eight consecutive channels: 16-byte loads (c % 8 == 0; every base is 16-byte aligned, checked at launch)
     const float* f = a.film ? a.film + static_cast<long>(n) * a.film_stride : nullptr;
+    float gm[8], bt[8], fs[8], fb[8];
+    ld8(a.gamma + c, gm);
+    ld8(a.beta + c, bt);
+    if (f) { ld8(f + c, fs); ld8(f + C + c, fb); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cpg;
-      const float ga = __ldg(a.gamma + c + j) * s_rstd[g];
-      const float be = __ldg(a.beta + c + j) - s_mean[g] * ga;
-      const float fs = f ? 1.0f + __ldg(f + c + j) : 1.0f;
-      const float fb = f ? __ldg(f + C + c + j) : 0.0f;
-      ka[j] = ga * fs;
-      kb[j] = be * fs + fb;
+      const float ga = gm[j] * s_rstd[g];
+      const float be = bt[j] - s_mean[g] * ga;
+      const float s1 = f ? 1.0f + fs[j] : 1.0f;
+      ka[j] = ga * s1;
+      kb[j] = f ? be * s1 + fb[j] : be;
     }
   }
   auto xform = [&](const float (&v)[8], float (&y)[8]) {
@@ -429,7 +439,14 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
   // the per-block prologue (group statistics, folded scale / offset per channel) is amortised over ppb pixels
   int ppb = PLa * (d.src0_is_op ? 64 : 32);
   while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 8 * kNumSMs) ppb >>= 1;
+  // A/B knob (whole-step timing on one box): SGDM_GN_PPB_SHIFT = k scales the pixels per block by 2^k
+  static const int ppb_shift = getenv("SGDM_GN_PPB_SHIFT") ? atoi(getenv("SGDM_GN_PPB_SHIFT")) : 0;
+  if (ppb_shift > 0) ppb <<= ppb_shift;
+  if (ppb_shift < 0) ppb = ppb >> (-ppb_shift) > PLa ? ppb >> (-ppb_shift) : PLa;
   if (ppb > n_iter) ppb = n_iter;
+  if ((reinterpret_cast<uintptr_t>(d.gamma) | reinterpret_cast<uintptr_t>(d.beta) | reinterpret_cast<uintptr_t>(d.film)) & 15 ||
+      (d.film && (d.film_stride & 3)))
+    return 1;
   GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
                 d.silu, d.resample, d.chunks, ppb, PLa, d.partial, gn_fused(d) ? d.final : nullptr, d.out, d.raw_out,
                 d.pool_out};
@@ -905,6 +922,22 @@ int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks
   const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
   pack_conv_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ks, cin_pad,
                                                                                    ktot, k_off, ci_map);
+  return SGDM_LAUNCH_OK();
+}
+// Output head with folded horizontal taps (ConvDesc::hfold): dst[(s * Cout + co)][r * cin_pad + ci] = w[co][ci][r][s],
+// 16 rows of 3 * cin_pad columns (rows >= 3 * Cout and padded channels stay zero).
+__global__ void pack_conv_weight_hfold_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin,
+                                              int cin_pad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * 9 * Cin) return;
+  const int ci = idx % Cin, tap = (idx / Cin) % 9, co = idx / (9 * Cin);
+  const int r = tap / 3, s = tap - 3 * r;
+  dst[static_cast<long>(s * Cout + co) * (3 * cin_pad) + r * cin_pad + ci] = to_op(w[((static_cast<long>(co) * Cin + ci) * 3 + r) * 3 + s]);
+}
+int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s) {
+  if (3 * Cout > 16) return 1;
+  const int total = Cout * 9 * Cin;
+  pack_conv_weight_hfold_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cin, cin_pad);
   return SGDM_LAUNCH_OK();
 }
 __global__ void add_bias_kernel(const float* a, const float* b, float* out, int n) {

@@ -164,6 +164,39 @@ def test_conv_tcgen05_vs_torch(L, case):
         assert e < (2e-3 if out == "op" else 2e-5), f"{label} conv mismatch {e}"
 
 
+HFOLD_CASES = [
+    (3, 64, 64, 128, 3, "64x64 head of config 2 (2-row tiles)"),
+    (2, 32, 32, 64, 3, "32x32 head of config 1"),
+    (5, 16, 16, 128, 3, "16x16, odd batch"),
+    (300, 16, 16, 64, 3, "600 tiles > 148 CTAs: ring and exchange-buffer reuse"),
+    (2, 32, 32, 128, 5, "Cout=5: 15 folded columns"),
+    (1, 128, 128, 64, 4, "128-wide rows (one row per tile), Cout=4"),
+]
+
+
+@pytest.mark.parametrize("case", HFOLD_CASES, ids=[c[-1] for c in HFOLD_CASES])
+def test_conv_head_folded_horizontal_taps(L, case):
+    """The output head with the three horizontal taps folded into the GEMM N dimension (ConvDesc::hfold)
+    against torch conv2d on the same rounded operands; also against the plain per-tap kernel path."""
+    B, H, W, Cin, Cout, note = case
+    g = torch.Generator(device="cuda").manual_seed(hash(note) % 2**31)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(Cin * 9)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=1)
+    out = torch.full((B, Cout, H, W), float("nan"), device="cuda")
+    scratch = torch.empty(16 * 3 * Cin, dtype=L._op, device="cuda")
+    ck(L, L.sgdm_k_conv_head_hfold(S(), P(x), B, H, W, Cin, P(w), P(scratch), P(bias), P(out), Cout))
+    torch.cuda.synchronize()
+    e = relerr(out, ref)
+    print(f"[conv head hfold {note}] rel_l2={e:.3e}")
+    assert e < 2e-5
+    if Cout <= 3:
+        wp, bn = pack_weight(L, w)
+        out2 = run_conv(L, x, wp, bn, 3, 1, Cout, H, W, bias=bias, out="nchw")
+        assert relerr(out, out2) < 2e-6
+
+
 STATS_CASES = [
     # (B, H, W, Cin, Cout, ks, res_mode, out, block_n, gran, note)
     (3, 16, 16, 64, 256, 3, 1, "f32", 256, 4, "fp32 out + residual, N=256, gran 4"),

@@ -34,7 +34,7 @@ def run(name, B, H, Cin, Cout, ks, out, res, stats, pair, iters=10, halo=-1):
     L.sgdm_debug_set_conv_halo(halo)
     def go():
         rc = L.sgdm_k_conv_stats(S(), P(x), B, H, H, Cin, None, 0, P(wp), ks, 1, H, H, Cout, P(bias), P(r), 1 if res else 0,
-                                 P(o32), P(oop), None, 0, 0, P(st), 4)
+                                 P(o32), P(oop), None, 0, 0, P(st), 4, None, None, 0)
         assert rc == 0, L.sgdm_last_error().decode()
     for _ in range(3): go()
     torch.cuda.synchronize()
