@@ -191,29 +191,23 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
   if (a.use_tc != 0 && attn_tc_applicable(a)) return attn_tc_launch(a, s);
   const int Tkv = a.n_extra + a.T;
   const int tkv_pad = (Tkv + 63) / 64 * 64;
-  if (a.D != 32 && a.D != 64) return 1;
+  if (a.D != 32 && a.D != 64 && a.D != 128) return 1;  // head dims of the reference configs (mc 64 / 128 / 256, 8 heads)
   const int LD = a.D + 8;
   const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + kAttnQ) * LD * sizeof(op_t);
   if (smem > 200 * 1024) return 1;
   const dim3 grid((a.T + kAttnQ - 1) / kAttnQ, a.heads, a.B);
-  static size_t max_set[2] = {0, 0};  // opt-in dynamic smem limit, raised on demand
-  if (a.D == 64) {
-    if (smem > max_set[0]) {
-      if (cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)) != cudaSuccess)
+  static size_t max_set[3] = {0, 0, 0};  // opt-in dynamic smem limit, raised on demand
+  auto run = [&](auto kernel, size_t& limit) {
+    if (smem > limit) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return 1;
-      max_set[0] = smem;
+      limit = smem;
     }
-    attn_kernel<64><<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
-  } else {
-    if (smem > max_set[1]) {
-      if (cudaFuncSetAttribute(attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)) != cudaSuccess)
-        return 1;
-      max_set[1] = smem;
-    }
-    attn_kernel<32><<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
-  }
+    kernel<<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
+    return 0;
+  };
+  if (a.D == 64 ? run(attn_kernel<64>, max_set[0]) : a.D == 32 ? run(attn_kernel<32>, max_set[1]) : run(attn_kernel<128>, max_set[2]))
+    return 1;
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -32,7 +32,7 @@ constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int kBarBytes = 512;
 constexpr int kBiasBytes = 2 * 256 * 4;  // bias of the tile's columns, double-buffered by tile parity
 constexpr int kEpiBuf = 4096;            // one epilogue staging buffer: 32 rows x 128 B
-constexpr int kMaxEpiBufs = 6;
+constexpr int kMaxEpiBufs = 8;  // barrier slots per warp; the policy below uses up to max_epi_bufs() of them
 constexpr int kEpi2Bytes = 4 * 2 * 2048;  // staging of the optional 16-bit copy: 32 rows x 64 B, double-buffered per warp
 
 // ---- shared-window accessors (explicit state space: the 1024-byte alignment of the dynamic smem base
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
+        int q_tap = 0, q_cc = 0, q_r = 0;
         for (int q = 0; q < n_st; ++q) {
           const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
@@ -205,10 +206,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           uint8_t* wgt_dst = act_dst + p.act_bytes;
           int cc, kb0;
           if (main_st) {
-            const int tap = q / p.kc1;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
-            cc = q - tap * p.kc1;
-            const int r = p.halo ? 0 : tap / p.ks;
+            // (tap, chunk) and (r, s) of the tap are walked with counters: no integer divisions per K block
+            const int tap = q_tap;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
+            cc = q_cc;
+            const int r = p.halo ? 0 : q_r;
             const int s_tap = p.hfold ? p.pad : p.halo ? tap : tap - r * p.ks;  // hfold: no horizontal shift
+            if (++q_cc == p.kc1) {
+              q_cc = 0;
+              ++q_tap;
+              if (q_tap - q_r * p.ks == p.ks) ++q_r;
+            }
             kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q;
             if (!skip_a) {
               if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
@@ -395,20 +402,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // residual prefetch cursor: runs NB-2 chunks ahead of the processing cursor (in-flight residual bytes
       // per SM = 4 warps x (NB-2) x 4 KB must cover HBM latency x the residual read rate).  NB slots per warp:
       // res_mode 1: the 4 KB staging buffers themselves; res_mode 2: 2 KB slots behind two staging buffers.
+      // The cursor's tile coordinates (integer divisions: ~600 clk on one lane, measured as a constant residual
+      // wait per chunk when they were redone for every chunk) are derived once per tile.
       int pre_tile = tile_begin, pre_i = 0;
-      uint32_t g = 0, gp = 0;  // chunks processed / residual tiles requested
+      int pre_r0 = 0, pre_c0 = 0;  // output row (or, res_mode 2, source row) / column of chunk 0 of pre_tile
+      auto set_pre = [&]() {
+        if (pre_tile >= total_tiles) return;
+        chunk_coords(pre_tile, 0, pre_r0, pre_c0);
+        if (tma_res2) pre_r0 = src_row(pre_r0);
+      };
+      set_pre();
+      // chunks processed (g; slot g % NB and ring-pass parity kept incrementally: NB is a runtime value) and the
+      // slot of the next residual request
+      uint32_t g = 0, gslot = 0, gphase = 0, pslot = 0;
       auto res_slot_addr = [&](uint32_t slot) { return tma_res ? ebuf0 + slot * kEpiBuf : ebuf0 + 2 * kEpiBuf + slot * 2048; };
       auto issue_res = [&]() {
         if (pre_tile >= total_tiles) return;
         if (lane == 0) {
-          int r0, c0;
-          chunk_coords(pre_tile, pre_i, r0, c0);
-          const uint32_t slot = gp % NB;
+          // chunk pre_i of the tile: 32 rows further down (swap-AB) or cpc columns further right
+          const int r0 = p.swap_ab ? pre_r0 + 32 * pre_i : pre_r0;
+          const int c0 = p.swap_ab ? pre_c0 : pre_c0 + cpc * pre_i;
+          const uint32_t slot = pslot;
           mbar_arrive_expect_tx(&rbar[slot], tma_res ? kEpiBuf : 2048);
-          tma_load_2d_a(&p.tmRes, smem_u32(&rbar[slot]), res_slot_addr(slot), c0, tma_res ? r0 : src_row(r0));
+          tma_load_2d_a(&p.tmRes, smem_u32(&rbar[slot]), res_slot_addr(slot), c0, r0);
         }
-        ++gp;
-        if (++pre_i == n_chunks) { pre_i = 0; pre_tile += tile_step; }
+        if (++pslot == NB) pslot = 0;
+        if (++pre_i == n_chunks) { pre_i = 0; pre_tile += tile_step; set_pre(); }
       };
       if (tma_res || tma_res2)
         for (uint32_t k = 0; k + 2 < NB; ++k) issue_res();
@@ -444,7 +463,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         tc_fence_after();
         SGDM_T(0);
         for (int i = 0; i < n_chunks; ++i, ++g) {
-          const uint32_t b = tma_res2 ? (g & 1) : (g % NB);
+          const uint32_t b = tma_res2 ? (g & 1) : gslot;
           const uint32_t baddr = ebuf0 + b * kEpiBuf;
           const uint32_t b2addr = epi2_all + (wq * 2 + (g & 1)) * 2048;  // 16-bit copy tile (second output)
           const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
@@ -461,7 +480,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           SGDM_T(1);
           if (tma_res || tma_res2) {
             issue_res();
-            mbar_wait(&rbar[g % NB], (g / NB) & 1);
+            mbar_wait(&rbar[gslot], gphase);
           }
           SGDM_T(2);
           // All shared-memory loads of a phase are issued back to back before their first use (the accessors
@@ -550,7 +569,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 4; ++c) rr[c] = lds128(rowaddr + (((4 * hf + c) ^ x7) << 4));
               } else if (tma_res2) {
-                const uint32_t ra = res_slot_addr(g % NB) + s_r * 128;
+                const uint32_t ra = res_slot_addr(gslot) + s_r * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) rr[c] = lds128(ra + (((4 * hf + c) ^ (s_r & 7)) << 4));
               }
@@ -680,6 +699,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           SGDM_T(6);
           t_acc_[7] += 1;
+          if (++gslot == NB) { gslot = 0; gphase ^= 1; }
         }
         tc_fence_before();
         __syncwarp();
@@ -841,9 +861,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
       // trade ring depth beyond the minimum for a deeper residual ring
-      while (n_stages > min_stages && (budget - n_stages * stage_bytes) / (4 * kEpiBuf) < kMaxEpiBufs) --n_stages;
+      static const int max_bufs = getenv("SGDM_MAX_EPI_BUFS") ? max(3, min(kMaxEpiBufs, atoi(getenv("SGDM_MAX_EPI_BUFS")))) : 6;
+      while (n_stages > min_stages && (budget - n_stages * stage_bytes) / (4 * kEpiBuf) < max_bufs) --n_stages;
       p.epi_bufs = (budget - n_stages * stage_bytes) / (4 * kEpiBuf);
-      if (p.epi_bufs > kMaxEpiBufs) p.epi_bufs = kMaxEpiBufs;
+      if (p.epi_bufs > max_bufs) p.epi_bufs = max_bufs;
     }
     break;
   }

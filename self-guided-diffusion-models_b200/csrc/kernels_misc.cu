@@ -393,7 +393,7 @@ int gn_chunks_for(int B, int HW, int C) {
 
 static int gn_check(const GnDesc& d) {
   const int C = d.C0 + d.C1, HW = d.H * d.W;
-  if (C % 32 || C > 1024 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;
+  if (C % 32 || C > 2048 || d.C0 % 8 || d.C1 % 8 || HW % d.chunks) return 1;  // 2048: the mc = 256 skip concats
   return 0;
 }
 
@@ -414,6 +414,7 @@ int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
 
 int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
   if (gn_check(d) || (d.src0_is_op && d.C1)) return 1;  // a 16-bit concat only comes with producer statistics
+  if (!d.src0_is_op && d.C0 + d.C1 > 1024) return 1;    // one thread per 4 channels, 256 threads
   const int C = d.C0 + d.C1, HW = d.H * d.W;
   if (d.src0_is_op) {
     const int C8 = C / 8;

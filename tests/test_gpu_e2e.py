@@ -288,6 +288,68 @@ def test_oracle_parity_on_fresh_seeded_inputs():
         assert e <= EPS_TOL
 
 
+VARIANT_CFGS = {
+    # config/dynamic/unet_fast_s64.yaml: model_channels 256 (shrunk to 32x32 so the CPU oracle stays quick)
+    "unet_fast_s64 (mc=256)": dict(kind="unet_fast", image_size=32, in_channels=3, out_channels=3, model_channels=256,
+                                   num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
+                                   resblock_updown=True, cond_dim=100, condition_method="label", layout_dim=0,
+                                   context_dim=None, cond_token_num=0, scale_type="imagen"),
+    # BASELINE config 3: self-labeled cluster guidance, cond_dim 5000
+    "cfg3 cluster cond_dim=5000": dict(kind="unet_fast", image_size=32, in_channels=3, out_channels=3, model_channels=128,
+                                       num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
+                                       resblock_updown=True, cond_dim=5000, condition_method="cluster", layout_dim=0,
+                                       context_dim=None, cond_token_num=0, scale_type="imagen"),
+    # scale_type 'cfg' (openaimodel.py:857: (1 + w) eps_c - w eps_u) on the cross-attention UNet
+    "unetca clusterlayout, scale_type=cfg": dict(kind="unetca_fast", image_size=32, in_channels=3, out_channels=3,
+                                                 model_channels=64, num_res_blocks=2, channel_mult=[1, 2, 4],
+                                                 attention_resolutions=[4], num_heads=8, resblock_updown=False, cond_dim=100,
+                                                 condition_method="clusterlayout", layout_dim=1, context_dim=32,
+                                                 cond_token_num=1, scale_type="cfg"),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(VARIANT_CFGS))
+def test_variant_configs_vs_oracle(name):
+    """`dynamic` variants outside the golden files, on fresh seeded inputs: CUDA path vs the CPU oracle
+    (itself pinned to the reference on the same architecture families)."""
+    need_gpu()
+    from oracle import unet as ounet
+    from sgdm_b200 import synthetic
+    import test_host_mirror as thm
+
+    cfg = VARIANT_CFGS[name]
+    saved = thm.CONDITION
+    if cfg["scale_type"] != "imagen":
+        from types import SimpleNamespace as NS
+        thm.CONDITION = NS(scale_type=cfg["scale_type"], clusterlayout=NS(layout_dim=1, how="lost"),
+                           stegoclusterlayout=NS(layout_dim=27), layout=NS(layout_dim=21))
+    try:
+        m = build_model(cfg)
+    finally:
+        thm.CONDITION = saved
+    shapes = [(n, tuple(v.shape)) for n, v in m.state_dict().items()]
+    m.load_state_dict(synthetic.synthetic_state_dict(shapes, 3))
+    m = m.cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    B, H = 2, cfg["image_size"]
+    g = torch.Generator().manual_seed(91)
+    x = torch.randn(B, 3, H, H, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    data = synthetic.synthetic_batch(cfg["condition_method"], B, cfg["cond_dim"], H, cfg["layout_dim"], seed=92)
+    if cfg["condition_method"] == "clusterlayout":
+        kw = dict(cond=data["cluster"].float(), layout=data["lostbboxmask"].float())
+    else:
+        kw = dict(cond=data[cfg["condition_method"]])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref = ounet.forward_with_cond_scale(sd, cfg, x, t, 2.0, **kw)
+    got = m.forward_with_cond_scale(x.cuda(), t.cuda(), 2.0, **dev(kw))
+    e = rel_l2(got.cpu(), ref)
+    print(f"[variant {name}] guided eps rel_l2 vs oracle = {e:.3e}")
+    assert e <= EPS_TOL
+
+
 def smoke_check():
     """Used by __graft_entry__.smoke(): one guided step + one DDIM update vs the oracle."""
     from oracle import sampler as osamp

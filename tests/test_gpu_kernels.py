@@ -397,6 +397,8 @@ ATTN_CASES = [
     (2, 256, 8, 64, 17, True, "multi-query + 17 context/null keys (Attention_LR)"),
     (2, 16, 8, 32, 17, True, "MQA, T=16 d=32"),
     (1, 100, 4, 64, 5, True, "ragged T=100"),
+    (2, 256, 8, 128, 0, False, "legacy, T=256 d=128 (unet_fast_s64: mc=256)"),
+    (2, 64, 8, 128, 0, False, "legacy, T=64 d=128"),
 ]
 
 

@@ -75,6 +75,15 @@ if os.environ.get("KNOBS"):
             run(name, B, H, Cin, Cout, ks, "op", False, False, pair)
     L.sgdm_debug_set_conv_knobs(0, 0)
     sys.exit(0)
+if os.environ.get("RESIDUAL"):
+    # residual-epilogue experiments: fp32 out + residual + statistics, optional ring-depth cap (EXP_STAGES);
+    # combine with SGDM_MAX_EPI_BUFS (read once per process)
+    L.sgdm_debug_set_conv_knobs(int(os.environ.get("EXP_STAGES", "0")), 0)
+    for name in sys.argv[1:] or ["proj 512->512 1x1 @16 B512", "conv 128->128 3x3 @64 B512", "conv 512->512 3x3 @16 B512"]:
+        B, H, Cin, Cout, ks = SHAPES[name]
+        run(name, B, H, Cin, Cout, ks, "f32", True, True, -1)
+    L.sgdm_debug_set_conv_knobs(0, 0)
+    sys.exit(0)
 if os.environ.get("HALO"):
     SHAPES["last 128->3 3x3 @64 B512"] = (512, 64, 128, 3, 3)
     for name in ("conv 512->512 3x3 @16 B512", "conv 256->256 3x3 @32 B512", "conv 128->128 3x3 @64 B512", "first 64->128 3x3 @64 B512"):
