@@ -143,6 +143,7 @@ struct sgdm_engine {
   float* out_gn_b = nullptr;
   float* freqs = nullptr;
   int* ci_map_first = nullptr;
+  bool first_im2col = false;  // first conv as a 1x1 GEMM over an im2col'd input (PrepDesc::im2col)
   std::vector<void*> owned;
   bool device_ready = false;
   std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + variant
@@ -460,6 +461,9 @@ int setup_device(sgdm_engine* e) {
   // fused emb projection
   if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E) || dalloc(e, &e->b_emb, e->NE)) return 1;
 
+  // 3 + 3 (+1) input channels: the whole 3x3 neighbourhood fits the 64-channel input row (SGDM_FIRST_IM2COL=0: A/B)
+  e->first_im2col = 9 * (2 * c.in_channels + c.layout_dim) <= 64 &&
+                    !(getenv("SGDM_FIRST_IM2COL") && atoi(getenv("SGDM_FIRST_IM2COL")) == 0);
   // first conv channel map: dst [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0] <- src [x(Cimg) | layout(L)]
   {
     std::vector<int> m(64, -1);
@@ -552,6 +556,17 @@ int setup_device(sgdm_engine* e) {
       if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
       if (bind_f32(e, pp + ".bias", &cw.b)) return 1;
       const int* map = L.kind == L_CONV_IN ? e->ci_map_first : nullptr;
+      if (L.kind == L_CONV_IN && e->first_im2col) {
+        // [Npad][64]: K = tap * (2 Cimg + L) + entry; the buffer (sized for the 3x3 packing) is reused
+        op_t* dst = cw.w;
+        const int co = cw.cout, cimg = e->cfg.in_channels, ld = e->cfg.layout_dim;
+        if (bind_loader(e, pp + ".weight", [=](const float* src, cudaStream_t st) {
+              ++g_launches;
+              return pack_first_conv_im2col_launch(src, dst, co, cimg, ld, st);
+            }))
+          return 1;
+        return 0;
+      }
       if (bind_loader(e, pp + ".weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0, map))) return 1;
     }
     return 0;
@@ -936,6 +951,7 @@ struct Builder {
       pd.freqs = e->freqs;
       pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = c.cond_dim; pd.mc = mc;
       pd.x_in = x_in; pd.t_emb = t_emb; pd.cond_masked = cond_m; pd.drop = drop;
+      pd.im2col = e->first_im2col ? 1 : 0;
     }
     auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,
                    int silu_out, int accumulate) {
@@ -989,9 +1005,10 @@ struct Builder {
       h.p = stream_alloc(px * cw.cout);
       ConvDesc d;
       d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
+      if (e->first_im2col) { d.ks = 1; d.pad = 0; }  // the taps are channels of the im2col'd input
       d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
       attach_outputs(h, px, d);
-      conv(d, cw.cin);
+      conv(d, e->first_im2col ? 9 * cw.cin : cw.cin);
       hs.push_back(h);
     }
     Act none;

@@ -67,6 +67,10 @@ struct PrepDesc {
   int B = 0, Bp = 0;                 // Bp = B or 2B; row r reads sample r % B
   int Cimg = 3, H = 0, W = 0, L = 0, cond_dim = 0, mc = 0;
   op_t* x_in = nullptr;              // NHWC op_t [Bp, H, W, 64]: [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0]
+  // im2col: the 64 channels of pixel (y, x) hold the 3x3 neighbourhood instead, channel tap * (2 Cimg + L) + j =
+  // entry j of the row above at pixel (y + r - 1, x + s - 1) (zero outside the image), tap = 3 r + s: the first conv
+  // becomes a 1x1 GEMM with ONE 64-wide K block (9 (2 Cimg + L) <= 64; pack_first_conv_im2col_launch)
+  int im2col = 0;
   float* t_emb = nullptr;            // [Bp, mc]  [cos | sin]
   float* cond_masked = nullptr;      // [Bp, cond_dim]
 };
@@ -134,6 +138,8 @@ int lincomb_launch(const float* const* a, const float* c, int n_terms, float div
 // ---- weight packing --------------------------------------------------------------------------
 // torch conv weight fp32 [Cout, Cin, ks, ks] -> op_t dst[co][k_off + (r*ks+s)*cin_pad + ci] (row length ktot);
 // channels ci >= Cin (padding) are left untouched (buffers are zero-initialised).
+// first conv as a 1x1 GEMM over PrepDesc::im2col input: dst[co][tap * ce + j], ce = 2 Cimg + L, from w [Cout, Cimg + L, 3, 3]
+int pack_first_conv_im2col_launch(const float* w, op_t* dst, int Cout, int Cimg, int L, cudaStream_t s);
 int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s);
 int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
                             const int* ci_map, cudaStream_t s);

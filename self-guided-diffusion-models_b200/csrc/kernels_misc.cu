@@ -632,6 +632,35 @@ __global__ void prep_x_kernel(const PrepDesc d) {
   __align__(16) op_t v[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) v[j] = to_op(0.f);
+  if (d.im2col) {
+    const int y = pix / d.W, x = pix - y * d.W, ce = 2 * d.Cimg + d.L;
+    // static indexing of v (registers): walk the 64 slots, decode (tap, entry) of each
+    int tap = 0, j = 0;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+      if (tap < 9) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
+          const int pp = yy * d.W + xx;
+          if (j < 2 * d.Cimg) {
+            const int c = j < d.Cimg ? j : j - d.Cimg;
+            const float xv = d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pp];
+            const op_t hi = to_op(xv);
+            v[k] = j < d.Cimg ? hi : to_op(xv - from_op(hi));
+          } else {
+            const int l = j - 2 * d.Cimg;
+            v[k] = to_op(drop ? d.null_layout[pp] : d.layout[(static_cast<long>(b) * d.L + l) * HW + pp]);
+          }
+        }
+        if (++j == ce) { j = 0; ++tap; }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(d.x_in + idx * 64);
+    const uint4* srcv = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = srcv[q];
+    return;
+  }
   for (int c = 0; c < d.Cimg; ++c) {
     const float xv = d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pix];
     const op_t hi = to_op(xv);
@@ -666,7 +695,7 @@ __global__ void prep_emb_kernel(const PrepDesc d) {
   }
 }
 int prep_launch(const PrepDesc& d, cudaStream_t s) {
-  if (2 * d.Cimg + d.L > 64) return 1;
+  if (2 * d.Cimg + d.L > 64 || (d.im2col && 9 * (2 * d.Cimg + d.L) > 64)) return 1;
   const long npx = static_cast<long>(d.Bp) * d.H * d.W;
   prep_x_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
   const long ne = static_cast<long>(d.Bp) * (d.mc / 2) + static_cast<long>(d.Bp) * d.cond_dim;
@@ -932,6 +961,19 @@ int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks
   const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
   pack_conv_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ks, cin_pad,
                                                                                    ktot, k_off, ci_map);
+  return SGDM_LAUNCH_OK();
+}
+__global__ void pack_first_conv_im2col_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cimg, int L) {
+  const int ce = 2 * Cimg + L, idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * 9 * ce) return;
+  const int j = idx % ce, tap = (idx / ce) % 9, co = idx / (9 * ce);
+  const int ci = j < Cimg ? j : j < 2 * Cimg ? j - Cimg : Cimg + (j - 2 * Cimg);  // hi and lo halves share the weight
+  dst[static_cast<long>(co) * 64 + tap * ce + j] = to_op(w[(static_cast<long>(co) * (Cimg + L) + ci) * 9 + tap]);
+}
+int pack_first_conv_im2col_launch(const float* w, op_t* dst, int Cout, int Cimg, int L, cudaStream_t s) {
+  if (9 * (2 * Cimg + L) > 64) return 1;
+  const int total = Cout * 9 * (2 * Cimg + L);
+  pack_first_conv_im2col_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cimg, L);
   return SGDM_LAUNCH_OK();
 }
 // Output head with folded horizontal taps (ConvDesc::hfold): dst[(s * Cout + co)][r * cin_pad + ci] = w[co][ci][r][s],
