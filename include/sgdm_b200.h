@@ -154,6 +154,9 @@ int sgdm_debug_set_conv_pair(int mode);
 int sgdm_debug_set_attn_tc(int mode);
 /* halo mode of 3x3 stride-1 convs (one staged activation tile shared by the three vertical taps), same values */
 int sgdm_debug_set_conv_halo(int mode);
+/* K blocks of 32 channels (64-byte rows, SWIZZLE_64B) for halo-mode convs: -1 = only where 64-channel halo stages do
+ * not fit beside the epilogue staging (default), 0 = never, 1 = every halo-mode conv (tests) */
+int sgdm_debug_set_conv_k32(int mode);
 /* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array
  * of 16 int64 (NULL = off); slot meaning in csrc/kernel_conv.cu */
 int sgdm_debug_set_conv_timing(void* device_counters16);

@@ -195,6 +195,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same split in two: the address-independent upper word for 128-byte rows / SWIZZLE_128B (SBO 1024, layout 2) or
+// 64-byte rows / SWIZZLE_64B (SBO 512, layout 4; the K-major tile of a 32-element K block), and the address bits.
+__device__ __forceinline__ uint64_t umma_smem_desc_hi(bool sw64) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((sw64 ? 512u : 1024u) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(sw64 ? 4 : 2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t umma_smem_desc_lo(uint32_t addr) { return static_cast<uint64_t>((addr >> 4) & 0x3FFFu); }
 // kind::f16 instruction descriptor: fp32 accumulator, A/B 16-bit (fmt), both K-major, MxN.
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t m, uint32_t n) {
   return (1u << 4) | (SGDM_UMMA_FMT << 7) | (SGDM_UMMA_FMT << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

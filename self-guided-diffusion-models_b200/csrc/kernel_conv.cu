@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
             kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q;
             if (!skip_a) {
-              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
-              else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * 64, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
             }
           } else {
             cc = (q - n_main) * p.tps2;
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 // the skip source may be a channel concat of two tensors: [kc2a chunks of tmA2 | rest of tmA2b]
                 const CUtensorMap* tm2 = (cc + t) < p.kc2a ? &p.tmA2 : &p.tmA2b;
                 const int c2 = (cc + t) < p.kc2a ? (cc + t) : (cc + t) - p.kc2a;
-                if (kCtas == 2) tma_load_4d_pair(tm2, &full[stage], act_dst + t * p.act_tx, c2 * 64, 0, y0, img);
-                else tma_load_4d(tm2, &full[stage], act_dst + t * p.act_tx, c2 * 64, 0, y0, img);
+                if (kCtas == 2) tma_load_4d_pair(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
+                else tma_load_4d(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
               }
             }
           }
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
               // (hfold: the packed K axis is (vertical tap, channel) only)
               const int kb = kb0 + (main_st ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
-              if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n + cta_rank * b_rows);
-              else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * 64, n_tile * block_n);
+              if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n + cta_rank * b_rows);
+              else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n);
             }
           }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0 && cta_rank == 0) {
       // ------------------------------------------------------------ MMA issuer (the leader CTA in pair mode)
       const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
+      const int nk16 = p.kblk >> 4;
+      const uint64_t desc_hi = umma_smem_desc_hi(p.kblk == 32);
       uint32_t stage = 0, phase = 0, it = 0;
       long long t_full = 0, t_acc = 0;
       const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
@@ -277,14 +279,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t wgt_t = wgt_addr + t * p.wgt_bytes;
             const uint32_t a_addr = p.swap_ab ? wgt_t : act_t;  // M-side operand
             const uint32_t b_addr = p.swap_ab ? act_t : wgt_t;  // N-side operand
+            // K block = 64 channels (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B): 4 or 2 K16 slices
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (kCtas == 2)
-                umma_f16_pair(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                              (q | t | k) != 0 ? 1u : 0u);
-              else
-                umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                         (q | t | k) != 0 ? 1u : 0u);
+              if (k < nk16) {
+                const uint64_t da = desc_hi | umma_smem_desc_lo(a_addr + k * 32), db = desc_hi | umma_smem_desc_lo(b_addr + k * 32);
+                if (kCtas == 2) umma_f16_pair(d_tmem, da, db, idesc, (q | t | k) != 0 ? 1u : 0u);
+                else umma_f16(d_tmem, da, db, idesc, (q | t | k) != 0 ? 1u : 0u);
+              }
             }
           }
           // frees the smem stage (in both CTAs) when these MMAs retire; accumulator complete -> epilogue(s)
@@ -746,16 +748,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 #endif
 
 static int encode_nhwc(CUtensorMap* tm, const op_t* base, int B, int H, int W, int C, int bw, int bh, int bn,
-                       int stride, char* err, int errlen) {
+                       int stride, char* err, int errlen, int kblk = 64) {
   auto fn = get_encode_fn();
   if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable"); return 1; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(tm, SGDM_TMA_DTYPE, 4, const_cast<op_t*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled(A: B%d H%d W%d C%d box %dx%dx%d s%d) failed: %d", B, H, W, C, bw,
              bh, bn, stride, (int)r);
@@ -825,9 +827,6 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.hfold && (!halo || !d.out_nchw || 3 * d.Cout > 16 || d.in2 || d.swap_ab || pair))
     return fail("hfold needs the NCHW head (3 * Cout <= 16) in halo geometry, one CTA per tile");
   const int b_rows = d.block_n / (pair ? 2 : 1);  // weight rows per CTA and stage slot
-  p.wgt_tx = d.swap_ab ? kABytes : b_rows * 128;
-  p.wgt_bytes = (p.wgt_tx + 1023) / 1024 * 1024;
-  p.act_tx = tile_px * 128;
   p.epi_mode = d.out_nchw ? 0 : d.out_f32 ? 1 : 2;
   p.res_mode = d.res ? d.res_mode : 0;
   if (d.out_op2 && !d.out_f32) return fail("the 16-bit copy (out_op2) accompanies the fp32 output");
@@ -841,22 +840,47 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const int min_bufs = p.epi_mode == 0 ? (d.hfold ? 1 : 0) : p.res_mode == 1 ? 3 : p.res_mode == 2 ? 4 : 2;
   int n_stages = 0;
   bool pack_skip = true;  // three skip-source K blocks per halo stage (needs a 48 KB activation slot)
-  for (int pass = 0; pass < 3; ++pass) {
+  // K block: 64 channels, or 32 (half-size stages: 64-byte rows, SWIZZLE_64B) when that is what lets a halo
+  // ring fit beside the epilogue staging — the Cout = 128 swap-AB convs with a residual, whose 96 KB halo stages
+  // do not: per tile they pull 864 KB through L2 -> SM without the halo (measured at the ~11 TB/s L2 -> SM limit,
+  // tensor pipe 47 %), 576 KB with it.  ConvDesc::k32: -1 policy, 0 never, 1 force.
+  static const bool k32_env = !(getenv("SGDM_CONV_K32") && atoi(getenv("SGDM_CONV_K32")) == 0);
+  const bool halo_ok = halo;
+  int kblk = d.k32 == 1 ? 32 : 64;
+  if (kblk == 32 && ((d.Cin % 32) || !halo_ok || pair || d.hfold)) return fail("k32 needs a halo-mode conv, one CTA per tile");
+  for (int pass = 0; pass < 6; ++pass) {
+    const int row_bytes = kblk * 2;
+    p.kblk = kblk;
+    p.wgt_tx = (d.swap_ab ? kTileM : b_rows) * row_bytes;
+    p.wgt_bytes = (p.wgt_tx + 1023) / 1024 * 1024;
+    p.act_tx = tile_px * row_bytes;
     p.halo = halo ? 1 : 0;
     p.tps = halo ? 3 : 1;
-    p.act_tx_halo = (bh + 2) * bw * 128;
+    p.act_tx_halo = (bh + 2) * bw * row_bytes;
     p.act_bytes = halo ? p.act_tx_halo : p.act_tx;
-    p.halo_row_bytes = bw * 128;
+    p.halo_row_bytes = bw * row_bytes;
     // halo stages have three weight slots: let the fused 1x1-skip K blocks use them three at a time as well
     // (needs room for three plain activation tiles in the activation slot)
     p.tps2 = (halo && d.in2 && !d.swap_ab && pack_skip) ? 3 : 1;
     if (p.tps2 == 3 && p.act_bytes < 3 * p.act_tx) p.act_bytes = 3 * p.act_tx;
     const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;
-    const int min_stages = halo ? 2 : (stage_bytes > 32768 ? 3 : 4);
+    const int min_stages = halo ? (kblk == 32 ? 3 : 2) : (stage_bytes > 32768 ? 3 : 4);
     n_stages = (budget - 4 * min_bufs * kEpiBuf) / stage_bytes;
     if (n_stages > kMaxStages) n_stages = kMaxStages;
     if (n_stages < min_stages && p.tps2 == 3) { pack_skip = false; continue; }     // first give up the skip packing,
-    if (n_stages < min_stages && halo && d.halo != 1 && !d.hfold) { halo = false; continue; }  // then fall back to per-tap stages
+    // (policy: not with a fused 1x1-skip source in swap-AB mode — each of its 32-channel K blocks would take a whole
+    //  halo stage; measured +0.02 ms per such layer, against -0.055 ms for the plain ones)
+    if (n_stages < min_stages && halo && kblk == 64 && d.k32 != 0 && k32_env && !d.hfold && !pair &&
+        (d.k32 == 1 || !(d.in2 && d.swap_ab))) {
+      kblk = 32;  // then halve the K block,
+      pack_skip = true;
+      continue;
+    }
+    if (n_stages < min_stages && halo && d.halo != 1 && !d.hfold) {  // then fall back to per-tap stages of 64 channels
+      halo = false;
+      kblk = 64;
+      continue;
+    }
     if (n_stages < 2) return fail("shared memory budget: fewer than 2 stages");
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
@@ -879,10 +903,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
   out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
-  if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen)) return 1;
+  if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen, kblk)) return 1;
   if (d.in2) {
-    if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen)) return 1;
-    if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen)) return 1;
+    if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen, kblk)) return 1;
+    if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen, kblk)) return 1;
   }
   const int Ktot = d.hfold ? d.ks * d.Cin : d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
   const int npad = conv_npad(d.Cout, d.block_n);
@@ -890,11 +914,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     auto fn = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)b_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)(d.swap_ab ? kTileM : b_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&p.tmB, SGDM_TMA_DTYPE, 2, const_cast<op_t*>(d.w), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       snprintf(err, errlen, "cuTensorMapEncodeTiled(B: K%d N%d) failed: %d", Ktot, npad, (int)r);
       return 1;
@@ -908,9 +932,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.pad = d.pad;
   p.ks = d.ks;
   p.taps = d.ks * d.ks;
-  p.kc1 = d.Cin / 64;
-  p.kc2a = d.in2 ? d.C2 / 64 : 0;
-  p.kc2 = p.kc2a + (d.in2 && d.in2b ? d.C2b / 64 : 0);
+  p.kc1 = d.Cin / kblk;
+  p.kc2a = d.in2 ? d.C2 / kblk : 0;
+  p.kc2 = p.kc2a + (d.in2 && d.in2b ? d.C2b / kblk : 0);
   p.N_total = d.Cout;
   p.block_n = d.block_n;
   p.n_tiles = npad / d.block_n;

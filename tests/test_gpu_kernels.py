@@ -144,19 +144,27 @@ def test_conv_tcgen05_vs_torch(L, case):
     if ks == 3 and stride == 1 and (H * W) % 128 == 0 and W % 8 == 0:
         modes.append(("tcgen05 halo (3 vertical taps share one staged tile), policy pair/swap", 0 if Cout == 128 and out != "nchw" and res_mode != 2 else bn, 0, -1, 1))
         modes.append(("tcgen05 halo, 1-CTA", bn, 0, 0, 1))
-    for label, bn_arg, naive, pair, halo in modes:
+        # K blocks of 32 channels (64-byte rows, SWIZZLE_64B operands), forced: 1-CTA and, for Cout = 128, swap-AB
+        modes.append(("tcgen05 halo, 32-channel K blocks, 1-CTA", bn, 0, 0, 1, 1))
+        if Cout == 128 and out != "nchw" and res_mode != 2:
+            modes.append(("tcgen05 halo, 32-channel K blocks, swap-AB", 0, 0, 0, 1, 1))
+    for mode in modes:
+        label, bn_arg, naive, pair, halo = mode[:5]
+        k32 = mode[5] if len(mode) > 5 else -1
         L.sgdm_debug_set_conv_pair(pair)
         L.sgdm_debug_set_conv_halo(halo)
+        L.sgdm_debug_set_conv_k32(k32)
         try:
             got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
         except AssertionError as e:
-            if halo == 1 and ("halo mode needs" in str(e) or "shared memory budget" in str(e)):
+            if halo == 1 and ("halo mode needs" in str(e) or "shared memory budget" in str(e) or "k32 needs" in str(e)):
                 print(f"[conv {note}] {label}: not applicable ({e})")
                 continue
             raise
         finally:
             L.sgdm_debug_set_conv_pair(-1)
             L.sgdm_debug_set_conv_halo(-1)
+            L.sgdm_debug_set_conv_k32(-1)
         got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
         assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)
