@@ -157,6 +157,9 @@ int sgdm_debug_set_conv_halo(int mode);
 /* K blocks of 32 channels (64-byte rows, SWIZZLE_64B) for halo-mode convs: -1 = only where 64-channel halo stages do
  * not fit beside the epilogue staging (default), 0 = never, 1 = every halo-mode conv (tests) */
 int sgdm_debug_set_conv_k32(int mode);
+/* A-stationary main loop of 1x1 GEMMs (the m-tile's K blocks stay in shared memory across its n-tiles): -1 = policy
+ * (K <= 512 and >= 3 n-tiles), 0 = never, 1 = whenever K <= 512 (tests) */
+int sgdm_debug_set_conv_astat(int mode);
 /* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array
  * of 16 int64 (NULL = off); slot meaning in csrc/kernel_conv.cu */
 int sgdm_debug_set_conv_timing(void* device_counters16);

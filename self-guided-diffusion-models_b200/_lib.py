@@ -73,6 +73,7 @@ PROTOTYPES = {
     "sgdm_debug_set_conv_timing": (_i, [_vp]),
     "sgdm_debug_set_conv_halo": (_i, [_i]),
     "sgdm_debug_set_conv_k32": (_i, [_i]),
+    "sgdm_debug_set_conv_astat": (_i, [_i]),
     "sgdm_debug_set_attn_tc": (_i, [_i]),
     "sgdm_debug_set_conv_knobs": (_i, [_i, _i]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),

@@ -63,6 +63,7 @@ struct ConvDesc {
   // L2 -> SM drop 3x against halo mode, the MMA count 3x.  `w` is then packed [16][3 * Cin]:
   // row s * Cout + co, column r * Cin + c (pack_conv_weight_hfold_launch).
   int hfold = 0;
+  int a_stat = -1;              // A-stationary main loop for 1x1 GEMMs with >= 3 n-tiles and K <= 512: -1 policy, 0 off, 1 force
   int k32 = -1;                 // K block of 32 channels (SWIZZLE_64B halo stages): -1 policy, 0 never, 1 force
   int smem_reserve = 0;         // shared-memory bytes to leave free per SM (two-stream mode: co-resident GroupNorm CTAs)
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
@@ -87,6 +88,7 @@ struct alignas(64) ConvKernelParams {
   int n_stages, act_bytes, act_tx, act_tx_halo, wgt_bytes, wgt_tx;
   int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
   int hfold;                      // horizontal taps folded into the N dimension (output head)
+  int a_stat;                     // A-stationary 1x1 GEMM: the m-tile's activation K blocks stay resident across its n-tiles
   int kblk;                       // channels per K block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int tps2;                       // K blocks of the fused 1x1-skip source per stage (3 in halo mode, else 1)
   int epi_mode, epi_bufs;       // 0 NCHW direct | 1 fp32 NHWC | 2 16-bit NHWC; staging buffers per epilogue warp

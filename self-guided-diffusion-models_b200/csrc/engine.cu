@@ -32,6 +32,7 @@ static int g_conv_dbg_stages = 0, g_conv_dbg_flags = 0;
 static int g_conv_pair = -1;
 static int g_conv_halo = -1;
 static int g_conv_k32 = -1;
+static int g_conv_astat = -1;
 static int g_attn_tc = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
 
 static int fail(const char* fmt, ...) {
@@ -673,6 +674,7 @@ struct Builder {
     d.pair = g_conv_pair;
     d.halo = g_conv_halo;
     d.k32 = g_conv_k32;
+    d.a_stat = g_conv_astat;
     d.smem_reserve = smem_reserve;
     // A/B switches for whole-step timing (same process image, same box): SGDM_CONV_HALO / SGDM_CONV_PAIR = 0 | 1
     if (const char* ev = getenv("SGDM_CONV_HALO")) d.halo = atoi(ev) ? -1 : 0;
@@ -1204,6 +1206,10 @@ int sgdm_debug_set_conv_k32(int mode) {
   g_conv_k32 = mode;
   return 0;
 }
+int sgdm_debug_set_conv_astat(int mode) {
+  g_conv_astat = mode;
+  return 0;
+}
 int sgdm_debug_set_conv_knobs(int max_stages, int flags) {
   g_conv_dbg_stages = max_stages;
   g_conv_dbg_flags = flags;
@@ -1425,6 +1431,7 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.timing = g_conv_timing;
   d.halo = g_conv_halo;
   d.k32 = g_conv_k32;
+  d.a_stat = g_conv_astat;
   d.debug_stages = g_conv_dbg_stages;
   d.debug_flags = g_conv_dbg_flags;
   ++g_launches;

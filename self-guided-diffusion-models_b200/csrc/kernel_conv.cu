@@ -32,7 +32,7 @@ constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int kBarBytes = 512;
 constexpr int kBiasBytes = 2 * 256 * 4;  // bias of the tile's columns, double-buffered by tile parity
 constexpr int kEpiBuf = 4096;            // one epilogue staging buffer: 32 rows x 128 B
-constexpr int kMaxEpiBufs = 8;  // barrier slots per warp; the policy below uses up to max_epi_bufs() of them
+constexpr int kMaxEpiBufs = 6;
 constexpr int kEpi2Bytes = 4 * 2 * 2048;  // staging of the optional 16-bit copy: 32 rows x 64 B, double-buffered per warp
 
 // ---- shared-window accessors (explicit state space: the 1024-byte alignment of the dynamic smem base
@@ -115,8 +115,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   // [ring: n_stages x (act | weights)] [epilogue staging: 4 warps x epi_bufs x 4 KB]
   // [16-bit copy staging: 4 warps x 2 x 2 KB, only with a second output] [bias: 2 x 1 KB] [barriers]
   const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;  // [activation slot][tps weight slots]
-  uint8_t* ring = smem;
-  uint8_t* after_ring = smem + p.n_stages * stage_bytes;
+  // A-stationary mode (1x1 GEMMs with several n-tiles): the kc1 activation K blocks of the current m-tile stay
+  // resident in front of the ring, whose stages then hold weight tiles only (act_bytes = 0)
+  uint8_t* a_res = smem;
+  uint8_t* ring = smem + p.a_stat * p.kc1 * p.act_tx;
+  uint8_t* after_ring = ring + p.n_stages * stage_bytes;
   const int epi2_bytes = p.out2 ? kEpi2Bytes : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring + 4 * p.epi_bufs * kEpiBuf + epi2_bytes + kBiasBytes);
   uint64_t* full = bars;                         // [kMaxStages] TMA -> MMA
@@ -125,7 +128,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2] epilogue -> MMA
   uint64_t* rbars = bars + 2 * kMaxStages + 4;   // [4 warps][kMaxEpiBufs] residual tile landed
   uint64_t* bfree = bars + 2 * kMaxStages + 4 + 4 * kMaxEpiBufs;  // [2] all epilogue warps are done with a bias buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 4 * kMaxEpiBufs);
+  uint64_t* a_full = bars + 2 * kMaxStages + 6 + 4 * kMaxEpiBufs;  // [kMaxStages] A-stationary mode: resident A K block landed
+  uint64_t* a_empty = a_full + kMaxStages;                         // [kMaxStages] ... and may be replaced (last n-tile's MMA retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kMaxStages);
   const uint32_t epi_all = smem_u32(after_ring);
   const uint32_t epi2_all = epi_all + 4 * p.epi_bufs * kEpiBuf;
   const uint32_t sbias_all = epi2_all + epi2_bytes;
@@ -150,6 +155,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -173,6 +180,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   // work items: (m_tile, n_tile), or (pair of adjacent m_tiles, n_tile) per 2-CTA cluster
   const int total_tiles = (kCtas == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int tile_begin = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
+  // this CTA's (pair's) tile sequence: round-robin over all (m, n) tiles, or — A-stationary — round-robin over the
+  // m-tiles with all n-tiles of an m-tile back to back
+  const int tile_first = p.a_stat ? tile_begin * p.n_tiles : tile_begin;
+  // A-stationary: every CTA walks the n-tiles of its m-tile in a different rotation, so that at any moment the CTAs
+  // pull different weight tiles (all CTAs reading the same 16 KB of weights in lockstep serialises on its L2 slices)
+  const int n_rot = p.a_stat ? tile_begin % p.n_tiles : 0;
+  auto n_of = [&](int tile) {
+    const int n = tile % p.n_tiles + n_rot;
+    return n >= p.n_tiles ? n - p.n_tiles : n;
+  };
+  auto tile_next = [&](int tile) {
+    if (!p.a_stat) return tile + tile_step;
+    const int n = tile % p.n_tiles;
+    return n + 1 < p.n_tiles ? tile + 1 : tile - n + tile_step * p.n_tiles;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -182,9 +204,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t fill = 0;
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
       const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
-      for (int tile = tile_begin; tile < total_tiles; tile += tile_step) {
+      uint32_t a_it = 0;  // A-stationary: m-tiles loaded so far (parity of the resident slots)
+      for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile)) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
-        const int n_tile = tile % p.n_tiles;
+        const int n_pos = tile % p.n_tiles;  // position in this CTA's walk over the m-tile (A-stationary)
+        const int n_tile = n_of(tile);
         const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
@@ -197,6 +221,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const bool skip_b = (p.debug & 2) && fill >= static_cast<uint32_t>(n_stages);
           ++fill;
           const bool main_st = q < n_main;
+          if (p.a_stat) {
+            // resident A K block q of this m-tile: loaded with the first n-tile, into the slot the previous m-tile's
+            // last n-tile has just released; the ring stage carries the weight tile only
+            if (n_pos == 0) {
+              mbar_wait(&a_empty[q], (a_it & 1) ^ 1);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[q], kCtas * p.act_tx);
+              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &a_full[q], a_res + q * p.act_tx, q * p.kblk, 0, y0, img);
+              else tma_load_4d(&p.tmA, &a_full[q], a_res + q * p.act_tx, q * p.kblk, 0, y0, img);
+            }
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], kCtas * p.wgt_tx);
+            uint8_t* wdst = ring + stage * stage_bytes;
+            if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wdst, q * p.kblk, n_tile * block_n + cta_rank * b_rows);
+            else tma_load_2d(&p.tmB, &full[stage], wdst, q * p.kblk, n_tile * block_n);
+            if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
+            continue;
+          }
           // a stage of the fused 1x1-skip source holds up to tps2 plain (tile, weight) K blocks
           const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
           const uint32_t act_tx = (main_st && p.halo) ? p.act_tx_halo : (main_st ? p.act_tx : ntap * p.act_tx);
@@ -245,6 +285,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
+        if (p.a_stat && n_pos == 0) ++a_it;
       }
       if (p.timing) atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + 10, static_cast<unsigned long long>(t_prod));
     }
@@ -254,25 +295,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t idesc = umma_idesc(kTileM * kCtas, p.swap_ab ? 256 : block_n);
       const int nk16 = p.kblk >> 4;
       const uint64_t desc_hi = umma_smem_desc_hi(p.kblk == 32);
-      uint32_t stage = 0, phase = 0, it = 0;
+      uint32_t stage = 0, phase = 0, it = 0, a_it = 0;
       long long t_full = 0, t_acc = 0;
       const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
-      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+      for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const long long ta0 = p.timing ? clock64() : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         if (p.timing) t_acc += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        const int n_tile_a = p.a_stat ? tile % p.n_tiles : 0;  // A-stationary: position inside the m-tile
         for (int q = 0; q < n_st; ++q) {
           const long long tw0 = p.timing ? clock64() : 0;
+          if (p.a_stat && n_tile_a == 0) mbar_wait(&a_full[q], a_it & 1);  // this m-tile's resident A K block
           mbar_wait(&full[stage], phase);
           if (p.timing) t_full += clock64() - tw0;
           tc_fence_after();
           const bool main_st = q < n_main;
           const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
-          const uint32_t act_addr = smem_u32(ring + stage * stage_bytes);
-          const uint32_t wgt_addr = act_addr + p.act_bytes;
+          const uint32_t act_addr = p.a_stat ? smem_u32(a_res + q * p.act_tx) : smem_u32(ring + stage * stage_bytes);
+          const uint32_t wgt_addr = p.a_stat ? smem_u32(ring + stage * stage_bytes) : act_addr + p.act_bytes;
           for (int t = 0; t < ntap; ++t) {
             // halo: vertical tap t reads the staged rows starting t image rows further down
             const uint32_t act_t = act_addr + (main_st ? (p.halo ? t * p.halo_row_bytes : 0) : t * p.act_tx);
@@ -290,15 +333,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
           // frees the smem stage (in both CTAs) when these MMAs retire; accumulator complete -> epilogue(s)
+          const bool a_done = p.a_stat && n_tile_a == p.n_tiles - 1;  // last use of the resident A K block q
           if (kCtas == 2) {
             umma_commit_pair(&empty[stage]);
+            if (a_done) umma_commit_pair(&a_empty[q]);
             if (q == n_st - 1) umma_commit_pair(&tfull[acc]);
           } else {
             umma_commit(&empty[stage]);
+            if (a_done) umma_commit(&a_empty[q]);
             if (q == n_st - 1) umma_commit(&tfull[acc]);
           }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
+        if (p.a_stat && n_tile_a == p.n_tiles - 1) ++a_it;
       }
       if (p.timing) {
         atomicAdd(reinterpret_cast<unsigned long long*>(p.timing) + 8, static_cast<unsigned long long>(t_full));
@@ -332,9 +379,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (p.epi_mode == 0) {
       // final conv (Cout = 3 padded to N = 16), NCHW fp32 output: lanes = adjacent pixels -> coalesced already
       uint32_t it = 0;
-      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+      for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
-        const int n_tile = tile % p.n_tiles;
+        const int n_tile = n_of(tile);
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
         float bias_r[16];
@@ -386,7 +433,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // coordinates of chunk i of a tile: rows [row0, +32) x columns [col0, +cpc) of the output matrix
       auto chunk_coords = [&](int tile, int i, int& row0, int& col0) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
-        const int n_tile = tile % p.n_tiles;
+        const int n_tile = n_of(tile);
         if (p.swap_ab) {
           row0 = m_tile * p.tile_px + 32 * i;
           col0 = quarter * 32;
@@ -406,7 +453,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // res_mode 1: the 4 KB staging buffers themselves; res_mode 2: 2 KB slots behind two staging buffers.
       // The cursor's tile coordinates (integer divisions: ~600 clk on one lane, measured as a constant residual
       // wait per chunk when they were redone for every chunk) are derived once per tile.
-      int pre_tile = tile_begin, pre_i = 0;
+      int pre_tile = tile_first, pre_i = 0;
       int pre_r0 = 0, pre_c0 = 0;  // output row (or, res_mode 2, source row) / column of chunk 0 of pre_tile
       auto set_pre = [&]() {
         if (pre_tile >= total_tiles) return;
@@ -429,14 +476,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tma_load_2d_a(&p.tmRes, smem_u32(&rbar[slot]), res_slot_addr(slot), c0, r0);
         }
         if (++pslot == NB) pslot = 0;
-        if (++pre_i == n_chunks) { pre_i = 0; pre_tile += tile_step; set_pre(); }
+        if (++pre_i == n_chunks) { pre_i = 0; pre_tile = tile_next(pre_tile); set_pre(); }
       };
       if (tma_res || tma_res2)
         for (uint32_t k = 0; k + 2 < NB; ++k) issue_res();
 
       uint32_t it = 0;
       long long t_acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int tile = tile_begin; tile < total_tiles; tile += tile_step, ++it) {
+      for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
         int tile_row0, tile_col0;
@@ -885,24 +932,55 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
       // trade ring depth beyond the minimum for a deeper residual ring
-      static const int max_bufs = getenv("SGDM_MAX_EPI_BUFS") ? max(3, min(kMaxEpiBufs, atoi(getenv("SGDM_MAX_EPI_BUFS")))) : 6;
+      static const int max_bufs = getenv("SGDM_MAX_EPI_BUFS") ? max(3, min(kMaxEpiBufs, atoi(getenv("SGDM_MAX_EPI_BUFS")))) : kMaxEpiBufs;
       while (n_stages > min_stages && (budget - n_stages * stage_bytes) / (4 * kEpiBuf) < max_bufs) --n_stages;
       p.epi_bufs = (budget - n_stages * stage_bytes) / (4 * kEpiBuf);
       if (p.epi_bufs > max_bufs) p.epi_bufs = max_bufs;
     }
     break;
   }
+  // A-stationary main loop: a 1x1 GEMM with several n-tiles re-reads its activation rows once per n-tile (qkv: 6
+  // times, 1.6 GB through L2 -> SM for 0.13 GB of input).  With K <= 512 the m-tile's K blocks fit in shared memory
+  // (kc1 x 16 KB): they are loaded once per m-tile and the ring carries weight tiles only.  Policy: >= 3 n-tiles.
+  static const bool a_env = !(getenv("SGDM_CONV_ASTAT") && atoi(getenv("SGDM_CONV_ASTAT")) == 0);
+  int a_region = 0;
+  p.a_stat = 0;
+  {
+    const int n_tiles = conv_npad(d.Cout, d.block_n) / d.block_n;
+    const bool want = d.a_stat != 0 && a_env && d.ks == 1 && d.stride == 1 && !d.in2 && !d.swap_ab && !d.hfold &&
+                      p.epi_mode != 0 && p.kblk == 64 && !p.halo && d.Cin / 64 <= kMaxStages &&
+                      (d.a_stat == 1 || n_tiles >= 3);
+    if (want) {
+      const int region = (d.Cin / 64) * p.act_tx, stage = p.wgt_bytes;
+      int ns = (budget - 4 * min_bufs * kEpiBuf - region) / stage;
+      if (ns > kMaxStages) ns = kMaxStages;
+      if (ns >= 3) {
+        p.a_stat = 1;
+        a_region = region;
+        p.act_bytes = 0;
+        p.tps = 1;
+        p.tps2 = 1;
+        n_stages = ns;
+        p.epi_bufs = min_bufs;
+        if (p.res_mode == 1) p.epi_bufs = max(min_bufs, min(6, (budget - region - ns * stage) / (4 * kEpiBuf)));
+      } else if (d.a_stat == 1) {
+        return fail("A-stationary mode: the resident K blocks leave fewer than 3 ring stages");
+      }
+    } else if (d.a_stat == 1) {
+      return fail("A-stationary mode needs a plain 1x1 GEMM with K <= 512");
+    }
+  }
   // Without a residual the staging buffers only rotate as TMA-store sources: two suffice, up to two more are
   // taken from shared memory the K-block ring left over (never from the ring itself: measured, reserving them
   // up front costs halo-mode stages and 3.5 ms per step).  A/B knob: SGDM_EPI_BUFS_EXTRA=0 keeps two.
   static const bool extra_bufs = !(getenv("SGDM_EPI_BUFS_EXTRA") && atoi(getenv("SGDM_EPI_BUFS_EXTRA")) == 0);
   if (extra_bufs && p.epi_mode != 0 && p.res_mode == 0) {
-    const int left = budget - n_stages * (p.act_bytes + p.tps * p.wgt_bytes) - 4 * min_bufs * kEpiBuf;
+    const int left = budget - a_region - n_stages * (p.act_bytes + p.tps * p.wgt_bytes) - 4 * min_bufs * kEpiBuf;
     p.epi_bufs = min(4, min_bufs + left / (4 * kEpiBuf));
   }
   if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
-  out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes);
+  out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes) + a_region;
   if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen, kblk)) return 1;
   if (d.in2) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen, kblk)) return 1;
@@ -965,11 +1043,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   // shared memory: as many K-block stages as fit beside the epilogue staging
   out->pair = pair ? 1 : 0;
+  // (A-stationary: the work items of a CTA / pair are whole m-tiles)
   if (pair) {
-    const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
+    const int total = (p.m_tiles + 1) / 2 * (p.a_stat ? 1 : p.n_tiles);
     out->grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
   } else {
-    const int total = p.m_tiles * p.n_tiles;
+    const int total = p.m_tiles * (p.a_stat ? 1 : p.n_tiles);
     out->grid = total < kNumSMs ? total : kNumSMs;
   }
   static bool attr_set = false;

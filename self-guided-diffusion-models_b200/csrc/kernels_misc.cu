@@ -247,6 +247,16 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
+  const int cg = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int c = cg * 8;
+  // The per-channel parameters do not depend on the statistics: their loads are issued before the statistics are
+  // fetched and published, so the two L2 round trips of the block prologue overlap.
+  // eight consecutive channels: 16-byte loads (c % 8 == 0; every base is 16-byte aligned, checked at launch)
+  const float* f = a.film ? a.film + static_cast<long>(n) * a.film_stride : nullptr;
+  float gm[8], bt[8], fs[8], fb[8];
+  ld8(a.gamma + c, gm);
+  ld8(a.beta + c, bt);
+  if (f) { ld8(f + c, fs); ld8(f + C + c, fb); }
   if (a.final) {
     if (threadIdx.x < 32) {
       const float2 mr = a.final[n * 32 + threadIdx.x];
@@ -268,17 +278,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
   }
   __syncthreads();
-  const int cg = threadIdx.x % C8, lane = threadIdx.x / C8;
-  const int c = cg * 8;
   // y = ((v - mean) rstd gamma + beta) (1 + scale) + shift  ==  v * ka + kb
   float ka[8], kb[8];
   {
-    // eight consecutive channels: 16-byte loads (c % 8 == 0; every base is 16-byte aligned, checked at launch)
-    const float* f = a.film ? a.film + static_cast<long>(n) * a.film_stride : nullptr;
-    float gm[8], bt[8], fs[8], fb[8];
-    ld8(a.gamma + c, gm);
-    ld8(a.beta + c, bt);
-    if (f) { ld8(f + c, fs); ld8(f + C + c, fb); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cpg;

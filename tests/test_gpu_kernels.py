@@ -89,6 +89,8 @@ CONV_CASES = [
     (2, 16, 16, 512, 640, 1, 1, 0, 0, "op", "1x1, N=640 (5 tiles of 128)"),
     (2, 16, 16, 256, 320, 1, 1, 0, 0, "op", "1x1, N=320 (5 tiles of 64)"),
     (200, 1, 1, 384, 512, 1, 1, 0, 0, "f32", "linear, M=200 (ragged last tile)"),
+    (90, 16, 16, 512, 1536, 1, 1, 0, 0, "op", "1x1 qkv GEMM, 180 m-tiles x 6 n-tiles (A-stationary: slot reuse across m-tiles)"),
+    (80, 16, 16, 256, 768, 1, 1, 0, 1, "f32", "1x1, K=256, 3 n-tiles, residual, 160 m-tiles"),
     (5, 1, 1, 768, 1024, 1, 1, 0, 0, "f32", "linear, tiny M"),
     (2, 32, 32, 64, 3, 3, 1, 0, 0, "nchw", "final conv: N=3 padded to 16, NCHW epilogue"),
     (1, 64, 64, 128, 3, 3, 1, 0, 0, "nchw", "final conv at 64x64"),
@@ -148,16 +150,22 @@ def test_conv_tcgen05_vs_torch(L, case):
         modes.append(("tcgen05 halo, 32-channel K blocks, 1-CTA", bn, 0, 0, 1, 1))
         if Cout == 128 and out != "nchw" and res_mode != 2:
             modes.append(("tcgen05 halo, 32-channel K blocks, swap-AB", 0, 0, 0, 1, 1))
+    if ks == 1 and not skipC and Cin <= 512 and out != "nchw":
+        # A-stationary main loop (resident activation K blocks, weight-only ring), forced: 1-CTA and CTA pair
+        modes.append(("tcgen05 A-stationary, 1-CTA", bn, 0, 0, 0, -1, 1))
+        if bn >= 64:
+            modes.append(("tcgen05 A-stationary, CTA pair", bn, 0, 1, 0, -1, 1))
     for mode in modes:
         label, bn_arg, naive, pair, halo = mode[:5]
         k32 = mode[5] if len(mode) > 5 else -1
+        L.sgdm_debug_set_conv_astat(mode[6] if len(mode) > 6 else -1)
         L.sgdm_debug_set_conv_pair(pair)
         L.sgdm_debug_set_conv_halo(halo)
         L.sgdm_debug_set_conv_k32(k32)
         try:
             got = run_conv(L, x, wp, bn_arg, ks, stride, Cout, Ho, Wo, bias, in2, res, res_mode, out, naive)
         except AssertionError as e:
-            if halo == 1 and ("halo mode needs" in str(e) or "shared memory budget" in str(e) or "k32 needs" in str(e)):
+            if halo == 1 and ("halo mode needs" in str(e) or "shared memory budget" in str(e) or "k32 needs" in str(e)) or "A-stationary mode" in str(e):
                 print(f"[conv {note}] {label}: not applicable ({e})")
                 continue
             raise
@@ -165,6 +173,7 @@ def test_conv_tcgen05_vs_torch(L, case):
             L.sgdm_debug_set_conv_pair(-1)
             L.sgdm_debug_set_conv_halo(-1)
             L.sgdm_debug_set_conv_k32(-1)
+            L.sgdm_debug_set_conv_astat(-1)
         got = got.float() if out == "nchw" else got.float().permute(0, 3, 1, 2)
         assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)
