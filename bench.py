@@ -343,6 +343,7 @@ def main():
     ht = torch.empty((B,), dtype=torch.long).pin_memory()
 
     def e2e_step(i):
+        nonlocal hx, hout
         ht.fill_(i)
         dx = hx.to(device, non_blocking=True)
         dn = hn.to(device, non_blocking=True)
@@ -352,7 +353,7 @@ def main():
                                      denoise_sample_fn_kwargs=dict(cond=dc, cond_scale=2.0), noise=dn, index=i)
         hout.copy_(out, non_blocking=True)
         stream.synchronize()
-        hx.copy_(hout)
+        hx, hout = hout, hx  # the step's result is the next step's input: swap the pinned buffers, no host copy
 
     for _ in range(2):
         e2e_step(STEPS_PER_SAMPLE - 1)
