@@ -1111,13 +1111,17 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
     for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
+  // programmatic dependent launch pays in the launch-bound regime only (common.cuh): plans of at most 256 Ki pixel rows
+  pdl_mode() = !e->profiling && static_cast<long>(Bp) * e->cfg.image_size * e->cfg.image_size <= (1L << 18);
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (plan->ops[i](s)) {
       cudaError_t ce = cudaGetLastError();
+      pdl_mode() = false;
       return fail("launch %zu (%s) of %zu failed: %s", i, plan->meta[i].kind, plan->ops.size(), cudaGetErrorString(ce));
     }
     if (e->profiling) CUDA_TRY(cudaEventRecord(ev[i + 1], s));
   }
+  pdl_mode() = false;
   if (e->profiling) {  // profiling replays synchronise; never enabled inside a timed region
     CUDA_TRY(cudaStreamSynchronize(s));
     plan->prof_ms.assign(plan->ops.size(), 0.f);

@@ -52,6 +52,8 @@ template <int D>
 __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, int tkv_pad) {
   constexpr int LD = D + 8;  // padded row: conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_attn[];
+  pdl_launch_dependents();
+  pdl_wait();
   op_t* sK = reinterpret_cast<op_t*>(smem_attn);
   op_t* sV = sK + static_cast<long>(tkv_pad) * LD;
   op_t* sQ = sV + static_cast<long>(tkv_pad) * LD;
@@ -203,8 +205,7 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
         return 1;
       limit = smem;
     }
-    kernel<<<grid, kAttnThreads, smem, s>>>(a, tkv_pad);
-    return 0;
+    return launch_pdl(kernel, grid, dim3(kAttnThreads), smem, s, 1, a, tkv_pad) == cudaSuccess ? 0 : 1;
   };
   if (a.D == 64 ? run(attn_kernel<64>, max_set[0]) : a.D == 32 ? run(attn_kernel<32>, max_set[1]) : run(attn_kernel<128>, max_set[2]))
     return 1;

@@ -49,6 +49,7 @@ __device__ __forceinline__ float ex2f(float x) {
 __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_launch_dependents();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcStage);
   uint64_t* full = bars;            // [2] TMA -> MMA
   uint64_t* stage_free = bars + 2;  // [2] MMA (O_1 done) -> TMA
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -240,6 +242,7 @@ constexpr int kTc2Smem = 3 * kTcTile + 2 * kTc2P + 256;
 __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_launch_dependents();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTcTile + 2 * kTc2P);
   uint64_t* qk_full = bars;        // TMA -> MMA
   uint64_t* v_full = bars + 1;     // TMA -> MMA
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int n_my = blockIdx.x < p.pairs ? (p.pairs - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
 
   if (warp == 0) {
@@ -470,9 +474,9 @@ int attn_tc_launch(const AttnDesc& a, cudaStream_t s) {
   const int grid = p.pairs < kNumSMs ? p.pairs : kNumSMs;
   // SGDM_ATTN_TC_GEN = 1 selects the first-generation kernel (one softmax warpgroup, two-stage Q/K/V ring): A/B switch
   static const int gen = getenv("SGDM_ATTN_TC_GEN") ? atoi(getenv("SGDM_ATTN_TC_GEN")) : 2;
-  if (gen == 1) attn_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(p);
-  else attn_tc2_kernel<<<grid, kTc2Threads, kTc2Smem, s>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  const cudaError_t e = gen == 1 ? launch_pdl(attn_tc_kernel, dim3(grid), dim3(kTcThreads), kTcSmem, s, 1, p)
+                                 : launch_pdl(attn_tc2_kernel, dim3(grid), dim3(kTc2Threads), kTc2Smem, s, 1, p);
+  return e == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace sgdm

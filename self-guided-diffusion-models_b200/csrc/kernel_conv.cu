@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   // 128-byte swizzle of the TMA / UMMA tiles needs.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_launch_dependents();
   // [ring: n_stages x (act | weights)] [epilogue staging: 4 warps x epi_bufs x 4 KB]
   // [16-bit copy staging: 4 warps x 2 x 2 KB, only with a second output] [bias: 2 x 1 KB] [barriers]
   const int stage_bytes = p.act_bytes + p.tps * p.wgt_bytes;  // [activation slot][tps weight slots]
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above is CTA-private set-up; the preceding kernel's outputs are read from here on
 
   const int cta_rank = kCtas == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   // work items: (m_tile, n_tile), or (pair of adjacent m_tiles, n_tile) per 2-CTA cluster
@@ -1063,23 +1065,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 }
 
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
-  if (l.pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(l.grid);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = l.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, l.p) == cudaSuccess ? 0 : 1;
-  }
-  conv_gemm_kernel<1><<<l.grid, kConvThreads, l.smem, stream>>>(l.p);
-  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  const cudaError_t e = l.pair ? launch_pdl(conv_gemm_kernel<2>, dim3(l.grid), dim3(kConvThreads), l.smem, stream, 2, l.p)
+                               : launch_pdl(conv_gemm_kernel<1>, dim3(l.grid), dim3(kConvThreads), l.smem, stream, 1, l.p);
+  return e == cudaSuccess ? 0 : 1;
 }
 
 // --------------------------------------------------------------------- CUDA-core checker

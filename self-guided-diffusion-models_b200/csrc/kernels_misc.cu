@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const float2* __restri
                                                           const float2* __restrict__ st1, int C1, int HW,
                                                           int gran, int RL, float2* __restrict__ out) {
   __shared__ double s_s[512], s_q[512];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int C = C0 + C1, cpg = C / 32, epg = cpg / gran, rbs = HW >> 5;
   const int e0 = C0 / gran, e1 = C1 / gran, ne = e0 + e1;  // granules: ne * RL <= 512 threads
@@ -244,6 +246,8 @@ __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
 template <bool kHalfIn, int kResample, int kMinBlocks = 3>
 __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
@@ -410,8 +414,8 @@ int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
   const int ne = C / d.stat_gran, rbs = HW / 32;
   int RL = 1;
   while (RL * 2 * ne <= 512 && RL * 2 <= rbs && RL < 16) RL *= 2;
-  gn_finalize_kernel<<<d.B, ne * RL, 0, s>>>(d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, RL, d.final);
-  return SGDM_LAUNCH_OK();
+  return launch_pdl(gn_finalize_kernel, dim3(d.B), dim3(ne * RL), 0, s, 1, d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, RL,
+                    d.final) == cudaSuccess ? 0 : 1;
 }
 
 int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
@@ -460,18 +464,18 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
   // 3 blocks: gn_apply 10.4 -> 9.5 ms per step, the large launches at 6.3 TB/s.  SGDM_GN_OCC=4: A/B switch.
   static const int occ = getenv("SGDM_GN_OCC") ? atoi(getenv("SGDM_GN_OCC")) : 3;
   if (d.resample == 0 && occ == 3) {
-    if (d.src0_is_op) gn_apply_kernel<true, 0, 3><<<grid, threads, 0, s>>>(a);
-    else gn_apply_kernel<false, 0, 3><<<grid, threads, 0, s>>>(a);
+    if (d.src0_is_op) return launch_pdl(gn_apply_kernel<true, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else return launch_pdl(gn_apply_kernel<false, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
     return SGDM_LAUNCH_OK();
   }
   if (d.src0_is_op) {
-    if (d.resample == 0) gn_apply_kernel<true, 0, 4><<<grid, threads, 0, s>>>(a);
-    else if (d.resample == 1) gn_apply_kernel<true, 1><<<grid, threads, 0, s>>>(a);
-    else gn_apply_kernel<true, 2><<<grid, threads, 0, s>>>(a);
+    if (d.resample == 0) return launch_pdl(gn_apply_kernel<true, 0, 4>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else if (d.resample == 1) return launch_pdl(gn_apply_kernel<true, 1, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else return launch_pdl(gn_apply_kernel<true, 2, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
   } else {
-    if (d.resample == 0) gn_apply_kernel<false, 0, 4><<<grid, threads, 0, s>>>(a);
-    else if (d.resample == 1) gn_apply_kernel<false, 1><<<grid, threads, 0, s>>>(a);
-    else gn_apply_kernel<false, 2><<<grid, threads, 0, s>>>(a);
+    if (d.resample == 0) return launch_pdl(gn_apply_kernel<false, 0, 4>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else if (d.resample == 1) return launch_pdl(gn_apply_kernel<false, 1, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else return launch_pdl(gn_apply_kernel<false, 2, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
   }
   return SGDM_LAUNCH_OK();
 }
@@ -771,6 +775,8 @@ __device__ __forceinline__ void mix_coeffs(const MixDesc& m, int b, float& w, fl
 }
 
 __global__ void mix_kernel(const MixDesc m, float* __restrict__ out, long per_sample, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   float w, ow;
@@ -779,8 +785,7 @@ __global__ void mix_kernel(const MixDesc m, float* __restrict__ out, long per_sa
 }
 int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
-  mix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, eps_out, per_sample, total);
-  return SGDM_LAUNCH_OK();
+  return launch_pdl(mix_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, eps_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
 
 // Optional extras of the update kernels (sampling_kwargs dtp < 1 / noise_dropout > 0):
@@ -800,6 +805,8 @@ __global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const StepEx
                                  const float* __restrict__ noise, float* __restrict__ x_out,
                                  float* __restrict__ x0_out, float* __restrict__ eps_out, long per_sample,
                                  long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const int b = static_cast<int>(i / per_sample);
@@ -820,14 +827,15 @@ __global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const StepEx
 int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const StepExtras& ex, const float* x, const float* noise,
                      float* x_out, float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
-  ddim_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, ex, x, noise, x_out, x0_out, eps_out,
-                                                                             per_sample, total);
-  return SGDM_LAUNCH_OK();
+  return launch_pdl(ddim_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, c, ex, x, noise,
+                    x_out, x0_out, eps_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
 
 __global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const StepExtras ex, const float* __restrict__ x,
                                  const float* __restrict__ noise, float* __restrict__ x_out,
                                  float* __restrict__ x0_out, long per_sample, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const int b = static_cast<int>(i / per_sample);
@@ -847,9 +855,8 @@ __global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const StepEx
 int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const StepExtras& ex, const float* x, const float* noise,
                      float* x_out, float* x0_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
-  ddpm_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(m, c, ex, x, noise, x_out, x0_out,
-                                                                             per_sample, total);
-  return SGDM_LAUNCH_OK();
+  return launch_pdl(ddpm_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, c, ex, x, noise,
+                    x_out, x0_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
 
 // s[b] = max(quantile(|x0[b, :]|, q), 1) with torch.quantile's default 'linear' interpolation
