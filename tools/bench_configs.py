@@ -36,7 +36,7 @@ CONFIGS = [
 ]
 
 
-def run(name, cfg, B, gflop, steps):
+def run(name, cfg, B, gflop, steps, families=False):
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     m = build_model(cfg)
@@ -86,6 +86,22 @@ def run(name, cfg, B, gflop, steps):
     ms = e0.elapsed_time(e1) / steps
     row = dict(config=name, batch=B, ms_per_step=round(ms, 3), samples_per_s_250_steps=round(B / (250 * ms / 1e3), 2),
                tflops=round(B * gflop / ms, 1))
+    if families:
+        # one profiled replay (CUDA events around every launch): per-family split and the slowest launches
+        import ctypes as C
+        _lib.check(lib.sgdm_set_profiling(m._h, 1))
+        step(x, nxt, T - 2 - steps)
+        torch.cuda.synchronize()
+        _lib.check(lib.sgdm_set_profiling(m._h, 0))
+        kind, pms, fl, by = C.c_char_p(), C.c_double(), C.c_double(), C.c_double()
+        fam, ops = {}, []
+        for j in range(lib.sgdm_profile_count(m._h)):
+            _lib.check(lib.sgdm_profile_get(m._h, j, C.byref(kind), C.byref(pms), C.byref(fl), C.byref(by)))
+            f = fam.setdefault(kind.value.decode(), [0.0, 0, 0.0])
+            f[0] += pms.value; f[1] += 1; f[2] += fl.value
+            ops.append((round(pms.value, 3), j, kind.value.decode(), round(fl.value / 1e9), round(by.value / 1e6)))
+        row["families_ms"] = {k: [round(v[0], 3), v[1], round(v[2] / (v[0] * 1e-3) / 1e12) if v[2] else None] for k, v in fam.items()}
+        row["slowest"] = sorted(ops, reverse=True)[:12]
     print(json.dumps(row), flush=True)
     del m, ld, eps_src
     torch.cuda.empty_cache()
@@ -95,8 +111,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--families", action="store_true", help="add the per-kernel-family split of one profiled step")
     a = ap.parse_args()
     for name, cfg, B, gflop in CONFIGS:
         if a.only and a.only not in name:
             continue
-        run(name, cfg, B, gflop, a.steps)
+        run(name, cfg, B, gflop, a.steps, a.families)
