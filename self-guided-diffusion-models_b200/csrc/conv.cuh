@@ -88,6 +88,7 @@ struct alignas(64) ConvKernelParams {
   int n_stages, act_bytes, act_tx, act_tx_halo, wgt_bytes, wgt_tx;
   int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
   int hfold;                      // horizontal taps folded into the N dimension (output head)
+  int kps;                        // K blocks per plain (non-halo) main stage: 1 or 2
   int a_stat;                     // A-stationary 1x1 GEMM: the m-tile's activation K blocks stay resident across its n-tiles
   int kblk;                       // channels per K block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int tps2;                       // K blocks of the fused 1x1-skip source per stage (3 in halo mode, else 1)

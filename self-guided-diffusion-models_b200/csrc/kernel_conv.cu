@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       long long t_prod = 0;
       uint32_t fill = 0;
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
-      const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
+      // main K blocks: halo stages hold the three vertical taps of one (horizontal tap, chunk); plain stages hold
+      // p.kps consecutive (tap, chunk) K blocks, each with its own activation tile and weight slot
+      const int n_blk = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1;
+      const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       uint32_t a_it = 0;  // A-stationary: m-tiles loaded so far (parity of the resident slots)
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile)) {
         const int m_tile = (tile / p.n_tiles) * kCtas + cta_rank;
@@ -240,8 +243,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             continue;
           }
           // a stage of the fused 1x1-skip source holds up to tps2 plain (tile, weight) K blocks
-          const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
-          const uint32_t act_tx = (main_st && p.halo) ? p.act_tx_halo : (main_st ? p.act_tx : ntap * p.act_tx);
+          const int ntap = main_st ? (p.halo ? p.tps : min(p.kps, n_blk - q * p.kps)) : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
+          const uint32_t act_tx = (main_st && p.halo) ? p.act_tx_halo : ntap * p.act_tx;
           if (cta_rank == 0)
             mbar_arrive_expect_tx(&full[stage], kCtas * ((skip_a ? 0u : act_tx) + (skip_b ? 0u : ntap * p.wgt_tx)));
           uint8_t* act_dst = ring + stage * stage_bytes;
@@ -249,19 +252,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           int cc, kb0;
           if (main_st) {
             // (tap, chunk) and (r, s) of the tap are walked with counters: no integer divisions per K block
-            const int tap = q_tap;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
-            cc = q_cc;
-            const int r = p.halo ? 0 : q_r;
-            const int s_tap = p.hfold ? p.pad : p.halo ? tap : tap - r * p.ks;  // hfold: no horizontal shift
-            if (++q_cc == p.kc1) {
-              q_cc = 0;
-              ++q_tap;
-              if (q_tap - q_r * p.ks == p.ks) ++q_r;
-            }
-            kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q;
-            if (!skip_a) {
-              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], act_dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
-              else tma_load_4d(&p.tmA, &full[stage], act_dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+            kb0 = 0;
+            for (int u = 0; u < (p.halo ? 1 : ntap); ++u) {
+              const int tap = q_tap;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
+              cc = q_cc;
+              const int r = p.halo ? 0 : q_r;
+              const int s_tap = p.hfold ? p.pad : p.halo ? tap : tap - r * p.ks;  // hfold: no horizontal shift
+              if (++q_cc == p.kc1) {
+                q_cc = 0;
+                ++q_tap;
+                if (q_tap - q_r * p.ks == p.ks) ++q_r;
+              }
+              if (u == 0) kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q * p.kps;
+              if (!skip_a) {
+                uint8_t* dst = act_dst + u * p.act_tx;
+                if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+                else tma_load_4d(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              }
             }
           } else {
             cc = (q - n_main) * p.tps2;
@@ -280,7 +287,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             for (int t = 0; t < ntap; ++t) {
               // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
               // (hfold: the packed K axis is (vertical tap, channel) only)
-              const int kb = kb0 + (main_st ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
+              // (plain stages: kps consecutive K blocks)
+              const int kb = kb0 + ((main_st && p.halo) ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
               if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n + cta_rank * b_rows);
               else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n);
             }
@@ -299,7 +307,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint64_t desc_hi = umma_smem_desc_hi(p.kblk == 32);
       uint32_t stage = 0, phase = 0, it = 0, a_it = 0;
       long long t_full = 0, t_acc = 0;
-      const int n_main = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
+      const int n_blk = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1;
+      const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const long long ta0 = p.timing ? clock64() : 0;
@@ -315,12 +324,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (p.timing) t_full += clock64() - tw0;
           tc_fence_after();
           const bool main_st = q < n_main;
-          const int ntap = main_st ? p.tps : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
+          const int ntap = main_st ? (p.halo ? p.tps : min(p.kps, n_blk - q * p.kps)) : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
           const uint32_t act_addr = p.a_stat ? smem_u32(a_res + q * p.act_tx) : smem_u32(ring + stage * stage_bytes);
           const uint32_t wgt_addr = p.a_stat ? smem_u32(ring + stage * stage_bytes) : act_addr + p.act_bytes;
           for (int t = 0; t < ntap; ++t) {
             // halo: vertical tap t reads the staged rows starting t image rows further down
-            const uint32_t act_t = act_addr + (main_st ? (p.halo ? t * p.halo_row_bytes : 0) : t * p.act_tx);
+            const uint32_t act_t = act_addr + ((main_st && p.halo) ? t * p.halo_row_bytes : t * p.act_tx);
             const uint32_t wgt_t = wgt_addr + t * p.wgt_bytes;
             const uint32_t a_addr = p.swap_ab ? wgt_t : act_t;  // M-side operand
             const uint32_t b_addr = p.swap_ab ? act_t : wgt_t;  // N-side operand
@@ -941,6 +950,28 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     }
     break;
   }
+  // Plain (non-halo) stages with TWO K blocks: the per-stage cost of the single MMA-issuing lane (barrier wait, fence,
+  // commit) is paid once per 8 MMAs instead of once per 4.  Only where three such stages fit.  SGDM_CONV_KPS=1: A/B.
+  static const int kps_max = getenv("SGDM_CONV_KPS") ? atoi(getenv("SGDM_CONV_KPS")) : 2;
+  p.kps = 1;
+  if (!p.halo && p.kblk == 64 && d.a_stat != 1) {
+    const int n_blk = d.ks * d.ks * (d.Cin / 64);
+    // (three blocks per stage only as two 96..144 KB stages, like the halo ring; two blocks need three stages)
+    for (int kps = min(kps_max, min(n_blk, 3)); kps >= 2; --kps) {
+      const int stage_k = kps * (p.act_tx + p.wgt_bytes);
+      int ns = (budget - 4 * min_bufs * kEpiBuf) / stage_k;
+      if (ns > kMaxStages) ns = kMaxStages;
+      if (ns < (kps == 3 ? 2 : 3)) continue;
+      p.kps = kps;
+      p.tps = kps;
+      p.act_bytes = kps * p.act_tx;
+      p.tps2 = d.in2 ? kps : 1;
+      n_stages = ns;
+      p.epi_bufs = min_bufs;
+      if (p.res_mode == 1) p.epi_bufs = max(min_bufs, min(kMaxEpiBufs, (budget - ns * stage_k) / (4 * kEpiBuf)));
+      break;
+    }
+  }
   // A-stationary main loop: a 1x1 GEMM with several n-tiles re-reads its activation rows once per n-tile (qkv: 6
   // times, 1.6 GB through L2 -> SM for 0.13 GB of input).  With K <= 512 the m-tile's K blocks fit in shared memory
   // (kc1 x 16 KB): they are loaded once per m-tile and the ring carries weight tiles only.  Policy: >= 3 n-tiles.
@@ -950,7 +981,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   {
     const int n_tiles = conv_npad(d.Cout, d.block_n) / d.block_n;
     const bool want = d.a_stat != 0 && a_env && d.ks == 1 && d.stride == 1 && !d.in2 && !d.swap_ab && !d.hfold &&
-                      p.epi_mode != 0 && p.kblk == 64 && !p.halo && d.Cin / 64 <= kMaxStages &&
+                      p.epi_mode != 0 && p.kblk == 64 && !p.halo && p.kps == 1 && d.Cin / 64 <= kMaxStages &&
                       (d.a_stat == 1 || n_tiles >= 3);
     if (want) {
       const int region = (d.Cin / 64) * p.act_tx, stage = p.wgt_bytes;
