@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (p.a_stat && n_tile_a == 0) mbar_wait(&a_full[q], a_it & 1);  // this m-tile's resident A K block
           mbar_wait(&full[stage], phase);
           if (p.timing) t_full += clock64() - tw0;
-          tc_fence_after();
+          if (!(p.debug & 4)) tc_fence_after();  // (tuning flag 4: measure the cost of this per-stage fence)
           const bool main_st = q < n_main;
           const int ntap = main_st ? (p.halo ? p.tps : min(p.kps, n_blk - q * p.kps)) : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
           const uint32_t act_addr = p.a_stat ? smem_u32(a_res + q * p.act_tx) : smem_u32(ring + stage * stage_bytes);
@@ -952,7 +952,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   // Plain (non-halo) stages with TWO K blocks: the per-stage cost of the single MMA-issuing lane (barrier wait, fence,
   // commit) is paid once per 8 MMAs instead of once per 4.  Only where three such stages fit.  SGDM_CONV_KPS=1: A/B.
-  static const int kps_max = getenv("SGDM_CONV_KPS") ? atoi(getenv("SGDM_CONV_KPS")) : 2;
+  static const int kps_max = getenv("SGDM_CONV_KPS") ? atoi(getenv("SGDM_CONV_KPS")) : 3;
   p.kps = 1;
   if (!p.halo && p.kblk == 64 && d.a_stat != 1) {
     const int n_blk = d.ks * d.ks * (d.Cin / 64);

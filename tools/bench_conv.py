@@ -68,7 +68,10 @@ if os.environ.get("KNOBS"):
     # mainloop experiments: ring depth and operand-reload knobs on one big layer
     name = os.environ.get("KNOB_SHAPE", "conv 512->512 3x3 @16 B512")
     B, H, Cin, Cout, ks = SHAPES[name]
-    for stages, flags in ((0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 1), (0, 2), (0, 3)):
+    knob_list = ((0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 1), (0, 2), (0, 3))
+    if os.environ.get("KNOB_FLAGS"):
+        knob_list = tuple((0, int(f)) for f in os.environ["KNOB_FLAGS"].split(","))
+    for stages, flags in knob_list:
         L.sgdm_debug_set_conv_knobs(stages, flags)
         for pair in ((-1,) if Cout == 128 else (0, 1)):
             print(f"stages<={stages} flags={flags}", end="  ")
