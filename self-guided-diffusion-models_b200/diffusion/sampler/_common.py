@@ -74,6 +74,7 @@ class GuidedEps:
         extra = set(self.kwargs) - {"cond", "layout", "cond_scale"}
         self.model = model if (model is not None and not extra) else None
         self.w, self.w_ptr, self.mode = 0.0, None, "generic"
+        self._w_tensor, self._w_keep = None, None
         self._keep = []
         if self.model is not None:
             m = self.model
@@ -85,9 +86,8 @@ class GuidedEps:
             else:
                 self.mode = "guided"
                 if torch.is_tensor(cs):
-                    wt = cs.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
-                    self._keep.append(wt)
-                    self.w_ptr = wt.data_ptr()
+                    # bound to the batch lazily in __call__ (B is known there): one entry per sample
+                    self._w_tensor = cs.detach().to(device=self.device, dtype=torch.float32).reshape(-1)
                 else:
                     self.w = float(cs)
             self.scale_type = m._scale_type()
@@ -113,6 +113,18 @@ class GuidedEps:
         m = self.model
         cond, layout = self._prepare(x, t)
         if self.mode == "guided":
+            if self._w_tensor is not None and self.w_ptr is None:
+                # same contract as forward_with_cond_scale: a 1-element tensor broadcasts, anything else must hold
+                # exactly one weight per sample (the kernel indexes w_per_sample[b] for b < B)
+                wt = self._w_tensor
+                if wt.numel() == 1:
+                    wt = wt.expand(x.shape[0])
+                if wt.numel() != x.shape[0]:
+                    raise AssertionError("tensor cond_scale must have one entry per sample "
+                                         f"(got {wt.numel()} for batch {x.shape[0]})")
+                wt = wt.contiguous()
+                self._w_keep = wt
+                self.w_ptr = wt.data_ptr()
             pc, pu = m.guided_pair_ptrs(x, t, cond, layout)
             return pc, pu, self.w, self.w_ptr, self.scale_type
         B = x.shape[0]

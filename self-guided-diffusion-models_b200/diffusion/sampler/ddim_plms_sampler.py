@@ -48,10 +48,14 @@ class DDIMSampler(object):
     @torch.no_grad()
     def sample(self, shape, sampling_kwargs=None, **kwargs):
         self.make_schedule(sampling_kwargs=sampling_kwargs)
-        if self.sampler_type == "ddim":
-            return self.ddim_sampling(shape, sampling_kwargs=sampling_kwargs, **kwargs)
-        elif self.sampler_type == "plms":
-            return self.plms_sampling(shape, sampling_kwargs=sampling_kwargs, **kwargs)
+        device = torch.device(self.device)
+        if device.type != "cuda":
+            raise _lib.SgdmError(f"sampler device is {device}: sgdm_b200 has no CPU path")
+        with torch.cuda.device(device):  # kernels launch on the CURRENT device: make it the sampler's
+            if self.sampler_type == "ddim":
+                return self.ddim_sampling(shape, sampling_kwargs=sampling_kwargs, **kwargs)
+            elif self.sampler_type == "plms":
+                return self.plms_sampling(shape, sampling_kwargs=sampling_kwargs, **kwargs)
         raise NotImplementedError
 
     def _setup(self, shape, sampling_kwargs, noise_tape):

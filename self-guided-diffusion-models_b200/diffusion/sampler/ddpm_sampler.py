@@ -55,7 +55,29 @@ class Schedule_DDPM(nn.Module):
         reg("posterior_log_variance_clipped", np.log(np.maximum(posterior_variance, 1e-20)))
         reg("posterior_mean_coef1", betas * np.sqrt(alphas_cumprod_prev) / (1.0 - alphas_cumprod))
         reg("posterior_mean_coef2", (1.0 - alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - alphas_cumprod))
+        # Training-side buffers (ddpm_sampler.py:85-103).  The sampling path never reads them, but `snr_derivative`
+        # and `SNR` are persistent, i.e. part of every reference checkpoint's `diffusion.sampler.*` keys: a strict
+        # load_state_dict needs them here.  `lvlb_weights` is non-persistent like the reference's.
+        if self.hparams.parameterization == "eps":
+            lvlb_weights = self.betas ** 2 / (2 * self.posterior_variance *
+                                              torch.tensor(alphas, dtype=torch.float32).to(dev) * (1 - self.alphas_cumprod))
+        elif self.hparams.parameterization == "x0":
+            lvlb_weights = 0.5 * np.sqrt(torch.Tensor(alphas_cumprod)) / (2.0 * 1 - torch.Tensor(alphas_cumprod))
+        else:
+            raise NotImplementedError("mu not supported")
+        lvlb_weights[0] = lvlb_weights[1]
+        self.register_buffer("lvlb_weights", lvlb_weights.to(dev), persistent=False)
+        assert not torch.isnan(self.lvlb_weights).all()
+        self.register_buffer("snr_derivative", torch.zeros(1000, dtype=torch.float32).to(dev))
+        self.register_buffer("SNR", torch.zeros(1000, dtype=torch.float32).to(dev))
 
+    def _x0_coefs(self, tab, i):
+        """(c_recip, c_recipm1) of `x_recon = c_recip * x - c_recipm1 * model_out` (ddpm_sampler.py:158-163):
+        predict_start_from_noise for parameterization 'eps'; for 'x0' the model output IS x_recon, which the same
+        fused kernel reproduces exactly with (0, -1): 0 * x - (-1 * out) == out bit for bit."""
+        if self.hparams.parameterization == "x0":
+            return 0.0, -1.0
+        return tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i]
 
     @torch.no_grad()
     def p_sample(self, x, t, clip_denoised=False, repeat_noise=False, temperature=1.0, noise_dropout=0.0,
@@ -81,8 +103,7 @@ class Schedule_DDPM(nn.Module):
         pc, pu, w, w_ptr, st = eps_src(x, t.to(device=device, dtype=torch.long).contiguous())
         nz = torch.randn(x.shape, device=device) if noise is None else noise.to(device, torch.float32).contiguous()
         out, x0 = torch.empty_like(x), torch.empty_like(x)
-        c = coef6(tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i],
-                  tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
+        c = coef6(*self._x0_coefs(tab, i), tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
                   tab["sigma"][i] if i != 0 else 0.0, temperature)
         stream = _lib.current_stream(device)
         extras = StepExtras(sampling_kwargs, x, noise_dropout=noise_dropout)
@@ -93,9 +114,16 @@ class Schedule_DDPM(nn.Module):
         return out, x0, None
 
     @torch.no_grad()
-    def sample(self, shape, sampling_kwargs=None, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,
-               condition_kwargs=None, noise_tape=None, **kwargs):
+    def sample(self, shape, sampling_kwargs=None, **kwargs):
         """Schedule_DDPM.sample (ddpm_sampler.py:194-238) -> (x, {'pred_x0','x_inter'})."""
+        device = torch.device(self.hparams.device)
+        if device.type != "cuda":
+            raise _lib.SgdmError(f"sampler device is {device}: sgdm_b200 has no CPU path")
+        with torch.cuda.device(device):  # kernels launch on the CURRENT device: make it the sampler's
+            return self._sample(shape, sampling_kwargs=sampling_kwargs, **kwargs)
+
+    def _sample(self, shape, sampling_kwargs=None, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,
+                condition_kwargs=None, noise_tape=None, **kwargs):
         check_supported(sampling_kwargs)
         temperature = sampling_kwargs["temperature"]
         timesteps = sampling_kwargs["num_timesteps"]
@@ -103,8 +131,6 @@ class Schedule_DDPM(nn.Module):
                                beta_schedule=self.hparams.beta_schedule, linear_start=self.hparams.linear_start,
                                linear_end=self.hparams.linear_end, cosine_s=self.hparams.cosine_s)
         device = torch.device(self.hparams.device)
-        if device.type != "cuda":
-            raise _lib.SgdmError(f"sampler device is {device}: sgdm_b200 has no CPU path")
         B = shape[0]
         lib, stream = _lib.lib(), _lib.current_stream(device)
         noise = NoiseSource(shape, device, noise_tape)
@@ -128,8 +154,7 @@ class Schedule_DDPM(nn.Module):
             pc, pu, w, w_ptr, st = eps_src(img, ts)
             nz = noise.next()
             x0 = torch.empty_like(img) if i in logs else None
-            c = coef6(tab["sqrt_recip_alphas_cumprod"][i], tab["sqrt_recipm1_alphas_cumprod"][i],
-                      tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
+            c = coef6(*self._x0_coefs(tab, i), tab["posterior_mean_coef1"][i], tab["posterior_mean_coef2"][i],
                       sigma[i] if i != 0 else 0.0, temperature[i])
             dyn, mul = extras.pointers(stream, 0, (pc, pu, w, w_ptr, st), c, img, B, per_sample)
             _lib.check(lib.sgdm_ddpm_step_ex(stream, pc, pu, w, w_ptr, st, c, clip, img.data_ptr(), nz.data_ptr(),

@@ -136,6 +136,7 @@ class EngineUNet(nn.Module):
             _attach(self, name, t, kind)
         self._loaded_sig = {}
         self._freqs_set = False
+        self._engine_device = None
         self.image_size = c.image_size
         self.in_channels = c.in_channels
         self.out_channels = c.out_channels
@@ -156,6 +157,12 @@ class EngineUNet(nn.Module):
         lib = _lib.lib()
         sd = dict(self.named_parameters())
         sd.update(dict(self.named_buffers()))
+        first = sd[self._inventory[0][0]]
+        _lib.require_cuda(first, f"parameter {self._inventory[0][0]}")
+        with torch.cuda.device(first.device):  # the engine allocates on the CURRENT device: make it the parameters'
+            self._sync_weights_on_device(lib, sd, force)
+
+    def _sync_weights_on_device(self, lib, sd, force):
         stream = None
         for name, shape in self._inventory:
             t = sd[name]
@@ -163,6 +170,11 @@ class EngineUNet(nn.Module):
             if not force and self._loaded_sig.get(name) == sig:
                 continue
             _lib.require_cuda(t, f"parameter {name}")
+            if self._engine_device is None:
+                self._engine_device = t.device  # the engine binds to the device of its first parameter
+            elif t.device != self._engine_device:
+                raise _lib.SgdmError(f"parameter {name} is on {t.device}; the engine was set up on {self._engine_device} "
+                                     "(build a new module to change devices)")
             if stream is None:
                 stream = _lib.current_stream(t.device)
             src = t.detach()
@@ -180,8 +192,20 @@ class EngineUNet(nn.Module):
             self._freqs_set = True
 
     # ------------------------------------------------------------------ helpers
-    def _prep_inputs(self, x, t, cond, layout):
+    def _check_x(self, x):
+        """The engine's plan is laid out for the configured geometry (it indexes x with its own C/H/W and writes
+        B*out_channels*image_size^2 floats): anything else must be an error here, not an out-of-bounds access.
+        (The reference module is fully convolutional; this drop-in supports the configured image_size only.)"""
         _lib.require_cuda(x, "x")
+        if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2] != self.image_size or x.shape[3] != self.image_size:
+            raise ValueError(f"x must be [B, {self.in_channels}, {self.image_size}, {self.image_size}] "
+                             f"(the engine is built for image_size={self.image_size}), got {tuple(x.shape)}")
+        dev = self._engine_device
+        if dev is not None and x.device != dev:
+            raise ValueError(f"x is on {x.device} but the engine's weights and workspace live on {dev}")
+
+    def _prep_inputs(self, x, t, cond, layout):
+        self._check_x(x)
         x = x.detach().float().contiguous()
         t = t.detach().to(device=x.device, dtype=torch.int64).contiguous()
         if self.cond_dim > 0:
@@ -196,7 +220,11 @@ class EngineUNet(nn.Module):
             if layout is None:
                 raise ValueError("layout is required for condition_method=%s" % self.condition_method)
             layout = layout.detach().to(x.device).to(torch.float32)
-            layout = layout.expand(x.shape[0], self._cfg.layout_dim, x.shape[2], x.shape[3]).contiguous()
+            L = self._cfg.layout_dim
+            if layout.dim() != 4 or layout.shape[1] != L or tuple(layout.shape[2:]) != tuple(x.shape[2:]) \
+                    or layout.shape[0] not in (1, x.shape[0]):
+                raise ValueError(f"layout must be [B, {L}, {x.shape[2]}, {x.shape[3]}], got {tuple(layout.shape)}")
+            layout = layout.expand(x.shape[0], L, x.shape[2], x.shape[3]).contiguous()
         else:
             layout = None
         return x, t, cond, layout
@@ -208,17 +236,19 @@ class EngineUNet(nn.Module):
         B = x.shape[0]
         drop = drop_mask.to(device=x.device, dtype=torch.uint8).contiguous()
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
-        _lib.check(_lib.lib().sgdm_forward(self._h, _lib.current_stream(x.device), _lib.ptr(x), _lib.ptr(t),
-                                           _lib.ptr(cond), _lib.ptr(layout), _lib.ptr(drop), B, _lib.ptr(out)))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sgdm_forward(self._h, _lib.current_stream(x.device), _lib.ptr(x), _lib.ptr(t),
+                                               _lib.ptr(cond), _lib.ptr(layout), _lib.ptr(drop), B, _lib.ptr(out)))
         return out
 
     def guided_pair_ptrs(self, x, t, cond, layout):
         """Batched cond||uncond pass; returns raw device pointers (eps_c, eps_u) into engine
         memory, valid until the next forward.  Inputs must already be prepared tensors."""
         pc, pu = C.c_void_p(), C.c_void_p()
-        _lib.check(_lib.lib().sgdm_forward_guided(self._h, _lib.current_stream(x.device), _lib.ptr(x), _lib.ptr(t),
-                                                  _lib.ptr(cond), _lib.ptr(layout), x.shape[0], C.byref(pc),
-                                                  C.byref(pu)))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sgdm_forward_guided(self._h, _lib.current_stream(x.device), _lib.ptr(x), _lib.ptr(t),
+                                                      _lib.ptr(cond), _lib.ptr(layout), x.shape[0], C.byref(pc),
+                                                      C.byref(pu)))
         return pc.value, pu.value
 
     def _scale_type(self):
@@ -278,8 +308,9 @@ class EngineUNet(nn.Module):
         else:
             w = float(cond_scale)
         per_sample = out[0].numel()
-        _lib.check(_lib.lib().sgdm_mix(_lib.current_stream(x.device), pc, pu, w, w_ptr, self._scale_type(),
-                                       _lib.ptr(out), B, per_sample))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sgdm_mix(_lib.current_stream(x.device), pc, pu, w, w_ptr, self._scale_type(),
+                                           _lib.ptr(out), B, per_sample))
         return out
 
     def convert_to_fp16(self):  # API parity (openaimodel.py:837-851); operand precision is fixed by the engine

@@ -266,7 +266,88 @@ def gen_sampling(model, cfg, batch):
     np.savez_compressed(os.path.join(HERE, "sampling_tiny.npz"), **arrays)
 
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# Trajectory goldens at the NAMED BASELINE configs (round 2):  python tests/golden/make_golden.py traj [name...]
+#   traj_cfg1   : config 1 exactly as BASELINE.json states it - 32x32, mc=64, B=16, DDIM-10 eta=0 (+ native-10, PLMS-10)
+#   traj_cfg2   : config 2 at B=2 - 250-step native DDPM (T=250) and DDIM-250 eta=0 (T=1000)
+#   traj_cfg4/5 : one DDIM-10 trajectory each of unetca_fast clusterlayout / stegoclusterlayout at true shapes
+# Every run is the unmodified reference's LatentDiffusion.p_sample_loop (diffusion/ddpm.py:108-122) with
+# torch.randn replaced by the seeded tape.
+TRAJ = {
+    "traj_cfg1": ("cfg1_cifar_label", 16, {
+        "ddim10_eta0": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
+        "native10": ("native", 10, dict(num_timesteps=10)),
+        "plms10": ("plms", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
+    }),
+    "traj_cfg2": ("cfg2_in64_label", 2, {
+        "native250": ("native", 250, dict(num_timesteps=250)),
+        "ddim250_eta0": ("ddim", 1000, dict(num_timesteps=250, ddim_eta=0.0)),
+    }),
+    "traj_cfg4": ("cfg4_voc_clusterlayout", 2, {
+        "ddim10_eta0": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
+    }),
+    "traj_cfg5": ("cfg5_coco_stego", 2, {
+        "ddim10_eta0": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
+    }),
+}
+
+
+@torch.no_grad()
+def gen_trajectories(tname):
+    import time
+
+    case, batch, runs = TRAJ[tname]
+    cfg, _ = CASES[case]
+    torch.manual_seed(0)
+    model = build_reference_unet(cfg)
+    named_shapes = load_synthetic(model, seed=7)
+    H = cfg["image_size"]
+    shape = (batch, 3, H, H)
+    data = synthetic.synthetic_batch(cfg["condition_method"], batch, cfg["cond_dim"], H, cfg["layout_dim"], seed=21)
+    arrays = {}
+    for rname, (method, T, over) in runs.items():
+        ld = ref_ddpm.LatentDiffusion(**diffusion_kwargs(T))
+        ld.set_denoise_fn(model.forward, model.forward_with_cond_scale)
+        skw = dict(sampling_method=method, vis=None, ddim_eta=0.0, log_num_per_prog=10, clip_denoised=True,
+                   dtp=1, temperature=1.0, noise_dropout=0, random_sample_condition=False,
+                   return_inter_dict=False, disable_tqdm=True)
+        skw.update(over)
+        kw = prepare_denoise_fn_kwargs_4sampling(FakeModule(cfg), dict(data), skw, cond_scale=2.0)
+        S = skw["num_timesteps"]
+        n_draws = S + 1 if method == "plms" else S
+        tape = synthetic.noise_tape(shape, n_draws, seed=1234)
+        real_randn = torch.randn
+        torch.randn = Tape(tape)
+        t0 = time.time()
+        try:
+            samples, inter = ld.p_sample_loop(method, shape, skw, denoise_sample_fn_kwargs=kw,
+                                              condition_kwargs=dict(cond_scale=2.0,
+                                                                    condition_method=cfg["condition_method"]))
+            used = torch.randn.k
+        finally:
+            torch.randn = real_randn
+        assert used == 1 + n_draws, (rname, used)
+        arrays[f"{rname}_samples"] = samples.numpy()
+        arrays[f"{rname}_pred_x0"] = inter["pred_x0"].numpy()
+        arrays[f"{rname}_x_inter"] = inter["x_inter"].numpy()
+        for k, v in kw.items():
+            if torch.is_tensor(v):
+                arrays["kw_" + k] = v.numpy()
+        print(tname, rname, tuple(samples.shape), tuple(inter["x_inter"].shape), f"{time.time() - t0:.1f}s",
+              "mean", samples.float().mean().item(), flush=True)
+    arrays["meta"] = np.frombuffer(json.dumps(dict(
+        runs={k: [v[0], v[1], v[2]] for k, v in runs.items()}, batch=batch, tape_seed=1234, data_seed=21,
+        cond_scale=2.0, weight_seed=7, unet_case=case)).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, f"{tname}.npz"), **arrays)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["traj"]:
+        for tname in (sys.argv[2:] or list(TRAJ)):
+            gen_trajectories(tname)
+        sys.exit(0)
     only = sys.argv[1:]
     gen_schedules()
     for name, (cfg, batch) in CASES.items():

@@ -202,6 +202,58 @@ def test_sampling_vs_reference_golden(run):
     assert ps >= (25.0 if run == "plms10" else PSNR_MIN)
 
 
+# Trajectories at the NAMED BASELINE configs (tests/golden/make_golden.py traj): the unmodified reference's
+# p_sample_loop on config 1 exactly as BASELINE.json states it (32x32, mc=64, B=16, DDIM-10 eta=0; + native-10,
+# PLMS-10), config 2 at B=2 over the FULL 250 steps (native DDPM with T=250, and DDIM-250 eta=0 on T=1000), and one
+# DDIM-10 trajectory of each unetca_fast condition type (configs 4 / 5) at true shapes.
+NAMED_TRAJ = [("traj_cfg1", "ddim10_eta0"), ("traj_cfg1", "native10"), ("traj_cfg1", "plms10"),
+              ("traj_cfg2", "native250"), ("traj_cfg2", "ddim250_eta0"),
+              ("traj_cfg4", "ddim10_eta0"), ("traj_cfg5", "ddim10_eta0")]
+X_INTER_TOL = 5e-2  # per logged step, relative L2 of x_t against the reference's fp32 trajectory
+
+
+def run_named_trajectory(tname, run, model=None):
+    from sgdm_b200 import synthetic
+
+    meta, g = load_npz(f"{tname}.npz")
+    umeta, _ = load_unet_case(meta["unet_case"])
+    m = cuda_model(umeta) if model is None else model
+    method, T, over = meta["runs"][run]
+    B, H = meta["batch"], umeta["cfg"]["image_size"]
+    ld = _ld(T)
+    ld.set_denoise_fn(m.forward, m.forward_with_cond_scale)
+    skw = dict(sampling_method=method, vis=None, ddim_eta=0.0, log_num_per_prog=10, clip_denoised=True, dtp=1,
+               temperature=1.0, noise_dropout=0, random_sample_condition=False, return_inter_dict=False,
+               disable_tqdm=True)
+    skw.update(over)
+    S = skw["num_timesteps"]
+    tape = synthetic.noise_tape((B, 3, H, H), S + 1 if method == "plms" else S, seed=meta["tape_seed"])
+    kw = {k[3:]: torch.from_numpy(v).cuda() for k, v in g.items() if k.startswith("kw_")}
+    kw["cond_scale"] = meta["cond_scale"]
+    samples, inter = ld.p_sample_loop(method, (B, 3, H, H), skw, denoise_sample_fn_kwargs=kw,
+                                      condition_kwargs=dict(cond_scale=2.0), noise_tape=tape)
+    torch.cuda.synchronize()
+    return samples, inter, g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tname,run", NAMED_TRAJ)
+def test_named_config_trajectory_vs_reference_golden(tname, run):
+    need_gpu()
+    samples, inter, g = run_named_trajectory(tname, run)
+    ref = torch.from_numpy(g[f"{run}_samples"])
+    assert samples.dtype == torch.uint8 and tuple(samples.shape) == tuple(ref.shape)
+    ps = psnr_u8(samples.cpu(), ref)
+    xi, xr = inter["x_inter"].cpu().float(), torch.from_numpy(g[f"{run}_x_inter"])
+    assert xi.shape == xr.shape
+    per_step = [rel_l2(xi[k], xr[k]) for k in range(xi.shape[0])]
+    p0 = psnr_u8(inter["pred_x0"].cpu(), torch.from_numpy(g[f"{run}_pred_x0"]))
+    print(f"[traj {tname}/{run}] final-sample PSNR = {ps:.2f} dB, pred_x0 PSNR = {p0:.2f} dB, x_inter rel_l2 per logged "
+          f"step = {' '.join(f'{e:.1e}' for e in per_step)}")
+    assert ps >= PSNR_MIN, f"{tname}/{run}: final-sample PSNR {ps:.2f} dB < {PSNR_MIN}"
+    assert max(per_step) <= X_INTER_TOL, f"{tname}/{run}: x_inter rel-L2 {max(per_step):.3e} > {X_INTER_TOL}"
+
+
 @pytest.mark.gpu
 def test_generic_callable_path_matches_fused_path():
     """A sampler driven by an arbitrary denoise_sample_fn (the reference contract) must give the
