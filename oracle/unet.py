@@ -21,9 +21,31 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------- helpers
-def _r(x, emu):
-    """Round to bf16 and back when emulating the kernels' operand precision."""
-    return x.bfloat16().float() if emu else x
+def _emu_kind(emu, kind):
+    if not emu:
+        return None
+    if isinstance(emu, dict):
+        return emu.get(kind)
+    return "bf16" if emu is True else emu
+
+
+def _r(x, emu, kind="a"):
+    """Round to the kernels' operand precision and back when emulating it.  `emu`: None (plain fp32 reference),
+    'bf16' / 'f16' (every operand), or a dict per operand kind {'a': activations, 'w': weights, 'h1': the
+    ResBlock-internal conv output the kernels keep in 16 bits, 'x': the image fed to the first conv, 'q': the
+    q / k / v tensors as the attention kernel reads them, 'p': attention probabilities, 'o': the attention output as stored}; 'f16x2' = hi + lo
+    split (two fp16 values, ~22 bits)."""
+    d = _emu_kind(emu, kind)
+    if d is None:
+        return x
+    if d == "bf16":
+        return x.bfloat16().float()
+    if d == "f16":
+        return x.half().float()
+    if d == "f16x2":
+        hi = x.half().float()
+        return hi + (x - hi).half().float()
+    raise ValueError(d)
 
 
 def timestep_embedding(timesteps, dim, max_period=10000):
@@ -44,12 +66,12 @@ def _gn(sd, p, x):
     return F.group_norm(x.float(), 32, sd[p + ".weight"], sd[p + ".bias"], eps=1e-5)
 
 
-def _conv(sd, p, x, emu, stride=1, padding=1):
-    return F.conv2d(_r(x, emu), _r(sd[p + ".weight"], emu), sd[p + ".bias"], stride=stride, padding=padding)
+def _conv(sd, p, x, emu, stride=1, padding=1, akind="a"):
+    return F.conv2d(_r(x, emu, akind), _r(sd[p + ".weight"], emu, "w"), sd[p + ".bias"], stride=stride, padding=padding)
 
 
 def _lin(sd, p, x, emu=False, bias=True):
-    return F.linear(_r(x, emu), _r(sd[p + ".weight"], emu), sd[p + ".bias"] if bias else None)
+    return F.linear(_r(x, emu), _r(sd[p + ".weight"], emu, "w"), sd[p + ".bias"] if bias else None)
 
 
 def _mlp2(sd, p, x):
@@ -128,7 +150,7 @@ def resblock(sd, p, x, emb, up, down, emu):
     elif down:
         h = F.avg_pool2d(h, 2, 2)
         x = F.avg_pool2d(x, 2, 2)
-    h = _conv(sd, p + ".in_layers.2", h, emu)
+    h = _r(_conv(sd, p + ".in_layers.2", h, emu), emu, "h1")  # the kernels keep h1 in the 16-bit operand type
     emb_out = _lin(sd, p + ".emb_layers.1", F.silu(emb), emu)[..., None, None]
     scale, shift = torch.chunk(emb_out, 2, dim=1)
     h = _gn(sd, p + ".out_layers.0", h) * (1 + scale) + shift
@@ -142,15 +164,15 @@ def attention_block(sd, p, x, heads, emu):
     """AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:365-371,403-420)."""
     b, c, hh, ww = x.shape
     xf = x.reshape(b, c, -1)
-    qkv = F.conv1d(_r(_gn(sd, p + ".norm", xf), emu), _r(sd[p + ".qkv.weight"], emu), sd[p + ".qkv.bias"])
-    qkv = _r(qkv, emu)
+    qkv = F.conv1d(_r(_gn(sd, p + ".norm", xf), emu), _r(sd[p + ".qkv.weight"], emu, "w"), sd[p + ".qkv.bias"])
+    qkv = _r(qkv, emu, "q")
     ch = c // heads
     q, k, v = qkv.reshape(b * heads, ch * 3, -1).split(ch, dim=1)
     scale = 1 / math.sqrt(math.sqrt(ch))
     w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
     w = torch.softmax(w.float(), dim=-1)
-    a = torch.einsum("bts,bcs->bct", _r(w, emu), v).reshape(b, -1, hh * ww)
-    h = F.conv1d(_r(a, emu), _r(sd[p + ".proj_out.weight"], emu), sd[p + ".proj_out.bias"])
+    a = torch.einsum("bts,bcs->bct", _r(w, emu, "p"), v).reshape(b, -1, hh * ww)
+    h = F.conv1d(_r(a, emu, "o"), _r(sd[p + ".proj_out.weight"], emu, "w"), sd[p + ".proj_out.bias"])
     return (xf + h).reshape(b, c, hh, ww)
 
 
@@ -164,8 +186,8 @@ def attention_lr(sd, p, x, context, heads, emu):
     b, c, hh, ww = x.shape
     xt = x.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
     xn = _ln(xt, sd[p + ".norm.gamma"], sd[p + ".norm.beta"])
-    q = F.linear(_r(xn, emu), _r(sd[p + ".to_q.weight"], emu))
-    kv = F.linear(_r(xn, emu), _r(sd[p + ".to_kv.weight"], emu))
+    q = F.linear(_r(xn, emu), _r(sd[p + ".to_q.weight"], emu, "w"))
+    kv = F.linear(_r(xn, emu), _r(sd[p + ".to_kv.weight"], emu, "w"))
     k, v = kv.chunk(2, dim=-1)
     d = q.shape[-1] // heads
     q = q.reshape(b, hh * ww, heads, d).permute(0, 2, 1, 3) * d**-0.5
@@ -177,11 +199,11 @@ def attention_lr(sd, p, x, context, heads, emu):
     ck, cv = ckv.chunk(2, dim=-1)
     k = torch.cat((ck, k), dim=-2)
     v = torch.cat((cv, v), dim=-2)
-    sim = torch.einsum("bhid,bjd->bhij", _r(q, emu), _r(k, emu))
+    sim = torch.einsum("bhid,bjd->bhij", _r(q, emu, "q"), _r(k, emu, "q"))
     attn = sim.softmax(dim=-1)
-    out = torch.einsum("bhij,bjd->bhid", _r(attn, emu), _r(v, emu))
+    out = torch.einsum("bhij,bjd->bhid", _r(attn, emu, "p"), _r(v, emu, "q"))
     out = out.permute(0, 2, 1, 3).reshape(b, hh * ww, heads * d)
-    out = F.linear(_r(out, emu), _r(sd[p + ".to_out.0.weight"], emu))
+    out = F.linear(_r(out, emu, "o"), _r(sd[p + ".to_out.0.weight"], emu, "w"))
     out = _ln(out, sd[p + ".to_out.1.gamma"], sd[p + ".to_out.1.beta"])
     return (xt + out).reshape(b, hh, ww, c).permute(0, 3, 1, 2)
 
@@ -191,8 +213,8 @@ def _run_block(sd, cfg, layers, h, emb, context, emu):
     ca = cfg["kind"] == "unetca_fast"
     for layer in layers:
         kind, p = layer[0], layer[1]
-        if kind == "conv":
-            h = _conv(sd, p, h, emu)
+        if kind == "conv":  # the first conv: the kernels feed the image as a hi + lo pair (kind "x")
+            h = _conv(sd, p, h, emu, akind="x")
         elif kind == "res":
             h = resblock(sd, p, h, emb, layer[4], layer[5], emu)
         elif kind == "attn":

@@ -31,9 +31,11 @@ class SgdmConfig(C.Structure):
         ("layout_dim", C.c_int32),
         ("context_dim", C.c_int32),
         ("cond_token_num", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 
+PRECISIONS = {"fp16": 0, "fp16x3": 1}  # sgdm_config.precision
 KIND_UNET_FAST = 0
 KIND_UNETCA_FAST = 1
 SCALE_TYPES = {"imagen": 0, "cfg": 1}

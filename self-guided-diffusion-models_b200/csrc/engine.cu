@@ -128,6 +128,13 @@ struct sgdm_engine {
   bool ca = false;
   int mc = 0, E = 0, NE = 0, heads = 0;
   int in_ch_total = 0;  // image + layout channels of the first conv
+  // precision 1 ("fp16 x3"): every conv / GEMM runs on split operands — activations [hi | hi | lo], weights
+  // [w_hi | w_lo | w_hi], 3x the K dimension through the SAME kernels — so products carry ~22-bit operands and the
+  // only 16-bit roundings left are inside the attention kernel.  h1 stays fp32.  ~3x the tensor work: the mode for
+  // deterministic samplers (DDIM eta=0, PLMS) on ill-conditioned nets, where fp16 rounding amplifies.
+  bool x3 = false;
+  int S = 1;        // K expansion of every GEMM: 3 in x3 mode
+  int xin_c = 64;   // channels of the prepared first-conv input
   std::vector<Param> params;
   std::unordered_map<std::string, int> pidx;
   std::vector<std::vector<Layer>> in_blocks, out_blocks;
@@ -270,7 +277,15 @@ int build_topology(sgdm_engine* e) {
   if (e->ca && (c.cond_token_num != 1 || c.context_dim <= 0 || c.cond_dim <= 0))
     return fail("unetca_fast: only cond_token_num == 1 with context_dim > 0 is supported (openaimodel_ca.py:960)");
   if (!e->ca && c.layout_dim > 1) return fail("unet_fast supports clusterlayout (layout_dim 1) only (openaimodel.py:623)");
-  if (2 * c.in_channels + c.layout_dim > 64) return fail("too many input channels");
+  if (c.precision != 0 && c.precision != 1) return fail("precision must be 0 (fp16 operands) or 1 (split fp16 x3), got %d", c.precision);
+  e->x3 = c.precision == 1;
+  e->S = e->x3 ? 3 : 1;
+  if (e->x3) {
+    e->xin_c = (3 * (c.in_channels + c.layout_dim) + 63) / 64 * 64;
+    if (e->xin_c > 256) return fail("too many input channels");
+  } else if (2 * c.in_channels + c.layout_dim > 64) {
+    return fail("too many input channels");
+  }
 
   // ---- top-level parameters, in the reference's registration order
   if (!e->ca) {
@@ -414,10 +429,11 @@ std::function<int(const float*, cudaStream_t)> copy_loader(float* dst, int64_t n
   };
 }
 std::function<int(const float*, cudaStream_t)> pack_loader(op_t* dst, int cout, int cin, int ks, int cin_pad,
-                                                           int ktot, int k_off, const int* ci_map = nullptr) {
+                                                           int ktot, int k_off, const int* ci_map = nullptr,
+                                                           int cin_part = 0) {
   return [=](const float* src, cudaStream_t s) {
     ++g_launches;
-    return pack_conv_weight_launch(src, dst, cout, cin, ks, cin_pad, ktot, k_off, ci_map, s);
+    return pack_conv_weight_launch(src, dst, cout, cin, ks, cin_pad, ktot, k_off, ci_map, s, cin_part);
   };
 }
 
@@ -461,10 +477,12 @@ int setup_device(sgdm_engine* e) {
   if (bind_f32(e, "out.0.weight", &e->out_gn_w) || bind_f32(e, "out.0.bias", &e->out_gn_b)) return 1;
 
   // fused emb projection
-  if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E) || dalloc(e, &e->b_emb, e->NE)) return 1;
+  const int S = e->S;                       // K expansion (3 in split-precision mode)
+  auto part = [&](int cin) { return e->x3 ? cin : 0; };  // pack_conv_weight_launch's cin_part
+  if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E * S) || dalloc(e, &e->b_emb, e->NE)) return 1;
 
   // 3 + 3 (+1) input channels: the whole 3x3 neighbourhood fits the 64-channel input row (SGDM_FIRST_IM2COL=0: A/B)
-  e->first_im2col = 9 * (2 * c.in_channels + c.layout_dim) <= 64 &&
+  e->first_im2col = !e->x3 && 9 * (2 * c.in_channels + c.layout_dim) <= 64 &&
                     !(getenv("SGDM_FIRST_IM2COL") && atoi(getenv("SGDM_FIRST_IM2COL")) == 0);
   // first conv channel map: dst [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0] <- src [x(Cimg) | layout(L)]
   {
@@ -487,18 +505,19 @@ int setup_device(sgdm_engine* e) {
           bind_f32(e, p + ".out_layers.0.weight", &r.gn2_w) || bind_f32(e, p + ".out_layers.0.bias", &r.gn2_b) ||
           bind_f32(e, p + ".in_layers.2.bias", &r.b1))
         return 1;
-      const int k1 = 9 * r.cin, k2 = 9 * r.cout + (r.skip ? r.cin : 0);
+      const int k1 = 9 * r.cin * S, k2 = (9 * r.cout + (r.skip ? r.cin : 0)) * S;
       const int np = conv_npad(r.cout, pick_block_n(r.cout));
       if (dalloc(e, &r.w1, static_cast<size_t>(np) * k1) || dalloc(e, &r.w2, static_cast<size_t>(np) * k2)) return 1;
-      if (bind_loader(e, p + ".in_layers.2.weight", pack_loader(r.w1, r.cout, r.cin, 3, r.cin, k1, 0))) return 1;
-      if (bind_loader(e, p + ".out_layers.3.weight", pack_loader(r.w2, r.cout, r.cout, 3, r.cout, k2, 0))) return 1;
+      if (bind_loader(e, p + ".in_layers.2.weight", pack_loader(r.w1, r.cout, r.cin, 3, S * r.cin, k1, 0, nullptr, part(r.cin)))) return 1;
+      if (bind_loader(e, p + ".out_layers.3.weight", pack_loader(r.w2, r.cout, r.cout, 3, S * r.cout, k2, 0, nullptr, part(r.cout)))) return 1;
       if (dalloc(e, &r.b2, r.cout) || dalloc(e, &r.bfused, r.cout)) return 1;
       float *b2 = r.b2, *bf = r.bfused;
       const int co = r.cout;
       if (r.skip) {
         if (dalloc(e, &r.bskip, r.cout)) return 1;
         float* bs = r.bskip;
-        if (bind_loader(e, p + ".skip_connection.weight", pack_loader(r.w2, r.cout, r.cin, 1, r.cin, k2, 9 * r.cout)))
+        if (bind_loader(e, p + ".skip_connection.weight",
+                        pack_loader(r.w2, r.cout, r.cin, 1, S * r.cin, k2, 9 * r.cout * S, nullptr, part(r.cin))))
           return 1;
         if (bind_loader(e, p + ".skip_connection.bias", [=](const float* src, cudaStream_t s) {
               if (cudaMemcpyAsync(bs, src, co * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return 1;
@@ -520,7 +539,8 @@ int setup_device(sgdm_engine* e) {
           return 1;
       }
       if (bind_loader(e, p + ".emb_layers.1.weight",
-               pack_loader(e->w_emb + static_cast<size_t>(r.emb_off) * e->E, 2 * r.cout, e->E, 1, e->E, e->E, 0)))
+               pack_loader(e->w_emb + static_cast<size_t>(r.emb_off) * e->E * S, 2 * r.cout, e->E, 1, S * e->E, S * e->E, 0,
+                           nullptr, part(e->E))))
         return 1;
       if (bind_loader(e, p + ".emb_layers.1.bias", copy_loader(e->b_emb + r.emb_off, 2 * r.cout))) return 1;
     } else if (L.kind == L_ATTN && !e->ca) {
@@ -529,11 +549,11 @@ int setup_device(sgdm_engine* e) {
       if (bind_f32(e, p + ".norm.weight", &a.norm_w) || bind_f32(e, p + ".norm.bias", &a.norm_b) ||
           bind_f32(e, p + ".qkv.bias", &a.bqkv) || bind_f32(e, p + ".proj_out.bias", &a.bproj))
         return 1;
-      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(3 * C, pick_block_n(3 * C))) * C) ||
-          dalloc(e, &a.wproj, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * C))
+      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(3 * C, pick_block_n(3 * C))) * C * S) ||
+          dalloc(e, &a.wproj, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * C * S))
         return 1;
-      if (bind_loader(e, p + ".qkv.weight", pack_loader(a.wqkv, 3 * C, C, 1, C, C, 0)) ||
-          bind_loader(e, p + ".proj_out.weight", pack_loader(a.wproj, C, C, 1, C, C, 0)))
+      if (bind_loader(e, p + ".qkv.weight", pack_loader(a.wqkv, 3 * C, C, 1, S * C, S * C, 0, nullptr, part(C))) ||
+          bind_loader(e, p + ".proj_out.weight", pack_loader(a.wproj, C, C, 1, S * C, S * C, 0, nullptr, part(C))))
         return 1;
     } else if (L.kind == L_ATTN) {
       AttnLRW& a = e->attn_lr[L.idx];
@@ -544,20 +564,22 @@ int setup_device(sgdm_engine* e) {
           bind_f32(e, p + ".null_kv", &a.null_kv) || bind_f32(e, p + ".to_out.1.gamma", &a.out_g) ||
           bind_f32(e, p + ".to_out.1.beta", &a.out_b))
         return 1;
-      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(nq, pick_block_n(nq))) * C) ||
-          dalloc(e, &a.wout, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * inner))
+      if (dalloc(e, &a.wqkv, static_cast<size_t>(conv_npad(nq, pick_block_n(nq))) * C * S) ||
+          dalloc(e, &a.wout, static_cast<size_t>(conv_npad(C, pick_block_n(C))) * inner * S))
         return 1;
-      if (bind_loader(e, p + ".to_q.weight", pack_loader(a.wqkv, inner, C, 1, C, C, 0)) ||
-          bind_loader(e, p + ".to_kv.weight", pack_loader(a.wqkv + static_cast<size_t>(inner) * C, 2 * a.dh, C, 1, C, C, 0)) ||
-          bind_loader(e, p + ".to_out.0.weight", pack_loader(a.wout, C, inner, 1, inner, inner, 0)))
+      if (bind_loader(e, p + ".to_q.weight", pack_loader(a.wqkv, inner, C, 1, S * C, S * C, 0, nullptr, part(C))) ||
+          bind_loader(e, p + ".to_kv.weight", pack_loader(a.wqkv + static_cast<size_t>(inner) * C * S, 2 * a.dh, C, 1, S * C, S * C, 0,
+                                                          nullptr, part(C))) ||
+          bind_loader(e, p + ".to_out.0.weight", pack_loader(a.wout, C, inner, 1, S * inner, S * inner, 0, nullptr, part(inner))))
         return 1;
     } else {  // conv layers: first conv, Downsample.op, Upsample.conv
       ConvW& cw = e->convs[L.idx];
       const std::string pp = L.kind == L_DOWN ? p + ".op" : L.kind == L_UP ? p + ".conv" : p;
+      if (e->x3) cw.cin_pad = L.kind == L_CONV_IN ? e->xin_c : 3 * cw.cin;  // split parts of cw.cin channels
       const int ktot = 9 * cw.cin_pad;
       if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
       if (bind_f32(e, pp + ".bias", &cw.b)) return 1;
-      const int* map = L.kind == L_CONV_IN ? e->ci_map_first : nullptr;
+      const int* map = (L.kind == L_CONV_IN && !e->x3) ? e->ci_map_first : nullptr;
       if (L.kind == L_CONV_IN && e->first_im2col) {
         // [Npad][64]: K = tap * (2 Cimg + L) + entry; the buffer (sized for the 3x3 packing) is reused
         op_t* dst = cw.w;
@@ -569,7 +591,7 @@ int setup_device(sgdm_engine* e) {
           return 1;
         return 0;
       }
-      if (bind_loader(e, pp + ".weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0, map))) return 1;
+      if (bind_loader(e, pp + ".weight", pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0, map, part(cw.cin)))) return 1;
     }
     return 0;
   };
@@ -586,12 +608,14 @@ int setup_device(sgdm_engine* e) {
       if (setup_layer(e->out_blocks[bi][li], prefix_of(e->out_blocks, "output_blocks", bi, li))) return 1;
   {
     ConvW& cw = e->conv_out;
+    cw.cin_pad = S * cw.cin;
     const int ktot = 9 * cw.cin_pad;
     if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
     if (bind_f32(e, "out.2.bias", &cw.b)) return 1;
     // both packings of the head's weights (36 KB each): which one a plan uses depends on the image geometry
-    if (3 * cw.cout <= 16 && dalloc(e, &cw.w_hfold, static_cast<size_t>(16) * 3 * cw.cin_pad)) return 1;
-    auto std_pack = pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0);
+    // (split-precision mode uses the plain packing only)
+    if (!e->x3 && 3 * cw.cout <= 16 && dalloc(e, &cw.w_hfold, static_cast<size_t>(16) * 3 * cw.cin_pad)) return 1;
+    auto std_pack = pack_loader(cw.w, cw.cout, cw.cin, 3, cw.cin_pad, ktot, 0, nullptr, part(cw.cin));
     op_t* wh = cw.w_hfold;
     const int co = cw.cout, ci = cw.cin, cp = cw.cin_pad;
     if (bind_loader(e, "out.2.weight", [=](const float* src, cudaStream_t st) {
@@ -652,6 +676,8 @@ struct Builder {
   // lose about as much and eps rel-L2 rises 1.9e-3 -> 2.2e-3 (DDIM-10 PSNR 43.7 -> 41.3 dB): off by default.
   bool use16 = getenv("SGDM_GN16") != nullptr && atoi(getenv("SGDM_GN16")) != 0;
   int smem_reserve = 0;
+  int S = 1;          // e->S: channel expansion of every operand tensor (3 in split-precision mode)
+  int split3 = 0;     // e->x3
   void attach_outputs(Act& o, size_t rows, ConvDesc& c, bool allow16 = true) {
     o.has_stats = stats_ok(o.H, o.W);
     o.stats = stats_alloc(rows, o.C, o.H, o.W);
@@ -690,7 +716,8 @@ struct Builder {
       return;
     }
     const double M = static_cast<double>(Bp) * d.Hout * d.Wout;
-    const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin) + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
+    // algorithmic K: the reference's channel counts (split-precision mode executes 3x that)
+    const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin / S) + (d.in2 ? (d.C2 + (d.in2b ? d.C2b : 0)) / S : 0);
     const double flops = 2.0 * M * d.Cout * k_real;
     const double in_px = static_cast<double>(Bp) * d.Hin * d.Win;
     const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * (d.C2 + (d.in2b ? d.C2b : 0)) * 2 : 0) +
@@ -735,12 +762,12 @@ struct Builder {
     const int C = a.C + b.C, H = a.H, W = a.W;
     const int Ho = r.down ? H / 2 : r.up ? H * 2 : H, Wo = r.down ? W / 2 : r.up ? W * 2 : W;
     const size_t px_in = static_cast<size_t>(Bp) * H * W, px_out = static_cast<size_t>(Bp) * Ho * Wo;
-    op_t* g1 = static_cast<op_t*>(scratch("gn_out", px_out * C * sizeof(op_t)));
+    op_t* g1 = static_cast<op_t*>(scratch("gn_out", px_out * C * S * sizeof(op_t)));
     // 16-bit input copies (with producer statistics) for every source: the GroupNorm reads 2 B instead of 4 B
     // per element and the fused 1x1 skip conv reads the copies directly (no raw concat copy).  A down block
     // pools its fp32 input for the residual, so it keeps the fp32 path.
     const bool in16 = a.has16 && a.has_stats && (b.C == 0 || (b.has16 && b.has_stats)) && !r.down;
-    op_t* raw = (r.skip && !in16) ? static_cast<op_t*>(scratch("raw_op", px_in * C * sizeof(op_t))) : nullptr;
+    op_t* raw = (r.skip && !in16) ? static_cast<op_t*>(scratch("raw_op", px_in * C * S * sizeof(op_t))) : nullptr;
     float* pooled = r.down ? static_cast<float*>(scratch("pooled", px_out * C * sizeof(float))) : nullptr;
     GnDesc g;
     g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
@@ -749,19 +776,26 @@ struct Builder {
     g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
     g.out = g1; g.raw_out = raw; g.pool_out = pooled;
     g.stats0 = a.stats; g.stats1 = b.stats;
+    g.split3 = split3;
     gn(g);
     // h1 only feeds the second GroupNorm: kept in the 16-bit operand type (halves its HBM traffic;
     // measured cost on eps: rel-L2 1.65e-3 -> 1.96e-3, DESIGN.md "operand precision")
-    op_t* h1 = static_cast<op_t*>(scratch("h1", px_out * r.cout * sizeof(op_t)));
+    // (split-precision mode: h1 stays fp32)
+    op_t* h1 = split3 ? nullptr : static_cast<op_t*>(scratch("h1", px_out * r.cout * sizeof(op_t)));
+    float* h1f = split3 ? static_cast<float*>(scratch("h1f", px_out * r.cout * sizeof(float))) : nullptr;
     float2* h1_stats = static_cast<float2*>(scratch("h1_stats", stats_elems(px_out, r.cout) * sizeof(float2)));
     if (!stats_ok(Ho, Wo)) h1_stats = nullptr;
     ConvDesc c1;
-    c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
-    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.out_op = h1; c1.stats = h1_stats;
+    c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C * S; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
+    c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.stats = h1_stats;
+    if (split3) c1.out_f32 = h1f;
+    else c1.out_op = h1;
     conv(c1);
-    op_t* g2 = static_cast<op_t*>(scratch("gn_out", px_out * r.cout * sizeof(op_t)));
+    op_t* g2 = static_cast<op_t*>(scratch("gn_out", px_out * r.cout * S * sizeof(op_t)));
     GnDesc gg;
-    gg.src0 = h1; gg.src0_is_op = 1; gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
+    if (split3) { gg.src0 = h1f; gg.src0_is_op = 0; gg.split3 = 1; }
+    else { gg.src0 = h1; gg.src0_is_op = 1; }
+    gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
     gg.film = dry ? nullptr : emb_out + r.emb_off; gg.film_stride = e->NE; gg.silu = 1; gg.out = g2;
     gg.stats0 = h1_stats;
     gn(gg);
@@ -769,14 +803,14 @@ struct Builder {
     o.C = r.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(px_out * r.cout);
     ConvDesc c2;
-    c2.in = g2; c2.Hin = Ho; c2.Win = Wo; c2.Cin = r.cout; c2.w = r.w2; c2.ks = 3; c2.stride = 1; c2.pad = 1;
+    c2.in = g2; c2.Hin = Ho; c2.Win = Wo; c2.Cin = r.cout * S; c2.w = r.w2; c2.ks = 3; c2.stride = 1; c2.pad = 1;
     c2.Hout = Ho; c2.Wout = Wo; c2.Cout = r.cout; c2.out_f32 = o.p;
     // (an upsampled-residual epilogue needs its shared memory for the residual slots: no 16-bit copy there)
     attach_outputs(o, px_out, c2, !(r.up && !r.skip));
     if (r.skip) {
       c2.bias = r.bfused;
       if (in16) { c2.in2 = a.p16; c2.C2 = a.C; c2.in2b = b.C ? b.p16 : nullptr; c2.C2b = b.C; }
-      else { c2.in2 = raw; c2.C2 = C; }
+      else { c2.in2 = raw; c2.C2 = C * S; }
     } else {
       c2.bias = r.bfused;
       c2.res = r.down ? pooled : a.p;
@@ -790,16 +824,17 @@ struct Builder {
   Act attention(const AttnW& w, Act a) {
     const int C = a.C, T = a.H * a.W, dh = C / e->heads;
     const size_t rows = static_cast<size_t>(Bp) * T;
-    op_t* g = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
+    op_t* g = static_cast<op_t*>(scratch("gn_out", rows * C * S * sizeof(op_t)));
     GnDesc gd;
     gd.H = a.H; gd.W = a.W; gd.C0 = C; gd.gamma = w.norm_w; gd.beta = w.norm_b; gd.silu = 0; gd.out = g;
+    gd.split3 = split3;
     if (a.has16 && a.has_stats) { gd.src0 = a.p16; gd.src0_is_op = 1; }
     else gd.src0 = a.p;
     gd.stats0 = a.stats;
     gn(gd);
     op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * 3 * C * sizeof(op_t)));
     ConvDesc c1;
-    c1.in = g; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
+    c1.in = g; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C * S; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
     c1.Hout = a.H; c1.Wout = a.W; c1.Cout = 3 * C; c1.bias = w.bqkv; c1.out_op = qkv;
     conv(c1);
     op_t* att = static_cast<op_t*>(scratch("att", rows * C * sizeof(op_t)));
@@ -817,29 +852,43 @@ struct Builder {
     Act o = a;
     o.p = stream_alloc(rows * C);
     ConvDesc c2;
-    c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = C; c2.w = w.wproj; c2.ks = 1; c2.stride = 1; c2.pad = 0;
+    c2.in = expand_att(att, rows, C); c2.Hin = a.H; c2.Win = a.W; c2.Cin = C * S; c2.w = w.wproj; c2.ks = 1; c2.stride = 1; c2.pad = 0;
     c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.bias = w.bproj; c2.res = a.p; c2.res_mode = 1; c2.out_f32 = o.p;
     attach_outputs(o, rows, c2);
     conv(c2);
     return o;
   }
 
+  // split-precision mode: the attention output exists in the operand type only -> [v | v | 0] rows for the
+  // projection GEMM's [w_hi | w_lo | w_hi] weights
+  const op_t* expand_att(op_t* att, size_t rows, int C) {
+    if (!split3) return att;
+    op_t* att3 = static_cast<op_t*>(scratch("att3", rows * C * 3 * sizeof(op_t)));
+    const long n = static_cast<long>(rows);
+    push([=](cudaStream_t s) {
+      ++g_launches;
+      return expand3_launch(att, att3, n, C, s);
+    });
+    return att3;
+  }
+
   // Attention_LR.forward (crossattetion_lr.py:81-142)
   Act attention_lr(const AttnLRW& w, Act a) {
     const int C = a.C, T = a.H * a.W, dh = w.dh, inner = dh * e->heads, nq = inner + 2 * dh;
     const size_t rows = static_cast<size_t>(Bp) * T;
-    op_t* ln = static_cast<op_t*>(scratch("gn_out", rows * C * sizeof(op_t)));
+    op_t* ln = static_cast<op_t*>(scratch("gn_out", rows * C * S * sizeof(op_t)));
     {
       const float* x = a.p;
       const float *g = w.norm_g, *b = w.norm_b;
+      const int sp = split3;
       push([=](cudaStream_t s) {
         ++g_launches;
-        return layernorm_launch(x, g, b, nullptr, ln, nullptr, static_cast<long>(rows), C, s);
+        return layernorm_launch(x, g, b, nullptr, ln, nullptr, static_cast<long>(rows), C, s, sp);
       });
     }
     op_t* qkv = static_cast<op_t*>(scratch("qkv", rows * nq * sizeof(op_t)));
     ConvDesc c1;
-    c1.in = ln; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
+    c1.in = ln; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C * S; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
     c1.Hout = a.H; c1.Wout = a.W; c1.Cout = nq; c1.out_op = qkv;
     conv(c1);
     op_t* ck = static_cast<op_t*>(scratch("ctx_k", static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
@@ -868,7 +917,7 @@ struct Builder {
          static_cast<double>(rows) * (nq + inner) * 2);
     float* tmp = static_cast<float*>(scratch("tmpf", rows * C * sizeof(float)));
     ConvDesc c2;
-    c2.in = att; c2.Hin = a.H; c2.Win = a.W; c2.Cin = inner; c2.w = w.wout; c2.ks = 1; c2.stride = 1; c2.pad = 0;
+    c2.in = expand_att(att, rows, inner); c2.Hin = a.H; c2.Win = a.W; c2.Cin = inner * S; c2.w = w.wout; c2.ks = 1; c2.stride = 1; c2.pad = 0;
     c2.Hout = a.H; c2.Wout = a.W; c2.Cout = C; c2.out_f32 = tmp;
     conv(c2);
     Act o = a;
@@ -891,20 +940,20 @@ struct Builder {
   Act resample_conv(const ConvW& cw, Act a, bool up) {
     const int Hc = up ? a.H * 2 : a.H, Wc = up ? a.W * 2 : a.W;  // conv input size
     const int Ho = up ? Hc : a.H / 2, Wo = up ? Wc : a.W / 2;
-    op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * Hc * Wc * a.C * sizeof(op_t)));
+    op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * Hc * Wc * a.C * S * sizeof(op_t)));
     {
       const float* src = a.p;
-      const int B = Bp, H = a.H, W = a.W, C = a.C, u = up ? 1 : 0;
+      const int B = Bp, H = a.H, W = a.W, C = a.C, u = up ? 1 : 0, sp = split3;
       push([=](cudaStream_t s) {
         ++g_launches;
-        return cast_launch(src, raw, B, H, W, C, u, s);
+        return cast_launch(src, raw, B, H, W, C, u, s, sp);
       });
     }
     Act o;
     o.C = cw.cout; o.H = Ho; o.W = Wo;
     o.p = stream_alloc(static_cast<size_t>(Bp) * Ho * Wo * cw.cout);
     ConvDesc c;
-    c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
+    c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C * S; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
     c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
     attach_outputs(o, static_cast<size_t>(Bp) * Ho * Wo, c);
     conv(c);
@@ -937,12 +986,12 @@ struct Builder {
     const int mc = e->mc, ted = 4 * mc, H = c.image_size, W = c.image_size;
     const size_t px = static_cast<size_t>(Bp) * H * W;
     // ---- prologue buffers
-    op_t* x_in = static_cast<op_t*>(scratch("x_in", px * 64 * sizeof(op_t)));
+    op_t* x_in = static_cast<op_t*>(scratch("x_in", px * e->xin_c * sizeof(op_t)));
     float* t_emb = static_cast<float*>(scratch("t_emb", static_cast<size_t>(Bp) * mc * sizeof(float)));
     float* cond_m = static_cast<float*>(scratch("cond_m", static_cast<size_t>(Bp) * (c.cond_dim + 1) * sizeof(float)));
     float* hid = static_cast<float*>(scratch("hid", static_cast<size_t>(Bp) * ted * sizeof(float)));
     float* emb = static_cast<float*>(scratch("emb", static_cast<size_t>(Bp) * e->E * sizeof(float)));
-    op_t* emb_act = static_cast<op_t*>(scratch("emb_act", static_cast<size_t>(Bp) * e->E * sizeof(op_t)));
+    op_t* emb_act = static_cast<op_t*>(scratch("emb_act", static_cast<size_t>(Bp) * e->E * S * sizeof(op_t)));
     emb_out = static_cast<float*>(scratch("emb_out", static_cast<size_t>(Bp) * e->NE * sizeof(float)));
     unsigned char* drop = static_cast<unsigned char*>(scratch("drop", Bp));
     float* eps = static_cast<float*>(scratch("eps", px * c.out_channels * sizeof(float)));
@@ -956,6 +1005,7 @@ struct Builder {
       pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = c.cond_dim; pd.mc = mc;
       pd.x_in = x_in; pd.t_emb = t_emb; pd.cond_masked = cond_m; pd.drop = drop;
       pd.im2col = e->first_im2col ? 1 : 0;
+      pd.split3 = split3; pd.xc = e->xin_c;
     }
     auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,
                    int silu_out, int accumulate) {
@@ -991,12 +1041,13 @@ struct Builder {
     // all ResBlock emb_layers = SiLU + Linear, as one GEMM (openaimodel.py:262-268,309)
     {
       const long n = static_cast<long>(Bp) * e->E;
+      const int Ew = e->E, sp = split3;
       push([=](cudaStream_t s) {
         ++g_launches;
-        return silu_cast_launch(emb, emb_act, n, s);
+        return silu_cast_launch(emb, emb_act, n, s, Ew, sp);
       });
       ConvDesc d;
-      d.in = emb_act; d.Hin = 1; d.Win = 1; d.Cin = e->E; d.w = e->w_emb; d.ks = 1; d.stride = 1; d.pad = 0;
+      d.in = emb_act; d.Hin = 1; d.Win = 1; d.Cin = e->E * S; d.w = e->w_emb; d.ks = 1; d.stride = 1; d.pad = 0;
       d.Hout = 1; d.Wout = 1; d.Cout = e->NE; d.bias = e->b_emb; d.out_f32 = emb_out;
       conv(d);
     }
@@ -1008,7 +1059,7 @@ struct Builder {
       h.C = cw.cout; h.H = H; h.W = W;
       h.p = stream_alloc(px * cw.cout);
       ConvDesc d;
-      d.in = x_in; d.Hin = H; d.Win = W; d.Cin = 64; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
+      d.in = x_in; d.Hin = H; d.Win = W; d.Cin = e->xin_c; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
       if (e->first_im2col) { d.ks = 1; d.pad = 0; }  // the taps are channels of the im2col'd input
       d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
       attach_outputs(h, px, d);
@@ -1027,15 +1078,16 @@ struct Builder {
       h = run_layers(layers, h, skip);
     }
     // out = GN + SiLU + conv3x3 -> eps NCHW (openaimodel.py:830-835,956)
-    op_t* g = static_cast<op_t*>(scratch("gn_out", px * h.C * sizeof(op_t)));
+    op_t* g = static_cast<op_t*>(scratch("gn_out", px * h.C * S * sizeof(op_t)));
     GnDesc gd;
     gd.H = H; gd.W = W; gd.C0 = h.C; gd.gamma = e->out_gn_w; gd.beta = e->out_gn_b; gd.silu = 1; gd.out = g;
+    gd.split3 = split3;
     if (h.has16 && h.has_stats) { gd.src0 = h.p16; gd.src0_is_op = 1; }
     else gd.src0 = h.p;
     gd.stats0 = h.stats;
     gn(gd);
     ConvDesc d;
-    d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
+    d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C * S; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
     d.Hout = H; d.Wout = W; d.Cout = c.out_channels; d.bias = e->conv_out.b; d.out_nchw = eps;
     // horizontal-tap folding (ConvDesc::hfold) whenever the head's tiles are whole image rows; SGDM_CONV_HFOLD=0: A/B
     const bool fold_env = !(getenv("SGDM_CONV_HFOLD") && atoi(getenv("SGDM_CONV_HFOLD")) == 0);
@@ -1059,6 +1111,8 @@ int get_plan(sgdm_engine* e, int Bp, Plan** out, int variant = 0) {
   plan->Bp = Bp;
   Builder b;
   b.e = e; b.plan = plan.get(); b.Bp = Bp;
+  b.S = e->S; b.split3 = e->x3 ? 1 : 0;
+  if (e->x3) b.use16 = false;
   b.smem_reserve = e->split_streams ? 4096 : 0;
   b.dry = true;
   b.build();

@@ -32,6 +32,9 @@ struct GnDesc {
   const float2* stats1 = nullptr;
   int stat_gran = 4;
   float2* final = nullptr;       // scratch [B][32]
+  // Split-precision operand output (engine precision 1): `out` / `raw_out` rows have 3 (C0 + C1) channels
+  // [hi | hi | lo], hi = op(v), lo = op(v - hi) (kernels_misc.cu: store8_split3).  fp32 sources only.
+  int split3 = 0;
 };
 int gn_chunks_for(int B, int HW, int C);
 int gn_launch(const GnDesc& d, cudaStream_t s);        // stats (or finalise) + apply
@@ -42,13 +45,16 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s);  // pass 2 only
 // ---- LayerNorm over channels (Attention_LR, crossattetion_lr.py:36-43) -------------------
 // mode 0: out_op = LN(x)*gamma+beta ; mode 1: out_f32 = res + LN(x)*gamma+beta
 int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
-                     float* out_f32, long rows, int C, cudaStream_t s);
+                     float* out_f32, long rows, int C, cudaStream_t s, int split3 = 0);
 
 // ---- casts --------------------------------------------------------------------------------
 // fp32 NHWC -> op_t NHWC, optionally nearest-2x upsampled (Upsample, openaimodel_ca.py:121-131)
-int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s);
-// dst[i] = op(silu(src[i]))   (ResBlock.emb_layers[0], openaimodel.py:262-263)
-int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s);
+// (split3: rows of 3C channels [hi | hi | lo], the split-precision operand layout of engine precision 1)
+int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s, int split3 = 0);
+// dst[i] = op(silu(src[i]))   (ResBlock.emb_layers[0], openaimodel.py:262-263); split3: src rows of C channels
+int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s, int C = 0, int split3 = 0);
+// op_t [rows, C] -> [rows, 3C] = [v | v | 0] (a 16-bit-only tensor as the activation side of a split-precision GEMM)
+int expand3_launch(const op_t* src, op_t* dst, long rows, int C, cudaStream_t s);
 
 // ---- fp32 small linear: out[m, n] (+)= act(bias[n] + sum_k in[m,k] W[n,k]) -----------------
 int linear_f32_launch(const float* in, long in_stride, const float* W, const float* bias, float* out,
@@ -71,6 +77,8 @@ struct PrepDesc {
   // entry j of the row above at pixel (y + r - 1, x + s - 1) (zero outside the image), tap = 3 r + s: the first conv
   // becomes a 1x1 GEMM with ONE 64-wide K block (9 (2 Cimg + L) <= 64; pack_first_conv_im2col_launch)
   int im2col = 0;
+  // split-precision input (engine precision 1): x_in has xc channels [hi(x, layout) | hi(x, layout) | lo(x, layout) | 0]
+  int split3 = 0, xc = 64;
   float* t_emb = nullptr;            // [Bp, mc]  [cos | sin]
   float* cond_masked = nullptr;      // [Bp, cond_dim]
 };
@@ -141,8 +149,9 @@ int lincomb_launch(const float* const* a, const float* c, int n_terms, float div
 // first conv as a 1x1 GEMM over PrepDesc::im2col input: dst[co][tap * ce + j], ce = 2 Cimg + L, from w [Cout, Cimg + L, 3, 3]
 int pack_first_conv_im2col_launch(const float* w, op_t* dst, int Cout, int Cimg, int L, cudaStream_t s);
 int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s);
+// cin_part > 0: split-precision packing, three parts of cin_part channels [w_hi | w_lo | w_hi] per tap (3 cin_part <= cin_pad)
 int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
-                            const int* ci_map, cudaStream_t s);
+                            const int* ci_map, cudaStream_t s, int cin_part = 0);
 int add_bias_launch(const float* a, const float* b, float* out, int n, cudaStream_t s);
 
 }  // namespace sgdm

@@ -239,11 +239,32 @@ __device__ __forceinline__ void store8_op(op_t* dst, const float (&y)[8]) {
   uint4 o = make_uint4(pack_op2(y[0], y[1]), pack_op2(y[2], y[3]), pack_op2(y[4], y[5]), pack_op2(y[6], y[7]));
   *reinterpret_cast<uint4*>(dst) = o;
 }
+// Split-precision operand layout (engine precision 1, "fp16 x3"): a C-channel activation row becomes 3C channels
+// [hi | hi | lo] with hi = op(v), lo = op(v - hi); the matching weight rows are packed [w_hi | w_lo | w_hi]
+// (pack_conv_weight_kernel), so the unchanged GEMM accumulates a_hi w_hi + a_hi w_lo + a_lo w_hi in fp32:
+// the product of two ~22-bit operands.  `row` points at channel c of the first part, C = channels per part.
+__device__ __forceinline__ void store8_split3(op_t* row, int C, const float (&y)[8]) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = from_op(to_op(y[j]));
+    lo[j] = y[j] - hi[j];
+  }
+  store8_op(row, hi);
+  store8_op(row + C, hi);
+  store8_op(row + 2 * C, lo);
+}
+// out[(row) * (kSplit ? 3C : C) + c ...]
+template <bool kSplit>
+__device__ __forceinline__ void gn_store8(op_t* base, long row, int C, int c, const float (&y)[8]) {
+  if (kSplit) store8_split3(base + row * 3 * C + c, C, y);
+  else store8_op(base + row * C + c, y);
+}
 
 // Pass 2: normalise + affine (+FiLM) (+SiLU), write op_t NHWC, optionally pooled / upsampled.
 // Thread = (8-channel slice cg, pixel lane): the folded per-channel scale/offset live in
 // registers for the whole block; the block walks `ppb` pixels.
-template <bool kHalfIn, int kResample, int kMinBlocks = 3>
+template <bool kHalfIn, int kResample, int kMinBlocks = 3, bool kSplit = false>
 __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
   pdl_launch_dependents();
@@ -308,7 +329,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
   const int p_end = min(p_begin + a.ppb, n_iter);
   if (kResample == 0) {
     int pix = p_begin + lane;
-    if (kHalfIn) {
+    if (kHalfIn && !kSplit) {
       // 16-bit source(s): eight pixels = 8 x 16-byte loads in flight per thread, kept packed.  A thread's
       // 8-channel slice lies in exactly one of the two concat sources.
       const bool first = c < a.C0;
@@ -338,16 +359,16 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         xform(v[u], y);
-        store8_op(a.out + (static_cast<long>(n) * HW + pix + u * a.PLa) * C + c, y);
-        if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix + u * a.PLa) * C + c, v[u]);
+        gn_store8<kSplit>(a.out, static_cast<long>(n) * HW + pix + u * a.PLa, C, c, y);
+        if (a.raw_out) gn_store8<kSplit>(a.raw_out, static_cast<long>(n) * HW + pix + u * a.PLa, C, c, v[u]);
       }
     }
     for (; pix < p_end; pix += a.PLa) {
       float v[8], y[8];
       gn_load8<kHalfIn>(a, n, pix, c, v);
       xform(v, y);
-      store8_op(a.out + (static_cast<long>(n) * HW + pix) * C + c, y);
-      if (a.raw_out) store8_op(a.raw_out + (static_cast<long>(n) * HW + pix) * C + c, v);
+      gn_store8<kSplit>(a.out, static_cast<long>(n) * HW + pix, C, c, y);
+      if (a.raw_out) gn_store8<kSplit>(a.raw_out, static_cast<long>(n) * HW + pix, C, c, v);
     }
   } else if (kResample == 1) {
     for (int pix = p_begin + lane; pix < p_end; pix += a.PLa) {
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[j] *= 0.25f; racc[j] *= 0.25f; }
       const long o = (static_cast<long>(n) * n_iter + pix) * C + c;
-      store8_op(a.out + o, acc);
+      gn_store8<kSplit>(a.out, static_cast<long>(n) * n_iter + pix, C, c, acc);
       if (a.pool_out) {
         *reinterpret_cast<float4*>(a.pool_out + o) = make_float4(racc[0], racc[1], racc[2], racc[3]);
         *reinterpret_cast<float4*>(a.pool_out + o + 4) = make_float4(racc[4], racc[5], racc[6], racc[7]);
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
       const int yi = pix / a.W, xi = pix - yi * a.W;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        store8_op(a.out + ((static_cast<long>(n) * a.H * 2 + 2 * yi + (k >> 1)) * W2 + 2 * xi + (k & 1)) * C + c, y);
+        gn_store8<kSplit>(a.out, (static_cast<long>(n) * a.H * 2 + 2 * yi + (k >> 1)) * W2 + 2 * xi + (k & 1), C, c, y);
     }
   }
 }
@@ -459,6 +480,12 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
                 d.pool_out};
   const dim3 grid((n_iter + ppb - 1) / ppb, d.B);
   const int threads = C8 * PLa;
+  if (d.split3) {  // split-precision operands (engine precision 1): fp32 sources only (h1 stays fp32 in that mode)
+    if (d.src0_is_op) return 1;
+    if (d.resample == 0) return launch_pdl(gn_apply_kernel<false, 0, 3, true>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else if (d.resample == 1) return launch_pdl(gn_apply_kernel<false, 1, 3, true>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    else return launch_pdl(gn_apply_kernel<false, 2, 3, true>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+  }
   // Resident blocks per SM of the plain (no resample) instances: 3 x 256 threads without spills, or 4 at 64
   // registers with ~200 bytes of spills per thread.  Measured on B200 (config 2, batch 256, same box):
   // 3 blocks: gn_apply 10.4 -> 9.5 ms per step, the large launches at 6.3 TB/s.  SGDM_GN_OCC=4: A/B switch.
@@ -488,7 +515,7 @@ int gn_launch(const GnDesc& d, cudaStream_t s) {
 // One warp per row of C channels (C % 128 == 0, C <= 1024); two-pass in registers.
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ res,
-                                 op_t* __restrict__ out_op, float* __restrict__ out_f32, long rows, int C) {
+                                 op_t* __restrict__ out_op, float* __restrict__ out_f32, long rows, int C, int split3) {
   const long row = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -521,23 +548,30 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
         y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
       }
       *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+    } else if (split3) {  // [hi | hi | lo] parts of a 3C-channel row (see store8_split3)
+      const float4 hi = make_float4(from_op(to_op(y.x)), from_op(to_op(y.y)), from_op(to_op(y.z)), from_op(to_op(y.w)));
+      const uint2 h = make_uint2(pack_op2(hi.x, hi.y), pack_op2(hi.z, hi.w));
+      op_t* o = out_op + row * 3 * C + c;
+      *reinterpret_cast<uint2*>(o) = h;
+      *reinterpret_cast<uint2*>(o + C) = h;
+      *reinterpret_cast<uint2*>(o + 2 * C) = make_uint2(pack_op2(y.x - hi.x, y.y - hi.y), pack_op2(y.z - hi.z, y.w - hi.w));
     } else {
       *reinterpret_cast<uint2*>(out_op + row * C + c) = make_uint2(pack_op2(y.x, y.y), pack_op2(y.z, y.w));
     }
   }
 }
 int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
-                     float* out_f32, long rows, int C, cudaStream_t s) {
+                     float* out_f32, long rows, int C, cudaStream_t s, int split3) {
   if (C % 128 || C > 1024) return 1;
   const long threads = rows * 32;
   layernorm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(x, gamma, beta, res, out_op, out_f32,
-                                                                              rows, C);
+                                                                              rows, C, split3);
   return SGDM_LAUNCH_OK();
 }
 
 // =========================================================================== casts
 __global__ void cast_kernel(const float* __restrict__ src, op_t* __restrict__ dst, int H, int W, int C, int up2,
-                            long items) {
+                            long items, int split3) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (idx >= items) return;
   const int C8 = C >> 3;
@@ -547,30 +581,63 @@ __global__ void cast_kernel(const float* __restrict__ src, op_t* __restrict__ ds
   const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
   const float4 hi = __ldg(reinterpret_cast<const float4*>(p + 4));
   const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  auto put = [&](long row) {
+    if (split3) store8_split3(dst + row * 3 * C + cg * 8, C, v);
+    else store8_op(dst + row * C + cg * 8, v);
+  };
   if (!up2) {
-    store8_op(dst + pixg * C + cg * 8, v);
+    put(pixg);
   } else {
     const long n = pixg / (static_cast<long>(H) * W);
     const int pix = pixg - n * H * W;
     const int y = pix / W, x = pix - y * W;
     for (int dy = 0; dy < 2; ++dy)
-      for (int dx = 0; dx < 2; ++dx)
-        store8_op(dst + ((n * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * C + cg * 8, v);
+      for (int dx = 0; dx < 2; ++dx) put((n * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx);
   }
 }
-int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s) {
+int cast_launch(const float* src, op_t* dst, int B, int H, int W, int C, int up2, cudaStream_t s, int split3) {
   if (C % 8) return 1;
   const long items = static_cast<long>(B) * H * W * (C / 8);
-  cast_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, s>>>(src, dst, H, W, C, up2, items);
+  cast_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, s>>>(src, dst, H, W, C, up2, items, split3);
   return SGDM_LAUNCH_OK();
 }
 
-__global__ void silu_cast_kernel(const float* __restrict__ src, op_t* __restrict__ dst, long n) {
+// dst[r, c] = op(silu(src[r, c])); split3: rows of 3C channels [hi | hi | lo]
+__global__ void silu_cast_kernel(const float* __restrict__ src, op_t* __restrict__ dst, long n, int C, int split3) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  if (i < n) dst[i] = to_op(silu(src[i]));
+  if (i >= n) return;
+  const float v = silu(src[i]);
+  if (!split3) { dst[i] = to_op(v); return; }
+  const long r = i / C;
+  const int c = static_cast<int>(i - r * C);
+  const op_t hi = to_op(v);
+  op_t* o = dst + r * 3 * C + c;
+  o[0] = hi;
+  o[C] = hi;
+  o[2 * C] = to_op(v - from_op(hi));
 }
-int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s) {
-  silu_cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s, int C, int split3) {
+  silu_cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n, C > 0 ? C : 1, split3);
+  return SGDM_LAUNCH_OK();
+}
+
+// 16-bit [rows, C] -> [rows, 3C] = [v | v | 0]: a tensor that only exists in the operand type (the attention output)
+// as the activation side of a split-precision GEMM (v w_hi + v w_lo).
+__global__ void expand3_kernel(const op_t* __restrict__ src, op_t* __restrict__ dst, long items, int C8) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= items) return;
+  const long row = idx / C8;
+  const int cg = static_cast<int>(idx - row * C8);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (row * C8 + cg) * 8));
+  uint4* o = reinterpret_cast<uint4*>(dst + (row * 3 * C8 + cg) * 8);
+  o[0] = v;
+  o[C8] = v;
+  o[2 * C8] = make_uint4(0u, 0u, 0u, 0u);
+}
+int expand3_launch(const op_t* src, op_t* dst, long rows, int C, cudaStream_t s) {
+  if (C % 8) return 1;
+  const long items = rows * (C / 8);
+  expand3_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, s>>>(src, dst, items, C / 8);
   return SGDM_LAUNCH_OK();
 }
 
@@ -682,6 +749,27 @@ __global__ void prep_x_kernel(const PrepDesc d) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) dst[j] = srcv[j];
 }
+// Split-precision first-conv input (engine precision 1): xc channels per pixel,
+// [hi(x, layout) | hi(x, layout) | lo(x, layout) | 0] with parts of Cimg + L channels (see store8_split3).
+__global__ void prep_x_split_kernel(const PrepDesc d) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const int HW = d.H * d.W;
+  if (idx >= static_cast<long>(d.Bp) * HW) return;
+  const int r = idx / HW, pix = idx - static_cast<long>(r) * HW;
+  const int b = r % d.B;
+  const bool drop = d.drop && d.drop[r];
+  const int cp = d.Cimg + d.L;
+  op_t* o = d.x_in + idx * d.xc;
+  for (int c = 0; c < cp; ++c) {
+    const float v = c < d.Cimg ? d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pix]
+                               : (drop ? d.null_layout[pix] : d.layout[(static_cast<long>(b) * d.L + (c - d.Cimg)) * HW + pix]);
+    const op_t hi = to_op(v);
+    o[c] = hi;
+    o[cp + c] = hi;
+    o[2 * cp + c] = to_op(v - from_op(hi));
+  }
+  for (int c = 3 * cp; c < d.xc; ++c) o[c] = to_op(0.f);
+}
 __global__ void prep_emb_kernel(const PrepDesc d) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   const int half = d.mc / 2;
@@ -701,9 +789,14 @@ __global__ void prep_emb_kernel(const PrepDesc d) {
   }
 }
 int prep_launch(const PrepDesc& d, cudaStream_t s) {
-  if (2 * d.Cimg + d.L > 64 || (d.im2col && 9 * (2 * d.Cimg + d.L) > 64)) return 1;
   const long npx = static_cast<long>(d.Bp) * d.H * d.W;
-  prep_x_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
+  if (d.split3) {
+    if (3 * (d.Cimg + d.L) > d.xc || d.im2col) return 1;
+    prep_x_split_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
+  } else {
+    if (2 * d.Cimg + d.L > 64 || (d.im2col && 9 * (2 * d.Cimg + d.L) > 64)) return 1;
+    prep_x_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
+  }
   const long ne = static_cast<long>(d.Bp) * (d.mc / 2) + static_cast<long>(d.Bp) * d.cond_dim;
   prep_emb_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, s>>>(d);
   return SGDM_LAUNCH_OK();
@@ -951,25 +1044,33 @@ int lincomb_launch(const float* const* a, const float* c, int n_terms, float div
 }
 
 // =========================================================================== weight packing
+// cin_part > 0: split-precision packing (engine precision 1).  The K row of a tap then holds three parts of cin_part
+// channels [w_hi | w_lo | w_hi] (w_hi = op(w), w_lo = op(w - w_hi)), zero-padded to cin_pad, matching activation rows
+// [a_hi | a_hi | a_lo] (store8_split3).
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin, int ks,
-                                        int cin_pad, int ktot, int k_off, const int* __restrict__ ci_map) {
+                                        int cin_pad, int ktot, int k_off, const int* __restrict__ ci_map, int cin_part) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
+  const int width = cin_part > 0 ? 3 * cin_part : cin_pad;
+  const long total = static_cast<long>(Cout) * ks * ks * width;
   if (idx >= total) return;
-  const int cj = idx % cin_pad;
-  const int tap = (idx / cin_pad) % (ks * ks);
-  const int co = idx / (static_cast<long>(cin_pad) * ks * ks);
-  const int ci = ci_map ? ci_map[cj] : (cj < Cin ? cj : -1);
+  const int cj = idx % width;
+  const int tap = (idx / width) % (ks * ks);
+  const int co = idx / (static_cast<long>(width) * ks * ks);
+  const int part = cin_part > 0 ? cj / cin_part : 0;
+  const int c = cin_part > 0 ? cj - part * cin_part : cj;
+  const int ci = ci_map ? ci_map[c] : (c < Cin ? c : -1);
   if (ci < 0) return;
   const int r = tap / ks, s = tap - r * ks;
-  dst[static_cast<long>(co) * ktot + k_off + tap * cin_pad + cj] =
-      to_op(w[((static_cast<long>(co) * Cin + ci) * ks + r) * ks + s]);
+  const float wv = w[((static_cast<long>(co) * Cin + ci) * ks + r) * ks + s];
+  const op_t hi = to_op(wv);
+  dst[static_cast<long>(co) * ktot + k_off + tap * cin_pad + cj] = part == 1 ? to_op(wv - from_op(hi)) : hi;
 }
 int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
-                            const int* ci_map, cudaStream_t s) {
-  const long total = static_cast<long>(Cout) * ks * ks * cin_pad;
+                            const int* ci_map, cudaStream_t s, int cin_part) {
+  if (cin_part > 0 && 3 * cin_part > cin_pad) return 1;
+  const long total = static_cast<long>(Cout) * ks * ks * (cin_part > 0 ? 3 * cin_part : cin_pad);
   pack_conv_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ks, cin_pad,
-                                                                                   ktot, k_off, ci_map);
+                                                                                   ktot, k_off, ci_map, cin_part);
   return SGDM_LAUNCH_OK();
 }
 __global__ void pack_first_conv_im2col_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cimg, int L) {

@@ -82,10 +82,20 @@ class EngineUNet(nn.Module):
     _KIND = None
     _FLOAT_SHORTCUT = True  # unet_fast: is_number accepts float; unetca_fast: int only
 
-    def _build(self, cfg_fields, condition, condition_method):
+    def _build(self, cfg_fields, condition, condition_method, precision=None):
+        """`precision` (not a reference kwarg; optional): 'fp16' = 16-bit GEMM operands, the throughput path;
+        'fp16x3' = split-precision operands (~fp32 products, ~3x the tensor work) for deterministic samplers on
+        ill-conditioned networks.  Default: $SGDM_PRECISION, else 'fp16'."""
+        import os
+
         self.condition = condition
         self.condition_method = condition_method
+        precision = precision or os.environ.get("SGDM_PRECISION") or "fp16"
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         c = _lib.SgdmConfig()
+        c.precision = _lib.PRECISIONS[precision]
         for k, v in cfg_fields.items():
             if k in ("channel_mult", "attention_resolutions"):
                 vals = [int(a) for a in v]

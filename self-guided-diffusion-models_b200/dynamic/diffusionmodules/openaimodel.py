@@ -39,6 +39,7 @@ class UNetModel(EngineUNet):
         cond_dim=None,
         condition=None,
         condition_method=None,
+        precision=None,  # sgdm_b200 only: 'fp16' (default) | 'fp16x3' (EngineUNet._build)
     ):
         super().__init__()
         if num_heads == -1:
@@ -70,7 +71,7 @@ class UNetModel(EngineUNet):
                  attention_resolutions=attention_resolutions, num_heads=num_heads,
                  resblock_updown=int(bool(resblock_updown)), cond_dim=cond_dim, layout_dim=layout_dim,
                  context_dim=0, cond_token_num=0),
-            condition, condition_method)
+            condition, condition_method, precision)
 
     def forward(self, x, timesteps=None, cond=None, layout=None, cond_drop_prob=0.0, image_batch_ids=None):
         return self._forward_impl(x, timesteps, cond, layout, cond_drop_prob)

@@ -43,6 +43,7 @@ class UNetModel(EngineUNet):
         use_cls_token_as_pooled=None,
         condition=None,
         condition_method=None,
+        precision=None,  # sgdm_b200 only: 'fp16' (default) | 'fp16x3' (EngineUNet._build)
     ):
         super().__init__()
         if num_heads == -1:
@@ -80,7 +81,7 @@ class UNetModel(EngineUNet):
                  attention_resolutions=attention_resolutions, num_heads=num_heads, resblock_updown=0,
                  cond_dim=cond_dim, layout_dim=layout_dim, context_dim=context_dim,
                  cond_token_num=cond_token_num),
-            condition, condition_method)
+            condition, condition_method, precision)
 
     def forward(self, x, timesteps=None, cond_drop_prob=0.0, cond=None, layout=None):
         assert cond is not None and len(cond.shape) == 2  # openaimodel_ca.py:960-961

@@ -17,14 +17,14 @@ CONDITION = NS(scale_type="imagen", clusterlayout=NS(layout_dim=1, how="lost"),
                stegoclusterlayout=NS(layout_dim=27), layout=NS(layout_dim=21))
 
 
-def build_model(cfg):
+def build_model(cfg, precision=None):
     from sgdm_b200.dynamic.diffusionmodules import openaimodel, openaimodel_ca
 
     common = dict(image_size=cfg["image_size"], in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
                   model_channels=cfg["model_channels"], attention_resolutions=cfg["attention_resolutions"],
                   num_res_blocks=cfg["num_res_blocks"], channel_mult=cfg["channel_mult"], num_heads=cfg["num_heads"],
                   use_scale_shift_norm=True, use_checkpoint=False, use_fp16=False, cond_dim=cfg["cond_dim"],
-                  condition_method=cfg["condition_method"], condition=CONDITION)
+                  condition_method=cfg["condition_method"], condition=CONDITION, precision=precision)
     if cfg["kind"] == "unet_fast":  # kwargs of config/dynamic/unet_fast.yaml
         return openaimodel.UNetModel(dropout=0.1, resblock_updown=True, **common)
     return openaimodel_ca.UNetModel(dropout=0.0, use_ca_block=True, transformer_depth=1, legacy=False,
