@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py — guided 64x64 samples/sec (CFG UNet step) on B200, ms per UNet step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config {1..5}] [--scaling weak|strong] [--batch B]
 
-Workload (BASELINE.json configs[1]): ImageNet-64 label guidance, unet_fast model_channels=128,
-cond_dim=1000, cond_scale=2, 250-step DDPM ("native"), batch 256 per GPU, random-init weights
-(zero-initialised tensors re-randomised), synthetic one-hot labels, host-seeded noise.
+Default workload = BASELINE.json configs[1] ("config 2"): ImageNet-64 label guidance, unet_fast
+model_channels=128, cond_dim=1000, cond_scale=2, 250-step DDPM ("native"), batch 256 per GPU, random-init weights
+(seeded; the reference's zero-initialised tensors re-randomised), synthetic one-hot labels.  `--config N` selects
+another BASELINE.json config (1: CIFAR-10 32x32 DDIM-10 batch 16; 3: cluster guidance cond_dim 5000; 4 / 5:
+unetca_fast clusterlayout / stegoclusterlayout, DDIM-250); `config.workload` in the JSON line names it.
 
-A "step" is one pass of the hot path over one batch: the batched cond||uncond UNet eps
-prediction + the fused guidance-mix / posterior update.  `value` = trajectory samples per
-second = (batch over all ranks) / (250 * seconds per step); `ms_per_step` is the per-step time.
+A "step" is one pass of the hot path over one batch: the batched cond||uncond UNet eps prediction + the fused
+guidance-mix / sampler update.  The timed region is ONE K-step reverse trajectory of the whole job through the
+product's own public API — `sgdm_b200.parallel.sample_sharded` -> `LatentDiffusion.p_sample_loop` -> the fused
+sampler — including its per-trajectory work (weight re-pack check, schedule tables, device RNG draws, logged
+intermediates, uint8 conversion) and, for N > 1, the final NCCL all-gather of the samples.  K defaults to the
+config's full trajectory (250 steps for config 2), so by default nothing is extrapolated; with --steps K < steps per
+sample the K-step trajectory is scaled to the full length.  W warm-up steps run as a separate trajectory first.
 
-  value      inputs resident in HBM, fused sampler path (what p_sample_loop runs)
-  e2e        the same step through the reference-facing API with HOST (pinned) buffers:
-             H2D of x_t, t, noise (and cond), forward_with_cond_scale + p_sample, D2H of x_{t-1}
-  roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of its
-             launches in one step / their CUDA-event time, vs MEASURED_PEAKS.json
+  value      samples / s of the whole job: (batch over all ranks) / (steps_per_sample * seconds per step),
+             inputs resident in HBM (conditions on the device, noise drawn on the device)
+  e2e        the same step through the reference-facing per-step API with HOST (pinned) buffers: H2D of x_t, t,
+             noise (and cond / layout), p_sample / p_sample_ddim (forward_with_cond_scale + update), D2H of x_{t-1}
+  roofline   the dominant kernel family (tcgen05 implicit-GEMM conv / GEMM): algorithmic FLOPs of its launches in
+             one step / their CUDA-event time (a profiled replay, events around every launch), vs MEASURED_PEAKS.json
   cpu_baseline / --impl reference
-             the reference algorithm on the host CPU (oracle port, torch fp32, all cores),
-             on a bounded sample (small batch), same metric definition
+             the reference algorithm on the host CPU: the oracle port (`oracle/`, torch fp32, all host threads;
+             /root/reference itself is not present on the GPU box) on a bounded sample of the same workload
+             (config 1: the whole B=16 10-step trajectory; 64x64 configs: a short trajectory at a small batch).
+             That arm never imports the product package's engine (weights come from the oracle's own inventory).
 """
 import argparse
 import ctypes as C
@@ -31,20 +41,49 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-STEPS_PER_SAMPLE = 250
-GFLOP_PER_GUIDED_SAMPLE_STEP = 158.534  # SURVEY.md §8d / BASELINE.md §2, config 2
 METRIC = "guided 64x64 samples/sec (CFG UNet step)"
-UNIT = "samples/s (250-step DDPM trajectories; one step = CFG UNet eps + posterior update)"
+WEIGHT_SEED = 7
 
-CFG = dict(kind="unet_fast", image_size=64, in_channels=3, out_channels=3, model_channels=128, num_res_blocks=2,
-           channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8, resblock_updown=True, cond_dim=1000,
-           condition_method="label", layout_dim=0, context_dim=None, cond_token_num=0, scale_type="imagen")
+_BASE = dict(in_channels=3, out_channels=3, num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4],
+             num_heads=8, scale_type="imagen")
+# BASELINE.json configs; gflop = algorithmic GFLOP per guided sample-step (SURVEY.md §8d / BASELINE.md §2)
+CONFIGS = {
+    1: dict(workload="CIFAR-10 32x32 label guidance, unet_fast mc=64, cond_dim=10, cond_scale=2, DDIM-10 (eta=0), batch 16 "
+                     "[BASELINE.json configs[0]]",
+            cfg=dict(_BASE, kind="unet_fast", image_size=32, model_channels=64, resblock_updown=True, cond_dim=10,
+                     condition_method="label", layout_dim=0, context_dim=None, cond_token_num=0),
+            method="ddim", steps=10, batch=16, strong_total=16, gflop=9.874, cpu_batch=16),
+    2: dict(workload="ImageNet-64 label guidance, unet_fast mc=128, cond_dim=1000, cond_scale=2, 250-step DDPM (native), "
+                     "batch 256 per GPU [BASELINE.json configs[1]]",
+            cfg=dict(_BASE, kind="unet_fast", image_size=64, model_channels=128, resblock_updown=True, cond_dim=1000,
+                     condition_method="label", layout_dim=0, context_dim=None, cond_token_num=0),
+            method="native", steps=250, batch=256, strong_total=256, gflop=158.534, cpu_batch=4),
+    3: dict(workload="ImageNet-64 self-labeled cluster guidance, unet_fast mc=128, cond_dim=5000, cond_scale=2, 250-step DDPM "
+                     "(native), batch 256 [BASELINE.json configs[2]]",
+            cfg=dict(_BASE, kind="unet_fast", image_size=64, model_channels=128, resblock_updown=True, cond_dim=5000,
+                     condition_method="cluster", layout_dim=0, context_dim=None, cond_token_num=0),
+            method="native", steps=250, batch=256, strong_total=256, gflop=158.538, cpu_batch=4),
+    4: dict(workload="VOC-64 self-boxed clusterlayout guidance, unetca_fast context_dim=32 cond_token_num=1 cond_dim=100, "
+                     "cond_scale=2, DDIM-250 (eta=0), batch 256 [BASELINE.json configs[3]]",
+            cfg=dict(_BASE, kind="unetca_fast", image_size=64, model_channels=128, resblock_updown=False, cond_dim=100,
+                     condition_method="clusterlayout", layout_dim=1, context_dim=32, cond_token_num=1),
+            method="ddim", steps=250, batch=256, strong_total=256, gflop=135.290, cpu_batch=4),
+    5: dict(workload="COCO-Stuff-64 self-segmented stegoclusterlayout guidance (layout_dim=27), unetca_fast cond_dim=27, "
+                     "cond_scale=2, DDIM-250 (eta=0), batch 1024 over 8 GPUs = 128 per GPU [BASELINE.json configs[4]]",
+            cfg=dict(_BASE, kind="unetca_fast", image_size=64, model_channels=128, resblock_updown=False, cond_dim=27,
+                     condition_method="stegoclusterlayout", layout_dim=27, context_dim=32, cond_token_num=1),
+            method="ddim", steps=250, batch=128, strong_total=1024, gflop=135.780, cpu_batch=4),
+}
+
+
+def unit_of(c):
+    kind = "DDPM" if c["method"] == "native" else "DDIM"
+    return f"samples/s ({c['steps']}-step {kind} trajectories; one step = CFG UNet eps + sampler update)"
 
 
 def ncu_conv_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch, from the committed `ncu --set full`
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch, from the newest committed `ncu --set full`
     capture of one step (profiles/*ncu_conv_gemm*.csv, written by tools/ncu_summary.py); None if absent."""
     import csv
     import glob
@@ -74,9 +113,10 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return dict(tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), hbm=p["hbm_gbs"], src="measured (MEASURED_PEAKS.json, sustained)")
+        return dict(tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), burst=p.get("bf16_tflops"), hbm=p["hbm_gbs"],
+                    src="measured (MEASURED_PEAKS.json: bf16_tflops_sustained — the kernels are timed inside a long step)")
     except Exception:
-        return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+        return dict(tflops=1400.0, burst=None, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -131,118 +171,169 @@ class ClockSampler:
         return dict(sm_mhz=med, sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
 
 
-def build_reference_init_state(model, seed=0):
-    """reference-style init, then every zero-initialised tensor re-randomised N(0, 0.02)."""
-    import torch
-
-    g = torch.Generator().manual_seed(seed + 1)
-    torch.manual_seed(seed)
-    with torch.no_grad():
-        for name, p in list(model.named_parameters()):
-            if p.requires_grad and p.abs().max() == 0:
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+# ---------------------------------------------------------------------------------------------- workload pieces
+def sampling_kwargs(c, n_steps):
+    return dict(sampling_method=c["method"], vis=None, num_timesteps=n_steps, ddim_eta=0.0, log_num_per_prog=10,
+                clip_denoised=True, dtp=1, temperature=1.0, noise_dropout=0, random_sample_condition=False,
+                return_inter_dict=False, disable_tqdm=True)
 
 
-def make_model(device):
-    import torch
-    from test_host_mirror import build_model
-
-    torch.manual_seed(0)
-    m = build_model(CFG)
-    build_reference_init_state(m)
-    return m.to(device).eval()
+def model_timesteps(c, n_steps):
+    """T of the LatentDiffusion that makes an n-step trajectory: the native sampler walks all of its T steps
+    (ddpm_sampler.py:37-38); DDIM takes n of T = 4n (stride 4 like DDIM-250 on T=1000)."""
+    return n_steps if c["method"] == "native" else 4 * n_steps
 
 
-def cpu_reference_arm(steps, warmup, batch, threads=None):
-    """The reference algorithm on the host CPU: oracle port, fp32, all host threads."""
-    import torch
-    from oracle import sampler as osamp  # noqa: F401  (the checker doubles as the timed CPU baseline)
-    from oracle import schedule as osched
-    from oracle import unet as ounet
+def diffusion_kwargs(T, device):
+    return dict(given_betas=None, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
+                v_posterior=0.0, parameterization="eps", device=str(device), num_timesteps=T, loss_type="l2")
+
+
+def condition_tensors(c, batch, seed):
+    """This rank's synthetic conditions in the reference's formats, as host tensors."""
     from sgdm_b200 import synthetic
-    from test_host_mirror import build_model
 
-    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: set the count explicitly)
-    try:
+    cfg = c["cfg"]
+    data = synthetic.synthetic_batch(cfg["condition_method"], batch, cfg["cond_dim"], cfg["image_size"], cfg["layout_dim"],
+                                     seed=seed)
+    if cfg["condition_method"] == "clusterlayout":
+        return dict(cond=data["cluster"].float(), layout=data["lostbboxmask"].float())
+    if cfg["condition_method"] == "stegoclusterlayout":
+        return dict(cond=data["stego_attr"].float(), layout=data["stegomask"].float())
+    return dict(cond=data[cfg["condition_method"]])
+
+
+def cpu_reference_arm(c, steps, warmup, batch, threads=None):
+    """The reference algorithm on the host CPU: the oracle port's own sampler loop (fp32, all host threads) over a
+    `steps`-step trajectory at `batch` samples, after a `warmup`-step one.  Imports nothing of the engine."""
+    import torch
+    from oracle import sampler as osamp
+    from oracle import unet as ounet
+    from sgdm_b200 import synthetic  # pure-torch seeded tensors; does not load the CUDA library
+
+    try:  # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: set the count explicitly)
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
     torch.set_num_threads(threads or avail)
     cores = torch.get_num_threads()
-    torch.manual_seed(0)
-    m = build_model(CFG)
-    build_reference_init_state(m)
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    tab = osched.ddpm_tables(STEPS_PER_SAMPLE)
-    tape = synthetic.noise_tape((batch, 3, 64, 64), 1, seed=1234)
-    cond = synthetic.synthetic_batch("label", batch, 1000, 64, seed=4321)["label"]
-    x = tape["x_T"]
-    kw = dict(clip_denoised=True, dtp=1)
+    cfg = c["cfg"]
+    sd = synthetic.synthetic_state_dict(ounet.param_shapes(cfg), WEIGHT_SEED)
+    kw = condition_tensors(c, batch, 4321)
+    H = cfg["image_size"]
+    eps_fn = lambda x, t: ounet.forward_with_cond_scale(sd, cfg, x, t, 2.0, **kw)
 
-    def step(x, i):
-        t = torch.full((batch,), i, dtype=torch.long)
-        eps = ounet.forward_with_cond_scale(sd, CFG, x, t, 2.0, cond=cond)
-        x0 = osamp._ext(tab["sqrt_recip_alphas_cumprod"], t, x) * x - osamp._ext(tab["sqrt_recipm1_alphas_cumprod"], t, x) * eps
-        x0 = osamp.clip_x0(x0, True, 1)
-        mean = osamp._ext(tab["posterior_mean_coef1"], t, x) * x0 + osamp._ext(tab["posterior_mean_coef2"], t, x) * x
-        return mean + (0.5 * osamp._ext(tab["posterior_log_variance_clipped"], t, x)).exp() * tape["noise"][0]
+    def trajectory(n):
+        tape = synthetic.noise_tape((batch, 3, H, H), n, seed=1234)
+        skw = sampling_kwargs(c, n)
+        with torch.no_grad():
+            return osamp.p_sample_loop(c["method"], eps_fn, tape, dict(num_timesteps=model_timesteps(c, n)), skw)
 
-    with torch.no_grad():
-        for w in range(warmup):
-            x = step(x, STEPS_PER_SAMPLE - 1 - w)
-        t0 = time.perf_counter()
-        for k in range(steps):
-            x = step(x, STEPS_PER_SAMPLE - 1 - warmup - k)
-        dt = time.perf_counter() - t0
+    if warmup > 0:
+        trajectory(max(warmup, 2))
+    t0 = time.perf_counter()
+    trajectory(steps)
+    dt = time.perf_counter() - t0
     ms = dt / steps * 1e3
-    value = batch / (STEPS_PER_SAMPLE * ms / 1e3)
-    return dict(value=value, ms_per_step=ms, cores=cores, batch=batch,
-                sample=f"{steps} guided steps at batch {batch} (of the batch-256 workload), after {warmup} warm-up")
+    value = batch / (c["steps"] * ms / 1e3)
+    whole = steps == c["steps"] and batch == c["batch"]
+    sample = (f"the whole workload: one {steps}-step trajectory at batch {batch}" if whole else
+              f"one {steps}-step trajectory at batch {batch} (of the batch-{c['batch']}, {c['steps']}-step workload)")
+    return dict(value=value, ms_per_step=ms, cores=cores, batch=batch, sample=sample + f", after a {max(warmup, 2) if warmup else 0}-step warm-up")
+
+
+def build_gpu_model(c, device):
+    """The drop-in UNet with the same seeded weights the CPU arm uses (inventory from the module itself)."""
+    import torch
+    from types import SimpleNamespace as NS
+
+    from sgdm_b200 import synthetic
+    from sgdm_b200.dynamic.diffusionmodules import openaimodel, openaimodel_ca
+
+    cfg = c["cfg"]
+    condition = NS(scale_type=cfg["scale_type"], clusterlayout=NS(layout_dim=1, how="lost"),
+                   stegoclusterlayout=NS(layout_dim=27), layout=NS(layout_dim=21))
+    common = dict(image_size=cfg["image_size"], in_channels=3, out_channels=3, model_channels=cfg["model_channels"],
+                  attention_resolutions=cfg["attention_resolutions"], num_res_blocks=cfg["num_res_blocks"],
+                  channel_mult=cfg["channel_mult"], num_heads=cfg["num_heads"], use_scale_shift_norm=True,
+                  use_checkpoint=False, use_fp16=False, cond_dim=cfg["cond_dim"], condition_method=cfg["condition_method"],
+                  condition=condition)
+    if cfg["kind"] == "unet_fast":  # kwargs of config/dynamic/unet_fast.yaml
+        m = openaimodel.UNetModel(dropout=0.1, resblock_updown=True, **common)
+    else:  # config/dynamic/unetca_fast.yaml + README overrides
+        m = openaimodel_ca.UNetModel(dropout=0.0, use_ca_block=True, transformer_depth=1, legacy=False,
+                                     cond_token_num=cfg["cond_token_num"], context_dim=cfg["context_dim"],
+                                     use_cls_token_as_pooled=True, **common)
+    shapes = [(n, tuple(v.shape)) for n, v in m.state_dict().items()]
+    m.load_state_dict(synthetic.synthetic_state_dict(shapes, WEIGHT_SEED))
+    return m.to(device).eval()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (0 = the config's full trajectory; reference arm: bounded)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sgdm_b200", choices=["sgdm_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch per GPU; strong: the config's total batch (cfg3: 256, cfg5: 1024) split over the GPUs")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak) / total batch (strong); 0 = the config's")
+    ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline steps (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-launch profile of one step to this JSON file")
     ap.add_argument("--ncu", action="store_true", help="minimal run for profiling under ncu: warm-up + timed steps only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    c = CONFIGS[args.config]
+    UNIT = unit_of(c)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    config = dict(workload="ImageNet-64 label guidance, unet_fast mc=128, cond_dim=1000, cond_scale=2, "
-                           "250-step DDPM (native), batch 256 per GPU [BASELINE.json configs[1]]",
-                  per_gpu_batch=args.batch, global_batch=args.batch * world, steps_per_sample=STEPS_PER_SAMPLE,
-                  image="3x64x64", parallelism=f"batch-sharded x{world}, no data-path collective, final all-gather of uint8 samples",
+    if args.scaling == "strong":
+        total = args.batch or c["strong_total"]
+        if total % world:
+            raise SystemExit(f"strong scaling: total batch {total} is not divisible by {world} GPUs")
+        B = total // world
+    else:
+        B = args.batch or c["batch"]
+        total = B * world
+    K = args.steps or c["steps"]
+    H = c["cfg"]["image_size"]
+    config = dict(workload=c["workload"], config_id=args.config, per_gpu_batch=B, global_batch=total,
+                  steps_per_sample=c["steps"], sampler=c["method"], image=f"3x{H}x{H}",
+                  parallelism=f"batch-sharded x{world}, no data-path collective, final all-gather of uint8 samples",
+                  timed_region=f"one {K}-step trajectory through parallel.sample_sharded -> LatentDiffusion.p_sample_loop"
+                               + ("" if K == c["steps"] else f" (scaled to {c['steps']} steps)"),
                   l2="per-step working set (activations, several GB at batch 256) is far larger than the 126 MB L2; no extra flush")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(args.steps, args.warmup, args.cpu_batch)
-        line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+        cb = args.cpu_batch or c["cpu_batch"]
+        # bounded: the whole of config 1; for the 64x64 configs at most 30 steps at the small batch (~10-30 s)
+        ks = min(K, c["steps"] if args.config == 1 else 30)
+        r = cpu_reference_arm(c, ks, args.warmup, cb)
+        line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps or ks, warmup=args.warmup,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                     dtype="f32", data="synthetic", impl="reference", config=config,
-                    cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                    cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                      kind_note="oracle/ port of the reference's pure-PyTorch path: /root/reference does not exist "
+                                                "on the GPU box; the port is pinned to the unmodified reference by tests/golden"),
                     e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    note="reference = the reference algorithm (oracle port of the pure-PyTorch path) on the host CPU; "
-                         "ms_per_step is for the bounded sample batch, value is normalised per sample")
+                    note="ms_per_step is for the bounded sample batch; value is normalised per sample "
+                         f"({r['batch']} samples / ({c['steps']} steps x s per step))")
         print(json.dumps(line), flush=True)
         return
 
     import torch
     import torch.distributed as dist
 
-    from sgdm_b200 import _lib, synthetic
+    from sgdm_b200 import _lib, parallel
     from sgdm_b200.diffusion.ddpm import LatentDiffusion
 
     if not torch.cuda.is_available():
@@ -252,56 +343,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.lib()
-    B = args.batch
-    model = make_model(device)
-    ld = LatentDiffusion(given_betas=None, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
-                         v_posterior=0.0, parameterization="eps", device=str(device), num_timesteps=STEPS_PER_SAMPLE,
-                         loss_type="l2")
-    ld.set_denoise_fn(model.forward, model.forward_with_cond_scale)
-    sampler = ld.sampler
-    skw = dict(sampling_method="native", num_timesteps=STEPS_PER_SAMPLE, ddim_eta=0.0, log_num_per_prog=10,
-               clip_denoised=True, dtp=1, temperature=1.0, noise_dropout=0)
-    # synthetic inputs: this rank's shard of the global batch
-    tape = synthetic.noise_tape((B, 3, 64, 64), 1, seed=1234 + rank)
-    cond_host = synthetic.synthetic_batch("label", B, 1000, 64, seed=4321 + rank)["label"]
-    x = tape["x_T"].to(device)
-    noise = tape["noise"][0].to(device)
-    cond = cond_host.to(device)
-    kw = dict(cond=cond, cond_scale=2.0)
+    model = build_gpu_model(c, device)
+    # this rank's shard of the synthetic conditions, resident on the device
+    kw_host = condition_tensors(c, B, 4321 + rank)
+    kw = {k: v.to(device) for k, v in kw_host.items()}
+    kw["cond_scale"] = 2.0
     stream = torch.cuda.current_stream()
+    shape = (total, 3, H, H)
 
-    from sgdm_b200.diffusion.sampler._common import GuidedEps, coef6
+    def make_ld(n):
+        ld = LatentDiffusion(**diffusion_kwargs(model_timesteps(c, n), device))
+        ld.set_denoise_fn(model.forward, model.forward_with_cond_scale)
+        return ld
 
-    eps_src = GuidedEps(ld.denoise_sample_fn, kw, device)
-    tabs = {k: getattr(sampler, k).detach().cpu() for k in
-            ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
-             "posterior_log_variance_clipped")}
-    sigma = (0.5 * tabs["posterior_log_variance_clipped"]).exp()
-    nxt = torch.empty_like(x)
-    per_sample = x[0].numel()
-
-    def fused_step(xc, xn, i):
-        """exactly what Schedule_DDPM.sample does per step"""
-        ts = torch.full((B,), i, device=device, dtype=torch.long)
-        pc, pu, w, w_ptr, st = eps_src(xc, ts)
-        c = coef6(tabs["sqrt_recip_alphas_cumprod"][i], tabs["sqrt_recipm1_alphas_cumprod"][i],
-                  tabs["posterior_mean_coef1"][i], tabs["posterior_mean_coef2"][i], sigma[i] if i else 0.0, 1.0)
-        _lib.check(lib.sgdm_ddpm_step(stream.cuda_stream, pc, pu, w, w_ptr, st, c, 1, xc.data_ptr(), noise.data_ptr(),
-                                      xn.data_ptr(), None, B, per_sample))
+    def trajectory(ld, n):
+        """the product's multi-GPU entry point; conditions are pre-sharded, noise is drawn on the device"""
+        return parallel.sample_sharded(ld, c["method"], shape, sampling_kwargs(c, n), denoise_sample_fn_kwargs=kw,
+                                       condition_kwargs=dict(cond_scale=2.0), presharded=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (builds the plan, packs weights)
-    i = STEPS_PER_SAMPLE - 1
-    for _ in range(args.warmup):
-        fused_step(x, nxt, i)
-        x, nxt = nxt, x
-        i -= 1
+    # ---- warm-up: a W-step trajectory (builds the plan, packs the weights, initialises NCCL)
+    ld_w, ld_k = make_ld(args.warmup), make_ld(K)
+    trajectory(ld_w, args.warmup)
     barrier()
-    # ---- timed region: K steps + the trajectory-end uint8 conversion and all-gather
+    # ---- timed region: one K-step trajectory of the whole job
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -310,76 +379,90 @@ def main():
     launches0 = lib.sgdm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
-        fused_step(x, nxt, max(i, 0))
-        x, nxt = nxt, x
-        i -= 1
-    u8 = torch.empty(x.shape, dtype=torch.uint8, device=device)
-    _lib.check(lib.sgdm_to_uint8(stream.cuda_stream, x.data_ptr(), u8.data_ptr(), x.numel()))
-    if world > 1:
-        gathered = torch.empty((world,) + tuple(u8.shape), dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(gathered, u8)
+    samples, _ = trajectory(ld_k, K)
     e1.record(stream)
     barrier()
     launches = lib.sgdm_launch_count() - launches0
+    assert samples.dtype == torch.uint8 and tuple(samples.shape) == shape
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = B * world / (STEPS_PER_SAMPLE * ms_step / 1e3)
+    ms_step = float(t.item()) / K
+    value = total / (c["steps"] * ms_step / 1e3)
 
     if args.ncu:
         if rank == 0:
             print(json.dumps(dict(ncu_mode=True, ms_per_step_under_profiler=ms_step)), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
 
-    # ---- e2e: reference-facing API with host buffers (H2D + forward_with_cond_scale + p_sample + D2H per step)
-    hx = tape["x_T"].clone().pin_memory()
-    hn = tape["noise"][0].clone().pin_memory()
-    hcond = cond_host.clone().pin_memory()
-    hout = torch.empty_like(hx).pin_memory()
-    ht = torch.empty((B,), dtype=torch.long).pin_memory()
+    # ---- e2e: the reference-facing per-step API with host buffers (H2D + eps + update + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        from sgdm_b200 import synthetic
 
-    def e2e_step(i):
-        nonlocal hx, hout
-        ht.fill_(i)
-        dx = hx.to(device, non_blocking=True)
-        dn = hn.to(device, non_blocking=True)
-        dt_ = ht.to(device, non_blocking=True)
-        dc = hcond.to(device, non_blocking=True)
-        out, _, _ = sampler.p_sample(dx, dt_, temperature=1.0, sampling_kwargs=skw, denoise_sample_fn=ld.denoise_sample_fn,
-                                     denoise_sample_fn_kwargs=dict(cond=dc, cond_scale=2.0), noise=dn, index=i)
-        hout.copy_(out, non_blocking=True)
-        stream.synchronize()
-        hx, hout = hout, hx  # the step's result is the next step's input: swap the pinned buffers, no host copy
+        n_e2e = max(3, min(K, 10))
+        ld_e = make_ld(n_e2e + 2)
+        skw_e = sampling_kwargs(c, n_e2e + 2)
+        tape = synthetic.noise_tape((B, 3, H, H), 1, seed=1234 + rank)
+        hx, hn = tape["x_T"].clone().pin_memory(), tape["noise"][0].clone().pin_memory()
+        hkw = {k: v.clone().pin_memory() for k, v in kw_host.items()}
+        hout = torch.empty_like(hx).pin_memory()
+        ht = torch.empty((B,), dtype=torch.long).pin_memory()
+        if c["method"] == "native":
+            sampler = ld_e.sampler
+            t_of = lambda idx: idx
+        else:
+            sampler = ld_e.sampler_list["ddim"]
+            sampler.make_schedule(dict(skw_e, alphas_cumprod=ld_e.sampler.alphas_cumprod))
+            t_of = lambda idx: int(sampler.ddim_timesteps[idx])
 
-    for _ in range(2):
-        e2e_step(STEPS_PER_SAMPLE - 1)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    n_e2e = max(3, min(args.steps, 10))
-    for k in range(n_e2e):
-        e2e_step(STEPS_PER_SAMPLE - 2 - k)
-    e1.record(stream)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e  # host clock: the D2H + sync are part of the step
-    t = torch.tensor([e2e_ms], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = B * world / (STEPS_PER_SAMPLE * e2e_ms / 1e3)
-    h2d = hx.numel() * 4 + hn.numel() * 4 + ht.numel() * 8 + hcond.numel() * 8
-    d2h = hout.numel() * 4
+        def e2e_step(idx):
+            nonlocal hx, hout
+            ht.fill_(t_of(idx))
+            dx = hx.to(device, non_blocking=True)
+            dn = hn.to(device, non_blocking=True)
+            dt_ = ht.to(device, non_blocking=True)
+            dkw = {k: v.to(device, non_blocking=True) for k, v in hkw.items()}
+            dkw["cond_scale"] = 2.0
+            if c["method"] == "native":
+                out, _, _ = sampler.p_sample(dx, dt_, temperature=1.0, sampling_kwargs=skw_e,
+                                             denoise_sample_fn=ld_e.denoise_sample_fn, denoise_sample_fn_kwargs=dkw,
+                                             noise=dn, index=idx)
+            else:
+                out, _, _ = sampler.p_sample_ddim(dx, dt_, idx, sampling_kwargs=skw_e, denoise_sample_fn=ld_e.denoise_sample_fn,
+                                                  denoise_sample_fn_kwargs=dkw, noise=dn)
+            hout.copy_(out, non_blocking=True)
+            stream.synchronize()
+            hx, hout = hout, hx  # the step's result is the next step's input: swap the pinned buffers, no host copy
+
+        for _ in range(2):
+            e2e_step(n_e2e + 1)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(n_e2e):
+            e2e_step(n_e2e - k)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e  # host clock: the D2H + sync are part of the step
+        t = torch.tensor([e2e_ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d = hx.numel() * 4 + hn.numel() * 4 + ht.numel() * 8 + sum(v.numel() * v.element_size() for v in hkw.values())
+        e2e = dict(value=total / (c["steps"] * e2e_ms / 1e3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=hout.numel() * 4, steps=n_e2e)
 
     # ---- roofline of the dominant kernel: one profiled step (events around every launch)
     roof = None
-    fam = {}
     if rank == 0:
+        fam = {}
+        xg = torch.randn((B, 3, H, H), device=device)
+        tg = torch.full((B,), 5, device=device, dtype=torch.long)
         _lib.check(lib.sgdm_set_profiling(model._h, 1))
-        fused_step(x, nxt, 5)
+        model.forward_with_cond_scale(xg, tg, **kw)
         torch.cuda.synchronize()
         _lib.check(lib.sgdm_set_profiling(model._h, 0))
         kind, ms, fl, by = C.c_char_p(), C.c_double(), C.c_double(), C.c_double()
@@ -403,15 +486,17 @@ def main():
                     conv[q] += fam[k_][q]
         total_ms = sum(f["ms"] for f in fam.values())
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
-        traffic, traffic_src = ncu_conv_traffic()
+        traffic, traffic_src = ncu_conv_traffic() if args.config == 2 and B == 256 else (None, None)
         roof = dict(bound="tensor", kernel="conv_gemm_kernel (tcgen05 implicit GEMM: conv3x3 + 1x1/linear GEMMs)",
-                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic,
+                    achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
+                    frac_of_burst=ach / pk["burst"] if pk.get("burst") else None, traffic=traffic,
                     traffic_unit="bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step)",
                     traffic_source=traffic_src, algorithmic_bytes_per_launch=(fam.get("conv3x3", {}).get("bytes", 0.0) + fam.get("gemm1x1", {}).get("bytes", 0.0)) / max(conv["launches"], 1),
                     peak_source=pk["src"], launches_per_step=conv["launches"],
                     avg_launch_ms=conv["ms"] / max(conv["launches"], 1),
                     flops_per_step=conv["flops"], share_of_step=conv["ms"] / total_ms if total_ms else None,
-                    whole_step_tflops=GFLOP_PER_GUIDED_SAMPLE_STEP * 1e9 * B / (ms_step * 1e-3) / 1e12,
+                    whole_step_tflops=c["gflop"] * 1e9 * B / (ms_step * 1e-3) / 1e12,
+                    whole_step_frac=c["gflop"] * 1e9 * B / (ms_step * 1e-3) / 1e12 / pk["tflops"],
                     families={k_: dict(ms=round(v["ms"], 3), launches=v["launches"],
                                        tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 and v["flops"] else None,
                                        gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] else None)
@@ -419,17 +504,17 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cs = args.cpu_steps or 30  # ~10-30 s of host work at batch 4
-        r = cpu_reference_arm(cs, 1, args.cpu_batch)
+        cb = args.cpu_batch or c["cpu_batch"]
+        cs = args.cpu_steps or (c["steps"] if args.config == 1 else 30)  # ~10-30 s of host work
+        r = cpu_reference_arm(c, cs, 1, cb)
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                    ms_per_step_at_sample_batch=r["ms_per_step"])
 
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                     dtype=f"{lib.sgdm_operand_dtype().decode()} operands, f32 accumulate / residual stream / sampler state",
-                    data="synthetic", config=config, clocks=clk,
-                    e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    data="synthetic", config=config, clocks=clk, e2e=e2e,
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -229,6 +229,79 @@ def _run_block(sd, cfg, layers, h, emb, context, emu):
 
 
 # --------------------------------------------------------------------------- forward
+def param_shapes(cfg):
+    """(name, shape) inventory of the reference module's state_dict for `cfg`, restating the constructors'
+    registration (openaimodel.py:566-835, openaimodel_ca.py:540-836, crossattetion_lr.py:56-79): lets the CPU
+    baseline build seeded weights without instantiating anything else.  Checked against the reference-generated
+    inventories stored in tests/golden/unet_*.npz (tests/test_oracle_golden.py)."""
+    mc, ted = cfg["model_channels"], 4 * cfg["model_channels"]
+    cd, L, H = cfg["cond_dim"], cfg.get("layout_dim", 0) or 0, cfg["image_size"]
+    ca = cfg["kind"] == "unetca_fast"
+    out = []
+    add = lambda n, *shape: out.append((n, tuple(shape)))
+    if cd > 0 or ca:
+        add("null_cond_emb", 1, cd)
+    if L > 0:
+        add("null_layout_emb", 1, 1, H, H)
+    add("time_embed.0.weight", ted, mc); add("time_embed.0.bias", ted)
+    add("time_embed.2.weight", ted, ted); add("time_embed.2.bias", ted)
+    if not ca:
+        if cd > 0:
+            add("mlp_cond.0.weight", ted // 2, cd); add("mlp_cond.0.bias", ted // 2)
+            add("mlp_cond.2.weight", ted // 2, ted // 2); add("mlp_cond.2.bias", ted // 2)
+        E = ted + (ted // 2 if cd > 0 else 0)
+    else:
+        ctx = cfg["context_dim"]
+        add("norm_cond.weight", ctx); add("norm_cond.bias", ctx)
+        add("to_time_tokens.0.weight", mc, mc); add("to_time_tokens.0.bias", mc)
+        add("to_time_tokens.2.weight", ctx * 8, mc); add("to_time_tokens.2.bias", ctx * 8)
+        add("cond_mlp.0.weight", ted, cd); add("cond_mlp.0.bias", ted)
+        add("cond_mlp.2.weight", ted, ted); add("cond_mlp.2.bias", ted)
+        add("to_cond_tokens.0.weight", ctx * 8, cd); add("to_cond_tokens.0.bias", ctx * 8)
+        mid_d = int(math.sqrt(ctx * cd))  # to_cond_tokens_2d: built for every cond_token_num > 0, used only when > 1
+        add("to_cond_tokens_2d.0.weight", mid_d, cd); add("to_cond_tokens_2d.0.bias", mid_d)
+        add("to_cond_tokens_2d.2.weight", mid_d, mid_d); add("to_cond_tokens_2d.2.bias", mid_d)
+        add("to_cond_tokens_2d.4.weight", mid_d, mid_d); add("to_cond_tokens_2d.4.bias", mid_d)
+        add("to_cond_tokens_2d.6.weight", ctx, mid_d); add("to_cond_tokens_2d.6.bias", ctx)
+        E = ted
+    heads = cfg["num_heads"]
+    inp, mid, outb = topology(cfg)
+    for layers in inp + [mid] + outb:
+        for layer in layers:
+            kind, p = layer[0], layer[1]
+            if kind == "conv":
+                add(p + ".weight", mc, cfg["in_channels"] + L, 3, 3); add(p + ".bias", mc)
+            elif kind == "res":
+                cin, cout = layer[2], layer[3]
+                add(p + ".in_layers.0.weight", cin); add(p + ".in_layers.0.bias", cin)
+                add(p + ".in_layers.2.weight", cout, cin, 3, 3); add(p + ".in_layers.2.bias", cout)
+                add(p + ".emb_layers.1.weight", 2 * cout, E); add(p + ".emb_layers.1.bias", 2 * cout)
+                add(p + ".out_layers.0.weight", cout); add(p + ".out_layers.0.bias", cout)
+                add(p + ".out_layers.3.weight", cout, cout, 3, 3); add(p + ".out_layers.3.bias", cout)
+                if cin != cout:
+                    add(p + ".skip_connection.weight", cout, cin, 1, 1); add(p + ".skip_connection.bias", cout)
+            elif kind == "attn" and not ca:
+                ch = layer[2]
+                add(p + ".norm.weight", ch); add(p + ".norm.bias", ch)
+                add(p + ".qkv.weight", 3 * ch, ch, 1); add(p + ".qkv.bias", 3 * ch)
+                add(p + ".proj_out.weight", ch, ch, 1); add(p + ".proj_out.bias", ch)
+            elif kind == "attn":
+                ch, dh, ctx = layer[2], layer[2] // heads, cfg["context_dim"]
+                add(p + ".null_kv", 2, dh)
+                add(p + ".norm.gamma", ch); add(p + ".norm.beta", ch)
+                add(p + ".to_q.weight", dh * heads, ch); add(p + ".to_kv.weight", 2 * dh, ch)
+                add(p + ".to_context.0.weight", ctx); add(p + ".to_context.0.bias", ctx)
+                add(p + ".to_context.1.weight", 2 * dh, ctx); add(p + ".to_context.1.bias", 2 * dh)
+                add(p + ".to_out.0.weight", ch, dh * heads)
+                add(p + ".to_out.1.gamma", ch); add(p + ".to_out.1.beta", ch)
+            elif kind in ("down", "up"):
+                ch, q = layer[2], (".op" if kind == "down" else ".conv")
+                add(p + q + ".weight", ch, ch, 3, 3); add(p + q + ".bias", ch)
+    add("out.0.weight", mc); add("out.0.bias", mc)
+    add("out.2.weight", cfg["out_channels"], mc, 3, 3); add("out.2.bias", cfg["out_channels"])
+    return out
+
+
 def unet_forward(sd, cfg, x, timesteps, cond=None, layout=None, drop_mask=None, emu=None):
     """UNetModel.forward (openaimodel.py:904-956 / openaimodel_ca.py:917-1033).
 

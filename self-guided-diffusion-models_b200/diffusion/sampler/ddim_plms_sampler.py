@@ -78,6 +78,29 @@ class DDIMSampler(object):
                                                 nxt.data_ptr(), _lib.ptr(x0), _lib.ptr(eps_out), B, per_sample, dyn, mul))
 
     @torch.no_grad()
+    def p_sample_ddim(self, x, t, index, condition_kwargs=None, sampling_kwargs=None, denoise_sample_fn=None,
+                      denoise_sample_fn_kwargs=None, repeat_noise=False, noise=None):
+        """One DDIM step, the reference's per-step entry point (ddim_plms_sampler.py:345-391) -> (x_prev, pred_x0,
+        None): guided eps + the fused Eq.12 update.  make_schedule() must have run; `t` is batch-uniform and
+        `index` its position in ddim_timesteps.  `noise` is an optional host-supplied draw (default: torch.randn on
+        the device, drawn even when sigma = 0 like the reference).  The reference's third return value
+        (pred_x0_unclipped) is not materialised."""
+        check_supported(sampling_kwargs)
+        if repeat_noise:
+            raise NotImplementedError("repeat_noise")
+        device = x.device
+        with torch.cuda.device(device):
+            x = x.detach().float().contiguous()
+            eps = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device, fresh_weights=False)(
+                x, t.to(device=device, dtype=torch.long).contiguous())
+            nz = torch.randn(x.shape, device=device) if noise is None else noise.to(device, torch.float32).contiguous()
+            self._extras = StepExtras(sampling_kwargs, x)
+            out, x0 = torch.empty_like(x), torch.empty_like(x)
+            self._step(_lib.current_stream(device), eps, int(index), 1 if sampling_kwargs["clip_denoised"] else 0,
+                       sampling_kwargs["temperature"], x, nz, out, x0, x.shape[0], x[0].numel())
+        return out, x0, None
+
+    @torch.no_grad()
     def ddim_sampling(self, shape, sampling_kwargs, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,
                       condition_kwargs=None, noise_tape=None, **kwargs):
         device, noise, img = self._setup(shape, sampling_kwargs, noise_tape)

@@ -32,7 +32,10 @@ def shard_tree(obj, lo, hi, n):
 def shard_tape(tape, lo, hi):
     if tape is None:
         return None
-    return {"x_T": tape["x_T"][lo:hi], "noise": tape["noise"][:, lo:hi]}
+    out = {"x_T": tape["x_T"][lo:hi], "noise": tape["noise"][:, lo:hi]}
+    if "dropout_mul" in tape:  # the F.dropout factors of noise_dropout > 0 runs travel with the noise
+        out["dropout_mul"] = tape["dropout_mul"][:, lo:hi]
+    return out
 
 
 def all_gather_samples(local, n_total, group=None):
@@ -53,10 +56,12 @@ def all_gather_samples(local, n_total, group=None):
 
 @torch.no_grad()
 def sample_sharded(diffusion, sampling_method, shape, sampling_kwargs, denoise_sample_fn_kwargs=None,
-                   condition_kwargs=None, noise_tape=None, group=None, gather_intermediates=False):
+                   condition_kwargs=None, noise_tape=None, group=None, gather_intermediates=False, presharded=False):
     """`LatentDiffusion.p_sample_loop` over a batch sharded across the ranks of `group`.
 
-    shape is the GLOBAL shape [B, C, H, W]; kwargs / tape are global and sliced here.
+    shape is the GLOBAL shape [B, C, H, W]; kwargs / tape are global and sliced here — or, with
+    `presharded=True`, already this rank's shard (each rank loads only its own conditions: at batch 1024 the global
+    stegoclusterlayout one-hot layout alone is 450 MB).
     Returns (samples uint8 [B, C, H, W] on every rank, intermediates of the LOCAL shard, or
     gathered pred_x0 when gather_intermediates)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -64,10 +69,13 @@ def sample_sharded(diffusion, sampling_method, shape, sampling_kwargs, denoise_s
     n = shape[0]
     lo, hi = shard_bounds(n, rank, world)
     local_shape = (hi - lo,) + tuple(shape[1:])
-    kw = shard_tree(denoise_sample_fn_kwargs or {}, lo, hi, n)
+    if presharded:
+        kw, tape = dict(denoise_sample_fn_kwargs or {}), noise_tape
+    else:
+        kw, tape = shard_tree(denoise_sample_fn_kwargs or {}, lo, hi, n), shard_tape(noise_tape, lo, hi)
     samples, inter = diffusion.p_sample_loop(sampling_method, local_shape, sampling_kwargs,
                                              denoise_sample_fn_kwargs=kw, condition_kwargs=condition_kwargs,
-                                             **({"noise_tape": shard_tape(noise_tape, lo, hi)} if noise_tape is not None else {}))
+                                             **({"noise_tape": tape} if tape is not None else {}))
     if world == 1:
         return samples, inter
     full = all_gather_samples(samples, n, group)

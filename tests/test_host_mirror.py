@@ -159,3 +159,22 @@ def test_condition_mirror_bit_exact():
         assert kw.pop("cond_scale") == 2.0 and set(kw) == set(ref)
         for k in ref:
             assert kw[k].dtype == ref[k].dtype and torch.equal(kw[k], ref[k])
+
+
+def test_bench_reference_arm_never_maps_the_product_library():
+    """`bench.py --impl reference` is the CPU arm: the oracle port only, weights from the oracle's own inventory.
+    The product's CUDA library must not even be mapped into that process (the driver records loaded .so files)."""
+    import json
+    import subprocess
+    import sys
+
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--config', '1', '--steps', '2', '--warmup', '0'];\n"
+            "import bench; bench.main();\n"
+            "print('MAPPED', 'libsgdm_b200' in open('/proc/self/maps').read())")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[-1] == "MAPPED False", lines[-1]
+    line = json.loads(lines[-2])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["config_id"] == 1

@@ -154,3 +154,12 @@ def test_named_config_trajectories_match_reference(tname, run):
     diff = (u8.int() - ref_u8.int()).abs()
     assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 0.01
     assert rel_l2(inter["x_inter"], torch.from_numpy(g[f"{run}_x_inter"])) < 1e-4
+
+
+@pytest.mark.parametrize("name", UNET_CASES)
+def test_oracle_param_inventory_matches_reference(name):
+    """oracle.unet.param_shapes (what bench.py's CPU arm builds its weights from) == the reference module's state_dict."""
+    meta, _ = load_unet_case(name)
+    ref = {n: tuple(s) for n, s in meta["named_shapes"]}
+    got = dict(ounet.param_shapes(meta["cfg"]))
+    assert got == ref, (sorted(set(ref) ^ set(got))[:8], [k for k in ref if k in got and got[k] != ref[k]][:8])
