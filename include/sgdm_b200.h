@@ -144,6 +144,14 @@ int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
 /* Per-launch timing of one forward (bench.py roofline): with profiling on, the next forward
  * brackets every launch of its plan with CUDA events on `stream` and synchronises at the end.
  * Each record: kernel family, measured ms, algorithmic FLOPs and algorithmic HBM bytes. */
+/* CUDA-graph replay of a plan's static launch list (captured once per plan on first use; the prologue that reads
+ * the caller's inputs stays outside): -1 = policy (launch-bound plans only: at most 256 Ki pixel rows), 0 = off,
+ * 1 = on.  Same kernels, same order, same values as the stream replay. */
+int sgdm_set_graph_mode(sgdm_handle h, int mode);
+/* dev_out[t] = order-independent 64-bit hash of the bit pattern of the n fp32 tensors whose device pointers /
+ * element counts are in the DEVICE arrays dev_ptrs / dev_numel.  One launch: lets the host detect parameter writes
+ * that bypass its bookkeeping (`.data` copies of the reference's EMA swap, dynamic/ema.py:46-53). */
+int sgdm_fingerprint(void* stream, const void* const* dev_ptrs, const int64_t* dev_numel, int n, uint64_t* dev_out);
 int sgdm_set_profiling(sgdm_handle h, int on);
 int sgdm_profile_count(sgdm_handle h);
 int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double* flops, double* bytes);

@@ -66,6 +66,8 @@ PROTOTYPES = {
     "sgdm_dyn_threshold": (_i, [_vp, _i, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _vp, _d, _vp, _vp, _i, _i64]),
     "sgdm_lincomb": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_f), _f, _vp, _i64]),
     "sgdm_to_uint8": (_i, [_vp, _vp, _vp, _i64]),
+    "sgdm_set_graph_mode": (_i, [_vp, _i]),
+    "sgdm_fingerprint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sgdm_set_profiling": (_i, [_vp, _i]),
     "sgdm_profile_count": (_i, [_vp]),
     "sgdm_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),

@@ -111,12 +111,16 @@ struct Plan {
   std::vector<OpMeta> meta;
   std::vector<float> prof_ms;  // filled by a profiled replay
   std::vector<void*> owned;
+  // CUDA-graph replay of the launch list (launch-bound plans): captured once on first use
+  cudaGraphExec_t gexec = nullptr;
+  bool graph_tried = false;
   // prologue inputs are bound per call through these
   PrepDesc prep;
   float* eps = nullptr;        // [Bp, Cout, H, W] fp32 NCHW
   unsigned char* drop = nullptr;
   size_t bytes = 0;
   ~Plan() {
+    if (gexec) cudaGraphExecDestroy(gexec);
     for (void* p : owned) cudaFree(p);
   }
 };
@@ -164,6 +168,10 @@ struct sgdm_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profiling = false;
   Plan* last_profiled = nullptr;
+  // CUDA-graph replay: -1 policy (plans in the launch-bound regime, the same threshold as programmatic dependent
+  // launch), 0 never, 1 always.  The launch list of a plan is static (engine-owned workspace pointers only), so it
+  // is captured once per plan; only the prologue (which reads the caller's x / t / cond / layout) stays outside.
+  int graph_mode = -1;
 
   ~sgdm_engine() {
     if (side) cudaStreamDestroy(side);
@@ -1166,7 +1174,38 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
     CUDA_TRY(cudaEventRecord(ev[0], s));
   }
   // programmatic dependent launch pays in the launch-bound regime only (common.cuh): plans of at most 256 Ki pixel rows
-  pdl_mode() = !e->profiling && static_cast<long>(Bp) * e->cfg.image_size * e->cfg.image_size <= (1L << 18);
+  const bool small_plan = static_cast<long>(Bp) * e->cfg.image_size * e->cfg.image_size <= (1L << 18);
+  pdl_mode() = !e->profiling && small_plan;
+  // ... where replaying the whole launch list as ONE graph launch pays even more (config 1: ~170 launches of 5-10 us)
+  const bool want_graph = !e->profiling && !g_naive_conv && (e->graph_mode == 1 || (e->graph_mode < 0 && small_plan));
+  if (want_graph && !plan->gexec && !plan->graph_tried) {
+    plan->graph_tried = true;
+    // captured on a private stream: the caller's stream may be the legacy default stream, which cannot capture
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cap = nullptr;
+    bool ok = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      for (size_t i = 0; ok && i < plan->ops.size(); ++i) ok = plan->ops[i](cap) == 0;
+      cudaError_t ce = cudaStreamEndCapture(cap, &graph);  // always end the capture, also after a failed launch
+      ok = ok && ce == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&plan->gexec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (cap) cudaStreamDestroy(cap);
+    if (!ok) {  // fall back to stream replay for this plan (and clear the sticky-free error state)
+      plan->gexec = nullptr;
+      cudaGetLastError();
+      if (e->graph_mode == 1) { pdl_mode() = false; return fail("CUDA-graph capture of the launch list failed"); }
+    }
+  }
+  if (want_graph && plan->gexec) {
+    pdl_mode() = false;
+    CUDA_TRY(cudaGraphLaunch(plan->gexec, s));
+    g_launches += static_cast<int64_t>(plan->ops.size());
+    *plan_out = plan;
+    return 0;
+  }
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (plan->ops[i](s)) {
       cudaError_t ce = cudaGetLastError();
@@ -1283,6 +1322,7 @@ int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   std::unique_ptr<sgdm_engine> e(new sgdm_engine());
   e->cfg = *cfg;
   if (const char* ev = getenv("SGDM_SPLIT_STREAMS")) e->split_streams = atoi(ev) != 0;
+  if (const char* ev = getenv("SGDM_GRAPH")) e->graph_mode = atoi(ev) != 0 ? 1 : 0;  // A/B: force graph replay on / off
   if (build_topology(e.get())) return 1;
   *out = e.release();
   return 0;
@@ -1329,6 +1369,19 @@ int sgdm_set_timestep_freqs(sgdm_handle h, const float* host_freqs, int n) {
   return 0;
 }
 
+int sgdm_set_graph_mode(sgdm_handle h, int mode) {
+  if (!h || mode < -1 || mode > 1) return fail("graph mode must be -1 (policy), 0 (off) or 1 (on)");
+  h->graph_mode = mode;
+  return 0;
+}
+int sgdm_fingerprint(void* stream, const void* const* dev_ptrs, const int64_t* dev_numel, int n, uint64_t* dev_out) {
+  if (n <= 0 || !dev_ptrs || !dev_numel || !dev_out) return fail("fingerprint: bad arguments");
+  ++g_launches;
+  return fingerprint_launch(dev_ptrs, reinterpret_cast<const long long*>(dev_numel), n,
+                            reinterpret_cast<unsigned long long*>(dev_out), static_cast<cudaStream_t>(stream))
+             ? fail("fingerprint launch failed")
+             : 0;
+}
 int sgdm_set_profiling(sgdm_handle h, int on) {
   h->profiling = on != 0;
   return 0;

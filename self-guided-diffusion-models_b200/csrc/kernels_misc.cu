@@ -1102,6 +1102,34 @@ int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, 
   pack_conv_weight_hfold_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cin, cin_pad);
   return SGDM_LAUNCH_OK();
 }
+// =========================================================================== parameter fingerprint
+// out[t] = order-independent 64-bit hash of the bit pattern of tensor t (position-mixed, so permutations and
+// single-bit changes move it).  Lets the host detect parameter writes that bypass autograd's version counter
+// (`param.data.copy_`, as the reference's EMA swap does, dynamic/ema.py:46-53) with ONE launch and one small
+// read-back instead of re-packing every tensor.  grid = (tensors, slices); `out` must be zeroed.
+__global__ void fingerprint_kernel(const void* const* __restrict__ ptrs, const long long* __restrict__ numel,
+                                   unsigned long long* __restrict__ out) {
+  const int t = blockIdx.x;
+  const long long n = numel[t];
+  const unsigned int* p = static_cast<const unsigned int*>(ptrs[t]);
+  unsigned long long h = 0;
+  for (long long i = blockIdx.y * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.y) * blockDim.x) {
+    unsigned long long v = static_cast<unsigned long long>(p[i]) + 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(i + 1);
+    v ^= v >> 29;
+    v *= 0xBF58476D1CE4E5B9ull;
+    v ^= v >> 32;
+    h += v;
+  }
+  for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(out + t, h);
+}
+int fingerprint_launch(const void* const* ptrs, const long long* numel, int n, unsigned long long* out, cudaStream_t s) {
+  if (cudaMemsetAsync(out, 0, static_cast<size_t>(n) * sizeof(unsigned long long), s) != cudaSuccess) return 1;
+  fingerprint_kernel<<<dim3(n, 8), 256, 0, s>>>(ptrs, numel, out);
+  return SGDM_LAUNCH_OK();
+}
+
 __global__ void add_bias_kernel(const float* a, const float* b, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);

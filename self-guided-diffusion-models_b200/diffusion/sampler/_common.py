@@ -91,9 +91,10 @@ class GuidedEps:
                 else:
                     self.w = float(cs)
             self.scale_type = m._scale_type()
-            if fresh_weights:  # once per trajectory: also catches `.data` writes (ema_scope)
-                m.invalidate_weight_cache()
-            m.sync_weights()
+            if fresh_weights:  # once per trajectory: the device-side fingerprint also catches `.data` writes (ema_scope)
+                m.refresh_weights()
+            else:
+                m.sync_weights()
             self._prepared = None
 
     def _prepare(self, x, t):

@@ -145,6 +145,7 @@ class EngineUNet(nn.Module):
                 kind = "param"
             _attach(self, name, t, kind)
         self._loaded_sig = {}
+        self._fp_tables, self._fp_last = None, None
         self._freqs_set = False
         self._engine_device = None
         self.image_size = c.image_size
@@ -156,11 +157,55 @@ class EngineUNet(nn.Module):
 
     # ------------------------------------------------------------------ weights
     def invalidate_weight_cache(self):
-        """Forget the packed copies: the next call re-packs every tensor.  Needed only after writes
-        that bypass autograd's version counter (`param.data.copy_(...)`, as the reference's
-        `ema_scope` does, dynamic/ema.py:46-53); the samplers call this at the start of every
-        trajectory, so sampling under `ema_scope` is always correct."""
+        """Forget the packed copies: the next call re-packs every tensor (the blunt tool; `refresh_weights`
+        finds out which tensors actually changed)."""
         self._loaded_sig = {}
+        self._fp_last = None
+
+    # Writes that bypass autograd's version counter (`param.data.copy_(...)`, as the reference's `ema_scope` does,
+    # dynamic/ema.py:46-53) are invisible to the (data_ptr, _version) signature.  They are caught by a DEVICE-SIDE
+    # FINGERPRINT: one kernel hashes the bits of every parameter tensor (sgdm_fingerprint), 8 bytes per tensor come
+    # back, and exactly the tensors whose hash moved are re-packed.  Cost: one ~50 us launch + one small read-back
+    # instead of ~300 pack launches, so it runs at the start of EVERY sampler trajectory and (unless
+    # `check_weights = False`) in front of every standalone forward call.
+    check_weights = True
+
+    def _fingerprint(self):
+        lib = _lib.lib()
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        tensors = [sd[name] for name, _ in self._inventory]
+        key = tuple(t.data_ptr() for t in tensors)
+        dev = tensors[0].device
+        if self._fp_tables is None or self._fp_tables[0] != key:
+            for name, t in zip((n for n, _ in self._inventory), tensors):
+                _lib.require_cuda(t, f"parameter {name}")
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    return None  # exotic storage: fall back to re-packing everything
+            ptrs = torch.tensor(key, dtype=torch.int64, device=dev)
+            numel = torch.tensor([t.numel() for t in tensors], dtype=torch.int64, device=dev)
+            out = torch.zeros(len(tensors), dtype=torch.int64, device=dev)
+            self._fp_tables = (key, ptrs, numel, out)
+        _, ptrs, numel, out = self._fp_tables
+        with torch.cuda.device(dev):
+            _lib.check(lib.sgdm_fingerprint(_lib.current_stream(dev), ptrs.data_ptr(), numel.data_ptr(), len(tensors),
+                                            out.data_ptr()))
+        return out.cpu()  # 8 bytes per tensor; synchronises the stream
+
+    def refresh_weights(self):
+        """Bring the engine's packed copies in line with the parameters, whatever way they were written: tensors
+        whose (data_ptr, _version) changed are re-packed as always, and so are tensors whose device-side hash moved
+        since they were packed (`.data` writes)."""
+        fp = self._fingerprint()
+        if fp is None:
+            self.invalidate_weight_cache()
+        elif self._fp_last is not None and len(self._fp_last) == len(fp):
+            for i in torch.nonzero(fp != self._fp_last).flatten().tolist():
+                self._loaded_sig.pop(self._inventory[i][0], None)
+        else:
+            self._loaded_sig = {}
+        self.sync_weights()
+        self._fp_last = fp
 
     def sync_weights(self, force=False):
         """(Re)pack every tensor whose storage or version changed since the last call."""
@@ -241,7 +286,7 @@ class EngineUNet(nn.Module):
 
     def _raw_forward(self, x, t, cond, layout, drop_mask):
         """eps for an explicit boolean drop mask [B] (True = null embeddings)."""
-        self.sync_weights()
+        self.refresh_weights() if self.check_weights else self.sync_weights()
         x, t, cond, layout = self._prep_inputs(x, t, cond, layout)
         B = x.shape[0]
         drop = drop_mask.to(device=x.device, dtype=torch.uint8).contiguous()
@@ -303,7 +348,7 @@ class EngineUNet(nn.Module):
             eps = self._raw_forward(dbl(x), dbl(t), dbl(cond), dbl(layout), mask)
             eps_c, eps_u = torch.chunk(eps, 2, dim=0)
             return self.get_guided_score(z=eps_u, zc=eps_c, w=cond_scale)
-        self.sync_weights()
+        self.refresh_weights() if self.check_weights else self.sync_weights()
         x, t, cond, layout = self._prep_inputs(x, t, cond, layout)
         pc, pu = self.guided_pair_ptrs(x, t, cond, layout)
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)

@@ -96,6 +96,40 @@ def test_two_stream_guided_forward_is_bit_identical(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1_cifar_label", "unetca_clusterlayout_tiny"])
+def test_cuda_graph_replay_is_bit_identical(name):
+    """sgdm_set_graph_mode: the plan's static launch list replayed as one CUDA graph gives the same bits as the
+    stream replay, call after call (the prologue that reads the caller's tensors stays outside the graph)."""
+    need_gpu()
+    from sgdm_b200 import _lib
+
+    meta, a = load_unet_case(name)
+    m = cuda_model(meta)
+    kw = dev(kwargs_from_arrays(a))
+    x, t = a["x"].cuda(), a["t"].cuda()
+    _lib.check(_lib.lib().sgdm_set_graph_mode(m._h, 0))
+    ref = m.forward_with_cond_scale(x, t, meta["cond_scale"], **kw).clone()
+    ref1 = m.forward_with_cond_scale(x, t, 1, **kw).clone()
+    _lib.check(_lib.lib().sgdm_set_graph_mode(m._h, 1))
+    try:
+        n0 = _lib.lib().sgdm_launch_count()
+        for _ in range(3):  # capture on the first call, replays afterwards
+            g = m.forward_with_cond_scale(x, t, meta["cond_scale"], **kw).clone()
+            assert torch.equal(g, ref)
+        assert torch.equal(m.forward_with_cond_scale(x, t, 1, **kw), ref1)
+        # new inputs through the same captured graph
+        x2 = torch.randn_like(x)
+        g2 = m.forward_with_cond_scale(x2, t, meta["cond_scale"], **kw).clone()
+        assert _lib.lib().sgdm_launch_count() - n0 > 300
+    finally:
+        _lib.check(_lib.lib().sgdm_set_graph_mode(m._h, -1))
+    _lib.check(_lib.lib().sgdm_set_graph_mode(m._h, 0))
+    assert torch.equal(m.forward_with_cond_scale(x2, t, meta["cond_scale"], **kw), g2)
+    _lib.check(_lib.lib().sgdm_set_graph_mode(m._h, -1))
+    assert rel_l2(ref.cpu(), a["eps_guided"]) <= EPS_TOL
+
+
+@pytest.mark.gpu
 def test_unetca_float_one_is_doubled_path():
     need_gpu()
     meta, a = load_unet_case("unetca_clusterlayout_tiny")
@@ -125,14 +159,25 @@ def test_weight_cache_follows_in_place_updates():
                 p.mul_(1.5)
     e1 = m.forward_with_cond_scale(x, t, 2.0, **kw).clone()
     assert rel_l2(e1.cpu(), e0.cpu()) > 1e-3
-    # (2) `.data` write, as LitEma.copy_to / restore do: invisible to the version counter;
-    #     picked up by invalidate_weight_cache(), which every sampler trajectory calls first
+    # (2) `.data` write, as LitEma.copy_to / restore do: invisible to the version counter; caught by the device-side
+    #     parameter fingerprint in front of every standalone call and at the start of every sampler trajectory
     with torch.no_grad():
         for k, p in m.named_parameters():
             p.data.copy_(backup[k])
-    m.invalidate_weight_cache()
     e2 = m.forward_with_cond_scale(x, t, 2.0, **kw)
     assert torch.equal(e2, e0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith("emb_layers.1.bias"):
+                p.data.add_(0.25)
+    e3 = m.forward_with_cond_scale(x, t, 2.0, **kw).clone()
+    assert rel_l2(e3.cpu(), e0.cpu()) > 1e-3, "a .data write went unnoticed"
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            p.data.copy_(backup[k])
+    #     ... and the blunt tool still works
+    m.invalidate_weight_cache()
+    assert torch.equal(m.forward_with_cond_scale(x, t, 2.0, **kw), e0)
     # (3) a sampler trajectory started after a `.data` swap uses the swapped weights
     from sgdm_b200 import synthetic
 
