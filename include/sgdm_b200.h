@@ -216,6 +216,13 @@ int sgdm_k_groupnorm_fused(void* stream, const void* src0, int src0_is_op, const
                            int stat_gran, void* out_op, void* raw_out_op, float* pool_out);
 int sgdm_k_layernorm(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
                      void* out_op, float* out_f32, int64_t rows, int C);
+/* out_f32 = res + LN(x) gamma + beta, plus the GroupNorm partial statistics of the output: stats[(row / 32) *
+ * (C / stat_gran) + c / stat_gran] = {sum, sum of squares} over 32 rows x stat_gran (2 | 4) channels; rows % 32 == 0 */
+int sgdm_k_layernorm_stats(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
+                           float* out_f32, float* stats, int stat_gran, int64_t rows, int C);
+/* split-precision operand layout of sgdm_config.precision = 1: out_op [rows, 3C] = [hi | hi | lo] of LN(x) gamma + beta */
+int sgdm_k_layernorm_split3(void* stream, const float* x, const float* gamma, const float* beta, void* out_op,
+                            int64_t rows, int C);
 int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_head_stride, const void* k,
                      int64_t k_row_stride, int k_head_stride, const void* v, int64_t v_row_stride,
                      int v_head_stride, const void* k_extra, const void* v_extra, int n_extra, void* out,

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "sgdm_k_groupnorm_fused": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp,
                                      _vp]),
     "sgdm_k_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i]),
+    "sgdm_k_layernorm_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i]),
+    "sgdm_k_layernorm_split3": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i]),
     "sgdm_k_attention": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _f]),
     "sgdm_k_linear_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),
     "sgdm_k_conv_head_hfold": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),

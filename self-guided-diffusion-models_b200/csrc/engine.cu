@@ -899,17 +899,10 @@ struct Builder {
     c1.in = ln; c1.Hin = a.H; c1.Win = a.W; c1.Cin = C * S; c1.w = w.wqkv; c1.ks = 1; c1.stride = 1; c1.pad = 0;
     c1.Hout = a.H; c1.Wout = a.W; c1.Cout = nq; c1.out_op = qkv;
     conv(c1);
-    op_t* ck = static_cast<op_t*>(scratch("ctx_k", static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
-    op_t* cv = static_cast<op_t*>(scratch("ctx_v", static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
-    CtxDesc cd;
-    cd.time_tokens = time_tokens; cd.cond_tokens = cond_tokens;
-    cd.norm_w = dry ? nullptr : e->f32["norm_cond.weight"]; cd.norm_b = dry ? nullptr : e->f32["norm_cond.bias"];
-    cd.ln_w = w.ctx_ln_w; cd.ln_b = w.ctx_ln_b; cd.lin_w = w.ctx_w; cd.lin_b = w.ctx_b; cd.null_kv = w.null_kv;
-    cd.Bp = Bp; cd.ctx = e->cfg.context_dim; cd.dh = dh; cd.k_out = ck; cd.v_out = cv;
-    push([cd](cudaStream_t s) {
-      ++g_launches;
-      return context_kv_launch(cd, s);
-    });
+    // context K/V rows of this site: produced for ALL sites by one launch in the prologue (context_kv_all)
+    const int site = static_cast<int>(&w - e->attn_lr.data());
+    op_t* ck = static_cast<op_t*>(scratch("ctx_k" + std::to_string(site), static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
+    op_t* cv = static_cast<op_t*>(scratch("ctx_v" + std::to_string(site), static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
     op_t* att = static_cast<op_t*>(scratch("att", rows * inner * sizeof(op_t)));
     AttnDesc ad;
     ad.q = qkv; ad.q_row_stride = nq; ad.q_head_stride = dh;
@@ -930,15 +923,21 @@ struct Builder {
     conv(c2);
     Act o = a;
     o.p = stream_alloc(rows * C);
-    o.stats = nullptr;  // produced by the LayerNorm kernel: consumers run the standalone statistics pass
-    o.p16 = nullptr; o.has_stats = false; o.has16 = false;
+    // the LayerNorm + residual kernel emits the GroupNorm partial statistics of its output like a conv epilogue does
+    o.p16 = nullptr; o.has16 = false;
+    o.has_stats = stats_ok(o.H, o.W) && (rows % 32) == 0;
+    o.stats = o.has_stats ? stats_alloc(rows, C, o.H, o.W) : nullptr;
     {
       const float* x = a.p;
       const float *g = w.out_g, *b = w.out_b;
       float* op = o.p;
+      float2* st = o.stats;
+      const int gran = stat_gran();
+      const bool with_stats = o.has_stats;
       push([=](cudaStream_t s) {
         ++g_launches;
-        return layernorm_launch(tmp, g, b, x, nullptr, op, static_cast<long>(rows), C, s);
+        return with_stats ? layernorm_res_stats_launch(tmp, g, b, x, op, st, gran, static_cast<long>(rows), C, s)
+                          : layernorm_launch(tmp, g, b, x, nullptr, op, static_cast<long>(rows), C, s);
       });
     }
     return o;
@@ -1045,6 +1044,26 @@ struct Builder {
       lin(t_emb, mc, "to_time_tokens.0", hid, ted, mc, mc, 1, 0);
       lin(hid, ted, "to_time_tokens.2", time_tokens, 8 * ctx, 8 * ctx, mc, 0, 0);
       lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
+      // context K/V rows of every Attention_LR site (they depend on t / cond only): one launch, grid.y = sites
+      CtxDesc cd;
+      cd.time_tokens = time_tokens; cd.cond_tokens = cond_tokens;
+      cd.norm_w = dry ? nullptr : e->f32["norm_cond.weight"]; cd.norm_b = dry ? nullptr : e->f32["norm_cond.bias"];
+      cd.Bp = Bp; cd.ctx = ctx; cd.n_sites = static_cast<int>(e->attn_lr.size());
+      if (cd.n_sites > kMaxCtxSites) { fail("too many Attention_LR sites (%d)", cd.n_sites); err = 1; return; }
+      for (int i = 0; i < cd.n_sites; ++i) {
+        const AttnLRW& w = e->attn_lr[i];
+        cd.dh = w.dh;
+        CtxSite& st = cd.site[i];
+        st.ln_w = w.ctx_ln_w; st.ln_b = w.ctx_ln_b; st.lin_w = w.ctx_w; st.lin_b = w.ctx_b; st.null_kv = w.null_kv;
+        st.k_out = static_cast<op_t*>(scratch("ctx_k" + std::to_string(i), static_cast<size_t>(Bp) * 17 * w.dh * sizeof(op_t)));
+        st.v_out = static_cast<op_t*>(scratch("ctx_v" + std::to_string(i), static_cast<size_t>(Bp) * 17 * w.dh * sizeof(op_t)));
+      }
+      for (int i = 1; i < cd.n_sites; ++i)
+        if (e->attn_lr[i].dh != e->attn_lr[0].dh) { fail("Attention_LR sites with different head dims"); err = 1; return; }
+      push([cd](cudaStream_t s) {
+        ++g_launches;
+        return context_kv_launch(cd, s);
+      });
     }
     // all ResBlock emb_layers = SiLU + Linear, as one GEMM (openaimodel.py:262-268,309)
     {
@@ -1613,6 +1632,22 @@ int sgdm_k_layernorm(void* stream, const float* x, const float* gamma, const flo
   ++g_launches;
   return layernorm_launch(x, gamma, beta, res, static_cast<op_t*>(out_op), out_f32, rows, C,
                           static_cast<cudaStream_t>(stream))
+             ? fail("layernorm launch failed")
+             : 0;
+}
+int sgdm_k_layernorm_stats(void* stream, const float* x, const float* gamma, const float* beta, const float* res,
+                           float* out_f32, float* stats, int stat_gran, int64_t rows, int C) {
+  ++g_launches;
+  return layernorm_res_stats_launch(x, gamma, beta, res, out_f32, reinterpret_cast<float2*>(stats), stat_gran, rows, C,
+                                    static_cast<cudaStream_t>(stream))
+             ? fail("layernorm_stats launch failed (C %% 128, C <= 1024, rows %% 32, stat_gran 2 | 4)")
+             : 0;
+}
+int sgdm_k_layernorm_split3(void* stream, const float* x, const float* gamma, const float* beta, void* out_op,
+                            int64_t rows, int C) {
+  ++g_launches;
+  return layernorm_launch(x, gamma, beta, nullptr, static_cast<op_t*>(out_op), nullptr, rows, C,
+                          static_cast<cudaStream_t>(stream), 1)
              ? fail("layernorm launch failed")
              : 0;
 }

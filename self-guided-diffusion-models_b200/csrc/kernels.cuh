@@ -46,6 +46,10 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s);  // pass 2 only
 // mode 0: out_op = LN(x)*gamma+beta ; mode 1: out_f32 = res + LN(x)*gamma+beta
 int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
                      float* out_f32, long rows, int C, cudaStream_t s, int split3 = 0);
+// out_f32 = res + LN(x) gamma + beta, plus the GroupNorm partial statistics of the output in ConvDesc::stats format
+// ({sum, sum sq} per 32-row block x stat_gran channels); rows % 32 == 0
+int layernorm_res_stats_launch(const float* x, const float* gamma, const float* beta, const float* res, float* out_f32,
+                               float2* stats, int stat_gran, long rows, int C, cudaStream_t s);
 
 // ---- casts --------------------------------------------------------------------------------
 // fp32 NHWC -> op_t NHWC, optionally nearest-2x upsampled (Upsample, openaimodel_ca.py:121-131)
@@ -87,19 +91,24 @@ int prep_launch(const PrepDesc& d, cudaStream_t s);
 // context K/V for Attention_LR: norm_cond LayerNorm over [time tokens | cond tokens]
 // (openaimodel_ca.py:973,1017) then per-site to_context = LayerNorm + Linear(ctx -> 2*dh)
 // (crossattetion_lr.py:75,103-106), null_kv appended as key 16 (:95-97).
-struct CtxDesc {
-  const float* time_tokens = nullptr;  // [Bp, 8*ctx]
-  const float* cond_tokens = nullptr;  // [Bp, 8*ctx]
-  const float* norm_w = nullptr;       // norm_cond [ctx]
-  const float* norm_b = nullptr;
+constexpr int kMaxCtxSites = 12;
+struct CtxSite {                       // per Attention_LR site
   const float* ln_w = nullptr;         // to_context.0 [ctx]
   const float* ln_b = nullptr;
   const float* lin_w = nullptr;        // to_context.1 [2*dh, ctx]
   const float* lin_b = nullptr;        // [2*dh]
   const float* null_kv = nullptr;      // [2, dh]
-  int Bp = 0, ctx = 32, dh = 64;
   op_t* k_out = nullptr;               // [Bp, 17, dh]
   op_t* v_out = nullptr;
+};
+struct CtxDesc {
+  const float* time_tokens = nullptr;  // [Bp, 8*ctx]
+  const float* cond_tokens = nullptr;  // [Bp, 8*ctx]
+  const float* norm_w = nullptr;       // norm_cond [ctx]
+  const float* norm_b = nullptr;
+  int Bp = 0, ctx = 32, dh = 64;
+  int n_sites = 0;                     // all sites in one launch (grid.y)
+  CtxSite site[kMaxCtxSites];
 };
 int context_kv_launch(const CtxDesc& d, cudaStream_t s);
 

@@ -560,6 +560,102 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     }
   }
 }
+// out = res + LN(x) gamma + beta (the tail of Attention_LR, crossattetion_lr.py:139-142) that ALSO emits the
+// GroupNorm partial statistics of its output in the conv epilogue's format (ConvDesc::stats: {sum, sum of squares}
+// per 32-row block and `gran` adjacent channels), so the GroupNorm that follows needs no pass over the tensor.
+// Block = 8 warps = 32 consecutive rows (4 per warp); a lane's float4 j covers channels (j * 32 + lane) * 4 .. + 3,
+// i.e. one granule of 4 or two of 2; fixed summation order (rows of a warp, then the 8 warps in order).
+template <int kGran>
+__global__ void __launch_bounds__(256) layernorm_res_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const float* __restrict__ res,
+                                                                  float* __restrict__ out, float2* __restrict__ stats, long rows,
+                                                                  int C) {
+  constexpr int G = 4 / kGran;  // granules per float4
+  __shared__ float2 part[8][256 * G];  // [warp][granule] (C <= 1024: C / kGran <= 256 * G)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = C >> 7;
+  const long row0 = blockIdx.x * 32L;
+  float sa[8][G], qa[8][G];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int g = 0; g < G; ++g) { sa[j][g] = 0.f; qa[j][g] = 0.f; }
+  // (the loads of the warp's NEXT row are issued before the current row is reduced: two rows in flight)
+  float4 vn[8];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + (row0 + warp * 4) * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) vn[j] = __ldg(xr + j * 32 + lane);
+  }
+  for (int rr = 0; rr < 4; ++rr) {
+    const long row = row0 + warp * 4 + rr;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) v[j] = vn[j];
+    if (rr + 1 < 4) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (row + 1) * C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) vn[j] = __ldg(xr + j * 32 + lane);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) s += v[j].x + v[j].y + v[j].z + v[j].w;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) {
+        const int c = (j * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float4 r = __ldg(reinterpret_cast<const float4*>(res + row * C + c));
+        const float4 y = make_float4((v[j].x - mean) * rstd * g.x + b.x + r.x, (v[j].y - mean) * rstd * g.y + b.y + r.y,
+                                     (v[j].z - mean) * rstd * g.z + b.z + r.z, (v[j].w - mean) * rstd * g.w + b.w + r.w);
+        *reinterpret_cast<float4*>(out + row * C + c) = y;
+        if (G == 1) {
+          sa[j][0] += (y.x + y.y) + (y.z + y.w);
+          qa[j][0] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+        } else {
+          sa[j][0] += y.x + y.y; qa[j][0] += y.x * y.x + y.y * y.y;
+          sa[j][G - 1] += y.z + y.w; qa[j][G - 1] += y.z * y.z + y.w * y.w;
+        }
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv)
+#pragma unroll
+      for (int g = 0; g < G; ++g) part[warp][(j * 32 + lane) * G + g] = make_float2(sa[j][g], qa[j][g]);
+  __syncthreads();
+  const int ng = C / kGran;
+  for (int e = threadIdx.x; e < ng; e += 256) {
+    float2 t = part[0][e];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += part[w][e].x; t.y += part[w][e].y; }
+    stats[blockIdx.x * static_cast<long>(ng) + e] = t;
+  }
+}
+int layernorm_res_stats_launch(const float* x, const float* gamma, const float* beta, const float* res, float* out_f32,
+                               float2* stats, int stat_gran, long rows, int C, cudaStream_t s) {
+  if (C % 128 || C > 1024 || (rows % 32) || !res || !stats || (stat_gran != 2 && stat_gran != 4)) return 1;
+  const unsigned grid = static_cast<unsigned>(rows / 32);
+  if (stat_gran == 4) layernorm_res_stats_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, res, out_f32, stats, rows, C);
+  else layernorm_res_stats_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, res, out_f32, stats, rows, C);
+  return SGDM_LAUNCH_OK();
+}
 int layernorm_launch(const float* x, const float* gamma, const float* beta, const float* res, op_t* out_op,
                      float* out_f32, long rows, int C, cudaStream_t s, int split3) {
   if (C % 128 || C > 1024) return 1;
@@ -803,9 +899,12 @@ int prep_launch(const PrepDesc& d, cudaStream_t s) {
 }
 
 // =========================================================================== context K/V
+// grid = (samples, attention sites): the context tokens depend on (t, cond) only, so the K/V rows of ALL Attention_LR
+// sites are produced by one launch in the prologue instead of one launch per site inside the chain.
 __global__ void context_kv_kernel(const CtxDesc d) {
   extern __shared__ float sm[];
   const int ctx = d.ctx, dh = d.dh;
+  const CtxSite& w = d.site[blockIdx.y];
   float* tok = sm;            // [16][ctx]
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < 16 * ctx; i += blockDim.x) {
@@ -818,33 +917,51 @@ __global__ void context_kv_kernel(const CtxDesc d) {
   if (threadIdx.x < 16) {
     float* row = tok + threadIdx.x * ctx;
     for (int pass = 0; pass < 2; ++pass) {
-      const float* w = pass == 0 ? d.norm_w : d.ln_w;
-      const float* b = pass == 0 ? d.norm_b : d.ln_b;
+      const float* g = pass == 0 ? d.norm_w : w.ln_w;
+      const float* b = pass == 0 ? d.norm_b : w.ln_b;
       float mean = 0.f;
       for (int j = 0; j < ctx; ++j) mean += row[j];
       mean /= ctx;
       float var = 0.f;
       for (int j = 0; j < ctx; ++j) { const float dlt = row[j] - mean; var += dlt * dlt; }
       const float rstd = rsqrtf(var / ctx + 1e-5f);
-      for (int j = 0; j < ctx; ++j) row[j] = (row[j] - mean) * rstd * w[j] + b[j];
+      for (int j = 0; j < ctx; ++j) row[j] = (row[j] - mean) * rstd * g[j] + b[j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 2 * dh; i += blockDim.x) {
-    const int t = i / (2 * dh), o = i - t * 2 * dh;
-    float acc = d.lin_b[o];
-    const float* w = d.lin_w + static_cast<long>(o) * ctx;
-    for (int j = 0; j < ctx; ++j) acc += tok[t * ctx + j] * w[j];
-    if (o < dh) d.k_out[(static_cast<long>(n) * 17 + t) * dh + o] = to_op(acc);
-    else d.v_out[(static_cast<long>(n) * 17 + t) * dh + (o - dh)] = to_op(acc);
+  // thread = output feature o: its weight row is read once (16-byte loads of whole lines) and used for all 16 tokens
+  // (token values are shared-memory broadcasts); same j-ascending summation order per output as before
+  for (int o = threadIdx.x; o < 2 * dh; o += blockDim.x) {
+    const float* wr = w.lin_w + static_cast<long>(o) * ctx;
+    float acc[16];
+    const float bias = w.lin_b[o];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[t] = bias;
+    for (int j = 0; j < ctx; j += 4) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const float4 tv = *reinterpret_cast<const float4*>(tok + t * ctx + j);
+        acc[t] += tv.x * wv.x;
+        acc[t] += tv.y * wv.y;
+        acc[t] += tv.z * wv.z;
+        acc[t] += tv.w * wv.w;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      if (o < dh) w.k_out[(static_cast<long>(n) * 17 + t) * dh + o] = to_op(acc[t]);
+      else w.v_out[(static_cast<long>(n) * 17 + t) * dh + (o - dh)] = to_op(acc[t]);
+    }
   }
   for (int o = threadIdx.x; o < dh; o += blockDim.x) {
-    d.k_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(d.null_kv[o]);
-    d.v_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(d.null_kv[dh + o]);
+    w.k_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(w.null_kv[o]);
+    w.v_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(w.null_kv[dh + o]);
   }
 }
 int context_kv_launch(const CtxDesc& d, cudaStream_t s) {
-  context_kv_kernel<<<d.Bp, 128, 16 * d.ctx * sizeof(float), s>>>(d);
+  if (d.n_sites < 1 || d.n_sites > kMaxCtxSites || (d.ctx % 4)) return 1;
+  context_kv_kernel<<<dim3(d.Bp, d.n_sites), 128, 16 * d.ctx * sizeof(float), s>>>(d);
   return SGDM_LAUNCH_OK();
 }
 

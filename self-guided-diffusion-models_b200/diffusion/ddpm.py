@@ -52,11 +52,21 @@ class LatentDiffusion(nn.Module):
         sampling_kwargs_current.update(dict(alphas_cumprod=self.sampler.alphas_cumprod,
                                             alphas_cumprod_prev=self.sampler.alphas_cumprod_prev,
                                             betas=self.sampler.betas))
+        # DDIM returns its intermediates on the CPU like the reference (ddim_plms_sampler.py:331-335): they are kept on
+        # the device until pred_x0 is uint8 and then moved ONCE through pinned memory (asynchronous copies, one
+        # synchronisation) instead of a pageable fp32 round trip
+        on_cpu = sampling_method == "ddim"
+        extra = dict(device_intermediates=True) if on_cpu else {}
         samples, intermediates = self.sampler_list[sampling_method].sample(
-            shape=shape, denoise_sample_fn=self.denoise_sample_fn, sampling_kwargs=sampling_kwargs_current, **kwargs)
+            shape=shape, denoise_sample_fn=self.denoise_sample_fn, sampling_kwargs=sampling_kwargs_current, **extra, **kwargs)
         samples = clip_unnormalize_to_zero_to_255(samples)
-        p0 = intermediates["pred_x0"]
-        was_cpu = not p0.is_cuda
-        p0 = clip_unnormalize_to_zero_to_255(p0.to(samples.device))
-        intermediates["pred_x0"] = p0.cpu() if was_cpu else p0
+        intermediates["pred_x0"] = clip_unnormalize_to_zero_to_255(intermediates["pred_x0"])
+        if on_cpu:
+            host = {}
+            for k in ("pred_x0", "x_inter"):
+                t = intermediates[k]
+                host[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host[k].copy_(t, non_blocking=True)
+            torch.cuda.current_stream(samples.device).synchronize()
+            intermediates.update(host)
         return samples, intermediates

@@ -102,7 +102,11 @@ class DDIMSampler(object):
 
     @torch.no_grad()
     def ddim_sampling(self, shape, sampling_kwargs, denoise_sample_fn=None, denoise_sample_fn_kwargs=None,
-                      condition_kwargs=None, noise_tape=None, **kwargs):
+                      condition_kwargs=None, noise_tape=None, device_intermediates=False, **kwargs):
+        """ddim_sampling (ddim_plms_sampler.py:302-343).  The reference moves the logged intermediates to the CPU
+        inside the loop (:331-335); here they stay on the device until the end and are then copied once
+        (`device_intermediates=True`: not at all — LatentDiffusion.p_sample_loop converts pred_x0 to uint8 on the
+        device first and moves both through pinned memory)."""
         device, noise, img = self._setup(shape, sampling_kwargs, noise_tape)
         B = shape[0]
         stream = _lib.current_stream(device)
@@ -125,8 +129,10 @@ class DDIMSampler(object):
             if index in logs:
                 out["x_inter"].append(img.clone().unsqueeze(0))
                 out["pred_x0"].append(x0.unsqueeze(0))
-        out["x_inter"] = torch.cat(out["x_inter"], 0).cpu()
-        out["pred_x0"] = torch.cat(out["pred_x0"], 0).cpu()
+        out["x_inter"] = torch.cat(out["x_inter"], 0)
+        out["pred_x0"] = torch.cat(out["pred_x0"], 0)
+        if not device_intermediates:
+            out = {k: v.cpu() for k, v in out.items()}
         return img, out
 
     @torch.no_grad()

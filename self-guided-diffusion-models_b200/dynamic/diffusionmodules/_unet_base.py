@@ -36,6 +36,20 @@ class _Node(nn.Module):
     """Anonymous container: lets parameters live at dotted paths like
     `input_blocks.3.0.in_layers.2.weight` without re-creating the layer classes."""
 
+    _root = None  # weakref to the owning EngineUNet (set by _attach)
+
+    def register_parameter(self, name, param):
+        super().register_parameter(name, param)
+        root = self._root() if self._root is not None else None
+        if root is not None:
+            root._tensor_list = None  # a Parameter OBJECT was (re)placed: the cached tensor list is stale
+
+    def register_buffer(self, name, tensor, persistent=True):
+        super().register_buffer(name, tensor, persistent=persistent)
+        root = self._root() if self._root is not None else None
+        if root is not None:
+            root._tensor_list = None
+
 
 def _attach(root, dotted, tensor, kind):
     *path, leaf = dotted.split(".")
@@ -44,6 +58,7 @@ def _attach(root, dotted, tensor, kind):
         nxt = mod._modules.get(part)
         if nxt is None:
             nxt = _Node()
+            object.__setattr__(nxt, "_root", weakref.ref(root))
             mod.add_module(part, nxt)
         mod = nxt
     if kind == "buffer":
@@ -145,6 +160,7 @@ class EngineUNet(nn.Module):
                 kind = "param"
             _attach(self, name, t, kind)
         self._loaded_sig = {}
+        self._tensor_list = None
         self._fp_tables, self._fp_last = None, None
         self._freqs_set = False
         self._engine_device = None
@@ -172,8 +188,7 @@ class EngineUNet(nn.Module):
 
     def _fingerprint(self):
         lib = _lib.lib()
-        sd = dict(self.named_parameters())
-        sd.update(dict(self.named_buffers()))
+        sd = self._tensors()
         tensors = [sd[name] for name, _ in self._inventory]
         key = tuple(t.data_ptr() for t in tensors)
         dev = tensors[0].device
@@ -207,11 +222,29 @@ class EngineUNet(nn.Module):
         self.sync_weights()
         self._fp_last = fp
 
+    def _tensors(self):
+        """{name: tensor} of the inventory.  The module-tree walk (named_parameters over ~300 tensors) is cached: the
+        Parameter / buffer OBJECTS only change through register_parameter / register_buffer (hooked in _Node and
+        below), while `.to()`, load_state_dict, optimizer steps and EMA swaps update them in place."""
+        if self._tensor_list is None:
+            sd = dict(self.named_parameters())
+            sd.update(dict(self.named_buffers()))
+            self._tensor_list = {name: sd[name] for name, _ in self._inventory}
+        return self._tensor_list
+
+    def register_parameter(self, name, param):
+        super().register_parameter(name, param)
+        self.__dict__["_tensor_list"] = None
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._tensor_list = None  # conversions may replace the Parameter objects (torch.__future__ overwrite mode)
+        return out
+
     def sync_weights(self, force=False):
         """(Re)pack every tensor whose storage or version changed since the last call."""
         lib = _lib.lib()
-        sd = dict(self.named_parameters())
-        sd.update(dict(self.named_buffers()))
+        sd = self._tensors()
         first = sd[self._inventory[0][0]]
         _lib.require_cuda(first, f"parameter {self._inventory[0][0]}")
         with torch.cuda.device(first.device):  # the engine allocates on the CURRENT device: make it the parameters'

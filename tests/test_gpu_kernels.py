@@ -487,6 +487,43 @@ def test_layernorm(L):
         assert relerr(o2, ref + res) < 1e-5
 
 
+def test_layernorm_with_groupnorm_statistics(L):
+    """LayerNorm + residual that also emits the conv-epilogue-format GroupNorm partial sums of its output."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    for rows, C, gran in ((512, 512, 4), (64, 256, 2), (96, 1024, 4), (32, 128, 2)):
+        x = torch.randn(rows, C, device="cuda", generator=g) * 2 + 0.5
+        ga = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+        be = 0.1 * torch.randn(C, device="cuda", generator=g)
+        res = torch.randn(rows, C, device="cuda", generator=g)
+        out = torch.zeros(rows, C, device="cuda")
+        st = torch.zeros(rows // 32, C // gran, 2, device="cuda")
+        ck(L, L.sgdm_k_layernorm_stats(S(), P(x), P(ga), P(be), P(res), P(out), P(st), gran, rows, C))
+        ref2 = torch.zeros(rows, C, device="cuda")
+        ck(L, L.sgdm_k_layernorm(S(), P(x), P(ga), P(be), P(res), None, P(ref2), rows, C))
+        torch.cuda.synchronize()
+        assert relerr(out, F.layer_norm(x, (C,), ga, be) + res) < 1e-5
+        assert torch.equal(out, ref2)  # same arithmetic as the plain kernel
+        blk = out.double().view(rows // 32, 32, C // gran, gran)
+        assert relerr(st[..., 0].double(), blk.sum((1, 3))) < 1e-5
+        assert relerr(st[..., 1].double(), (blk * blk).sum((1, 3))) < 1e-5
+
+
+def test_split_precision_operand_layout(L):
+    """[hi | hi | lo] rows (sgdm_config.precision = 1): hi + lo reproduces the fp32 value to ~2^-22."""
+    g = torch.Generator(device="cuda").manual_seed(32)
+    rows, C = 96, 256
+    x = torch.randn(rows, C, device="cuda", generator=g) * 3
+    ga = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    be = 0.1 * torch.randn(C, device="cuda", generator=g)
+    o = torch.zeros(rows, 3 * C, dtype=L._op, device="cuda")
+    ck(L, L.sgdm_k_layernorm_split3(S(), P(x), P(ga), P(be), P(o), rows, C))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (C,), ga, be)
+    hi, hi2, lo = o[:, :C].float(), o[:, C:2 * C].float(), o[:, 2 * C:].float()
+    assert torch.equal(hi, hi2)
+    assert relerr(hi, ref) < 1e-3 and relerr(hi + lo, ref) < (1e-5 if L._op == torch.float16 else 1e-4)
+
+
 def test_linear_f32(L):
     g = torch.Generator(device="cuda").manual_seed(5)
     for M, N, K in ((32, 512, 128), (5, 256, 1000), (130, 70, 33), (512, 256, 5000)):

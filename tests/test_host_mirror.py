@@ -178,3 +178,24 @@ def test_bench_reference_arm_never_maps_the_product_library():
     line = json.loads(lines[-2])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["config_id"] == 1
+
+
+def test_cached_tensor_list_follows_parameter_replacement():
+    """EngineUNet caches the (name -> tensor) list the weight sync walks; replacing a Parameter OBJECT (not just its
+    data) or converting the module must drop that cache."""
+    import torch
+
+    meta, _ = load_unet_case("unet_fast_label_tiny")
+    m = build_model(meta["cfg"])
+    t0 = m._tensors()
+    assert m._tensors() is t0  # cached
+    name = "input_blocks.1.0.in_layers.2.weight"
+    node = m.get_submodule("input_blocks.1.0.in_layers.2")
+    new = torch.nn.Parameter(torch.zeros_like(node.weight))
+    node.weight = new
+    assert m._tensors()[name] is new
+    m.null_cond_emb = torch.nn.Parameter(torch.ones_like(m.null_cond_emb), requires_grad=False)
+    assert m._tensors()["null_cond_emb"] is m.null_cond_emb
+    t1 = m._tensors()
+    m.double()
+    assert m._tensors() is not t1 and m._tensors()[name].dtype == torch.float64
