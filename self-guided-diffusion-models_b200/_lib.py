@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgdm_b200.so")
+# SGDM_LIB selects another build of the same library (tests: the -DSGDM_OPERAND_BF16 variant)
+LIB_PATH = os.environ.get("SGDM_LIB") or os.path.join(_HERE, "libsgdm_b200.so")
 
 MAX_DIMS = 8
 

@@ -530,6 +530,99 @@ def test_variant_configs_vs_oracle(name):
     assert e <= EPS_TOL
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["unet_fast_label_tiny", "unetca_stego_tiny"])
+def test_checkpoint_like_activation_ranges(name):
+    """fp16 operands have range, not just precision, to lose: trained checkpoints carry FiLM `(1 + scale)` factors and
+    residual-stream magnitudes far above the N(0, small) synthetic weights of the other tests.  The weights are
+    re-scaled so that post-FiLM activations reach ~1e2 .. ~1e4 and the residual stream ~1e1 .. ~1e3 (the oracle
+    reports the maxima); the CUDA path must stay finite (conversions saturate, never inf) and keep the eps
+    tolerance as long as nothing exceeds the fp16 range (65504)."""
+    need_gpu()
+    from oracle import unet as ounet
+    from sgdm_b200 import synthetic
+
+    meta, a = load_unet_case(name)
+    cfg = meta["cfg"]
+    base = synthetic.synthetic_state_dict([(n, tuple(s)) for n, s in meta["named_shapes"]], meta["weight_seed"])
+    kw_cpu = kwargs_from_arrays(a)
+    x, t = a["x"], a["t"]
+    for film_gain, stream_gain in ((8.0, 4.0), (60.0, 12.0), (600.0, 40.0), (8000.0, 300.0)):
+        sd = {k: v.clone() for k, v in base.items()}
+        for k in sd:
+            if ".emb_layers.1." in k:
+                sd[k] *= film_gain            # FiLM scale / shift
+            if ".out_layers.3.weight" in k or ".proj_out.weight" in k or ".to_out.0.weight" in k:
+                sd[k] *= stream_gain          # what every block adds to the residual stream
+        # activation maxima seen by the fp32 oracle: hook F.group_norm inputs (residual stream, h1) and conv inputs
+        import torch.nn.functional as F
+
+        peak = {"gn_in": 0.0, "conv_in": 0.0}
+        real_gn, real_conv = F.group_norm, F.conv2d
+
+        def gn(xx, *args, **kwargs):
+            peak["gn_in"] = max(peak["gn_in"], float(xx.abs().max()))
+            return real_gn(xx, *args, **kwargs)
+
+        def conv(xx, *args, **kwargs):
+            peak["conv_in"] = max(peak["conv_in"], float(xx.abs().max()))
+            return real_conv(xx, *args, **kwargs)
+
+        F.group_norm, F.conv2d = gn, conv
+        try:
+            with torch.no_grad():
+                ref = ounet.forward_with_cond_scale(sd, cfg, x, t, 2.0, **kw_cpu)
+        finally:
+            F.group_norm, F.conv2d = real_gn, real_conv
+        m = build_model(cfg)
+        m.load_state_dict(sd)
+        m = m.cuda().eval()
+        got = m.forward_with_cond_scale(x.cuda(), t.cuda(), 2.0, **dev(kw_cpu))
+        assert torch.isfinite(got).all(), f"non-finite eps at gains {film_gain}/{stream_gain}"
+        e = rel_l2(got.cpu(), ref)
+        in_range = peak["conv_in"] < 6.0e4
+        print(f"[ranges {name}] FiLM x{film_gain:g}, stream x{stream_gain:g}: max |GroupNorm input| {peak['gn_in']:.3g}, "
+              f"max |conv input| {peak['conv_in']:.3g} -> eps rel_l2 {e:.3e}" + ("" if in_range else "  (beyond the fp16 range: saturating)"))
+        if in_range:
+            assert e <= EPS_TOL, f"{name}: eps rel-L2 {e:.3e} with activations up to {peak['conv_in']:.3g}"
+
+
+@pytest.mark.gpu
+def test_bf16_operand_build_kernel_suite_and_eps():
+    """The -DSGDM_OPERAND_BF16 build (libsgdm_b200_bf16.so, same sources, bf16 instead of fp16 operands): every
+    kernel unit test passes against it, and its end-to-end eps error is what DESIGN.md forecasts (~1.3e-2: above
+    the 1e-2 tolerance, which is why fp16 is the shipped operand type)."""
+    need_gpu()
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "self-guided-diffusion-models_b200", "libsgdm_b200_bf16.so")
+    if not os.path.exists(lib):
+        pytest.skip("bf16 variant not built (__graft_entry__.build())")
+    env = dict(os.environ, SGDM_LIB=lib)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-x", "-m", "gpu",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1500, cwd=root)
+    tail = (r.stdout + r.stderr)[-1500:]
+    assert r.returncode == 0, tail
+    print("[bf16 build] kernel suite:", r.stdout.strip().splitlines()[-1])
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); import torch\n"
+        "from sgdm_b200 import _lib\n"
+        "assert _lib.lib().sgdm_operand_dtype() == b'bf16'\n"
+        "from common import load_unet_case, kwargs_from_arrays, rel_l2\n"
+        "from test_gpu_e2e import cuda_model, dev\n"
+        "for name in ('cfg1_cifar_label', 'unetca_stego_tiny'):\n"
+        "    meta, a = load_unet_case(name); m = cuda_model(meta); kw = dev(kwargs_from_arrays(a))\n"
+        "    e = m.forward_with_cond_scale(a['x'].cuda(), a['t'].cuda(), meta['cond_scale'], **kw)\n"
+        "    assert torch.isfinite(e).all()\n"
+        "    print('BF16_EPS', name, rel_l2(e.cpu(), a['eps_guided']))\n")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
+    errs = [float(l.split()[-1]) for l in r.stdout.splitlines() if l.startswith("BF16_EPS")]
+    print("[bf16 build] guided eps rel_l2 vs reference:", " ".join(f"{e:.3e}" for e in errs))
+    assert len(errs) == 2 and max(errs) < 3e-2 and min(errs) > EPS_TOL / 4  # clearly the 8-bit-mantissa regime
+
+
 def smoke_check():
     """Used by __graft_entry__.smoke(): one guided step + one DDIM update vs the oracle."""
     from oracle import sampler as osamp

@@ -38,6 +38,11 @@ def ck(lib, rc):
     assert rc == 0, lib.sgdm_last_error().decode()
 
 
+def out_tol(lib, fp16_tol):
+    """Tolerance for a kernel OUTPUT stored in the operand type: its final rounding is 8x coarser in the bf16 build."""
+    return fp16_tol if lib._op == torch.float16 else 8 * fp16_tol
+
+
 def relerr(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
@@ -178,7 +183,7 @@ def test_conv_tcgen05_vs_torch(L, case):
         assert torch.isfinite(got).all(), f"non-finite output ({label})"
         e = relerr(got, ref)
         print(f"[conv {note}] {label} rel_l2={e:.3e}")
-        assert e < (2e-3 if out == "op" else 2e-5), f"{label} conv mismatch {e}"
+        assert e < (out_tol(L, 2e-3) if out == "op" else 2e-5), f"{label} conv mismatch {e}"
 
 
 HFOLD_CASES = [
@@ -337,7 +342,7 @@ def test_groupnorm_from_epilogue_stats(L, case):
     ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
     e = relerr(out.float().permute(0, 3, 1, 2), ref)
     print(f"[gn fused stats {note}] rel_l2={e:.3e}")
-    assert e < 1e-3
+    assert e < out_tol(L, 1e-3)
 
 
 def test_conv_rejects_bad_shapes(L):
@@ -398,9 +403,9 @@ def test_groupnorm(L, case):
         ref = F.interpolate(ref, scale_factor=2, mode="nearest")
     e = relerr(out.float().permute(0, 3, 1, 2), ref)
     print(f"[gn {note}{' (16-bit source)' if half_in else ''}] rel_l2={e:.3e}")
-    assert e < 1e-3  # output is rounded to the 16-bit operand type (2^-11 relative for fp16)
+    assert e < out_tol(L, 1e-3)  # output is rounded to the 16-bit operand type (2^-11 relative for fp16)
     if raw:
-        assert relerr(raw_out.float(), x) < 1e-3
+        assert relerr(raw_out.float(), x) < out_tol(L, 1e-3)
     if pool is not None:
         assert relerr(pool.permute(0, 3, 1, 2), F.avg_pool2d(xc, 2, 2)) < 1e-6
 
@@ -467,7 +472,7 @@ def test_attention(L, case):
     e = relerr(out.float(), ref)
     print(f"[attn {note}] rel_l2={e:.3e}")
     assert torch.isfinite(out.float()).all()
-    assert e < 3e-3  # P and the output are rounded to 16 bits
+    assert e < out_tol(L, 3e-3)  # P and the output are rounded to 16 bits
 
 
 def test_layernorm(L):
@@ -483,7 +488,7 @@ def test_layernorm(L):
         ck(L, L.sgdm_k_layernorm(S(), P(x), P(ga), P(be), P(res), None, P(o2), rows, C))
         torch.cuda.synchronize()
         ref = F.layer_norm(x, (C,), ga, be)
-        assert relerr(o1.float(), ref) < 1e-3
+        assert relerr(o1.float(), ref) < out_tol(L, 1e-3)
         assert relerr(o2, ref + res) < 1e-5
 
 
@@ -521,7 +526,7 @@ def test_split_precision_operand_layout(L):
     ref = F.layer_norm(x, (C,), ga, be)
     hi, hi2, lo = o[:, :C].float(), o[:, C:2 * C].float(), o[:, 2 * C:].float()
     assert torch.equal(hi, hi2)
-    assert relerr(hi, ref) < 1e-3 and relerr(hi + lo, ref) < (1e-5 if L._op == torch.float16 else 1e-4)
+    assert relerr(hi, ref) < out_tol(L, 1e-3) and relerr(hi + lo, ref) < (1e-5 if L._op == torch.float16 else 1e-4)
 
 
 def test_linear_f32(L):
