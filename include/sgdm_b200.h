@@ -94,12 +94,6 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u);
 
-/* Two-stream mode of sgdm_forward_guided (default: environment SGDM_SPLIT_STREAMS, else off): the conditional
- * and the unconditional rows run as two plans on `stream` and on an engine-owned side stream (forked / joined
- * with events, no host synchronisation), so that HBM-bound kernels of one half overlap tensor-bound kernels of
- * the other.  Same values as the single-plan mode.  Switching drops the cached plans. */
-int sgdm_set_split_streams(sgdm_handle h, int on);
-
 /* eps = (1-w) eps_u + w eps_c (imagen) | (1+w) eps_c - w eps_u (cfg); w scalar (a double, like the
  * Python number the reference multiplies with: 1-w is formed in double, then rounded to fp32), or
  * per sample when w_per_sample != NULL ([B] fp32 device; 1-w is then an fp32 op). */
@@ -158,10 +152,10 @@ int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double
 
 /* Count of kernels launched by this library since load (claim for bench.py `gpu_launches`). */
 int64_t sgdm_launch_count(void);
-/* bring-up switch: 1 routes every conv through the CUDA-core checker kernel (tests only) */
-int sgdm_debug_set_naive_conv(int on);
-/* CTA-pair (tcgen05 cta_group::2) conv mode for plans / single-kernel calls created afterwards:
- * -1 = library policy (default), 0 = never, 1 = whenever the shape allows (tests, A/B timing) */
+/* Mode overrides for the SINGLE-KERNEL entry points below (sgdm_k_conv*, sgdm_k_attention) made afterwards by the
+ * calling thread — unit tests force every geometry of the conv / attention kernels through them.  Thread-local; an
+ * engine's plans never read them (they follow the kernels' own policy).
+ * CTA-pair (tcgen05 cta_group::2) conv mode: -1 = library policy (default), 0 = never, 1 = whenever the shape allows */
 int sgdm_debug_set_conv_pair(int mode);
 /* tcgen05 self-attention kernel (T = 256, head dim 64): -1 = whenever applicable (default), 0 = mma.sync kernel */
 int sgdm_debug_set_attn_tc(int mode);
@@ -176,9 +170,6 @@ int sgdm_debug_set_conv_astat(int mode);
 /* tuning aid: single-kernel conv calls made afterwards add per-role stall cycle counts to this device array
  * of 16 int64 (NULL = off); slot meaning in csrc/kernel_conv.cu */
 int sgdm_debug_set_conv_timing(void* device_counters16);
-/* tuning aid for single-kernel conv calls: cap the K-block ring depth (0 = no cap); flags 1 / 2 stop
- * re-loading the activation / weight operand after the first ring fill (timing experiments, WRONG results) */
-int sgdm_debug_set_conv_knobs(int max_stages, int flags);
 
 /* ---- single-kernel entry points (unit parity tests). 16-bit tensors are `op` = fp16 (or bf16). ---- */
 /* conv / GEMM: in [B,Hin,Win,Cin] op NHWC; in2 optional [B,Hout,Wout,C2]; w packed [Npad][ks*ks*Cin + C2] op */

@@ -58,7 +58,6 @@ PROTOTYPES = {
     "sgdm_set_timestep_freqs": (_i, [_vp, _vp, _i]),
     "sgdm_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgdm_forward_guided": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_vp)]),
-    "sgdm_set_split_streams": (_i, [_vp, _i]),
     "sgdm_mix": (_i, [_vp, _vp, _vp, _d, _vp, _i, _vp, _i, _i64]),
     "sgdm_ddim_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _vp, _i, _i64]),
     "sgdm_ddpm_step": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64]),
@@ -73,14 +72,12 @@ PROTOTYPES = {
     "sgdm_profile_count": (_i, [_vp]),
     "sgdm_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
     "sgdm_launch_count": (_i64, []),
-    "sgdm_debug_set_naive_conv": (_i, [_i]),
     "sgdm_debug_set_conv_pair": (_i, [_i]),
     "sgdm_debug_set_conv_timing": (_i, [_vp]),
     "sgdm_debug_set_conv_halo": (_i, [_i]),
     "sgdm_debug_set_conv_k32": (_i, [_i]),
     "sgdm_debug_set_conv_astat": (_i, [_i]),
     "sgdm_debug_set_attn_tc": (_i, [_i]),
-    "sgdm_debug_set_conv_knobs": (_i, [_i, _i]),
     "sgdm_k_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
     "sgdm_k_conv_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
                                 _vp, _i, _vp, _vp, _i]),

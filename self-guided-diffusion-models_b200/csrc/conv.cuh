@@ -65,10 +65,7 @@ struct ConvDesc {
   int hfold = 0;
   int a_stat = -1;              // A-stationary main loop for 1x1 GEMMs with >= 3 n-tiles and K <= 512: -1 policy, 0 off, 1 force
   int k32 = -1;                 // K block of 32 channels (SWIZZLE_64B halo stages): -1 policy, 0 never, 1 force
-  int smem_reserve = 0;         // shared-memory bytes to leave free per SM (two-stream mode: co-resident GroupNorm CTAs)
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
-  int debug_stages = 0;         // tuning only: cap the K-block ring depth
-  int debug_flags = 0;          // tuning only: 1 = stop re-loading the activation operand, 2 = the weight operand (WRONG results)
 };
 
 struct alignas(64) ConvKernelParams {
@@ -101,7 +98,6 @@ struct alignas(64) ConvKernelParams {
   float2* stats;
   int stat_gran;
   long long* timing;
-  int debug;
 };
 
 struct ConvLaunch {

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <functional>
 #include <map>
 #include <memory>
@@ -25,15 +26,15 @@
 using namespace sgdm;
 
 static thread_local char g_err[1024] = "";
-static int64_t g_launches = 0;
-static int g_naive_conv = 0;
-static long long* g_conv_timing = nullptr;
-static int g_conv_dbg_stages = 0, g_conv_dbg_flags = 0;
-static int g_conv_pair = -1;
-static int g_conv_halo = -1;
-static int g_conv_k32 = -1;
-static int g_conv_astat = -1;
-static int g_attn_tc = -1;  // -1 policy | 0 never | 1 whenever possible (tests / A-B timing)
+static std::atomic<int64_t> g_launches{0};
+// Mode overrides of the single-kernel entry points (sgdm_k_conv*, sgdm_k_attention): unit tests force each geometry
+// of the conv / attention kernels through these.  Thread-local, and never read by an engine (plans use the policy).
+static thread_local long long* g_conv_timing = nullptr;
+static thread_local int g_conv_pair = -1;
+static thread_local int g_conv_halo = -1;
+static thread_local int g_conv_k32 = -1;
+static thread_local int g_conv_astat = -1;
+static thread_local int g_attn_tc = -1;  // -1 policy | 0 never | 1 whenever possible
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -114,6 +115,7 @@ struct Plan {
   // CUDA-graph replay of the launch list (launch-bound plans): captured once on first use
   cudaGraphExec_t gexec = nullptr;
   bool graph_tried = false;
+  uint64_t last_use = 0;  // LRU stamp (sgdm_engine::plan_clock)
   // prologue inputs are bound per call through these
   PrepDesc prep;
   float* eps = nullptr;        // [Bp, Cout, H, W] fp32 NCHW
@@ -159,13 +161,8 @@ struct sgdm_engine {
   bool first_im2col = false;  // first conv as a 1x1 GEMM over an im2col'd input (PrepDesc::im2col)
   std::vector<void*> owned;
   bool device_ready = false;
-  std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + variant
-  // Two-stream mode of the guided forward: the conditional and the unconditional half run as two independent
-  // plans on two streams, so that the HBM-bound kernels of one half (GroupNorm, attention) overlap the
-  // tensor-bound conv kernels of the other half on the same SMs.
-  bool split_streams = false;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::map<int, std::unique_ptr<Plan>> plans;  // key = batch rows
+  uint64_t plan_clock = 0;                      // LRU stamp source
   bool profiling = false;
   Plan* last_profiled = nullptr;
   // CUDA-graph replay: -1 policy (plans in the launch-bound regime, the same threshold as programmatic dependent
@@ -174,9 +171,6 @@ struct sgdm_engine {
   int graph_mode = -1;
 
   ~sgdm_engine() {
-    if (side) cudaStreamDestroy(side);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
     plans.clear();
     for (void* p : owned) cudaFree(p);
   }
@@ -489,9 +483,8 @@ int setup_device(sgdm_engine* e) {
   auto part = [&](int cin) { return e->x3 ? cin : 0; };  // pack_conv_weight_launch's cin_part
   if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E * S) || dalloc(e, &e->b_emb, e->NE)) return 1;
 
-  // 3 + 3 (+1) input channels: the whole 3x3 neighbourhood fits the 64-channel input row (SGDM_FIRST_IM2COL=0: A/B)
-  e->first_im2col = !e->x3 && 9 * (2 * c.in_channels + c.layout_dim) <= 64 &&
-                    !(getenv("SGDM_FIRST_IM2COL") && atoi(getenv("SGDM_FIRST_IM2COL")) == 0);
+  // 3 + 3 (+1) input channels: the whole 3x3 neighbourhood fits the 64-channel input row
+  e->first_im2col = !e->x3 && 9 * (2 * c.in_channels + c.layout_dim) <= 64;
   // first conv channel map: dst [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0] <- src [x(Cimg) | layout(L)]
   {
     std::vector<int> m(64, -1);
@@ -679,11 +672,10 @@ struct Builder {
     if (!stats_ok(H, W)) return nullptr;
     return reinterpret_cast<float2*>(stream_alloc(2 * stats_elems(rows, C)));
   }
-  // Optional (SGDM_GN16=1): 16-bit GroupNorm-input copies written by the producing conv's epilogue next to the
-  // fp32 tensor.  Measured on B200 (config 2, batch 256): gn_apply 9.7 -> 8.3 ms, but the epilogue-bound convs
-  // lose about as much and eps rel-L2 rises 1.9e-3 -> 2.2e-3 (DDIM-10 PSNR 43.7 -> 41.3 dB): off by default.
-  bool use16 = getenv("SGDM_GN16") != nullptr && atoi(getenv("SGDM_GN16")) != 0;
-  int smem_reserve = 0;
+  // (16-bit GroupNorm-input copies written by the producing conv's epilogue next to the fp32 tensor — ConvDesc::out_op2,
+  //  Act::p16 — were measured in round 1: gn_apply 9.7 -> 8.3 ms, but the epilogue-bound convs lose as much and eps
+  //  rel-L2 rises 13 %.  The engine never asks for them; the kernel capability stays for its unit tests.)
+  const bool use16 = false;
   int S = 1;          // e->S: channel expansion of every operand tensor (3 in split-precision mode)
   int split3 = 0;     // e->x3
   void attach_outputs(Act& o, size_t rows, ConvDesc& c, bool allow16 = true) {
@@ -703,18 +695,10 @@ struct Builder {
   void conv(ConvDesc d, int real_cin = 0) {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
-    d.swap_ab = (conv_can_swap(d) && !getenv("SGDM_NO_SWAP")) ? 1 : 0;
+    d.swap_ab = conv_can_swap(d) ? 1 : 0;
     d.stat_gran = stat_gran();
-    d.pair = g_conv_pair;
-    d.halo = g_conv_halo;
-    d.k32 = g_conv_k32;
-    d.a_stat = g_conv_astat;
-    d.smem_reserve = smem_reserve;
-    // A/B switches for whole-step timing (same process image, same box): SGDM_CONV_HALO / SGDM_CONV_PAIR = 0 | 1
-    if (const char* ev = getenv("SGDM_CONV_HALO")) d.halo = atoi(ev) ? -1 : 0;
-    if (const char* ev = getenv("SGDM_CONV_PAIR")) d.pair = atoi(ev) ? -1 : 0;
+    // geometry (pair / halo / 32-channel K blocks / A-stationary): the kernel's own policy (conv.cuh, conv_prepare)
     if (d.hfold) { d.halo = 1; d.pair = 0; }
-    if (d.in2 && d.swap_ab && getenv("SGDM_CONV_HALO_SKIP") != nullptr) d.halo = 0;  // A/B: swap-AB skip blocks take a whole halo stage each
     if (dry) return;
     auto l = std::make_shared<ConvLaunch>();
     char msg[256];
@@ -733,7 +717,7 @@ struct Builder {
                          (d.res ? M * d.Cout * 4 / (d.res_mode == 2 ? 4 : 1) : 0);
     push([l](cudaStream_t s) {
       ++g_launches;
-      return g_naive_conv ? conv_launch_naive(l->desc, s) : conv_launch(*l, s);
+      return conv_launch(*l, s);
     }, d.ks == 3 ? "conv3x3" : "gemm1x1", flops, bytes);
   }
   void gn(GnDesc d) {
@@ -852,7 +836,7 @@ struct Builder {
     ad.v = dry ? nullptr : qkv + 2 * dh; ad.v_row_stride = 3 * C; ad.v_head_stride = 3 * dh;
     ad.out = att; ad.o_row_stride = C; ad.B = Bp; ad.T = T; ad.heads = e->heads; ad.D = dh;
     ad.scale = 1.0f / sqrtf(static_cast<float>(dh));  // (ch^-1/4 on q) * (ch^-1/4 on k)
-    ad.use_tc = getenv("SGDM_ATTN_TC") ? (atoi(getenv("SGDM_ATTN_TC")) ? -1 : 0) : g_attn_tc;
+    ad.use_tc = -1;  // tcgen05 kernel whenever the shape allows
     push([ad](cudaStream_t s) {
       ++g_launches;
       return attn_launch(ad, s);
@@ -1116,9 +1100,8 @@ struct Builder {
     ConvDesc d;
     d.in = g; d.Hin = H; d.Win = W; d.Cin = h.C * S; d.w = e->conv_out.w; d.ks = 3; d.stride = 1; d.pad = 1;
     d.Hout = H; d.Wout = W; d.Cout = c.out_channels; d.bias = e->conv_out.b; d.out_nchw = eps;
-    // horizontal-tap folding (ConvDesc::hfold) whenever the head's tiles are whole image rows; SGDM_CONV_HFOLD=0: A/B
-    const bool fold_env = !(getenv("SGDM_CONV_HFOLD") && atoi(getenv("SGDM_CONV_HFOLD")) == 0);
-    if (fold_env && e->conv_out.w_hfold && W <= 128 && (128 % W) == 0 && (W % 8) == 0 && ((H * W) % 128) == 0) {
+    // horizontal-tap folding (ConvDesc::hfold) whenever the head's tiles are whole image rows
+    if (e->conv_out.w_hfold && W <= 128 && (128 % W) == 0 && (W % 8) == 0 && ((H * W) % 128) == 0) {
       d.hfold = 1;
       d.w = e->conv_out.w_hfold;
     }
@@ -1126,21 +1109,27 @@ struct Builder {
   }
 };
 
-int get_plan(sgdm_engine* e, int Bp, Plan** out, int variant = 0) {
-  auto it = e->plans.find(2 * Bp + variant);
+int get_plan(sgdm_engine* e, int Bp, Plan** out) {
+  auto it = e->plans.find(Bp);
   if (it != e->plans.end()) {
+    it->second->last_use = ++e->plan_clock;
     *out = it->second.get();
     return 0;
   }
-  // keep at most 3 plans alive (workspace is large)
-  while (e->plans.size() >= 4) e->plans.erase(e->plans.begin());
+  // keep at most 3 plans alive (a plan owns its workspace: config 2 at 512 rows is ~31 GB): evict the least
+  // recently used one — never a plan handed out during this call, there is only one per call
+  while (e->plans.size() >= 3) {
+    auto lru = e->plans.begin();
+    for (auto p = e->plans.begin(); p != e->plans.end(); ++p)
+      if (p->second->last_use < lru->second->last_use) lru = p;
+    if (e->last_profiled == lru->second.get()) e->last_profiled = nullptr;
+    e->plans.erase(lru);
+  }
   std::unique_ptr<Plan> plan(new Plan());
   plan->Bp = Bp;
   Builder b;
   b.e = e; b.plan = plan.get(); b.Bp = Bp;
   b.S = e->S; b.split3 = e->x3 ? 1 : 0;
-  if (e->x3) b.use16 = false;
-  b.smem_reserve = e->split_streams ? 4096 : 0;
   b.dry = true;
   b.build();
   size_t total = b.stream_bytes;
@@ -1160,8 +1149,9 @@ int get_plan(sgdm_engine* e, int Bp, Plan** out, int variant = 0) {
   b.dry = false;
   b.build();
   if (b.err) return 1;
+  plan->last_use = ++e->plan_clock;
   *out = plan.get();
-  e->plans[2 * Bp + variant] = std::move(plan);
+  e->plans[Bp] = std::move(plan);
   return 0;
 }
 
@@ -1196,7 +1186,7 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
   const bool small_plan = static_cast<long>(Bp) * e->cfg.image_size * e->cfg.image_size <= (1L << 18);
   pdl_mode() = !e->profiling && small_plan;
   // ... where replaying the whole launch list as ONE graph launch pays even more (config 1: ~170 launches of 5-10 us)
-  const bool want_graph = !e->profiling && !g_naive_conv && (e->graph_mode == 1 || (e->graph_mode < 0 && small_plan));
+  const bool want_graph = !e->profiling && (e->graph_mode == 1 || (e->graph_mode < 0 && small_plan));
   if (want_graph && !plan->gexec && !plan->graph_tried) {
     plan->graph_tried = true;
     // captured on a private stream: the caller's stream may be the legacy default stream, which cannot capture
@@ -1245,48 +1235,6 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
   return 0;
 }
 
-// Guided forward in two-stream mode: plan A = the B conditional rows on the caller's stream, plan B = the B
-// unconditional rows on the engine's side stream; their launches are issued alternately so both queues stay
-// full.  GroupNorm is per sample and the conv / attention kernels are batch-invariant, so the values are the
-// ones of the single 2B-row plan (tests/test_gpu_e2e.py checks bit equality).
-int run_forward_split(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t, const float* cond,
-                      const float* layout, int B, Plan** plan_c, Plan** plan_u) {
-  if (!e->device_ready) return fail("no parameters loaded");
-  for (auto& p : e->params)
-    if (!p.loaded) return fail("parameter %s was never loaded", p.name.c_str());
-  if (e->cfg.cond_dim > 0 && cond == nullptr) return fail("cond is required (cond_dim=%d)", e->cfg.cond_dim);
-  if (e->cfg.layout_dim > 0 && layout == nullptr) return fail("layout is required (layout_dim=%d)", e->cfg.layout_dim);
-  if (!e->side) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  }
-  Plan *pa = nullptr, *pb = nullptr;
-  if (get_plan(e, B, &pa, 0) || get_plan(e, B, &pb, 1)) return 1;
-  CUDA_TRY(cudaEventRecord(e->ev_fork, s));  // the inputs (and the previous step's consumers of eps) are on s
-  CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-  CUDA_TRY(cudaMemsetAsync(pa->drop, 0, B, s));
-  CUDA_TRY(cudaMemsetAsync(pb->drop, 1, B, e->side));
-  PrepDesc pda = pa->prep, pdb = pb->prep;
-  pda.x = pdb.x = x; pda.t = pdb.t = reinterpret_cast<const long long*>(t);
-  pda.cond = pdb.cond = cond; pda.layout = pdb.layout = layout; pda.B = pdb.B = B;
-  g_launches += 4;
-  if (prep_launch(pda, s) || prep_launch(pdb, e->side)) return fail("prep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  const size_t n = pa->ops.size();
-  if (pb->ops.size() != n) return fail("internal: plan variants differ");
-  for (size_t i = 0; i < n; ++i) {
-    if (pa->ops[i](s) || pb->ops[i](e->side)) {
-      cudaError_t ce = cudaGetLastError();
-      return fail("launch %zu (%s) of %zu failed: %s", i, pa->meta[i].kind, n, cudaGetErrorString(ce));
-    }
-  }
-  CUDA_TRY(cudaEventRecord(e->ev_join, e->side));
-  CUDA_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
-  *plan_c = pa;
-  *plan_u = pb;
-  return 0;
-}
-
 }  // namespace
 
 // ======================================================================================= C ABI
@@ -1301,11 +1249,7 @@ const char* sgdm_operand_dtype(void) {
   return "f16";
 #endif
 }
-int64_t sgdm_launch_count(void) { return g_launches; }
-int sgdm_debug_set_naive_conv(int on) {
-  g_naive_conv = on;
-  return 0;
-}
+int64_t sgdm_launch_count(void) { return g_launches.load(); }
 int sgdm_debug_set_conv_pair(int mode) {
   g_conv_pair = mode;
   return 0;
@@ -1326,11 +1270,6 @@ int sgdm_debug_set_conv_astat(int mode) {
   g_conv_astat = mode;
   return 0;
 }
-int sgdm_debug_set_conv_knobs(int max_stages, int flags) {
-  g_conv_dbg_stages = max_stages;
-  g_conv_dbg_flags = flags;
-  return 0;
-}
 int sgdm_debug_set_conv_timing(void* device_counters16) {
   g_conv_timing = static_cast<long long*>(device_counters16);
   return 0;
@@ -1340,7 +1279,6 @@ int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   if (!cfg || !out) return fail("null argument");
   std::unique_ptr<sgdm_engine> e(new sgdm_engine());
   e->cfg = *cfg;
-  if (const char* ev = getenv("SGDM_SPLIT_STREAMS")) e->split_streams = atoi(ev) != 0;
   if (const char* ev = getenv("SGDM_GRAPH")) e->graph_mode = atoi(ev) != 0 ? 1 : 0;  // A/B: force graph replay on / off
   if (build_topology(e.get())) return 1;
   *out = e.release();
@@ -1426,21 +1364,8 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
   CUDA_TRY(cudaMemcpyAsync(eps_out, plan->eps, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
-int sgdm_set_split_streams(sgdm_handle h, int on) {
-  if (!h) return fail("null handle");
-  if ((on != 0) != h->split_streams) h->plans.clear();  // plans are laid out for one mode
-  h->split_streams = on != 0;
-  return 0;
-}
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u) {
-  if (h->split_streams && !h->profiling) {
-    Plan *pc = nullptr, *pu = nullptr;
-    if (run_forward_split(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, B, &pc, &pu)) return 1;
-    *eps_c = pc->eps;
-    *eps_u = pu->eps;
-    return 0;
-  }
   Plan* plan = nullptr;
   if (run_forward(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, nullptr, B, 2 * B, &plan)) return 1;
   const size_t n = static_cast<size_t>(B) * h->cfg.out_channels * h->cfg.image_size * h->cfg.image_size;
@@ -1562,8 +1487,6 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.halo = g_conv_halo;
   d.k32 = g_conv_k32;
   d.a_stat = g_conv_astat;
-  d.debug_stages = g_conv_dbg_stages;
-  d.debug_flags = g_conv_dbg_flags;
   ++g_launches;
   if (naive) return conv_launch_naive(d, static_cast<cudaStream_t>(stream)) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

@@ -24,9 +24,6 @@ namespace sgdm {
 
 constexpr int kTcT = 256, kTcD = 64;
 constexpr int kTcTile = kTcT * kTcD * 2;   // 32 KB: one [256 x 64] 16-bit tile
-constexpr int kTcStage = 3 * kTcTile;      // Q | K | V
-constexpr int kTcSmem = 2 * kTcStage + 256;
-constexpr int kTcThreads = 192;
 
 struct alignas(64) AttnTcParams {
   CUtensorMap tm;  // the packed [B*T, row_stride] matrix holding q, k and v column blocks
@@ -46,192 +43,15 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  pdl_launch_dependents();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcStage);
-  uint64_t* full = bars;            // [2] TMA -> MMA
-  uint64_t* stage_free = bars + 2;  // [2] MMA (O_1 done) -> TMA
-  uint64_t* s_ready = bars + 4;     // both S tiles complete -> softmax
-  uint64_t* p_ready = bars + 5;     // [2] P_j staged (4 warps) -> MMA
-  uint64_t* o_ready = bars + 7;     // [2] O_j complete -> softmax / epilogue
-  uint64_t* tfree = bars + 9;       // TMEM drained (4 warps) -> MMA of the next pair
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tm);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&stage_free[i], 1);
-      mbar_init(&p_ready[i], 4);
-      mbar_init(&o_ready[i], 1);
-    }
-    mbar_init(s_ready, 1);
-    mbar_init(tfree, 4);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x, ++it) {
-        const uint32_t st = it & 1;
-        const int n = pair / p.heads, h = pair - n * p.heads;
-        mbar_wait(&stage_free[st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[st], kTcStage);
-        uint8_t* base = smem + st * kTcStage;
-        tma_load_2d(&p.tm, &full[st], base, p.q_col + h * p.head_stride, n * kTcT);
-        tma_load_2d(&p.tm, &full[st], base + kTcTile, p.k_col + h * p.head_stride, n * kTcT);
-        tma_load_2d(&p.tm, &full[st], base + 2 * kTcTile, p.v_col + h * p.head_stride, n * kTcT);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc(128, 256);
-      const uint32_t idesc_o = umma_idesc(128, 64) | (1u << 16);  // B operand (V) is MN-major
-      uint32_t it = 0;
-      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x, ++it) {
-        const uint32_t st = it & 1, ph = it & 1;
-        const uint32_t base = smem_u32(smem + st * kTcStage);
-        mbar_wait(&full[st], (it >> 1) & 1);
-        mbar_wait(tfree, ph ^ 1);  // the previous pair's O tiles have been read out of TMEM
-        tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + j * 256, umma_smem_desc(base + j * 16384 + k * 32), umma_smem_desc(base + kTcTile + k * 32),
-                     idesc_s, k != 0 ? 1u : 0u);
-        }
-        umma_commit(s_ready);
-        for (int j = 0; j < 2; ++j) {
-          mbar_wait(&p_ready[j], ph);
-          tc_fence_after();
-          // P_j: four K-major [128 x 64] blocks of 16 KB laid over the Q and K tiles; V: rows = keys
-#pragma unroll
-          for (int kk = 0; kk < 16; ++kk)
-            umma_f16(tmem_base + j * 256, umma_smem_desc(base + (kk >> 2) * 16384 + (kk & 3) * 32),
-                     umma_smem_desc(base + 2 * kTcTile + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
-          umma_commit(&o_ready[j]);
-        }
-        umma_commit(&stage_free[st]);
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t x7 = r & 7;
-    uint32_t it = 0;
-    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x, ++it) {
-      const uint32_t st = it & 1, ph = it & 1;
-      const int n = pair / p.heads, h = pair - n * p.heads;
-      const uint32_t base = smem_u32(smem + st * kTcStage);
-      float inv_l[2];
-      auto store_o = [&](int j) {
-        // O_j row -> * 1/l -> 64 x 16-bit = 128 B of the output row
-        op_t* dst = p.out + (static_cast<long>(n) * kTcT + j * 128 + r) * p.o_row_stride + h * kTcD;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(lane_taddr + j * 256, v0);
-        tmem_ld_32x32(lane_taddr + j * 256 + 32, v1);
-        tmem_ld_wait();
-        const float s = inv_l[j];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t(&v)[32] = half == 0 ? v0 : v1;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 o = make_uint4(pack_op2(__uint_as_float(v[8 * c]) * s, __uint_as_float(v[8 * c + 1]) * s),
-                                       pack_op2(__uint_as_float(v[8 * c + 2]) * s, __uint_as_float(v[8 * c + 3]) * s),
-                                       pack_op2(__uint_as_float(v[8 * c + 4]) * s, __uint_as_float(v[8 * c + 5]) * s),
-                                       pack_op2(__uint_as_float(v[8 * c + 6]) * s, __uint_as_float(v[8 * c + 7]) * s));
-            *reinterpret_cast<uint4*>(dst + 32 * half + 8 * c) = o;
-          }
-        }
-      };
-      mbar_wait(s_ready, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t taddr = lane_taddr + j * 256;
-        // pass 1: row maximum over the 256 keys
-        float m = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + 32 * c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        }
-        const float mb = m * p.scale_log2;
-        if (j == 1) {
-          // the P buffers (Q / K tiles) are still read by the O_0 MMAs; O_0 is also ready to be stored then
-          mbar_wait(&o_ready[0], ph);
-          tc_fence_after();
-          store_o(0);
-        }
-        // pass 2: exponentials (log2 domain), row sum, P as 16-bit K-major operand.  (Measured slower: double-
-        // buffering the TMEM loads in registers, and 64-column loads — both end at 255 registers with spills.)
-        float l = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + 32 * c, v);
-          tmem_ld_wait();
-          float e[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            e[i] = ex2f(__uint_as_float(v[i]) * p.scale_log2 - mb);
-            l += e[i];
-          }
-          const uint32_t blk = base + (c >> 1) * 16384 + r * 128;  // K block of 64 keys
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t ci = (c & 1) * 4 + q;  // 16-byte chunk (8 keys) inside the 128-byte row
-            sts128u_(blk + ((ci ^ x7) << 4), make_uint4(pack_op2(e[8 * q], e[8 * q + 1]), pack_op2(e[8 * q + 2], e[8 * q + 3]),
-                                                        pack_op2(e[8 * q + 4], e[8 * q + 5]), pack_op2(e[8 * q + 6], e[8 * q + 7])));
-          }
-        }
-        inv_l[j] = 1.0f / l;
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[j]);
-      }
-      mbar_wait(&o_ready[1], ph);
-      tc_fence_after();
-      store_o(1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tfree);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
 // ------------------------------------------------------------------------------------------------------
-// Second generation: TWO softmax warpgroups, one per query tile, running concurrently (10 warps).
+// TWO softmax warpgroups, one per query tile, running concurrently (10 warps).
 //   warp 0 (one lane)  TMA producer: Q|K (64 KB) and V (32 KB) of the next pair as soon as the MMAs that read
 //                                    them have retired (Q, K: after both S MMAs; V: after both PV MMAs)
 //   warp 1 (one lane)  MMA issuer  : an event loop over the two query tiles; per tile strictly S_j, PV_j, S_j, ...
 //   warps 2..5 / 6..9  softmax of query tile 0 / 1: thread = query row, exact two-pass softmax from TMEM, P_j
 //                                    into its OWN 64 KB operand buffer, O_j read back, scaled, stored
-// The first generation ran the two tiles back to back on four warps and spent most of a pair waiting on the
-// TMEM-load round trips of one warp per scheduler; with a warp of each group on every scheduler the round trips
+// (A first generation, removed in round 2, ran the two tiles back to back on four warps and spent most of a pair waiting
+// on the TMEM-load round trips of one warp per scheduler: 1.55 vs 1.35 ms per step.)  With a warp of each group on every scheduler the round trips
 // of one tile hide behind the arithmetic of the other, and S / PV of one tile overlap the softmax of the other.
 // Shared memory: Q | K | V | P_0 | P_1 = 224 KB (single Q/K/V stage: the loads of the next pair are issued a whole
 // softmax ahead of their first use, so a second stage would buy nothing).
@@ -466,16 +286,11 @@ int attn_tc_launch(const AttnDesc& a, cudaStream_t s) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess)
-      return 1;
+    if (cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess) return 1;
     attr_set = true;
   }
   const int grid = p.pairs < kNumSMs ? p.pairs : kNumSMs;
-  // SGDM_ATTN_TC_GEN = 1 selects the first-generation kernel (one softmax warpgroup, two-stage Q/K/V ring): A/B switch
-  static const int gen = getenv("SGDM_ATTN_TC_GEN") ? atoi(getenv("SGDM_ATTN_TC_GEN")) : 2;
-  const cudaError_t e = gen == 1 ? launch_pdl(attn_tc_kernel, dim3(grid), dim3(kTcThreads), kTcSmem, s, 1, p)
-                                 : launch_pdl(attn_tc2_kernel, dim3(grid), dim3(kTc2Threads), kTc2Smem, s, 1, p);
+  const cudaError_t e = launch_pdl(attn_tc2_kernel, dim3(grid), dim3(kTc2Threads), kTc2Smem, s, 1, p);
   return e == cudaSuccess ? 0 : 1;
 }
 

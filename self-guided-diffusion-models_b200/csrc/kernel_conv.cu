@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       long long t_prod = 0;
-      uint32_t fill = 0;
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
       // main K blocks: halo stages hold the three vertical taps of one (horizontal tap, chunk); plain stages hold
       // p.kps consecutive (tap, chunk) K blocks, each with its own activation tile and weight slot
@@ -222,9 +221,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const long long tw0 = p.timing ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (p.timing) t_prod += clock64() - tw0;
-          const bool skip_a = (p.debug & 1) && fill >= static_cast<uint32_t>(n_stages);  // tuning only: stale smem
-          const bool skip_b = (p.debug & 2) && fill >= static_cast<uint32_t>(n_stages);
-          ++fill;
           const bool main_st = q < n_main;
           if (p.a_stat) {
             // resident A K block q of this m-tile: loaded with the first n-tile, into the slot the previous m-tile's
@@ -246,7 +242,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const int ntap = main_st ? (p.halo ? p.tps : min(p.kps, n_blk - q * p.kps)) : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
           const uint32_t act_tx = (main_st && p.halo) ? p.act_tx_halo : ntap * p.act_tx;
           if (cta_rank == 0)
-            mbar_arrive_expect_tx(&full[stage], kCtas * ((skip_a ? 0u : act_tx) + (skip_b ? 0u : ntap * p.wgt_tx)));
+            mbar_arrive_expect_tx(&full[stage], kCtas * (act_tx + ntap * p.wgt_tx));
           uint8_t* act_dst = ring + stage * stage_bytes;
           uint8_t* wgt_dst = act_dst + p.act_bytes;
           int cc, kb0;
@@ -264,34 +260,28 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 if (q_tap - q_r * p.ks == p.ks) ++q_r;
               }
               if (u == 0) kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q * p.kps;
-              if (!skip_a) {
-                uint8_t* dst = act_dst + u * p.act_tx;
-                if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
-                else tma_load_4d(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
-              }
+              uint8_t* dst = act_dst + u * p.act_tx;
+              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              else tma_load_4d(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
             }
           } else {
             cc = (q - n_main) * p.tps2;
             kb0 = p.taps * p.kc1 + cc;
-            if (!skip_a) {
-              for (int t = 0; t < ntap; ++t) {
-                // the skip source may be a channel concat of two tensors: [kc2a chunks of tmA2 | rest of tmA2b]
-                const CUtensorMap* tm2 = (cc + t) < p.kc2a ? &p.tmA2 : &p.tmA2b;
-                const int c2 = (cc + t) < p.kc2a ? (cc + t) : (cc + t) - p.kc2a;
-                if (kCtas == 2) tma_load_4d_pair(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
-                else tma_load_4d(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
-              }
+            for (int t = 0; t < ntap; ++t) {
+              // the skip source may be a channel concat of two tensors: [kc2a chunks of tmA2 | rest of tmA2b]
+              const CUtensorMap* tm2 = (cc + t) < p.kc2a ? &p.tmA2 : &p.tmA2b;
+              const int c2 = (cc + t) < p.kc2a ? (cc + t) : (cc + t) - p.kc2a;
+              if (kCtas == 2) tma_load_4d_pair(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
+              else tma_load_4d(tm2, &full[stage], act_dst + t * p.act_tx, c2 * p.kblk, 0, y0, img);
             }
           }
-          if (!skip_b) {
-            for (int t = 0; t < ntap; ++t) {
-              // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
-              // (hfold: the packed K axis is (vertical tap, channel) only)
-              // (plain stages: kps consecutive K blocks)
-              const int kb = kb0 + ((main_st && p.halo) ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
-              if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n + cta_rank * b_rows);
-              else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n);
-            }
+          for (int t = 0; t < ntap; ++t) {
+            // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
+            // (hfold: the packed K axis is (vertical tap, channel) only)
+            // (plain stages: kps consecutive K blocks)
+            const int kb = kb0 + ((main_st && p.halo) ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
+            if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n + cta_rank * b_rows);
+            else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n);
           }
           if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
         }
@@ -322,7 +312,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (p.a_stat && n_tile_a == 0) mbar_wait(&a_full[q], a_it & 1);  // this m-tile's resident A K block
           mbar_wait(&full[stage], phase);
           if (p.timing) t_full += clock64() - tw0;
-          if (!(p.debug & 4)) tc_fence_after();  // (tuning flag 4: measure the cost of this per-stage fence)
+          tc_fence_after();  // (measured in round 1: free)
           const bool main_st = q < n_main;
           const int ntap = main_st ? (p.halo ? p.tps : min(p.kps, n_blk - q * p.kps)) : min(p.tps2, p.kc2 - (q - n_main) * p.tps2);
           const uint32_t act_addr = p.a_stat ? smem_u32(a_res + q * p.act_tx) : smem_u32(ring + stage * stage_bytes);
@@ -889,8 +879,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.res_mode = d.res ? d.res_mode : 0;
   if (d.out_op2 && !d.out_f32) return fail("the 16-bit copy (out_op2) accompanies the fp32 output");
   p.out2 = d.out_op2 ? 1 : 0;
-  // smem_reserve: bytes left free on the SM so that small CTAs of a concurrent stream (GroupNorm) can co-reside
-  const int smem_cap = kSmemLimit - (d.smem_reserve > 0 ? d.smem_reserve : 0);
+  const int smem_cap = kSmemLimit;
   const int budget = smem_cap - kBarBytes - kBiasBytes - (p.out2 ? kEpi2Bytes : 0);
   // staging buffers per epilogue warp: 2 without a residual; res_mode 1 adds the in-place residual ring (>= 3,
   // up to 6: in-flight residual bytes per SM must cover HBM latency); res_mode 2 uses four 2 KB slots in two more
@@ -902,7 +891,6 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // ring fit beside the epilogue staging — the Cout = 128 swap-AB convs with a residual, whose 96 KB halo stages
   // do not: per tile they pull 864 KB through L2 -> SM without the halo (measured at the ~11 TB/s L2 -> SM limit,
   // tensor pipe 47 %), 576 KB with it.  ConvDesc::k32: -1 policy, 0 never, 1 force.
-  static const bool k32_env = !(getenv("SGDM_CONV_K32") && atoi(getenv("SGDM_CONV_K32")) == 0);
   const bool halo_ok = halo;
   int kblk = d.k32 == 1 ? 32 : 64;
   if (kblk == 32 && ((d.Cin % 32) || !halo_ok || pair || d.hfold)) return fail("k32 needs a halo-mode conv, one CTA per tile");
@@ -928,7 +916,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (n_stages < min_stages && p.tps2 == 3) { pack_skip = false; continue; }     // first give up the skip packing,
     // (policy: not with a fused 1x1-skip source in swap-AB mode — each of its 32-channel K blocks would take a whole
     //  halo stage; measured +0.02 ms per such layer, against -0.055 ms for the plain ones)
-    if (n_stages < min_stages && halo && kblk == 64 && d.k32 != 0 && k32_env && !d.hfold && !pair &&
+    if (n_stages < min_stages && halo && kblk == 64 && d.k32 != 0 && !d.hfold && !pair &&
         (d.k32 == 1 || !(d.in2 && d.swap_ab))) {
       kblk = 32;  // then halve the K block,
       pack_skip = true;
@@ -943,7 +931,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     p.epi_bufs = min_bufs;
     if (p.res_mode == 1) {
       // trade ring depth beyond the minimum for a deeper residual ring
-      static const int max_bufs = getenv("SGDM_MAX_EPI_BUFS") ? max(3, min(kMaxEpiBufs, atoi(getenv("SGDM_MAX_EPI_BUFS")))) : kMaxEpiBufs;
+      const int max_bufs = kMaxEpiBufs;  // (ring depths 4 / 6 / 8 measured in round 1: no difference)
       while (n_stages > min_stages && (budget - n_stages * stage_bytes) / (4 * kEpiBuf) < max_bufs) --n_stages;
       p.epi_bufs = (budget - n_stages * stage_bytes) / (4 * kEpiBuf);
       if (p.epi_bufs > max_bufs) p.epi_bufs = max_bufs;
@@ -952,7 +940,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   // Plain (non-halo) stages with TWO K blocks: the per-stage cost of the single MMA-issuing lane (barrier wait, fence,
   // commit) is paid once per 8 MMAs instead of once per 4.  Only where three such stages fit.  SGDM_CONV_KPS=1: A/B.
-  static const int kps_max = getenv("SGDM_CONV_KPS") ? atoi(getenv("SGDM_CONV_KPS")) : 3;
+  const int kps_max = 3;
   p.kps = 1;
   if (!p.halo && p.kblk == 64 && d.a_stat != 1) {
     const int n_blk = d.ks * d.ks * (d.Cin / 64);
@@ -975,12 +963,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // A-stationary main loop: a 1x1 GEMM with several n-tiles re-reads its activation rows once per n-tile (qkv: 6
   // times, 1.6 GB through L2 -> SM for 0.13 GB of input).  With K <= 512 the m-tile's K blocks fit in shared memory
   // (kc1 x 16 KB): they are loaded once per m-tile and the ring carries weight tiles only.  Policy: >= 3 n-tiles.
-  static const bool a_env = !(getenv("SGDM_CONV_ASTAT") && atoi(getenv("SGDM_CONV_ASTAT")) == 0);
   int a_region = 0;
   p.a_stat = 0;
   {
     const int n_tiles = conv_npad(d.Cout, d.block_n) / d.block_n;
-    const bool want = d.a_stat != 0 && a_env && d.ks == 1 && d.stride == 1 && !d.in2 && !d.swap_ab && !d.hfold &&
+    const bool want = d.a_stat != 0 && d.ks == 1 && d.stride == 1 && !d.in2 && !d.swap_ab && !d.hfold &&
                       p.epi_mode != 0 && p.kblk == 64 && !p.halo && p.kps == 1 && d.Cin / 64 <= kMaxStages &&
                       (d.a_stat == 1 || n_tiles >= 3);
     if (want) {
@@ -1005,13 +992,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   // Without a residual the staging buffers only rotate as TMA-store sources: two suffice, up to two more are
   // taken from shared memory the K-block ring left over (never from the ring itself: measured, reserving them
-  // up front costs halo-mode stages and 3.5 ms per step).  A/B knob: SGDM_EPI_BUFS_EXTRA=0 keeps two.
-  static const bool extra_bufs = !(getenv("SGDM_EPI_BUFS_EXTRA") && atoi(getenv("SGDM_EPI_BUFS_EXTRA")) == 0);
-  if (extra_bufs && p.epi_mode != 0 && p.res_mode == 0) {
+  // up front costs halo-mode stages and 3.5 ms per step).
+  if (p.epi_mode != 0 && p.res_mode == 0) {
     const int left = budget - a_region - n_stages * (p.act_bytes + p.tps * p.wgt_bytes) - 4 * min_bufs * kEpiBuf;
     p.epi_bufs = min(4, min_bufs + left / (4 * kEpiBuf));
   }
-  if (d.debug_stages > 0 && d.debug_stages < n_stages) n_stages = d.debug_stages;
   p.n_stages = n_stages;
   out->smem = smem_cap - budget + 4 * p.epi_bufs * kEpiBuf + n_stages * (p.act_bytes + p.tps * p.wgt_bytes) + a_region;
   if (encode_nhwc(&p.tmA, d.in, d.B, d.Hin, d.Win, d.Cin, bw, p.halo ? bh + 2 : bh, bn, d.stride, err, errlen, kblk)) return 1;
@@ -1059,7 +1044,6 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.stats = d.stats;
   p.stat_gran = d.stat_gran;
   p.timing = d.timing;
-  p.debug = d.debug_flags;
   // epilogue: output / residual tile maps
   if (p.epi_mode == 1) {
     if (encode_matrix_map(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;

@@ -467,10 +467,6 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
   // the per-block prologue (group statistics, folded scale / offset per channel) is amortised over ppb pixels
   int ppb = PLa * (d.src0_is_op ? 64 : 32);
   while (ppb > PLa && static_cast<long>(d.B) * ((n_iter + ppb - 1) / ppb) < 8 * kNumSMs) ppb >>= 1;
-  // A/B knob (whole-step timing on one box): SGDM_GN_PPB_SHIFT = k scales the pixels per block by 2^k
-  static const int ppb_shift = getenv("SGDM_GN_PPB_SHIFT") ? atoi(getenv("SGDM_GN_PPB_SHIFT")) : 0;
-  if (ppb_shift > 0) ppb <<= ppb_shift;
-  if (ppb_shift < 0) ppb = ppb >> (-ppb_shift) > PLa ? ppb >> (-ppb_shift) : PLa;
   if (ppb > n_iter) ppb = n_iter;
   if ((reinterpret_cast<uintptr_t>(d.gamma) | reinterpret_cast<uintptr_t>(d.beta) | reinterpret_cast<uintptr_t>(d.film)) & 15 ||
       (d.film && (d.film_stride & 3)))
@@ -486,25 +482,16 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
     else if (d.resample == 1) return launch_pdl(gn_apply_kernel<false, 1, 3, true>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
     else return launch_pdl(gn_apply_kernel<false, 2, 3, true>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
   }
-  // Resident blocks per SM of the plain (no resample) instances: 3 x 256 threads without spills, or 4 at 64
-  // registers with ~200 bytes of spills per thread.  Measured on B200 (config 2, batch 256, same box):
-  // 3 blocks: gn_apply 10.4 -> 9.5 ms per step, the large launches at 6.3 TB/s.  SGDM_GN_OCC=4: A/B switch.
-  static const int occ = getenv("SGDM_GN_OCC") ? atoi(getenv("SGDM_GN_OCC")) : 3;
-  if (d.resample == 0 && occ == 3) {
-    if (d.src0_is_op) return launch_pdl(gn_apply_kernel<true, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
-    else return launch_pdl(gn_apply_kernel<false, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
-    return SGDM_LAUNCH_OK();
-  }
+  // Three resident blocks of 256 threads per SM, spill-free (four at 64 registers spill ~200 bytes per thread:
+  // measured on B200, config 2 at batch 256, same box: gn_apply 10.4 -> 9.5 ms per step with three).
   if (d.src0_is_op) {
-    if (d.resample == 0) return launch_pdl(gn_apply_kernel<true, 0, 4>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+    if (d.resample == 0) return launch_pdl(gn_apply_kernel<true, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
     else if (d.resample == 1) return launch_pdl(gn_apply_kernel<true, 1, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
     else return launch_pdl(gn_apply_kernel<true, 2, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
-  } else {
-    if (d.resample == 0) return launch_pdl(gn_apply_kernel<false, 0, 4>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
-    else if (d.resample == 1) return launch_pdl(gn_apply_kernel<false, 1, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
-    else return launch_pdl(gn_apply_kernel<false, 2, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
   }
-  return SGDM_LAUNCH_OK();
+  if (d.resample == 0) return launch_pdl(gn_apply_kernel<false, 0, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+  else if (d.resample == 1) return launch_pdl(gn_apply_kernel<false, 1, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
+  return launch_pdl(gn_apply_kernel<false, 2, 3>, grid, dim3(threads), 0, s, 1, a) == cudaSuccess ? 0 : 1;
 }
 
 int gn_launch(const GnDesc& d, cudaStream_t s) {

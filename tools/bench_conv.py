@@ -64,28 +64,11 @@ SHAPES = {
     "conv 512->512 3x3 @16 B512": (512, 16, 512, 512, 3),
     "first 64->128 3x3 @64 B512": (512, 64, 64, 128, 3),
 }
-if os.environ.get("KNOBS"):
-    # mainloop experiments: ring depth and operand-reload knobs on one big layer
-    name = os.environ.get("KNOB_SHAPE", "conv 512->512 3x3 @16 B512")
-    B, H, Cin, Cout, ks = SHAPES[name]
-    knob_list = ((0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 1), (0, 2), (0, 3))
-    if os.environ.get("KNOB_FLAGS"):
-        knob_list = tuple((0, int(f)) for f in os.environ["KNOB_FLAGS"].split(","))
-    for stages, flags in knob_list:
-        L.sgdm_debug_set_conv_knobs(stages, flags)
-        for pair in ((-1,) if Cout == 128 else (0, 1)):
-            print(f"stages<={stages} flags={flags}", end="  ")
-            run(name, B, H, Cin, Cout, ks, "op", False, False, pair)
-    L.sgdm_debug_set_conv_knobs(0, 0)
-    sys.exit(0)
 if os.environ.get("RESIDUAL"):
-    # residual-epilogue experiments: fp32 out + residual + statistics, optional ring-depth cap (EXP_STAGES);
-    # combine with SGDM_MAX_EPI_BUFS (read once per process)
-    L.sgdm_debug_set_conv_knobs(int(os.environ.get("EXP_STAGES", "0")), 0)
+    # residual-epilogue experiments: fp32 out + residual + statistics
     for name in sys.argv[1:] or ["proj 512->512 1x1 @16 B512", "conv 128->128 3x3 @64 B512", "conv 512->512 3x3 @16 B512"]:
         B, H, Cin, Cout, ks = SHAPES[name]
         run(name, B, H, Cin, Cout, ks, "f32", True, True, -1)
-    L.sgdm_debug_set_conv_knobs(0, 0)
     sys.exit(0)
 if os.environ.get("HALO"):
     SHAPES["last 128->3 3x3 @64 B512"] = (512, 64, 128, 3, 3)
