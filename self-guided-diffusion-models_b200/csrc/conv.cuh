@@ -127,6 +127,9 @@ inline bool conv_can_swap(const ConvDesc& d) {
   return d.Cout == 128 && d.out_nchw == nullptr && !(d.res && d.res_mode == 2) && d.Wout <= 256 &&
          (256 % d.Wout) == 0 && ((HW % 256) == 0 || (256 % HW) == 0);
 }
+// (Measured, round 2: NOT swapping the one layer that is pure epilogue — the first conv as a K = 64 GEMM — in the hope
+//  that the thread-per-row epilogue is cheaper: 0.484 -> 0.534 ms.  Swap-AB stays the policy for every Cout = 128 layer.)
+inline bool conv_should_swap(const ConvDesc& d) { return conv_can_swap(d); }
 
 // CTA pairs need two m-tiles to share a weight tile of >= 64 output channels (each CTA stages block_n/2 rows).
 inline bool conv_pair_ok(const ConvDesc& d) { return !d.swap_ab && d.block_n >= 64 && (d.block_n % 32) == 0; }

@@ -695,7 +695,7 @@ struct Builder {
   void conv(ConvDesc d, int real_cin = 0) {
     d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
-    d.swap_ab = conv_can_swap(d) ? 1 : 0;
+    d.swap_ab = conv_should_swap(d) ? 1 : 0;
     d.stat_gran = stat_gran();
     // geometry (pair / halo / 32-channel K blocks / A-stationary): the kernel's own policy (conv.cuh, conv_prepare)
     if (d.hfold) { d.halo = 1; d.pair = 0; }
@@ -1481,7 +1481,7 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
   d.ks = ks; d.stride = stride; d.pad = ks == 3 ? 1 : 0; d.Hout = Hout; d.Wout = Wout; d.Cout = Cout;
   d.bias = bias; d.res = res; d.res_mode = res_mode; d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
   d.out_nchw = out_nchw; d.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
-  d.swap_ab = (block_n <= 0 && conv_can_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
+  d.swap_ab = (block_n <= 0 && conv_should_swap(d)) ? 1 : 0;  // block_n 0 = the engine's policy (incl. swap-AB)
   d.pair = g_conv_pair;
   d.timing = g_conv_timing;
   d.halo = g_conv_halo;
