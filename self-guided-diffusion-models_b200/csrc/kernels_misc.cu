@@ -153,6 +153,9 @@ struct GnApplyArgs {
   op_t* out; op_t* raw_out; float* pool_out;
 };
 
+// (Measured, round 2: doing this reduction in the prologue of every gn_apply block instead of a separate launch —
+//  49 launches of ~14 us per step — costs more than it saves at batch 256: gn_apply + finalise 10.2 -> 11.4 ms, the
+//  two dependent L2 round trips sit in front of every block's first load; config 1 gains 0.13 ms.  Not kept.)
 // Fused-statistics path: reduce the conv epilogue's partial sums (per 32-row block and channel
 // granule, see ConvDesc::stats) to {mean, rstd} per (sample, group).  One block per sample, one thread
 // per channel granule walking the sample's row blocks (consecutive threads read consecutive float2:
