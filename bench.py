@@ -372,7 +372,7 @@ def main():
     ld_w, ld_k = make_ld(args.warmup), make_ld(K)
     trajectory(ld_w, args.warmup)
     reps = 1
-    if K <= 25:
+    if K <= 25 and not args.ncu:
         trajectory(ld_k, K)
         if not args.steps:
             reps = -(-100 // K)

@@ -133,6 +133,13 @@ int sgdm_dyn_threshold(void* stream, int kind, const float* eps_c, const float* 
  * n_terms <= 4; `terms` and `coefs` are HOST arrays (of device pointers / floats). */
 int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const float* coefs, float div, float* out,
                  int64_t n);
+/* out = scale * (sum_k coefs[k]*terms[k]) — PNDM's multistep form `(1 / 24) * (55 e1 - 59 e2 + 37 e3 - 9 e4)`
+ * (diffusion/sampler/pndm_sampler.py:118-127) */
+int sgdm_lincomb_scaled(void* stream, int n_terms, const float* const* terms, const float* coefs, float scale, float* out,
+                        int64_t n);
+/* PNDM transfer x_next = x + d * (A * x - B * et) with separately rounded fp32 operations
+ * (PNDMScheduler.transfer, diffusion/sampler/pndm_sampler.py:128-141); d, A, B: host-computed fp32 scalars */
+int sgdm_pndm_transfer(void* stream, const float* x, const float* et, float d, float A, float B, float* out, int64_t n);
 int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
 
 /* Per-launch timing of one forward (bench.py roofline): with profiling on, the next forward

@@ -155,6 +155,49 @@ def plms_sample(eps_fn, tape, alphas_cumprod, num_ddpm, sampling_kwargs):
     return x, out
 
 
+def pndm_sample(eps_fn, tape, num_ddpm, sampling_kwargs, beta_start=1e-4, beta_end=2e-2):
+    """PNDM_Sampler.pndm_sampling + PNDMScheduler (diffusion/sampler/pndm_sampler.py:13-141,187-211): float32
+    `np.linspace` betas (NOT the DDPM's sqrt-linear schedule), float32 cumprod with a trailing 0.0, four Runge-Kutta
+    warm-up stages x 3, then the 4-term linear multistep; only x_T is drawn."""
+    n = sampling_kwargs["num_timesteps"]
+    betas = np.linspace(beta_start, beta_end, num_ddpm, dtype=np.float32)
+    ac = torch.from_numpy(np.array(list(np.cumprod(1.0 - betas, axis=0)) + [0.0], dtype=np.float32))
+    step = num_ddpm // n
+    times = list(range(0, num_ddpm, step))
+    w = np.array(times[-4:]).repeat(2) + np.tile(np.array([0, step // 2]), 4)
+    warm = list(reversed(w[:-1].repeat(2)[1:-1]))
+    steps = list(reversed(times[:-3]))
+
+    def transfer(x, t, t_next, et):
+        at, at_next = ac[t + 1].view(-1, 1, 1, 1), ac[t_next + 1].view(-1, 1, 1, 1)
+        x_delta = (at_next - at) * ((1 / (at.sqrt() * (at.sqrt() + at_next.sqrt()))) * x
+                                    - 1 / (at.sqrt() * (((1 - at_next) * at).sqrt() + ((1 - at) * at_next).sqrt())) * et)
+        return x + x_delta
+
+    image = tape["x_T"].clone()
+    b = image.shape[0]
+    cur_residual, cur_image, ets = 0, None, []
+    for t in range(len(warm)):
+        residual = eps_fn(image, torch.full((b,), int(warm[t]), dtype=torch.long))
+        t_prev, t_next = warm[t // 4 * 4], warm[min(t + 1, len(warm) - 1)]
+        if t % 4 == 0:
+            cur_residual = cur_residual + 1 / 6 * residual
+            ets.append(residual)
+            cur_image = image
+        elif (t - 1) % 4 == 0 or (t - 2) % 4 == 0:
+            cur_residual = cur_residual + 1 / 3 * residual
+        else:
+            residual = cur_residual + 1 / 6 * residual
+            cur_residual = 0
+        image = transfer(cur_image, t_prev, t_next, residual)
+    for t in range(len(steps)):
+        t_prev, t_next = steps[t], steps[min(t + 1, len(steps) - 1)]
+        ets.append(eps_fn(image, torch.full((b,), int(steps[t]), dtype=torch.long)))
+        residual = (1 / 24) * (55 * ets[-1] - 59 * ets[-2] + 37 * ets[-3] - 9 * ets[-4])
+        image = transfer(image, t_prev, t_next, residual)
+    return image, dict(pred_x0=image.unsqueeze(0), x_inter=image.unsqueeze(0))
+
+
 def p_sample_loop(method, eps_fn, tape, diffusion_cfg, sampling_kwargs):
     """LatentDiffusion.p_sample_loop (diffusion/ddpm.py:108-122): dispatch + uint8."""
     T = diffusion_cfg["num_timesteps"]
@@ -172,6 +215,9 @@ def p_sample_loop(method, eps_fn, tape, diffusion_cfg, sampling_kwargs):
         x, inter = ddim_sample(eps_fn, tape, tables["alphas_cumprod"], T, sampling_kwargs)
     elif method == "plms":
         x, inter = plms_sample(eps_fn, tape, tables["alphas_cumprod"], T, sampling_kwargs)
+    elif method == "pndm":
+        x, inter = pndm_sample(eps_fn, tape, T, sampling_kwargs, diffusion_cfg.get("linear_start", 1e-4),
+                               diffusion_cfg.get("linear_end", 2e-2))
     else:
         raise KeyError(method)
     inter = dict(inter)

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "sgdm_ddpm_step_ex": (_i, [_vp, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _i, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "sgdm_dyn_threshold": (_i, [_vp, _i, _vp, _vp, _d, _vp, _i, C.POINTER(_f), _vp, _d, _vp, _vp, _i, _i64]),
     "sgdm_lincomb": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_f), _f, _vp, _i64]),
+    "sgdm_lincomb_scaled": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_f), _f, _vp, _i64]),
+    "sgdm_pndm_transfer": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64]),
     "sgdm_to_uint8": (_i, [_vp, _vp, _vp, _i64]),
     "sgdm_set_graph_mode": (_i, [_vp, _i]),
     "sgdm_fingerprint": (_i, [_vp, _vp, _vp, _i, _vp]),

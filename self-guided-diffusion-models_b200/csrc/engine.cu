@@ -1456,6 +1456,17 @@ int sgdm_lincomb(void* stream, int n_terms, const float* const* terms, const flo
              ? fail("lincomb launch failed")
              : 0;
 }
+int sgdm_lincomb_scaled(void* stream, int n_terms, const float* const* terms, const float* coefs, float scale, float* out,
+                        int64_t n) {
+  ++g_launches;
+  return lincomb_launch(terms, coefs, n_terms, 1.f, out, n, static_cast<cudaStream_t>(stream), 1, scale)
+             ? fail("lincomb launch failed")
+             : 0;
+}
+int sgdm_pndm_transfer(void* stream, const float* x, const float* et, float d, float A, float B, float* out, int64_t n) {
+  ++g_launches;
+  return pndm_transfer_launch(x, et, d, A, B, out, n, static_cast<cudaStream_t>(stream)) ? fail("pndm transfer launch failed") : 0;
+}
 int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n) {
   ++g_launches;
   return to_uint8_launch(x, out, n, static_cast<cudaStream_t>(stream)) ? fail("to_uint8 launch failed") : 0;

@@ -150,7 +150,10 @@ int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const StepExtras& ex, 
 int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s);
 
 // out = (c0*a0 + c1*a1 + ...)/div, left to right (PLMS, ddim_plms_sampler.py:432-459)
-int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s);
+int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s,
+                   int use_scale = 0, float pre_scale = 1.f);
+// x_next = x + d * (A * x - B * et)   (PNDM transfer, pndm_sampler.py:128-141)
+int pndm_transfer_launch(const float* x, const float* et, float d, float A, float B, float* out, long n, cudaStream_t s);
 
 // ---- weight packing --------------------------------------------------------------------------
 // torch conv weight fp32 [Cout, Cin, ks, ks] -> op_t dst[co][k_off + (r*ks+s)*cin_pad + ci] (row length ktot);

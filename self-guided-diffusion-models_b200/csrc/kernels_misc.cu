@@ -1132,21 +1132,39 @@ int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s) 
 
 // PLMS multistep combination (ddim_plms_sampler.py:432-459): out = (c0 a0 + c1 a1 + ...) / div,
 // evaluated left to right with separately rounded products, like the unfused torch expression.
-struct LincombArgs { const float* a[4]; float c[4]; int n_terms; float div; };
+// (pre_scale: out = pre_scale * (sum), the form PNDM's `(1 / 24) * (55 e1 - 59 e2 + ...)` takes, pndm_sampler.py:125)
+struct LincombArgs { const float* a[4]; float c[4]; int n_terms; float div; float pre_scale; int use_scale; };
 __global__ void lincomb_kernel(const LincombArgs g, float* __restrict__ out, long n) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float acc = __fmul_rn(g.c[0], g.a[0][i]);
   for (int k = 1; k < g.n_terms; ++k) acc = __fadd_rn(acc, __fmul_rn(g.c[k], g.a[k][i]));
-  out[i] = __fdiv_rn(acc, g.div);
+  out[i] = g.use_scale ? __fmul_rn(g.pre_scale, acc) : __fdiv_rn(acc, g.div);
 }
-int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s) {
+int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s,
+                   int use_scale, float pre_scale) {
   if (n_terms < 1 || n_terms > 4) return 1;
   LincombArgs g;
   for (int k = 0; k < 4; ++k) { g.a[k] = k < n_terms ? a[k] : nullptr; g.c[k] = k < n_terms ? c[k] : 0.f; }
   g.n_terms = n_terms;
   g.div = div;
+  g.pre_scale = pre_scale;
+  g.use_scale = use_scale;
   lincomb_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(g, out, n);
+  return SGDM_LAUNCH_OK();
+}
+
+// PNDM transfer (pndm_sampler.py:128-141, Eq. 9 of the PNDM paper): x_next = x + d * (A * x - B * et) with the
+// reference's separately rounded fp32 operations; d = a_next - a_t, A and B are its fp32 scalar sub-expressions.
+__global__ void pndm_transfer_kernel(const float* __restrict__ x, const float* __restrict__ et, float d, float A, float B,
+                                     float* __restrict__ out, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float xi = x[i];
+  out[i] = __fadd_rn(xi, __fmul_rn(d, __fsub_rn(__fmul_rn(A, xi), __fmul_rn(B, et[i]))));
+}
+int pndm_transfer_launch(const float* x, const float* et, float d, float A, float B, float* out, long n, cudaStream_t s) {
+  pndm_transfer_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, et, d, A, B, out, n);
   return SGDM_LAUNCH_OK();
 }
 

@@ -1,8 +1,8 @@
 """Drop-in for diffusion/ddpm.py `LatentDiffusion` (sampling half).
 
 Same constructor kwargs, `set_denoise_fn`, sampler registry and `p_sample_loop`
-(diffusion/ddpm.py:24-43,108-122).  Training (`p_losses`) and the alternative samplers
-('pndm', 'tero') are out of scope of the hot path and raise.
+(diffusion/ddpm.py:24-43,108-122).  Training (`p_losses`) and the 'tero' sampler are out of scope of the hot path
+ and raise.
 """
 import copy
 
@@ -12,6 +12,7 @@ from torch import nn
 from ..diffusion_utils import clip_unnormalize_to_zero_to_255, dict2obj
 from .sampler.ddim_plms_sampler import DDIMSampler
 from .sampler.ddpm_sampler import Schedule_DDPM
+from .sampler.pndm_sampler import PNDM_Sampler
 
 
 class LatentDiffusion(nn.Module):
@@ -25,6 +26,9 @@ class LatentDiffusion(nn.Module):
                                 sampler_type="ddim"),
             "plms": DDIMSampler(ddpm_num_timesteps=self.hparams.num_timesteps, device=self.hparams.device,
                                 sampler_type="plms"),
+            "pndm": PNDM_Sampler(ddpm_num_timesteps=self.hparams.num_timesteps, beta_start=self.hparams.linear_start,
+                                 beta_end=self.hparams.linear_end, beta_schedule=self.hparams.beta_schedule,
+                                 device=self.hparams.device),
         }
 
     def set_denoise_fn(self, denoise_fn, denoise_sample_fn):

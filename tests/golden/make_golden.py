@@ -285,6 +285,10 @@ TRAJ = {
         "native250": ("native", 250, dict(num_timesteps=250)),
         "ddim250_eta0": ("ddim", 1000, dict(num_timesteps=250, ddim_eta=0.0)),
     }),
+    # PNDM (pndm_sampler.py): 12 Runge-Kutta warm-up evaluations + 7 multistep ones for num_timesteps = 10
+    "traj_cfg1_pndm": ("cfg1_cifar_label", 16, {
+        "pndm10": ("pndm", 1000, dict(num_timesteps=10)),
+    }),
     "traj_cfg4": ("cfg4_voc_clusterlayout", 2, {
         "ddim10_eta0": ("ddim", 1000, dict(num_timesteps=10, ddim_eta=0.0)),
     }),
@@ -316,7 +320,7 @@ def gen_trajectories(tname):
         skw.update(over)
         kw = prepare_denoise_fn_kwargs_4sampling(FakeModule(cfg), dict(data), skw, cond_scale=2.0)
         S = skw["num_timesteps"]
-        n_draws = S + 1 if method == "plms" else S
+        n_draws = S + 1 if method == "plms" else 0 if method == "pndm" else S
         tape = synthetic.noise_tape(shape, n_draws, seed=1234)
         real_randn = torch.randn
         torch.randn = Tape(tape)
@@ -331,11 +335,12 @@ def gen_trajectories(tname):
         assert used == 1 + n_draws, (rname, used)
         arrays[f"{rname}_samples"] = samples.numpy()
         arrays[f"{rname}_pred_x0"] = inter["pred_x0"].numpy()
-        arrays[f"{rname}_x_inter"] = inter["x_inter"].numpy()
+        if "x_inter" in inter:  # (PNDM returns dict(pred_x0=image) only)
+            arrays[f"{rname}_x_inter"] = inter["x_inter"].numpy()
         for k, v in kw.items():
             if torch.is_tensor(v):
                 arrays["kw_" + k] = v.numpy()
-        print(tname, rname, tuple(samples.shape), tuple(inter["x_inter"].shape), f"{time.time() - t0:.1f}s",
+        print(tname, rname, tuple(samples.shape), tuple(inter["pred_x0"].shape), f"{time.time() - t0:.1f}s",
               "mean", samples.float().mean().item(), flush=True)
     arrays["meta"] = np.frombuffer(json.dumps(dict(
         runs={k: [v[0], v[1], v[2]] for k, v in runs.items()}, batch=batch, tape_seed=1234, data_seed=21,

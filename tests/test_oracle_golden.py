@@ -130,6 +130,7 @@ def test_sampling_matches_reference(run):
 
 
 @pytest.mark.parametrize("tname,run", [("traj_cfg1", "ddim10_eta0"), ("traj_cfg1", "native10"), ("traj_cfg1", "plms10"),
+                                       ("traj_cfg1_pndm", "pndm10"),
                                        ("traj_cfg4", "ddim10_eta0"), ("traj_cfg5", "ddim10_eta0")])
 def test_named_config_trajectories_match_reference(tname, run):
     """The oracle on the trajectory goldens of the NAMED BASELINE configs (config 1 exactly as stated: 32x32, B=16,
@@ -145,7 +146,7 @@ def test_named_config_trajectories_match_reference(tname, run):
     skw = dict(ddim_eta=0.0, log_num_per_prog=10, clip_denoised=True, dtp=1, temperature=1.0, noise_dropout=0)
     skw.update(over)
     S = skw["num_timesteps"]
-    tape = synthetic.noise_tape((B, 3, H, H), S + 1 if method == "plms" else S, seed=meta["tape_seed"])
+    tape = synthetic.noise_tape((B, 3, H, H), S + 1 if method == "plms" else 0 if method == "pndm" else S, seed=meta["tape_seed"])
     eps_fn = lambda x, t: ounet.forward_with_cond_scale(sd, cfg, x, t, meta["cond_scale"], **kw)
     torch.set_num_threads(8)
     with torch.no_grad():
@@ -153,7 +154,8 @@ def test_named_config_trajectories_match_reference(tname, run):
     ref_u8 = torch.from_numpy(g[f"{run}_samples"])
     diff = (u8.int() - ref_u8.int()).abs()
     assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 0.01
-    assert rel_l2(inter["x_inter"], torch.from_numpy(g[f"{run}_x_inter"])) < 1e-4
+    if f"{run}_x_inter" in g:  # (PNDM returns no x_inter)
+        assert rel_l2(inter["x_inter"], torch.from_numpy(g[f"{run}_x_inter"])) < 1e-4
 
 
 @pytest.mark.parametrize("name", UNET_CASES)
