@@ -7,6 +7,12 @@ reference does; nothing here touches the GPU kernels (bit-exact by construction)
 """
 
 
+# every method whose condition is one [B, cond_dim] vector per sample passed through unchanged (condition.py:20-36):
+# the UNet sees them exactly like `label` / `cluster` (README.md:32,59 runs `attr` on unetca_fast)
+_VECTOR_METHODS = ["label", "attr", "feat", "knn_feat", "patchfeat", "centroid", "labelcentroid", "cluster", "clustermix",
+                   "clusterrandom", "labelcluster", "patchcluster"]
+
+
 def prepare_condition_kwargs(pl_module, batch_data):
     condition_method = pl_module.hparams.condition_method
     if condition_method is not None:
@@ -18,7 +24,7 @@ def prepare_condition_kwargs(pl_module, batch_data):
     dev = pl_module.device
     if condition_method is None:
         result.update(cond=None)
-    elif condition_method in ["label", "cluster"]:
+    elif condition_method in _VECTOR_METHODS:
         result.update(cond=batch_data[condition_method])
     elif condition_method in ["clusterlayout"]:
         how = pl_module.hparams.condition.clusterlayout.how
@@ -36,10 +42,10 @@ def prepare_condition_kwargs(pl_module, batch_data):
 def prepare_denoise_fn_kwargs_4sampling(pl_module, batch_data, sampling_kwargs, cond_scale):
     method = pl_module.hparams.condition_method
     if sampling_kwargs.get("random_sample_condition", False):
-        if method in ("label", "cluster"):
-            batch_data[method] = batch_data[method + "_random"]  # condition.py:104-110
+        if method in ("label", "cluster", "centroid", "knn_feat"):
+            batch_data[method] = batch_data[method + "_random"]  # randomsample_cond, condition.py:96-118
         else:
-            raise RuntimeError("random_sample_condition is only defined for label / cluster")
+            raise RuntimeError("random_sample_condition is not defined for condition_method=%s (condition.py:120-134)" % method)
     kw = prepare_condition_kwargs(pl_module, batch_data)
     kw.update(dict(cond_scale=cond_scale))
     kw.pop("cond_drop_prob")
