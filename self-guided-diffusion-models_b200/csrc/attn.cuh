@@ -20,5 +20,8 @@ int attn_launch(const AttnDesc& a, cudaStream_t s);
 // tcgen05 / TMEM self-attention for T = 256, D = 64 with q, k, v as column blocks of one packed matrix
 bool attn_tc_applicable(const AttnDesc& a);
 int attn_tc_launch(const AttnDesc& a, cudaStream_t s);
+// tcgen05 / TMEM Attention_LR: multi-query (one shared k / v head) over T = 256 self keys + <= 32 extra keys, D = 64
+bool attn_lr_tc_applicable(const AttnDesc& a);
+int attn_lr_tc_launch(const AttnDesc& a, cudaStream_t s);
 
 }  // namespace sgdm

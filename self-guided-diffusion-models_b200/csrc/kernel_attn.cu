@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
 
 int attn_launch(const AttnDesc& a, cudaStream_t s) {
   if (a.use_tc != 0 && attn_tc_applicable(a)) return attn_tc_launch(a, s);
+  if (a.use_tc != 0 && attn_lr_tc_applicable(a)) return attn_lr_tc_launch(a, s);
   const int Tkv = a.n_extra + a.T;
   const int tkv_pad = (Tkv + 63) / 64 * 64;
   if (a.D != 32 && a.D != 64 && a.D != 128) return 1;  // head dims of the reference configs (mc 64 / 128 / 256, 8 heads)
