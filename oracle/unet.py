@@ -239,7 +239,8 @@ def param_shapes(cfg):
     ca = cfg["kind"] == "unetca_fast"
     out = []
     add = lambda n, *shape: out.append((n, tuple(shape)))
-    if cd > 0 or ca:
+    has_cond = cd > 0 if not ca else cfg["cond_token_num"] > 0
+    if has_cond:
         add("null_cond_emb", 1, cd)
     if L > 0:
         add("null_layout_emb", 1, 1, H, H)
@@ -255,6 +256,9 @@ def param_shapes(cfg):
         add("norm_cond.weight", ctx); add("norm_cond.bias", ctx)
         add("to_time_tokens.0.weight", mc, mc); add("to_time_tokens.0.bias", mc)
         add("to_time_tokens.2.weight", ctx * 8, mc); add("to_time_tokens.2.bias", ctx * 8)
+        E = ted
+    if ca and has_cond:
+        ctx = cfg["context_dim"]
         add("cond_mlp.0.weight", ted, cd); add("cond_mlp.0.bias", ted)
         add("cond_mlp.2.weight", ted, ted); add("cond_mlp.2.bias", ted)
         add("to_cond_tokens.0.weight", ctx * 8, cd); add("to_cond_tokens.0.bias", ctx * 8)
@@ -325,6 +329,14 @@ def unet_forward(sd, cfg, x, timesteps, cond=None, layout=None, drop_mask=None, 
                 lm = torch.where(drop_mask[:, None, None, None], sd["null_layout_emb"], layout)
                 x = torch.cat((x, lm), dim=1)
             emb = torch.cat((emb, _mlp2(sd, "mlp_cond", cond_masked)), dim=-1)
+    elif cfg["cond_token_num"] == 0:
+        # no condition vector: the context is the time tokens, only the layout is guided (openaimodel_ca.py:944-958)
+        tt = _lin(sd, "to_time_tokens.2", F.silu(_lin(sd, "to_time_tokens.0", t_emb)))
+        context = tt.reshape(b, 8, cfg["context_dim"])
+        if method == "layout":
+            lm = torch.where(drop_mask[:, None, None, None], sd["null_layout_emb"], layout)
+            x = torch.cat((x, lm), dim=1)
+        context = F.layer_norm(context, context.shape[-1:], sd["norm_cond.weight"], sd["norm_cond.bias"])
     else:
         assert cfg["cond_token_num"] == 1 and cond.dim() == 2  # openaimodel_ca.py:960-961
         tt = _lin(sd, "to_time_tokens.2", F.silu(_lin(sd, "to_time_tokens.0", t_emb)))

@@ -276,8 +276,10 @@ int build_topology(sgdm_engine* e) {
   if (c.kind != SGDM_KIND_UNET_FAST && c.kind != SGDM_KIND_UNETCA_FAST) return fail("unknown kind %d", c.kind);
   if (mc % 64) return fail("model_channels must be a multiple of 64 (got %d)", mc);
   if (c.n_channel_mult < 1 || c.n_channel_mult > 8) return fail("bad channel_mult");
-  if (e->ca && (c.cond_token_num != 1 || c.context_dim <= 0 || c.cond_dim <= 0))
-    return fail("unetca_fast: only cond_token_num == 1 with context_dim > 0 is supported (openaimodel_ca.py:960)");
+  // unetca_fast: cond_token_num 1 (a [B, cond_dim] condition: cluster / attr / stego_attr ...) or 0 (no condition
+  // vector: the `layout`-only model, cond_dim == 0, openaimodel_ca.py:562-564,944-958)
+  if (e->ca && (c.context_dim <= 0 || !((c.cond_token_num == 1 && c.cond_dim > 0) || (c.cond_token_num == 0 && c.cond_dim == 0))))
+    return fail("unetca_fast: cond_token_num must be 1 (with cond_dim > 0) or 0 (with cond_dim == 0), and context_dim > 0");
   if (!e->ca && c.layout_dim > 1) return fail("unet_fast supports clusterlayout (layout_dim 1) only (openaimodel.py:623)");
   if (c.precision != 0 && c.precision != 1) return fail("precision must be 0 (fp16 operands) or 1 (split fp16 x3), got %d", c.precision);
   e->x3 = c.precision == 1;
@@ -306,7 +308,8 @@ int build_topology(sgdm_engine* e) {
     e->E = ted + (c.cond_dim > 0 ? ted / 2 : 0);
   } else {
     const int ctx = c.context_dim;
-    add_param(e, "null_cond_emb", {1, c.cond_dim});
+    const bool has_cond = c.cond_token_num > 0;
+    if (has_cond) add_param(e, "null_cond_emb", {1, c.cond_dim});
     if (c.layout_dim > 0) add_param(e, "null_layout_emb", {1, 1, c.image_size, c.image_size});
     add_param(e, "time_embed.0.weight", {ted, mc});
     add_param(e, "time_embed.0.bias", {ted});
@@ -318,23 +321,25 @@ int build_topology(sgdm_engine* e) {
     add_param(e, "to_time_tokens.0.bias", {mc});
     add_param(e, "to_time_tokens.2.weight", {ctx * 8, mc});
     add_param(e, "to_time_tokens.2.bias", {ctx * 8});
-    add_param(e, "cond_mlp.0.weight", {ted, c.cond_dim});
-    add_param(e, "cond_mlp.0.bias", {ted});
-    add_param(e, "cond_mlp.2.weight", {ted, ted});
-    add_param(e, "cond_mlp.2.bias", {ted});
-    add_param(e, "to_cond_tokens.0.weight", {ctx * 8, c.cond_dim});
-    add_param(e, "to_cond_tokens.0.bias", {ctx * 8});
-    // to_cond_tokens_2d is built by the reference for every cond_token_num > 0 but only used
-    // when cond_token_num > 1 (openaimodel_ca.py:605-614,998): accepted, never read.
-    const int mid = static_cast<int>(sqrt(static_cast<double>(ctx) * c.cond_dim));
-    add_param(e, "to_cond_tokens_2d.0.weight", {mid, c.cond_dim});
-    add_param(e, "to_cond_tokens_2d.0.bias", {mid});
-    add_param(e, "to_cond_tokens_2d.2.weight", {mid, mid});
-    add_param(e, "to_cond_tokens_2d.2.bias", {mid});
-    add_param(e, "to_cond_tokens_2d.4.weight", {mid, mid});
-    add_param(e, "to_cond_tokens_2d.4.bias", {mid});
-    add_param(e, "to_cond_tokens_2d.6.weight", {ctx, mid});
-    add_param(e, "to_cond_tokens_2d.6.bias", {ctx});
+    if (has_cond) {
+      add_param(e, "cond_mlp.0.weight", {ted, c.cond_dim});
+      add_param(e, "cond_mlp.0.bias", {ted});
+      add_param(e, "cond_mlp.2.weight", {ted, ted});
+      add_param(e, "cond_mlp.2.bias", {ted});
+      add_param(e, "to_cond_tokens.0.weight", {ctx * 8, c.cond_dim});
+      add_param(e, "to_cond_tokens.0.bias", {ctx * 8});
+      // to_cond_tokens_2d is built by the reference for every cond_token_num > 0 but only used
+      // when cond_token_num > 1 (openaimodel_ca.py:605-614,998): accepted, never read.
+      const int mid = static_cast<int>(sqrt(static_cast<double>(ctx) * c.cond_dim));
+      add_param(e, "to_cond_tokens_2d.0.weight", {mid, c.cond_dim});
+      add_param(e, "to_cond_tokens_2d.0.bias", {mid});
+      add_param(e, "to_cond_tokens_2d.2.weight", {mid, mid});
+      add_param(e, "to_cond_tokens_2d.2.bias", {mid});
+      add_param(e, "to_cond_tokens_2d.4.weight", {mid, mid});
+      add_param(e, "to_cond_tokens_2d.4.bias", {mid});
+      add_param(e, "to_cond_tokens_2d.6.weight", {ctx, mid});
+      add_param(e, "to_cond_tokens_2d.6.bias", {ctx});
+    }
     e->E = ted;
   }
   e->in_ch_total = c.in_channels + c.layout_dim;
@@ -885,20 +890,20 @@ struct Builder {
     conv(c1);
     // context K/V rows of this site: produced for ALL sites by one launch in the prologue (context_kv_all)
     const int site = static_cast<int>(&w - e->attn_lr.data());
-    op_t* ck = static_cast<op_t*>(scratch("ctx_k" + std::to_string(site), static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
-    op_t* cv = static_cast<op_t*>(scratch("ctx_v" + std::to_string(site), static_cast<size_t>(Bp) * 17 * dh * sizeof(op_t)));
+    op_t* ck = static_cast<op_t*>(scratch("ctx_k" + std::to_string(site), static_cast<size_t>(Bp) * n_ctx_rows() * dh * sizeof(op_t)));
+    op_t* cv = static_cast<op_t*>(scratch("ctx_v" + std::to_string(site), static_cast<size_t>(Bp) * n_ctx_rows() * dh * sizeof(op_t)));
     op_t* att = static_cast<op_t*>(scratch("att", rows * inner * sizeof(op_t)));
     AttnDesc ad;
     ad.q = qkv; ad.q_row_stride = nq; ad.q_head_stride = dh;
     ad.k = dry ? nullptr : qkv + inner; ad.k_row_stride = nq; ad.k_head_stride = 0;
     ad.v = dry ? nullptr : qkv + inner + dh; ad.v_row_stride = nq; ad.v_head_stride = 0;
-    ad.k_extra = ck; ad.v_extra = cv; ad.n_extra = 17;
+    ad.k_extra = ck; ad.v_extra = cv; ad.n_extra = n_ctx_rows();
     ad.out = att; ad.o_row_stride = inner; ad.B = Bp; ad.T = T; ad.heads = e->heads; ad.D = dh;
     ad.scale = 1.0f / sqrtf(static_cast<float>(dh));
     push([ad](cudaStream_t s) {
       ++g_launches;
       return attn_launch(ad, s);
-    }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * (T + 17) * dh,
+    }, "attention", 4.0 * Bp * e->heads * static_cast<double>(T) * (T + n_ctx_rows()) * dh,
          static_cast<double>(rows) * (nq + inner) * 2);
     float* tmp = static_cast<float*>(scratch("tmpf", rows * C * sizeof(float)));
     ConvDesc c2;
@@ -950,6 +955,9 @@ struct Builder {
     conv(c);
     return o;
   }
+
+  // extra key / value rows of every Attention_LR site: 8 time tokens (+ 8 condition tokens) + the null key
+  int n_ctx_rows() const { return (e->cfg.cond_token_num > 0 ? 16 : 8) + 1; }
 
   // buffers shared across the walk
   float* emb_out = nullptr;
@@ -1019,28 +1027,32 @@ struct Builder {
       }
     } else {
       const int ctx = c.context_dim;
+      const bool has_cond = c.cond_token_num > 0;
       // cond_mlp ADDED to the time embedding (openaimodel_ca.py:594-598,976-977)
-      lin(cond_m, c.cond_dim, "cond_mlp.0", hid, ted, ted, c.cond_dim, 1, 0);
-      lin(hid, ted, "cond_mlp.2", emb, e->E, ted, ted, 0, 1);
-      // to_time_tokens / to_cond_tokens (:586-604,942,972)
+      if (has_cond) {
+        lin(cond_m, c.cond_dim, "cond_mlp.0", hid, ted, ted, c.cond_dim, 1, 0);
+        lin(hid, ted, "cond_mlp.2", emb, e->E, ted, ted, 0, 1);
+      }
+      // to_time_tokens / to_cond_tokens (:586-604,942,972); cond_token_num == 0: the context is the time tokens (:944-945)
       time_tokens = static_cast<float*>(scratch("time_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float)));
-      cond_tokens = static_cast<float*>(scratch("cond_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float)));
+      cond_tokens = has_cond ? static_cast<float*>(scratch("cond_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float))) : nullptr;
       lin(t_emb, mc, "to_time_tokens.0", hid, ted, mc, mc, 1, 0);
       lin(hid, ted, "to_time_tokens.2", time_tokens, 8 * ctx, 8 * ctx, mc, 0, 0);
-      lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
+      if (has_cond) lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
       // context K/V rows of every Attention_LR site (they depend on t / cond only): one launch, grid.y = sites
       CtxDesc cd;
       cd.time_tokens = time_tokens; cd.cond_tokens = cond_tokens;
       cd.norm_w = dry ? nullptr : e->f32["norm_cond.weight"]; cd.norm_b = dry ? nullptr : e->f32["norm_cond.bias"];
       cd.Bp = Bp; cd.ctx = ctx; cd.n_sites = static_cast<int>(e->attn_lr.size());
+      cd.n_tok = has_cond ? 16 : 8;
       if (cd.n_sites > kMaxCtxSites) { fail("too many Attention_LR sites (%d)", cd.n_sites); err = 1; return; }
       for (int i = 0; i < cd.n_sites; ++i) {
         const AttnLRW& w = e->attn_lr[i];
         cd.dh = w.dh;
         CtxSite& st = cd.site[i];
         st.ln_w = w.ctx_ln_w; st.ln_b = w.ctx_ln_b; st.lin_w = w.ctx_w; st.lin_b = w.ctx_b; st.null_kv = w.null_kv;
-        st.k_out = static_cast<op_t*>(scratch("ctx_k" + std::to_string(i), static_cast<size_t>(Bp) * 17 * w.dh * sizeof(op_t)));
-        st.v_out = static_cast<op_t*>(scratch("ctx_v" + std::to_string(i), static_cast<size_t>(Bp) * 17 * w.dh * sizeof(op_t)));
+        st.k_out = static_cast<op_t*>(scratch("ctx_k" + std::to_string(i), static_cast<size_t>(Bp) * n_ctx_rows() * w.dh * sizeof(op_t)));
+        st.v_out = static_cast<op_t*>(scratch("ctx_v" + std::to_string(i), static_cast<size_t>(Bp) * n_ctx_rows() * w.dh * sizeof(op_t)));
       }
       for (int i = 1; i < cd.n_sites; ++i)
         if (e->attn_lr[i].dh != e->attn_lr[0].dh) { fail("Attention_LR sites with different head dims"); err = 1; return; }

@@ -98,7 +98,7 @@ struct CtxSite {                       // per Attention_LR site
   const float* lin_w = nullptr;        // to_context.1 [2*dh, ctx]
   const float* lin_b = nullptr;        // [2*dh]
   const float* null_kv = nullptr;      // [2, dh]
-  op_t* k_out = nullptr;               // [Bp, 17, dh]
+  op_t* k_out = nullptr;               // [Bp, n_tok + 1, dh]
   op_t* v_out = nullptr;
 };
 struct CtxDesc {
@@ -107,6 +107,7 @@ struct CtxDesc {
   const float* norm_w = nullptr;       // norm_cond [ctx]
   const float* norm_b = nullptr;
   int Bp = 0, ctx = 32, dh = 64;
+  int n_tok = 16;                      // context tokens: 8 time (+ 8 condition); k_out / v_out have n_tok + 1 rows per sample
   int n_sites = 0;                     // all sites in one launch (grid.y)
   CtxSite site[kMaxCtxSites];
 };

@@ -895,16 +895,16 @@ __global__ void context_kv_kernel(const CtxDesc d) {
   extern __shared__ float sm[];
   const int ctx = d.ctx, dh = d.dh;
   const CtxSite& w = d.site[blockIdx.y];
-  float* tok = sm;            // [16][ctx]
-  const int n = blockIdx.x;
-  for (int i = threadIdx.x; i < 16 * ctx; i += blockDim.x) {
+  float* tok = sm;            // [n_tok][ctx]
+  const int n = blockIdx.x, nt = d.n_tok, rows = nt + 1;
+  for (int i = threadIdx.x; i < nt * ctx; i += blockDim.x) {
     const int t = i / ctx, j = i - t * ctx;
     tok[i] = t < 8 ? d.time_tokens[(static_cast<long>(n) * 8 + t) * ctx + j]
                    : d.cond_tokens[(static_cast<long>(n) * 8 + (t - 8)) * ctx + j];
   }
   __syncthreads();
   // two LayerNorms back to back (norm_cond, then to_context.0), one thread per token
-  if (threadIdx.x < 16) {
+  if (threadIdx.x < nt) {
     float* row = tok + threadIdx.x * ctx;
     for (int pass = 0; pass < 2; ++pass) {
       const float* g = pass == 0 ? d.norm_w : w.ln_w;
@@ -931,6 +931,7 @@ __global__ void context_kv_kernel(const CtxDesc d) {
       const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
+        if (t >= nt) break;
         const float4 tv = *reinterpret_cast<const float4*>(tok + t * ctx + j);
         acc[t] += tv.x * wv.x;
         acc[t] += tv.y * wv.y;
@@ -940,17 +941,18 @@ __global__ void context_kv_kernel(const CtxDesc d) {
     }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      if (o < dh) w.k_out[(static_cast<long>(n) * 17 + t) * dh + o] = to_op(acc[t]);
-      else w.v_out[(static_cast<long>(n) * 17 + t) * dh + (o - dh)] = to_op(acc[t]);
+      if (t >= nt) break;
+      if (o < dh) w.k_out[(static_cast<long>(n) * rows + t) * dh + o] = to_op(acc[t]);
+      else w.v_out[(static_cast<long>(n) * rows + t) * dh + (o - dh)] = to_op(acc[t]);
     }
   }
   for (int o = threadIdx.x; o < dh; o += blockDim.x) {
-    w.k_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(w.null_kv[o]);
-    w.v_out[(static_cast<long>(n) * 17 + 16) * dh + o] = to_op(w.null_kv[dh + o]);
+    w.k_out[(static_cast<long>(n) * rows + nt) * dh + o] = to_op(w.null_kv[o]);
+    w.v_out[(static_cast<long>(n) * rows + nt) * dh + o] = to_op(w.null_kv[dh + o]);
   }
 }
 int context_kv_launch(const CtxDesc& d, cudaStream_t s) {
-  if (d.n_sites < 1 || d.n_sites > kMaxCtxSites || (d.ctx % 4)) return 1;
+  if (d.n_sites < 1 || d.n_sites > kMaxCtxSites || (d.ctx % 4) || (d.n_tok != 8 && d.n_tok != 16)) return 1;
   context_kv_kernel<<<dim3(d.Bp, d.n_sites), 128, 16 * d.ctx * sizeof(float), s>>>(d);
   return SGDM_LAUNCH_OK();
 }

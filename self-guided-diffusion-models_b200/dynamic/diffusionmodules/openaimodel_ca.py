@@ -54,18 +54,23 @@ class UNetModel(EngineUNet):
         if dims != 2: unsupported.append("dims != 2")
         if not use_scale_shift_norm: unsupported.append("use_scale_shift_norm=False")
         if not use_ca_block: unsupported.append("use_ca_block=False")
-        if cond_token_num != 1: unsupported.append("cond_token_num != 1")
+        if cond_token_num > 1: unsupported.append("cond_token_num > 1")
         if context_dim is None: unsupported.append("context_dim=None")
         if num_head_channels != -1: unsupported.append("num_head_channels")
         if resblock_updown: unsupported.append("resblock_updown")
         if not conv_resample: unsupported.append("conv_resample=False")
         if use_fp16: unsupported.append("use_fp16")
-        if condition_method == "layout": unsupported.append("condition_method=layout")
         if unsupported:
             raise NotImplementedError(
                 "sgdm_b200 unetca_fast covers config/dynamic/unetca_fast.yaml with the README overrides "
-                "(cond_token_num=1, context_dim=32); not built: " + ", ".join(unsupported))
+                "(cond_token_num=1 or 0, context_dim=32); not built: " + ", ".join(unsupported))
+        if cond_token_num == 0:
+            assert cond_dim == 0  # openaimodel_ca.py:562-564: no condition vector (the `layout`-only / unconditional model)
+            if condition_method == "clusterlayout":
+                raise NotImplementedError  # openaimodel_ca.py:947-948
         layout_dim = 0
+        if condition_method in ["layout"]:
+            layout_dim = condition.layout.layout_dim  # openaimodel_ca.py:634-641
         if condition_method in ["clusterlayout"]:
             layout_dim = condition.clusterlayout.layout_dim  # openaimodel_ca.py:617-624
         if condition_method in ["stegoclusterlayout"]:
@@ -84,7 +89,8 @@ class UNetModel(EngineUNet):
             condition, condition_method, precision)
 
     def forward(self, x, timesteps=None, cond_drop_prob=0.0, cond=None, layout=None):
-        assert cond is not None and len(cond.shape) == 2  # openaimodel_ca.py:960-961
+        if self.cond_token_num == 1:
+            assert cond is not None and len(cond.shape) == 2  # openaimodel_ca.py:960-961
         return self._forward_impl(x, timesteps, cond, layout, cond_drop_prob)
 
     def forward_with_cond_scale(self, x, t, cond_scale, cond=None, layout=None):

@@ -32,6 +32,12 @@ def prepare_condition_kwargs(pl_module, batch_data):
         if key is None:
             raise RuntimeError(how)
         result.update(cond=batch_data["cluster"].float().to(dev), layout=batch_data[key].float().to(dev))
+    elif condition_method in ["layout"]:  # layout-only guidance: no condition vector (condition.py:60-76)
+        how = pl_module.hparams.condition.layout.how
+        key = {"lost": "lostbboxmask", "oracle": "segmask", "stego": "stegomask"}.get(how)
+        if key is None:
+            raise RuntimeError(how)
+        result.update(layout=batch_data[key].float().to(dev))
     elif condition_method in ["stegoclusterlayout"]:
         result.update(cond=batch_data["stego_attr"].float().to(dev), layout=batch_data["stegomask"].float().to(dev))
     else:

@@ -86,7 +86,7 @@ def synthetic_batch(condition_method, batch, cond_dim, image_size, layout_dim=0,
         mx = (ar[None, :] >= x0[:, None]) & (ar[None, :] <= x1[:, None])
         my = (ar[None, :] >= y0[:, None]) & (ar[None, :] <= y1[:, None])
         out["lostbboxmask"] = (my[:, :, None] & mx[:, None, :]).long()[:, None]
-    elif condition_method == "stegoclusterlayout":
+    elif condition_method in ("stegoclusterlayout", "layout"):
         k = layout_dim
         blk = max(H // 4, 1)
         cls = torch.randint(0, k, (batch, H // blk, H // blk), generator=g)

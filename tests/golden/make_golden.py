@@ -59,6 +59,12 @@ CASES = {
              num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
              resblock_updown=False, cond_dim=27, condition_method="stegoclusterlayout", layout_dim=27,
              context_dim=32, cond_token_num=1, scale_type="imagen"), 2),
+    # layout-only guidance (cond_token_num = 0, cond_dim = 0: the reference's test_unittest.py `condition_method=layout` runs)
+    "unetca_layout_tiny": (
+        dict(kind="unetca_fast", image_size=16, in_channels=3, out_channels=3, model_channels=64,
+             num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
+             resblock_updown=False, cond_dim=0, condition_method="layout", layout_dim=21,
+             context_dim=32, cond_token_num=0, scale_type="imagen"), 2),
     # BASELINE.json configs at their true shapes (batch kept small: CPU reference)
     "cfg1_cifar_label": (
         dict(kind="unet_fast", image_size=32, in_channels=3, out_channels=3, model_channels=64,
@@ -113,7 +119,7 @@ class FakeModule:
     def __init__(self, cfg):
         self.hparams = dict2obj(dict(
             cond_dim=cfg["cond_dim"], condition_method=cfg["condition_method"], cond_drop_prob=0.1,
-            condition=dict(clusterlayout=dict(how="lost"), layout=dict(how="lost"))))
+            condition=dict(clusterlayout=dict(how="lost"), layout=dict(how="stego"))))
         self.training = False
         self.device = torch.device("cpu")
 

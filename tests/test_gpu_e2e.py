@@ -425,6 +425,10 @@ def test_full_size_properties_cfg2():
     # -> bit-identical results however the samples are batched (fixed reduction orders everywhere)
     sub = m.forward_with_cond_scale(x[5:9].contiguous(), t[5:9].contiguous(), 2.0, cond=cond[5:9].contiguous())
     assert torch.equal(sub, e1[5:9]), f"batch-composition dependence: rel_l2 {rel_l2(sub.cpu(), e1[5:9].cpu()):.3e}"
+    # ragged / minimal batches (odd tile counts in every conv geometry, a single sample): same bits again
+    for lo, hi in ((0, 1), (9, 12), (17, 24)):
+        sub = m.forward_with_cond_scale(x[lo:hi].contiguous(), t[lo:hi].contiguous(), 2.0, cond=cond[lo:hi].contiguous())
+        assert torch.equal(sub, e1[lo:hi]), f"batch {hi - lo}: rel_l2 {rel_l2(sub.cpu(), e1[lo:hi].cpu()):.3e}"
     # the first two samples are the golden inputs? no - but CFG linearity must hold exactly:
     c = m.forward_with_cond_scale(x, t, 1, cond=cond)
     u = m.forward_with_cond_scale(x, t, 0, cond=cond)
