@@ -146,8 +146,8 @@ int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
  * brackets every launch of its plan with CUDA events on `stream` and synchronises at the end.
  * Each record: kernel family, measured ms, algorithmic FLOPs and algorithmic HBM bytes. */
 /* CUDA-graph replay of a plan's static launch list (captured once per plan on first use; the prologue that reads
- * the caller's inputs stays outside): -1 = policy (launch-bound plans only: at most 256 Ki pixel rows), 0 = off,
- * 1 = on.  Same kernels, same order, same values as the stream replay. */
+ * the caller's inputs stays outside): -1 = policy (every plan; falls back to stream replay if the capture fails),
+ * 0 = off, 1 = on (a failed capture is an error).  Same kernels, same order, same values as the stream replay. */
 int sgdm_set_graph_mode(sgdm_handle h, int mode);
 /* dev_out[t] = order-independent 64-bit hash of the bit pattern of the n fp32 tensors whose device pointers /
  * element counts are in the DEVICE arrays dev_ptrs / dev_numel.  One launch: lets the host detect parameter writes
