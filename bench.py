@@ -242,7 +242,7 @@ def cpu_reference_arm(c, steps, warmup, batch, threads=None):
     return dict(value=value, ms_per_step=ms, cores=cores, batch=batch, sample=sample + f", after a {max(warmup, 2) if warmup else 0}-step warm-up")
 
 
-def build_gpu_model(c, device):
+def build_gpu_model(c, device, precision="fp16"):
     """The drop-in UNet with the same seeded weights the CPU arm uses (inventory from the module itself)."""
     import torch
     from types import SimpleNamespace as NS
@@ -257,7 +257,7 @@ def build_gpu_model(c, device):
                   attention_resolutions=cfg["attention_resolutions"], num_res_blocks=cfg["num_res_blocks"],
                   channel_mult=cfg["channel_mult"], num_heads=cfg["num_heads"], use_scale_shift_norm=True,
                   use_checkpoint=False, use_fp16=False, cond_dim=cfg["cond_dim"], condition_method=cfg["condition_method"],
-                  condition=condition)
+                  condition=condition, precision=precision)
     if cfg["kind"] == "unet_fast":  # kwargs of config/dynamic/unet_fast.yaml
         m = openaimodel.UNetModel(dropout=0.1, resblock_updown=True, **common)
     else:  # config/dynamic/unetca_fast.yaml + README overrides
@@ -279,6 +279,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch per GPU; strong: the config's total batch (cfg3: 256, cfg5: 1024) split over the GPUs")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak) / total batch (strong); 0 = the config's")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3"],
+                    help="engine precision mode (fp16x3 = split operands, ~3x the tensor work; parity mode, not the headline)")
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline steps (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,7 +345,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.lib()
-    model = build_gpu_model(c, device)
+    model = build_gpu_model(c, device, args.precision)
+    config["precision"] = args.precision
     # this rank's shard of the synthetic conditions, resident on the device
     kw_host = condition_tensors(c, B, 4321 + rank)
     kw = {k: v.to(device) for k, v in kw_host.items()}
@@ -528,7 +531,8 @@ def main():
         config["timed_trajectories"] = reps
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K * reps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
-                    dtype=f"{lib.sgdm_operand_dtype().decode()} operands, f32 accumulate / residual stream / sampler state",
+                    dtype=f"{lib.sgdm_operand_dtype().decode()} operands" + (" (split hi+lo, 3 products)" if args.precision == "fp16x3" else "")
+                          + ", f32 accumulate / residual stream / sampler state",
                     data="synthetic", config=config, clocks=clk, e2e=e2e,
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
