@@ -380,6 +380,22 @@ def main():
         if not args.steps:
             reps = -(-100 // K)
     barrier()
+    # ---- cross-check in round 1's protocol (a 20-step trajectory right after the warm-up, i.e. before the power cap
+    #      has pulled the clocks down): reported beside the headline so that the two rounds can be compared like for like
+    first20 = None
+    if K > 40 and not args.ncu:
+        ld_20 = make_ld(20)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record(stream)
+        trajectory(ld_20, 20)
+        s1.record(stream)
+        barrier()
+        t20 = torch.tensor([s0.elapsed_time(s1) / 20], device=device)
+        if world > 1:
+            dist.all_reduce(t20, op=dist.ReduceOp.MAX)
+        first20 = dict(steps=20, ms_per_step=float(t20.item()), value=total / (c["steps"] * float(t20.item()) / 1e3),
+                       note="round 1's protocol: 20 steps after a 3-step warm-up (clocks not yet settled under the power cap)")
     # ---- timed region: one K-step trajectory of the whole job
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -529,6 +545,8 @@ def main():
 
     if rank == 0:
         config["timed_trajectories"] = reps
+        if first20 is not None:
+            config["first_20_steps"] = first20
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K * reps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                     dtype=f"{lib.sgdm_operand_dtype().decode()} operands" + (" (split hi+lo, 3 products)" if args.precision == "fp16x3" else "")
