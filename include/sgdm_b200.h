@@ -145,6 +145,10 @@ int sgdm_to_uint8(void* stream, const float* x, uint8_t* out, int64_t n);
 /* Per-launch timing of one forward (bench.py roofline): with profiling on, the next forward
  * brackets every launch of its plan with CUDA events on `stream` and synchronises at the end.
  * Each record: kernel family, measured ms, algorithmic FLOPs and algorithmic HBM bytes. */
+/* Guided plans compute the part of the network the conditional and the unconditional half have in common (the first
+ * conv and the first ResBlock's GroupNorm + conv: identical x, no embedding yet) once for B rows instead of 2B
+ * (models without a layout input).  Same bits.  Default on; 0 switches it off for plans used afterwards (A/B, tests). */
+int sgdm_set_share_prefix(sgdm_handle h, int on);
 /* CUDA-graph replay of a plan's static launch list (captured once per plan on first use; the prologue that reads
  * the caller's inputs stays outside): -1 = policy (every plan; falls back to stream replay if the capture fails),
  * 0 = off, 1 = on (a failed capture is an error).  Same kernels, same order, same values as the stream replay. */

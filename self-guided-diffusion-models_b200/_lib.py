@@ -69,6 +69,7 @@ PROTOTYPES = {
     "sgdm_pndm_transfer": (_i, [_vp, _vp, _vp, _f, _f, _f, _vp, _i64]),
     "sgdm_to_uint8": (_i, [_vp, _vp, _vp, _i64]),
     "sgdm_set_graph_mode": (_i, [_vp, _i]),
+    "sgdm_set_share_prefix": (_i, [_vp, _i]),
     "sgdm_fingerprint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sgdm_set_profiling": (_i, [_vp, _i]),
     "sgdm_profile_count": (_i, [_vp]),

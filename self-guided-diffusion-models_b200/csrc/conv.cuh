@@ -34,6 +34,8 @@ struct ConvDesc {
   const float* bias = nullptr;  // [Cout]
   const float* res = nullptr;   // fp32 NHWC residual, see res_mode
   int res_mode = 0;             // 0 none | 1 same shape | 2 nearest-2x upsampled source [B,Hout/2,Wout/2,Cout]
+  int res_batch = 0;            // res_mode 1: the residual tensor has only this many samples; output sample n adds residual
+                                // sample n % res_batch (0 = B).  The shared CFG prefix of a guided plan (see GnDesc::src_mod0).
   float* out_f32 = nullptr;     // NHWC fp32 [B,Hout,Wout,Cout]
   op_t* out_op = nullptr;       // NHWC op_t
   float* out_nchw = nullptr;    // NCHW fp32 [B,Cout,Hout,Wout] (final conv, Cout = 3)
@@ -94,6 +96,7 @@ struct alignas(64) ConvKernelParams {
   const float* bias;
   const float* res;
   int res_mode;
+  int res_rows;  // rows of the residual matrix when it is shorter than the output (ConvDesc::res_batch), else 0
   float* out_nchw;
   float2* stats;
   int stat_gran;

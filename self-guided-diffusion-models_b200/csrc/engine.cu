@@ -98,6 +98,7 @@ struct Act {
   op_t* p16 = nullptr;      // the same tensor rounded to the 16-bit operand type (ConvDesc::out_op2): what the
                             // consuming GroupNorms and fused 1x1 skip convs read instead of the fp32 tensor
   bool has_stats = false, has16 = false;  // valid in the sizing (dry) pass too, where the pointers are null
+  int Bs = 0;  // > 0: the tensor holds only this many samples — the prefix the two CFG halves share (Builder::Bshare)
 };
 
 struct OpMeta {
@@ -161,7 +162,8 @@ struct sgdm_engine {
   bool first_im2col = false;  // first conv as a 1x1 GEMM over an im2col'd input (PrepDesc::im2col)
   std::vector<void*> owned;
   bool device_ready = false;
-  std::map<int, std::unique_ptr<Plan>> plans;  // key = batch rows
+  std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + (shared-prefix variant)
+  bool share_prefix = true;                     // SGDM_SHARE_PREFIX=0: A/B
   uint64_t plan_clock = 0;                      // LRU stamp source
   bool profiling = false;
   Plan* last_profiled = nullptr;
@@ -683,6 +685,12 @@ struct Builder {
   const bool use16 = false;
   int S = 1;          // e->S: channel expansion of every operand tensor (3 in split-precision mode)
   int split3 = 0;     // e->x3
+  // Guided plans (rows [0, B) conditional, [B, 2B) unconditional) without a layout input: x is the same in both halves and
+  // the embedding enters a ResBlock only at its second GroupNorm, so the first conv and the first ResBlock's
+  // GroupNorm + conv are IDENTICAL for row r and row r + B.  They are computed once, for Bshare = B rows; the first
+  // consumers that differ (that ResBlock's FiLM GroupNorm, its residual add, the last skip concat) read them with a
+  // batch modulo (GnDesc::src_mod*, ConvDesc::res_batch).  Same bits as the full computation (batch-invariant kernels).
+  int Bshare = 0;
   void attach_outputs(Act& o, size_t rows, ConvDesc& c, bool allow16 = true) {
     o.has_stats = stats_ok(o.H, o.W);
     o.stats = stats_alloc(rows, o.C, o.H, o.W);
@@ -698,7 +706,7 @@ struct Builder {
   }
 
   void conv(ConvDesc d, int real_cin = 0) {
-    d.B = Bp;
+    if (d.B == 0) d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
     d.swap_ab = conv_should_swap(d) ? 1 : 0;
     d.stat_gran = stat_gran();
@@ -712,11 +720,11 @@ struct Builder {
       err = 1;
       return;
     }
-    const double M = static_cast<double>(Bp) * d.Hout * d.Wout;
+    const double M = static_cast<double>(d.B) * d.Hout * d.Wout;
     // algorithmic K: the reference's channel counts (split-precision mode executes 3x that)
     const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin / S) + (d.in2 ? (d.C2 + (d.in2b ? d.C2b : 0)) / S : 0);
     const double flops = 2.0 * M * d.Cout * k_real;
-    const double in_px = static_cast<double>(Bp) * d.Hin * d.Win;
+    const double in_px = static_cast<double>(d.B) * d.Hin * d.Win;
     const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * (d.C2 + (d.in2b ? d.C2b : 0)) * 2 : 0) +
                          M * d.Cout * ((d.out_f32 || d.out_nchw) ? 4 : 2) + (d.out_op2 ? M * d.Cout * 2 : 0) +
                          (d.res ? M * d.Cout * 4 / (d.res_mode == 2 ? 4 : 1) : 0);
@@ -726,15 +734,15 @@ struct Builder {
     }, d.ks == 3 ? "conv3x3" : "gemm1x1", flops, bytes);
   }
   void gn(GnDesc d) {
-    d.B = Bp;
-    d.chunks = gn_chunks_for(Bp, d.H * d.W, d.C0 + d.C1);
+    if (d.B == 0) d.B = Bp;
+    d.chunks = gn_chunks_for(d.B, d.H * d.W, d.C0 + d.C1);
     d.partial = static_cast<double*>(scratch("gn_partial", static_cast<size_t>(Bp) * 16 * 32 * 2 * sizeof(double)));
     d.final = static_cast<float2*>(scratch("gn_final", static_cast<size_t>(Bp) * 32 * sizeof(float2)));
     d.stat_gran = stat_gran();
     if (dry) return;
     const bool fused = d.stats0 != nullptr && (d.C1 == 0 || d.stats1 != nullptr);
     if (!fused) { d.stats0 = nullptr; d.stats1 = nullptr; }
-    const double el = static_cast<double>(Bp) * d.H * d.W * (d.C0 + d.C1);
+    const double el = static_cast<double>(d.B) * d.H * d.W * (d.C0 + d.C1);
     const double out_el = d.resample == 1 ? el / 4 : d.resample == 2 ? el * 4 : el;
     const double in_b = d.src0_is_op ? 2 : 4;
     if (fused) {
@@ -766,8 +774,13 @@ struct Builder {
     const bool in16 = a.has16 && a.has_stats && (b.C == 0 || (b.has16 && b.has_stats)) && !r.down;
     op_t* raw = (r.skip && !in16) ? static_cast<op_t*>(scratch("raw_op", px_in * C * S * sizeof(op_t))) : nullptr;
     float* pooled = r.down ? static_cast<float*>(scratch("pooled", px_out * C * sizeof(float))) : nullptr;
+    // shared CFG prefix: a plain block fed by a shared tensor alone runs its first half (GroupNorm + conv) on the shared rows
+    const int Bb = (a.Bs > 0 && b.C == 0 && !r.skip && !r.down && !r.up) ? a.Bs : 0;
+    if (a.Bs > 0 && !Bb) { fail("internal: shared-prefix tensor reaches a block that cannot consume it"); err = 1; return a; }
     GnDesc g;
     g.H = H; g.W = W; g.C0 = a.C; g.C1 = b.C;
+    g.B = Bb;                // 0 = all rows
+    g.src_mod1 = b.Bs;       // the skip source of the last up block is the shared first-conv output
     if (in16) { g.src0 = a.p16; g.src1 = b.p16; g.src0_is_op = 1; }
     else { g.src0 = a.p; g.src1 = b.p; }
     g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
@@ -785,6 +798,7 @@ struct Builder {
     ConvDesc c1;
     c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C * S; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
     c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.stats = h1_stats;
+    c1.B = Bb;
     if (split3) c1.out_f32 = h1f;
     else c1.out_op = h1;
     conv(c1);
@@ -795,6 +809,7 @@ struct Builder {
     gg.H = Ho; gg.W = Wo; gg.C0 = r.cout; gg.gamma = r.gn2_w; gg.beta = r.gn2_b;
     gg.film = dry ? nullptr : emb_out + r.emb_off; gg.film_stride = e->NE; gg.silu = 1; gg.out = g2;
     gg.stats0 = h1_stats;
+    gg.src_mod0 = Bb;  // h1 of the shared rows, FiLM per row
     gn(gg);
     Act o;
     o.C = r.cout; o.H = Ho; o.W = Wo;
@@ -812,6 +827,7 @@ struct Builder {
       c2.bias = r.bfused;
       c2.res = r.down ? pooled : a.p;
       c2.res_mode = r.up ? 2 : 1;
+      c2.res_batch = Bb;
     }
     conv(c2);
     return o;
@@ -1085,6 +1101,8 @@ struct Builder {
       d.in = x_in; d.Hin = H; d.Win = W; d.Cin = e->xin_c; d.w = cw.w; d.ks = 3; d.stride = 1; d.pad = 1;
       if (e->first_im2col) { d.ks = 1; d.pad = 0; }  // the taps are channels of the im2col'd input
       d.Hout = H; d.Wout = W; d.Cout = cw.cout; d.bias = cw.b; d.out_f32 = h.p;
+      d.B = Bshare;
+      h.Bs = Bshare;
       attach_outputs(h, px, d);
       conv(d, e->first_im2col ? 9 * cw.cin : cw.cin);
       hs.push_back(h);
@@ -1121,8 +1139,17 @@ struct Builder {
   }
 };
 
-int get_plan(sgdm_engine* e, int Bp, Plan** out) {
-  auto it = e->plans.find(Bp);
+// A guided plan may share the prefix the two CFG halves have in common (Builder::Bshare): no layout input (the null
+// layout differs between the halves) and a plain first ResBlock.
+bool can_share_prefix(const sgdm_engine* e) {
+  if (e->cfg.layout_dim != 0 || e->in_blocks.size() < 2 || e->in_blocks[1].empty() || e->in_blocks[1][0].kind != L_RES) return false;
+  const ResW& r = e->res[e->in_blocks[1][0].idx];
+  return !r.skip && !r.down && !r.up && (e->cfg.image_size * e->cfg.image_size) % 32 == 0;  // (producer statistics needed)
+}
+
+int get_plan(sgdm_engine* e, int Bp, Plan** out, bool shared = false) {
+  const int key = 2 * Bp + (shared ? 1 : 0);
+  auto it = e->plans.find(key);
   if (it != e->plans.end()) {
     it->second->last_use = ++e->plan_clock;
     *out = it->second.get();
@@ -1142,6 +1169,7 @@ int get_plan(sgdm_engine* e, int Bp, Plan** out) {
   Builder b;
   b.e = e; b.plan = plan.get(); b.Bp = Bp;
   b.S = e->S; b.split3 = e->x3 ? 1 : 0;
+  b.Bshare = shared ? Bp / 2 : 0;
   b.dry = true;
   b.build();
   size_t total = b.stream_bytes;
@@ -1163,7 +1191,7 @@ int get_plan(sgdm_engine* e, int Bp, Plan** out) {
   if (b.err) return 1;
   plan->last_use = ++e->plan_clock;
   *out = plan.get();
-  e->plans[Bp] = std::move(plan);
+  e->plans[key] = std::move(plan);
   return 0;
 }
 
@@ -1175,7 +1203,9 @@ int run_forward(sgdm_engine* e, cudaStream_t s, const float* x, const int64_t* t
   if (e->cfg.cond_dim > 0 && cond == nullptr) return fail("cond is required (cond_dim=%d)", e->cfg.cond_dim);
   if (e->cfg.layout_dim > 0 && layout == nullptr) return fail("layout is required (layout_dim=%d)", e->cfg.layout_dim);
   Plan* plan = nullptr;
-  if (get_plan(e, Bp, &plan)) return 1;
+  // guided call (rows [0, B) conditional, [B, 2B) unconditional, the same x): the plan that computes the shared prefix once
+  const bool shared = drop == nullptr && Bp == 2 * B && e->share_prefix && can_share_prefix(e);
+  if (get_plan(e, Bp, &plan, shared)) return 1;
   if (drop) {
     CUDA_TRY(cudaMemcpyAsync(plan->drop, drop, Bp, cudaMemcpyDeviceToDevice, s));
   } else if (Bp == 2 * B) {
@@ -1294,6 +1324,7 @@ int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   std::unique_ptr<sgdm_engine> e(new sgdm_engine());
   e->cfg = *cfg;
   if (const char* ev = getenv("SGDM_GRAPH")) e->graph_mode = atoi(ev) != 0 ? 1 : 0;  // A/B: force graph replay on / off
+  if (const char* ev = getenv("SGDM_SHARE_PREFIX")) e->share_prefix = atoi(ev) != 0;  // A/B: shared CFG prefix of guided plans
   if (build_topology(e.get())) return 1;
   *out = e.release();
   return 0;
@@ -1340,6 +1371,11 @@ int sgdm_set_timestep_freqs(sgdm_handle h, const float* host_freqs, int n) {
   return 0;
 }
 
+int sgdm_set_share_prefix(sgdm_handle h, int on) {
+  if (!h) return fail("null handle");
+  h->share_prefix = on != 0;
+  return 0;
+}
 int sgdm_set_graph_mode(sgdm_handle h, int mode) {
   if (!h || mode < -1 || mode > 1) return fail("graph mode must be -1 (policy), 0 (off) or 1 (on)");
   h->graph_mode = mode;

@@ -470,8 +470,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (pre_tile >= total_tiles) return;
         if (lane == 0) {
           // chunk pre_i of the tile: 32 rows further down (swap-AB) or cpc columns further right
-          const int r0 = p.swap_ab ? pre_r0 + 32 * pre_i : pre_r0;
+          int r0 = p.swap_ab ? pre_r0 + 32 * pre_i : pre_r0;
           const int c0 = p.swap_ab ? pre_c0 : pre_c0 + cpc * pre_i;
+          if (p.res_rows) r0 %= p.res_rows;  // residual shared by the conditional / unconditional halves (tiles never straddle)
           const uint32_t slot = pslot;
           mbar_arrive_expect_tx(&rbar[slot], tma_res ? kEpiBuf : 2048);
           tma_load_2d_a(&p.tmRes, smem_u32(&rbar[slot]), res_slot_addr(slot), c0, r0);
@@ -1040,6 +1041,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.m_tiles = (p.M_total + tile_px - 1) / tile_px;
   p.bias = d.bias;
   p.res = d.res;
+  p.res_rows = 0;
+  if (d.res && d.res_mode == 1 && d.res_batch > 0 && d.res_batch < d.B) {
+    if (d.B % d.res_batch || (static_cast<long>(d.res_batch) * HW) % tile_px) return fail("res_batch must divide B and cover whole tiles");
+    p.res_rows = d.res_batch * HW;
+  }
   p.out_nchw = d.out_nchw;
   p.stats = d.stats;
   p.stat_gran = d.stat_gran;
@@ -1047,7 +1053,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // epilogue: output / residual tile maps
   if (p.epi_mode == 1) {
     if (encode_matrix_map(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
-    if (p.res_mode == 1 && encode_matrix_map(&p.tmRes, d.res, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
+    if (p.res_mode == 1 &&
+        encode_matrix_map(&p.tmRes, d.res, true, p.res_rows ? p.res_rows : p.M_total, d.Cout, 32, 128, err, errlen))
+      return 1;
     if (p.res_mode == 2 &&
         encode_matrix_map(&p.tmRes, d.res, true, static_cast<long>(d.B) * (d.Hout / 2) * (d.Wout / 2), d.Cout, 32, 128, err,
                       errlen, 16))

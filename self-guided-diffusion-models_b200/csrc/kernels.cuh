@@ -32,6 +32,10 @@ struct GnDesc {
   const float2* stats1 = nullptr;
   int stat_gran = 4;
   float2* final = nullptr;       // scratch [B][32]
+  // Source batch modulo: sample n of the OUTPUT reads sample n % src_mod of source 0 / 1 (0 = none).  The guided plan
+  // computes everything in front of the first FiLM once for the B rows that the conditional and the unconditional half
+  // share (identical x, identical weights); the first consumers that differ between the halves read it through this.
+  int src_mod0 = 0, src_mod1 = 0;
   // Split-precision operand output (engine precision 1): `out` / `raw_out` rows have 3 (C0 + C1) channels
   // [hi | hi | lo], hi = op(v), lo = op(v - hi) (kernels_misc.cu: store8_split3).  fp32 sources only.
   int split3 = 0;

@@ -151,6 +151,7 @@ struct GnApplyArgs {
   const double* partial;
   const float2* final;
   op_t* out; op_t* raw_out; float* pool_out;
+  int mod0, mod1;  // source batch modulo (GnDesc::src_mod0 / src_mod1), 0 = none
 };
 
 // (Measured, round 2: doing this reduction in the prologue of every gn_apply block instead of a separate launch —
@@ -163,7 +164,7 @@ struct GnApplyArgs {
 // order depends on the sample's shape only (batch-invariant bits).
 __global__ void __launch_bounds__(512) gn_finalize_kernel(const float2* __restrict__ st0, int C0,
                                                           const float2* __restrict__ st1, int C1, int HW,
-                                                          int gran, int RL, float2* __restrict__ out) {
+                                                          int gran, int RL, float2* __restrict__ out, int mod0, int mod1) {
   __shared__ double s_s[512], s_q[512];
   pdl_launch_dependents();
   pdl_wait();
@@ -174,7 +175,8 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const float2* __restri
   const int cg = threadIdx.x % ne, rl = threadIdx.x / ne;
   {
     const bool first = cg < e0;
-    const float2* p = first ? st0 + static_cast<long>(n) * rbs * e0 + cg : st1 + static_cast<long>(n) * rbs * e1 + (cg - e0);
+    const int ns = first ? (mod0 ? n % mod0 : n) : (mod1 ? n % mod1 : n);  // source sample (shared CFG prefix)
+    const float2* p = first ? st0 + static_cast<long>(ns) * rbs * e0 + cg : st1 + static_cast<long>(ns) * rbs * e1 + (cg - e0);
     const long ld = first ? e0 : e1;
     double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
     int rb = rl;
@@ -208,10 +210,10 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const float2* __restri
 }
 
 template <bool kHalfIn>
-__device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, int c, float (&v)[8]) {
+__device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n0, int n1, int pix, int c, float (&v)[8]) {
   const long HW = static_cast<long>(a.H) * a.W;
   if (c < a.C0) {
-    const long off = (static_cast<long>(n) * HW + pix) * a.C0 + c;
+    const long off = (static_cast<long>(n0) * HW + pix) * a.C0 + c;
     if (kHalfIn) {
       const uint4 r = __ldg(reinterpret_cast<const uint4*>(static_cast<const op_t*>(a.src0) + off));
       const float2 p0 = unpack_op2(r.x), p1 = unpack_op2(r.y), p2 = unpack_op2(r.z), p3 = unpack_op2(r.w);
@@ -222,7 +224,7 @@ __device__ __forceinline__ void gn_load8(const GnApplyArgs& a, int n, int pix, i
     const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
   } else {
-    const long off = (static_cast<long>(n) * HW + pix) * a.C1 + (c - a.C0);
+    const long off = (static_cast<long>(n1) * HW + pix) * a.C1 + (c - a.C0);
     if (kHalfIn) {  // both concat sources are 16-bit
       const uint4 r = __ldg(reinterpret_cast<const uint4*>(static_cast<const op_t*>(a.src1) + off));
       const float2 p0 = unpack_op2(r.x), p1 = unpack_op2(r.y), p2 = unpack_op2(r.z), p3 = unpack_op2(r.w);
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
   pdl_wait();
   const int C = a.C0 + a.C1, C8 = C >> 3, cpg = C / 32;
   const int n = blockIdx.y;
+  const int n0 = a.mod0 ? n % a.mod0 : n, n1 = a.mod1 ? n % a.mod1 : n;  // source samples (shared CFG prefix)
   const int HW = a.H * a.W;
   const int cg = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int c = cg * 8;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
       const bool first = c < a.C0;
       const long cs = first ? a.C0 : a.C1;
       const op_t* src = (first ? static_cast<const op_t*>(a.src0) + c : static_cast<const op_t*>(a.src1) + (c - a.C0)) +
-                        static_cast<long>(n) * HW * cs;
+                        static_cast<long>(first ? n0 : n1) * HW * cs;
       for (; pix + 7 * a.PLa < p_end; pix += 8 * a.PLa) {
         uint4 r[8];
 #pragma unroll
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
     for (; pix + 3 * a.PLa < p_end; pix += 4 * a.PLa) {  // four pixels (8 x 16-byte loads) in flight
       float v[4][8], y[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) gn_load8<kHalfIn>(a, n, pix + u * a.PLa, c, v[u]);
+      for (int u = 0; u < 4; ++u) gn_load8<kHalfIn>(a, n0, n1, pix + u * a.PLa, c, v[u]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         xform(v[u], y);
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
     }
     for (; pix < p_end; pix += a.PLa) {
       float v[8], y[8];
-      gn_load8<kHalfIn>(a, n, pix, c, v);
+      gn_load8<kHalfIn>(a, n0, n1, pix, c, v);
       xform(v, y);
       gn_store8<kSplit>(a.out, static_cast<long>(n) * HW + pix, C, c, y);
       if (a.raw_out) gn_store8<kSplit>(a.raw_out, static_cast<long>(n) * HW + pix, C, c, v);
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
       const int yo = pix / Wo, xo = pix - yo * Wo;
       float v[4][8], y[8], acc[8], racc[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) gn_load8<kHalfIn>(a, n, (2 * yo + (k >> 1)) * a.W + 2 * xo + (k & 1), c, v[k]);
+      for (int k = 0; k < 4; ++k) gn_load8<kHalfIn>(a, n0, n1, (2 * yo + (k >> 1)) * a.W + 2 * xo + (k & 1), c, v[k]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[j] = 0.f; racc[j] = 0.f; }
 #pragma unroll
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
     const int W2 = a.W * 2;
     for (int pix = p_begin + lane; pix < p_end; pix += a.PLa) {
       float v[8], y[8];
-      gn_load8<kHalfIn>(a, n, pix, c, v);
+      gn_load8<kHalfIn>(a, n0, n1, pix, c, v);
       xform(v, y);
       const int yi = pix / a.W, xi = pix - yi * a.W;
 #pragma unroll
@@ -439,7 +442,7 @@ int gn_finalize_launch(const GnDesc& d, cudaStream_t s) {
   int RL = 1;
   while (RL * 2 * ne <= 512 && RL * 2 <= rbs && RL < 16) RL *= 2;
   return launch_pdl(gn_finalize_kernel, dim3(d.B), dim3(ne * RL), 0, s, 1, d.stats0, d.C0, d.stats1, d.C1, HW, d.stat_gran, RL,
-                    d.final) == cudaSuccess ? 0 : 1;
+                    d.final, d.src_mod0, d.src_mod1) == cudaSuccess ? 0 : 1;
 }
 
 int gn_stats_launch(const GnDesc& d, cudaStream_t s) {
@@ -476,7 +479,8 @@ int gn_apply_launch(const GnDesc& d, cudaStream_t s) {
     return 1;
   GnApplyArgs a{d.src0, d.src1, d.H, d.W, d.C0, d.C1, d.gamma, d.beta, d.film, d.film_stride,
                 d.silu, d.resample, d.chunks, ppb, PLa, d.partial, gn_fused(d) ? d.final : nullptr, d.out, d.raw_out,
-                d.pool_out};
+                d.pool_out, d.src_mod0, d.src_mod1};
+  if ((d.src_mod0 || d.src_mod1) && !gn_fused(d)) return 1;  // the shared-prefix sources always carry producer statistics
   const dim3 grid((n_iter + ppb - 1) / ppb, d.B);
   const int threads = C8 * PLa;
   if (d.split3) {  // split-precision operands (engine precision 1): fp32 sources only (h1 stays fp32 in that mode)

@@ -100,6 +100,37 @@ def test_cuda_graph_replay_is_bit_identical(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,precision", [("cfg1_cifar_label", None), ("unet_fast_label_tiny", None), ("cfg2_in64_label", None),
+                                            ("unet_fast_label_tiny", "fp16x3")])
+def test_shared_cfg_prefix_is_bit_identical(name, precision):
+    """Guided plans compute the first conv and the first ResBlock's GroupNorm + conv once for the B rows the two CFG
+    halves share (sgdm_set_share_prefix): the same bits as computing them for all 2B rows."""
+    need_gpu()
+    from sgdm_b200 import _lib
+
+    meta, a = load_unet_case(name)
+    m = cuda_model(meta, precision)
+    kw = dev(kwargs_from_arrays(a))
+    g = torch.Generator().manual_seed(5)
+    B = 5
+    x = torch.randn(B, 3, meta["cfg"]["image_size"], meta["cfg"]["image_size"], generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    cond = kw["cond"][:1].expand(B, -1).contiguous()
+    n0 = _lib.lib().sgdm_launch_count()
+    shared = m.forward_with_cond_scale(x, t, 2.0, cond=cond).clone()
+    w = torch.linspace(0.5, 3.0, B).view(B, 1, 1, 1).cuda()
+    shared_w = m.forward_with_cond_scale(x, t, w, cond=cond).clone()
+    _lib.check(_lib.lib().sgdm_set_share_prefix(m._h, 0))
+    try:
+        full = m.forward_with_cond_scale(x, t, 2.0, cond=cond).clone()
+        full_w = m.forward_with_cond_scale(x, t, w, cond=cond).clone()
+    finally:
+        _lib.check(_lib.lib().sgdm_set_share_prefix(m._h, 1))
+    assert torch.equal(shared, full) and torch.equal(shared_w, full_w)
+    assert torch.isfinite(shared).all() and _lib.lib().sgdm_launch_count() > n0
+
+
+@pytest.mark.gpu
 def test_unetca_float_one_is_doubled_path():
     need_gpu()
     meta, a = load_unet_case("unetca_clusterlayout_tiny")
