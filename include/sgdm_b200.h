@@ -201,6 +201,12 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
 /* the output head (3x3, stride 1, pad 1, 3 * Cout <= 16, NCHW fp32 result) with the horizontal taps folded into the
  * GEMM's N dimension (openaimodel.py:830-835: the conv of self.out): w is the torch weight [Cout,Cin,3,3] fp32,
  * w_scratch 16 * 3 * Cin op elements for its packed form; needs tiles of whole image rows (W | 128, H*W % 128 == 0) */
+/* "nearest-2x upsample, then 3x3 conv" executed as four 2x2 parity convs on the low-resolution tensor (ConvDesc::up2):
+ * in [B, H, W, Cin] 16-bit NHWC, w fp32 [Cout, Cin, 3, 3] (packed into w_scratch: 4 * Cout * 9 * Cin 16-bit), output
+ * [B, 2H, 2W, Cout] fp32 or 16-bit, optional GroupNorm partial statistics of the output (sample n: row blocks
+ * [n * 4HW/32, (n+1) * 4HW/32)) */
+int sgdm_k_conv_up2(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
+                    const float* bias, float* out_f32, void* out_op, int Cout, float* stats, int stat_gran, int naive);
 int sgdm_k_conv_head_hfold(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
                            const float* bias, float* out_nchw, int Cout);
 /* packs a torch conv weight [Cout,Cin,ks,ks] fp32 into dst[co][k_off + tap*cin_pad + ci] (row length ktot) */

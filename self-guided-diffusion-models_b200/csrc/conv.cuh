@@ -65,6 +65,18 @@ struct ConvDesc {
   // L2 -> SM drop 3x against halo mode, the MMA count 3x.  `w` is then packed [16][3 * Cin]:
   // row s * Cout + co, column r * Cin + c (pack_conv_weight_hfold_launch).
   int hfold = 0;
+  // Sub-pixel execution of "nearest-2x upsample, then 3x3 conv" (the up ResBlocks of unet_fast, openaimodel.py:253-258,
+  // 301-306; Upsample of unetca_fast, openaimodel_ca.py:121-131).  Output pixel (2y+dy, 2x+dx) of that conv only ever sees
+  // the 2x2 low-resolution neighbourhood {y+dy-1, y+dy} x {x+dx-1, x+dx}, each reached by 1, 2 or 4 of the nine taps:
+  // four parity convs with 2x2 summed-tap kernels on the LOW-resolution tensor give the same sums with 16 instead of 36
+  // MACs per low-resolution pixel and channel pair (2.25x less tensor work, no upsampled operand tensor).
+  //   `in` is the low-resolution tensor [B, Hin, Win, Cin]; Hout = Hin, Wout = Win are the GEMM's pixel grid; the OUTPUT
+  //   tensor is [B, 2 Hout, 2 Wout, Cout]; the GEMM's N is 4 Cout (parity-major: n = (2 dy + dx) Cout + co), `w` is packed by
+  //   pack_conv_weight_up2_launch as [4 Cout][9 Cin] with tap (R, S) of parity (dy, dx) = sum of W[r, s] over
+  //   r in V(dy, R), s in V(dx, S), V(0,0) = {0}, V(0,1) = {1,2}, V(1,1) = {0,1}, V(1,2) = {2} (other taps unused);
+  //   statistics: sample n's row blocks are [(4 n + parity) HW/32 + block], i.e. contiguous per sample as gn_finalize expects.
+  // Needs the halo geometry (3x3, stride 1, tiles of whole rows), Cout % block_n == 0, no residual / skip source.
+  int up2 = 0;
   int a_stat = -1;              // A-stationary main loop for 1x1 GEMMs with >= 3 n-tiles and K <= 512: -1 policy, 0 off, 1 force
   int k32 = -1;                 // K block of 32 channels (SWIZZLE_64B halo stages): -1 policy, 0 never, 1 force
   long long* timing = nullptr;  // optional device array of 16 cycle counters (kernel_conv.cu, tuning only)
@@ -87,6 +99,7 @@ struct alignas(64) ConvKernelParams {
   int n_stages, act_bytes, act_tx, act_tx_halo, wgt_bytes, wgt_tx;
   int halo, tps, halo_row_bytes;  // halo mode: 3 vertical taps per stage read one staged tile at row offsets
   int hfold;                      // horizontal taps folded into the N dimension (output head)
+  int up2, cout_real, ntpp;       // sub-pixel mode (ConvDesc::up2): real output channels, n-tiles per parity
   int kps;                        // K blocks per plain (non-halo) main stage: 1 or 2
   int a_stat;                     // A-stationary 1x1 GEMM: the m-tile's activation K blocks stay resident across its n-tiles
   int kblk;                       // channels per K block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)

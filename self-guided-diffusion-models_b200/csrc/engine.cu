@@ -1557,6 +1557,27 @@ int sgdm_k_conv_stats(void* stream, const void* in, int B, int Hin, int Win, int
     return fail("conv launch: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
+// unit-test entry of the sub-pixel mode: in [B, H, W, Cin] (low resolution), w fp32 [Cout, Cin, 3, 3]; out [B, 2H, 2W, Cout]
+int sgdm_k_conv_up2(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
+                    const float* bias, float* out_f32, void* out_op, int Cout, float* stats, int stat_gran, int naive) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  g_launches += 3;
+  if (cudaMemsetAsync(w_scratch, 0, static_cast<size_t>(4) * Cout * 9 * Cin * sizeof(op_t), st) != cudaSuccess ||
+      pack_conv_weight_up2_launch(w, static_cast<op_t*>(w_scratch), Cout, Cin, Cin, st))
+    return fail("up2 weight pack failed");
+  ConvDesc d;
+  d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = H; d.Win = W; d.Cin = Cin; d.w = static_cast<const op_t*>(w_scratch);
+  d.ks = 3; d.stride = 1; d.pad = 1; d.Hout = H; d.Wout = W; d.Cout = Cout; d.bias = bias;
+  d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
+  d.stats = reinterpret_cast<float2*>(stats); d.stat_gran = stat_gran;
+  d.block_n = pick_block_n(Cout); d.up2 = 1; d.halo = 1; d.pair = g_conv_pair;
+  if (naive) return conv_launch_naive(d, st) ? fail("naive conv launch failed") : 0;
+  ConvLaunch l;
+  char msg[256];
+  if (conv_prepare(d, &l, msg, sizeof(msg))) return fail("%s", msg);
+  if (conv_launch(l, st)) return fail("conv launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
 int sgdm_k_conv_head_hfold(void* stream, const void* in, int B, int H, int W, int Cin, const float* w, void* w_scratch,
                            const float* bias, float* out_nchw, int Cout) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -69,6 +69,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* d, uint32_t src,
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* d, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(d)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
       // main K blocks: halo stages hold the three vertical taps of one (horizontal tap, chunk); plain stages hold
       // p.kps consecutive (tap, chunk) K blocks, each with its own activation tile and weight slot
-      const int n_blk = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1;
+      const int n_blk = (p.hfold ? 1 : p.up2 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;  // up2: two horizontal taps per parity
       const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       uint32_t a_it = 0;  // A-stationary: m-tiles loaded so far (parity of the resident slots)
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile)) {
@@ -216,6 +222,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int p0 = m_tile * p.tile_px;
         const int img = p0 / p.HW;
         const int y0 = (p0 - img * p.HW) / p.Wout;
+        // sub-pixel mode: this n-tile's output parity (dy, dx) selects the vertical taps {dy, dy+1} and horizontal {dx, dx+1}
+        const int par = p.up2 ? n_tile / p.ntpp : 0, up_dy = par >> 1, up_dx = par & 1;
         int q_tap = 0, q_cc = 0, q_r = 0;
         for (int q = 0; q < n_st; ++q) {
           const long long tw0 = p.timing ? clock64() : 0;
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               const int tap = q_tap;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
               cc = q_cc;
               const int r = p.halo ? 0 : q_r;
-              const int s_tap = p.hfold ? p.pad : p.halo ? tap : tap - r * p.ks;  // hfold: no horizontal shift
+              const int s_tap = p.hfold ? p.pad : p.halo ? tap + up_dx : tap - r * p.ks;  // hfold: no horizontal shift
               if (++q_cc == p.kc1) {
                 q_cc = 0;
                 ++q_tap;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             // halo: vertical tap t -> K block (t*ks + s)*kc1 + cc; skip source: consecutive K blocks
             // (hfold: the packed K axis is (vertical tap, channel) only)
             // (plain stages: kps consecutive K blocks)
-            const int kb = kb0 + ((main_st && p.halo) ? t * (p.hfold ? 1 : p.ks) * p.kc1 : t);
+            const int kb = kb0 + ((main_st && p.halo) ? (t + up_dy) * (p.hfold ? 1 : p.ks) * p.kc1 : t);
             if (kCtas == 2) tma_load_2d_pair(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n + cta_rank * b_rows);
             else tma_load_2d(&p.tmB, &full[stage], wgt_dst + t * p.wgt_bytes, kb * p.kblk, n_tile * block_n);
           }
@@ -297,10 +305,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint64_t desc_hi = umma_smem_desc_hi(p.kblk == 32);
       uint32_t stage = 0, phase = 0, it = 0, a_it = 0;
       long long t_full = 0, t_acc = 0;
-      const int n_blk = (p.hfold ? 1 : p.halo ? p.ks : p.taps) * p.kc1;
+      const int n_blk = (p.hfold ? 1 : p.up2 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;
       const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const int up_dy = p.up2 ? (n_of(tile) / p.ntpp) >> 1 : 0;  // sub-pixel mode: first vertical tap of this tile's parity
         const long long ta0 = p.timing ? clock64() : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         if (p.timing) t_acc += clock64() - ta0;
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t wgt_addr = p.a_stat ? smem_u32(ring + stage * stage_bytes) : act_addr + p.act_bytes;
           for (int t = 0; t < ntap; ++t) {
             // halo: vertical tap t reads the staged rows starting t image rows further down
-            const uint32_t act_t = act_addr + ((main_st && p.halo) ? t * p.halo_row_bytes : t * p.act_tx);
+            const uint32_t act_t = act_addr + ((main_st && p.halo) ? (t + up_dy) * p.halo_row_bytes : t * p.act_tx);
             const uint32_t wgt_t = wgt_addr + t * p.wgt_bytes;
             const uint32_t a_addr = p.swap_ab ? wgt_t : act_t;  // M-side operand
             const uint32_t b_addr = p.swap_ab ? act_t : wgt_t;  // N-side operand
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const bool tma_res = p.res_mode == 1;   // residual tile TMA-loaded INTO the staging buffer, added in place
     const bool tma_res2 = p.res_mode == 2;  // nearest-2x upsampled source: 16 source rows into a side slot
     const int sg_shift = p.stat_gran == 4 ? 2 : 1;
-    const int stat_ld = p.N_total >> sg_shift;  // stat entries per 32-row block
+    const int stat_ld = (p.up2 ? p.cout_real : p.N_total) >> sg_shift;  // stat entries per 32-row block
     const int x7 = lane & 7;
     const int rg = lane >> 3, cc = lane & 7;  // read-back layout: row group, 16-byte chunk
     // chunks per tile, columns per chunk
@@ -498,7 +507,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         {
           const int ncol = p.swap_ab ? 32 : block_n;
           for (int c = lane; c < ncol; c += 32)
-            sts32(sbias + c * 4, (p.bias != nullptr && tile_col0 + c < p.N_total) ? __ldg(p.bias + tile_col0 + c) : 0.f);
+            sts32(sbias + c * 4, (p.bias != nullptr && tile_col0 + c < p.N_total)
+                                     ? __ldg(p.bias + (p.up2 ? (tile_col0 + c) % p.cout_real : tile_col0 + c)) : 0.f);
           __syncwarp();
         }
         // res_mode 2: which of the 16 staged source rows this thread's output row reads (the rows a 32-row
@@ -519,6 +529,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t b2addr = epi2_all + (wq * 2 + (g & 1)) * 2048;  // 16-bit copy tile (second output)
           const int row0 = p.swap_ab ? tile_row0 + 32 * i : tile_row0;
           const int col0 = p.swap_ab ? tile_col0 : tile_col0 + cpc * i;
+          // sub-pixel mode: parity of this tile, output channel of the chunk, statistics row block (contiguous per sample)
+          const int up_par = p.up2 ? col0 / p.cout_real : 0;
+          const int ocol0 = p.up2 ? col0 - up_par * p.cout_real : col0;
+          const long srow = p.up2 ? (static_cast<long>(row0 / p.HW) * 4 + up_par) * (p.HW >> 5) + ((row0 % p.HW) >> 5)
+                                  : static_cast<long>(row0 >> 5);
           // the buffer written next (by the residual load for chunk g+NB-2, or by this chunk when there is
           // no residual) was last read by the TMA store of chunk g-2: all but the newest store must be done
           // (without a residual all NB buffers rotate as store sources: the store of chunk g-NB must be done)
@@ -668,9 +683,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                   qg[u] += __shfl_xor_sync(0xffffffffu, qg[u], o);
                 }
               }
-              const int col = col0 + 4 * cc;
-              if (rg == 0 && col < p.N_total && row0 < p.M_total) {
-                float2* dst = p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift);
+              const int col = ocol0 + 4 * cc;
+              if (rg == 0 && col0 + 4 * cc < p.N_total && row0 < p.M_total) {
+                float2* dst = p.stats + srow * stat_ld + (col >> sg_shift);
                 if (p.stat_gran == 4) dst[0] = make_float2(sg[0], qg[0]);
                 else *reinterpret_cast<float4*>(dst) = make_float4(sg[0], qg[0], sg[1], qg[1]);
               }
@@ -731,9 +746,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                   }
                 }
               }
-              const int col = col0 + 8 * cc;
-              if (rg == 0 && col < p.N_total && row0 < p.M_total) {
-                float4* dst = reinterpret_cast<float4*>(p.stats + static_cast<long>(row0 >> 5) * stat_ld + (col >> sg_shift));
+              const int col = ocol0 + 8 * cc;
+              if (rg == 0 && col0 + 8 * cc < p.N_total && row0 < p.M_total) {
+                float4* dst = reinterpret_cast<float4*>(p.stats + srow * stat_ld + (col >> sg_shift));
                 dst[0] = make_float4(sg[0], qg[0], sg[1], qg[1]);
                 if (p.stat_gran != 4) dst[1] = make_float4(sg[2], qg[2], sg[3], qg[3]);
               }
@@ -744,7 +759,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.tmOut, baddr, col0, row0);
+            if (p.up2)  // (c, dx, x, dy, image row): pixel (2y + dy, 2x + dx) of the 2x larger output
+              tma_store_5d(&p.tmOut, baddr, ocol0, up_par & 1, row0 % p.Wout, up_par >> 1, row0 / p.Wout);
+            else tma_store_2d(&p.tmOut, baddr, col0, row0);
             if (p.out2) tma_store_2d(&p.tmOut2, b2addr, col0, row0);  // same bulk group: one wait covers both
             bulk_commit();
           }
@@ -893,6 +910,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // do not: per tile they pull 864 KB through L2 -> SM without the halo (measured at the ~11 TB/s L2 -> SM limit,
   // tensor pipe 47 %), 576 KB with it.  ConvDesc::k32: -1 policy, 0 never, 1 force.
   const bool halo_ok = halo;
+  if (d.up2) {
+    if (!halo || d.swap_ab || d.res || d.in2 || d.out_nchw || d.out_op2 || d.hfold || d.k32 == 1 || (d.Cout % d.block_n) ||
+        (HW % 32) || (d.Wout < 32 && (32 % d.Wout)) || (d.Wout > 32 && (d.Wout % 32)))
+      return fail("up2 (sub-pixel) mode needs the halo geometry, Cout % block_n == 0, no residual / skip / NCHW output");
+  }
   int kblk = d.k32 == 1 ? 32 : 64;
   if (kblk == 32 && ((d.Cin % 32) || !halo_ok || pair || d.hfold)) return fail("k32 needs a halo-mode conv, one CTA per tile");
   for (int pass = 0; pass < 6; ++pass) {
@@ -902,7 +924,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     p.wgt_bytes = (p.wgt_tx + 1023) / 1024 * 1024;
     p.act_tx = tile_px * row_bytes;
     p.halo = halo ? 1 : 0;
-    p.tps = halo ? 3 : 1;
+    p.tps = halo ? (d.up2 ? 2 : 3) : 1;  // sub-pixel mode: two vertical taps per parity
     p.act_tx_halo = (bh + 2) * bw * row_bytes;
     p.act_bytes = halo ? p.act_tx_halo : p.act_tx;
     p.halo_row_bytes = bw * row_bytes;
@@ -917,6 +939,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (n_stages < min_stages && p.tps2 == 3) { pack_skip = false; continue; }     // first give up the skip packing,
     // (policy: not with a fused 1x1-skip source in swap-AB mode — each of its 32-channel K blocks would take a whole
     //  halo stage; measured +0.02 ms per such layer, against -0.055 ms for the plain ones)
+    if (n_stages < min_stages && d.up2) return fail("up2 mode: the halo ring does not fit");
     if (n_stages < min_stages && halo && kblk == 64 && d.k32 != 0 && !d.hfold && !pair &&
         (d.k32 == 1 || !(d.in2 && d.swap_ab))) {
       kblk = 32;  // then halve the K block,
@@ -1006,7 +1029,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen, kblk)) return 1;
   }
   const int Ktot = d.hfold ? d.ks * d.Cin : d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
-  const int npad = conv_npad(d.Cout, d.block_n);
+  const int npad = d.up2 ? 4 * d.Cout : conv_npad(d.Cout, d.block_n);
   {
     auto fn = get_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
@@ -1032,7 +1055,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.kc1 = d.Cin / kblk;
   p.kc2a = d.in2 ? d.C2 / kblk : 0;
   p.kc2 = p.kc2a + (d.in2 && d.in2b ? d.C2b / kblk : 0);
-  p.N_total = d.Cout;
+  p.N_total = d.up2 ? 4 * d.Cout : d.Cout;
+  p.up2 = d.up2 ? 1 : 0;
+  p.cout_real = d.Cout;
+  p.ntpp = d.up2 ? d.Cout / d.block_n : 0;
   p.block_n = d.block_n;
   p.n_tiles = npad / d.block_n;
   p.swap_ab = d.swap_ab;
@@ -1051,7 +1077,23 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.stat_gran = d.stat_gran;
   p.timing = d.timing;
   // epilogue: output / residual tile maps
-  if (p.epi_mode == 1) {
+  if (d.up2) {
+    // the 2x larger output [B, 2H, 2W, C] seen as (c, dx, x, dy, image row): one parity plane per store
+    auto fn = get_encode_fn();
+    const bool f32 = p.epi_mode == 1;
+    const int es = f32 ? 4 : 2, box_c = f32 ? 32 : 64;
+    const cuuint64_t C = (cuuint64_t)d.Cout, W = (cuuint64_t)d.Wout;
+    cuuint64_t dims[5] = {C, 2, W, 2, (cuuint64_t)d.B * d.Hout};
+    cuuint64_t strides[4] = {C * es, 2 * C * es, 2 * W * C * es, 4 * W * C * es};
+    const int bx = d.Wout < 32 ? d.Wout : 32;
+    cuuint32_t box[5] = {(cuuint32_t)box_c, 1, (cuuint32_t)bx, 1, (cuuint32_t)(32 / bx)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = f32 ? static_cast<void*>(d.out_f32) : static_cast<void*>(d.out_op);
+    CUresult r = fn(&p.tmOut, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : SGDM_TMA_DTYPE, 5, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(up2 output) failed: %d", (int)r); return 1; }
+  } else if (p.epi_mode == 1) {
     if (encode_matrix_map(&p.tmOut, d.out_f32, true, p.M_total, d.Cout, 32, 128, err, errlen)) return 1;
     if (p.res_mode == 1 &&
         encode_matrix_map(&p.tmRes, d.res, true, p.res_rows ? p.res_rows : p.M_total, d.Cout, 32, 128, err, errlen))
@@ -1069,6 +1111,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // shared memory: as many K-block stages as fit beside the epilogue staging
   out->pair = pair ? 1 : 0;
   // (A-stationary: the work items of a CTA / pair are whole m-tiles)
+  if (d.up2 && (p.kblk != 64 || !p.halo)) return fail("up2 mode: unexpected geometry");
   if (pair) {
     const int total = (p.m_tiles + 1) / 2 * (p.a_stat ? 1 : p.n_tiles);
     out->grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
@@ -1097,6 +1140,29 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
 __global__ void conv_naive_kernel(ConvDesc d, int npad) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   const long M = static_cast<long>(d.B) * d.Hout * d.Wout;
+  if (d.up2) {  // sub-pixel mode: one thread per output element of the 2x larger tensor, straight from the definition
+    const long total = M * 4 * d.Cout;
+    if (idx >= total) return;
+    const int co = idx % d.Cout;
+    const long px = idx / d.Cout;                      // output pixel in NHWC order of [B, 2H, 2W]
+    const int W2 = 2 * d.Wout, H2 = 2 * d.Hout;
+    const int X = px % W2, Y = (px / W2) % H2, b = px / (static_cast<long>(W2) * H2);
+    const int dy = Y & 1, dx = X & 1, yy = Y >> 1, xx = X >> 1;
+    const op_t* wr = d.w + static_cast<long>((2 * dy + dx) * d.Cout + co) * (9 * d.Cin);
+    float acc = 0.f;
+    for (int R = dy; R <= dy + 1; ++R)
+      for (int S = dx; S <= dx + 1; ++S) {
+        const int iy = yy + R - 1, ix = xx + S - 1;
+        if (iy < 0 || iy >= d.Hin || ix < 0 || ix >= d.Win) continue;
+        const op_t* a = d.in + ((static_cast<long>(b) * d.Hin + iy) * d.Win + ix) * d.Cin;
+        const op_t* w = wr + (R * 3 + S) * d.Cin;
+        for (int c = 0; c < d.Cin; ++c) acc += from_op(a[c]) * from_op(w[c]);
+      }
+    if (d.bias) acc += d.bias[co];
+    if (d.out_f32) d.out_f32[px * d.Cout + co] = acc;
+    if (d.out_op) d.out_op[px * d.Cout + co] = to_op(acc);
+    return;
+  }
   if (idx >= M * d.Cout) return;
   const int col = idx % d.Cout;
   const long m = idx / d.Cout;
@@ -1133,7 +1199,7 @@ __global__ void conv_naive_kernel(ConvDesc d, int npad) {
 }
 
 int conv_launch_naive(const ConvDesc& d, cudaStream_t stream) {
-  const long total = static_cast<long>(d.B) * d.Hout * d.Wout * d.Cout;
+  const long total = static_cast<long>(d.B) * d.Hout * d.Wout * d.Cout * (d.up2 ? 4 : 1);
   const int threads = 256;
   conv_naive_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
       d, conv_npad(d.Cout, d.block_n));

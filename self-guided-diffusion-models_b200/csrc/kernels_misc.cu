@@ -1204,6 +1204,33 @@ int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks
                                                                                    ktot, k_off, ci_map, cin_part);
   return SGDM_LAUNCH_OK();
 }
+// Sub-pixel packing (ConvDesc::up2): dst[(2 dy + dx) Cout + co][(R * 3 + S) * cin_pad + ci] = sum of w[co][ci][r][s] over
+// r in V(dy, R), s in V(dx, S) with V(0,0) = {0}, V(0,1) = {1,2}, V(1,1) = {0,1}, V(1,2) = {2}; the sums are formed in
+// fp32 and rounded once.  Taps a parity does not use stay zero (they are never read).
+__global__ void pack_conv_weight_up2_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin, int cin_pad) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long total = static_cast<long>(4) * Cout * 4 * Cin;
+  if (idx >= total) return;
+  const int ci = idx % Cin;
+  const int ab = (idx / Cin) % 4;                    // (a, b): which of the parity's 2 x 2 taps
+  const int co = (idx / (static_cast<long>(Cin) * 4)) % Cout;
+  const int par = idx / (static_cast<long>(Cin) * 4 * Cout);
+  const int dy = par >> 1, dx = par & 1, a = ab >> 1, b = ab & 1;
+  const int R = dy + a, S = dx + b;
+  // V(d, T): the original taps that land on low-resolution offset T - 1 for output parity d
+  const int r_lo = dy == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r_hi = dy == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+  const int s_lo = dx == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s_hi = dx == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+  const float* wp = w + (static_cast<long>(co) * Cin + ci) * 9;
+  float acc = 0.f;
+  for (int r = r_lo; r <= r_hi; ++r)
+    for (int s = s_lo; s <= s_hi; ++s) acc += wp[r * 3 + s];
+  dst[(static_cast<long>(par) * Cout + co) * (9 * cin_pad) + (R * 3 + S) * cin_pad + ci] = to_op(acc);
+}
+int pack_conv_weight_up2_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s) {
+  const long total = static_cast<long>(4) * Cout * 4 * Cin;
+  pack_conv_weight_up2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, cin_pad);
+  return SGDM_LAUNCH_OK();
+}
 __global__ void pack_first_conv_im2col_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cimg, int L) {
   const int ce = 2 * Cimg + L, idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * 9 * ce) return;

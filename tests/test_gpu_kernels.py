@@ -219,6 +219,74 @@ def test_conv_head_folded_horizontal_taps(L, case):
         assert relerr(out, out2) < 2e-6
 
 
+UP2_CASES = [
+    # (B, H, W, Cin, Cout, out, gran, note)  -- H, W are the LOW resolution
+    (3, 16, 16, 128, 256, "f32", 4, "16x16 -> 32x32, N = 4 x 256, odd batch"),
+    (2, 32, 32, 256, 256, "op", 4, "32x32 -> 64x64, 16-bit out"),
+    (2, 32, 32, 512, 512, "op", 0, "config-2 shape 512 -> 512, two n-tiles per parity, no statistics"),
+    (1, 64, 64, 64, 128, "f32", 2, "64x64 -> 128x128 (2-row tiles), block_n 128"),
+    (5, 8, 16, 192, 64, "f32", 2, "8x16 images, Cin = 192, N = 64"),
+    (40, 16, 16, 128, 256, "op", 4, "80 m-tiles x 4 parities: persistent loop, both accumulator stages"),
+]
+
+
+@pytest.mark.parametrize("case", UP2_CASES, ids=[c[-1] for c in UP2_CASES])
+def test_conv_subpixel_upsample_vs_torch(L, case):
+    """"nearest-2x upsample, then 3x3 conv" run as four 2x2 parity convs on the low-resolution tensor (ConvDesc::up2):
+    (a) against torch conv2d on the upsampled tensor (the definition; differs only by the single rounding of the summed
+    weights), (b) tightly against the same parity sums formed in torch, (c) the epilogue's GroupNorm statistics."""
+    B, H, W, Cin, Cout, out, gran, note = case
+    g = torch.Generator(device="cuda").manual_seed(abs(hash(note)) % 2**31)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(Cin * 9)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    xu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref_def = F.conv2d(xu, w, bias, padding=1)                                   # (a) unrounded weights
+    # (b) parity (dy, dx): 2x2 kernel over the low-resolution input, taps at offsets (dy-1+a, dx-1+b)
+    V = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    ref_par = torch.empty_like(ref_def)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    for dy in (0, 1):
+        for dx in (0, 1):
+            k = torch.zeros(Cout, Cin, 2, 2, device="cuda")
+            for a in (0, 1):
+                for b in (0, 1):
+                    k[:, :, a, b] = sum(w[:, :, r, s] for r in V[(dy, a)] for s in V[(dx, b)])
+            k = k.to(L._op).float()
+            o = F.conv2d(xp[:, :, dy:dy + H + 1, dx:dx + W + 1], k, bias)       # [B, Cout, H, W]
+            ref_par[:, :, dy::2, dx::2] = o
+    scratch = torch.empty(4 * Cout * 9 * Cin, dtype=L._op, device="cuda")
+    nblk = B * 4 * H * W // 32
+    for label, naive, pair in (("naive", 1, -1), ("tcgen05 1-CTA", 0, 0), ("tcgen05 CTA pair", 0, 1), ("policy", 0, -1)):
+        o32 = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device="cuda") if out == "f32" else None
+        oop = torch.zeros((B, 2 * H, 2 * W, Cout), dtype=L._op, device="cuda") if out == "op" else None
+        stats = torch.full((nblk, Cout // gran, 2), float("nan"), device="cuda") if gran and not naive else None
+        L.sgdm_debug_set_conv_pair(pair)
+        try:
+            ck(L, L.sgdm_k_conv_up2(S(), P(x), B, H, W, Cin, P(w.contiguous()), P(scratch), P(bias), P(o32), P(oop), Cout,
+                                    P(stats), gran or 4, naive))
+        finally:
+            L.sgdm_debug_set_conv_pair(-1)
+        torch.cuda.synchronize()
+        got = (o32 if o32 is not None else oop).float()
+        assert torch.isfinite(got).all(), label
+        e_def = relerr(got.permute(0, 3, 1, 2), ref_def)
+        e_par = relerr(got.permute(0, 3, 1, 2), ref_par)
+        print(f"[conv up2 {note}] {label}: vs definition {e_def:.3e}, vs parity sums {e_par:.3e}")
+        assert e_par < (out_tol(L, 2e-3) if out == "op" else 2e-5), label
+        assert e_def < out_tol(L, 3e-3), label
+        if stats is not None:
+            # sample n's 4HW/32 row blocks: parity-major, then 32-pixel blocks of the LOW-resolution raster
+            q = got.double().reshape(B, H, 2, W, 2, Cout).permute(0, 2, 4, 1, 3, 5).reshape(B, 4, H * W // 32, 32, Cout // gran, gran)
+            want = torch.stack([q.sum((3, 5)), (q * q).sum((3, 5))], -1).reshape(nblk, Cout // gran, 2)
+            assert torch.isfinite(stats).all(), label
+            assert relerr(stats, want) < 1e-5, label
+            # and per sample they add up to the sample's plain sums (what gn_finalize consumes)
+            tot = stats.double().reshape(B, -1, Cout // gran, 2).sum(1)
+            q2 = got.double().reshape(B, -1, Cout // gran, gran)
+            assert relerr(tot[..., 0], q2.sum((1, 3))) < 1e-6 or float(q2.sum((1, 3)).abs().max()) < 1e-3
+
+
 STATS_CASES = [
     # (B, H, W, Cin, Cout, ks, res_mode, out, block_n, gran, note)
     (3, 16, 16, 64, 256, 3, 1, "f32", 256, 4, "fp32 out + residual, N=256, gran 4"),
