@@ -63,6 +63,8 @@ struct Param {
 struct ResW {
   int cin = 0, cout = 0;
   bool up = false, down = false, skip = false;
+  int hin = 0;      // input resolution (H = W) of an up block
+  bool up2 = false; // conv1 of an up block in the sub-pixel mode (ConvDesc::up2): w1 holds the [4 cout][9 cin] parity packing
   float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *bskip = nullptr, *bfused = nullptr;
   op_t *w1 = nullptr, *w2 = nullptr;
@@ -81,6 +83,8 @@ struct AttnLRW {  // Attention_LR
 };
 struct ConvW {
   int cin = 0, cin_pad = 0, cout = 0;
+  int hin = 0;       // Upsample.conv: resolution (H = W) of the tensor being upsampled
+  bool up2 = false;  // Upsample.conv in the sub-pixel mode: w holds the parity packing
   op_t* w = nullptr;
   float* b = nullptr;
   op_t* w_hfold = nullptr;  // output head only: the [16][3 * cin_pad] packing of ConvDesc::hfold
@@ -164,6 +168,7 @@ struct sgdm_engine {
   bool device_ready = false;
   std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + (shared-prefix variant)
   bool share_prefix = true;                     // SGDM_SHARE_PREFIX=0: A/B
+  bool use_up2 = true;                          // SGDM_UP2=0: A/B (sub-pixel execution of upsample + conv)
   uint64_t plan_clock = 0;                      // LRU stamp source
   bool profiling = false;
   Plan* last_profiled = nullptr;
@@ -395,8 +400,13 @@ int build_topology(sgdm_engine* e) {
         layers.push_back({L_ATTN, add_attn(e, name("output_blocks.%d.%d", o, static_cast<int>(layers.size())), ch)});
       if (level && i == c.num_res_blocks) {
         const int li = static_cast<int>(layers.size());
-        if (updown) layers.push_back({L_RES, add_res(e, name("output_blocks.%d.%d", o, li), ch, ch, true, false)});
-        else layers.push_back({L_UP, add_conv(e, name("output_blocks.%d.%d", o, li) + ".conv", ch, ch)});
+        if (updown) {
+          layers.push_back({L_RES, add_res(e, name("output_blocks.%d.%d", o, li), ch, ch, true, false)});
+          e->res[layers.back().idx].hin = c.image_size / ds;
+        } else {
+          layers.push_back({L_UP, add_conv(e, name("output_blocks.%d.%d", o, li) + ".conv", ch, ch)});
+          e->convs[layers.back().idx].hin = c.image_size / ds;
+        }
         ds /= 2;
       }
       e->out_blocks.push_back(layers);
@@ -435,6 +445,12 @@ int64_t numel(const std::vector<int64_t>& s) {
 std::function<int(const float*, cudaStream_t)> copy_loader(float* dst, int64_t n) {
   return [dst, n](const float* src, cudaStream_t s) {
     return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
+  };
+}
+std::function<int(const float*, cudaStream_t)> pack_up2_loader(op_t* dst, int cout, int cin) {
+  return [=](const float* src, cudaStream_t s) {
+    ++g_launches;
+    return pack_conv_weight_up2_launch(src, dst, cout, cin, cin, s);
   };
 }
 std::function<int(const float*, cudaStream_t)> pack_loader(op_t* dst, int cout, int cin, int ks, int cin_pad,
@@ -515,8 +531,11 @@ int setup_device(sgdm_engine* e) {
         return 1;
       const int k1 = 9 * r.cin * S, k2 = (9 * r.cout + (r.skip ? r.cin : 0)) * S;
       const int np = conv_npad(r.cout, pick_block_n(r.cout));
-      if (dalloc(e, &r.w1, static_cast<size_t>(np) * k1) || dalloc(e, &r.w2, static_cast<size_t>(np) * k2)) return 1;
-      if (bind_loader(e, p + ".in_layers.2.weight", pack_loader(r.w1, r.cout, r.cin, 3, S * r.cin, k1, 0, nullptr, part(r.cin)))) return 1;
+      // up block: upsample + conv1 as four 2x2 parity convs on the low-resolution tensor (2.25x fewer MACs)
+      r.up2 = r.up && e->use_up2 && !e->x3 && conv_up2_applicable(r.hin, r.hin, r.cin, r.cout, pick_block_n(r.cout));
+      if (dalloc(e, &r.w1, static_cast<size_t>(r.up2 ? 4 * r.cout : np) * k1) || dalloc(e, &r.w2, static_cast<size_t>(np) * k2)) return 1;
+      if (bind_loader(e, p + ".in_layers.2.weight", r.up2 ? pack_up2_loader(r.w1, r.cout, r.cin)
+                                                          : pack_loader(r.w1, r.cout, r.cin, 3, S * r.cin, k1, 0, nullptr, part(r.cin)))) return 1;
       if (bind_loader(e, p + ".out_layers.3.weight", pack_loader(r.w2, r.cout, r.cout, 3, S * r.cout, k2, 0, nullptr, part(r.cout)))) return 1;
       if (dalloc(e, &r.b2, r.cout) || dalloc(e, &r.bfused, r.cout)) return 1;
       float *b2 = r.b2, *bf = r.bfused;
@@ -585,8 +604,10 @@ int setup_device(sgdm_engine* e) {
       const std::string pp = L.kind == L_DOWN ? p + ".op" : L.kind == L_UP ? p + ".conv" : p;
       if (e->x3) cw.cin_pad = L.kind == L_CONV_IN ? e->xin_c : 3 * cw.cin;  // split parts of cw.cin channels
       const int ktot = 9 * cw.cin_pad;
-      if (dalloc(e, &cw.w, static_cast<size_t>(conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
+      cw.up2 = L.kind == L_UP && e->use_up2 && !e->x3 && conv_up2_applicable(cw.hin, cw.hin, cw.cin, cw.cout, pick_block_n(cw.cout));
+      if (dalloc(e, &cw.w, static_cast<size_t>(cw.up2 ? 4 * cw.cout : conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
       if (bind_f32(e, pp + ".bias", &cw.b)) return 1;
+      if (cw.up2) return bind_loader(e, pp + ".weight", pack_up2_loader(cw.w, cw.cout, cw.cin));
       const int* map = (L.kind == L_CONV_IN && !e->x3) ? e->ci_map_first : nullptr;
       if (L.kind == L_CONV_IN && e->first_im2col) {
         // [Npad][64]: K = tap * (2 Cimg + L) + entry; the buffer (sized for the 3x3 packing) is reused
@@ -708,7 +729,8 @@ struct Builder {
   void conv(ConvDesc d, int real_cin = 0) {
     if (d.B == 0) d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
-    d.swap_ab = conv_should_swap(d) ? 1 : 0;
+    d.swap_ab = !d.up2 && conv_should_swap(d) ? 1 : 0;
+    if (d.up2) d.halo = 1;
     d.stat_gran = stat_gran();
     // geometry (pair / halo / 32-channel K blocks / A-stationary): the kernel's own policy (conv.cuh, conv_prepare)
     if (d.hfold) { d.halo = 1; d.pair = 0; }
@@ -720,7 +742,8 @@ struct Builder {
       err = 1;
       return;
     }
-    const double M = static_cast<double>(d.B) * d.Hout * d.Wout;
+    // (sub-pixel mode: the algorithmic figures are the reference's — 4 H W output pixels x 9 taps; 4/9 of them execute)
+    const double M = static_cast<double>(d.B) * d.Hout * d.Wout * (d.up2 ? 4 : 1);
     // algorithmic K: the reference's channel counts (split-precision mode executes 3x that)
     const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin / S) + (d.in2 ? (d.C2 + (d.in2b ? d.C2b : 0)) / S : 0);
     const double flops = 2.0 * M * d.Cout * k_real;
@@ -767,7 +790,7 @@ struct Builder {
     const int C = a.C + b.C, H = a.H, W = a.W;
     const int Ho = r.down ? H / 2 : r.up ? H * 2 : H, Wo = r.down ? W / 2 : r.up ? W * 2 : W;
     const size_t px_in = static_cast<size_t>(Bp) * H * W, px_out = static_cast<size_t>(Bp) * Ho * Wo;
-    op_t* g1 = static_cast<op_t*>(scratch("gn_out", px_out * C * S * sizeof(op_t)));
+    op_t* g1 = static_cast<op_t*>(scratch("gn_out", (r.up2 ? px_in : px_out) * C * S * sizeof(op_t)));
     // 16-bit input copies (with producer statistics) for every source: the GroupNorm reads 2 B instead of 4 B
     // per element and the fused 1x1 skip conv reads the copies directly (no raw concat copy).  A down block
     // pools its fp32 input for the residual, so it keeps the fp32 path.
@@ -783,7 +806,7 @@ struct Builder {
     g.src_mod1 = b.Bs;       // the skip source of the last up block is the shared first-conv output
     if (in16) { g.src0 = a.p16; g.src1 = b.p16; g.src0_is_op = 1; }
     else { g.src0 = a.p; g.src1 = b.p; }
-    g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : r.up ? 2 : 0;
+    g.gamma = r.gn1_w; g.beta = r.gn1_b; g.silu = 1; g.resample = r.down ? 1 : (r.up && !r.up2) ? 2 : 0;
     g.out = g1; g.raw_out = raw; g.pool_out = pooled;
     g.stats0 = a.stats; g.stats1 = b.stats;
     g.split3 = split3;
@@ -799,6 +822,7 @@ struct Builder {
     c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C * S; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
     c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.stats = h1_stats;
     c1.B = Bb;
+    if (r.up2) { c1.Hin = H; c1.Win = W; c1.Hout = H; c1.Wout = W; c1.up2 = 1; }  // low-resolution grid, [B, 2H, 2W, C] output
     if (split3) c1.out_f32 = h1f;
     else c1.out_op = h1;
     conv(c1);
@@ -952,10 +976,11 @@ struct Builder {
   Act resample_conv(const ConvW& cw, Act a, bool up) {
     const int Hc = up ? a.H * 2 : a.H, Wc = up ? a.W * 2 : a.W;  // conv input size
     const int Ho = up ? Hc : a.H / 2, Wo = up ? Wc : a.W / 2;
-    op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * Hc * Wc * a.C * S * sizeof(op_t)));
+    const bool up2 = up && cw.up2;
+    op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * (up2 ? a.H * a.W : Hc * Wc) * a.C * S * sizeof(op_t)));
     {
       const float* src = a.p;
-      const int B = Bp, H = a.H, W = a.W, C = a.C, u = up ? 1 : 0, sp = split3;
+      const int B = Bp, H = a.H, W = a.W, C = a.C, u = (up && !up2) ? 1 : 0, sp = split3;
       push([=](cudaStream_t s) {
         ++g_launches;
         return cast_launch(src, raw, B, H, W, C, u, s, sp);
@@ -968,6 +993,7 @@ struct Builder {
     c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C * S; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
     c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
     attach_outputs(o, static_cast<size_t>(Bp) * Ho * Wo, c);
+    if (up2) { c.Hin = a.H; c.Win = a.W; c.Hout = a.H; c.Wout = a.W; c.up2 = 1; }
     conv(c);
     return o;
   }
@@ -1324,6 +1350,7 @@ int sgdm_create(const sgdm_config* cfg, sgdm_handle* out) {
   std::unique_ptr<sgdm_engine> e(new sgdm_engine());
   e->cfg = *cfg;
   if (const char* ev = getenv("SGDM_GRAPH")) e->graph_mode = atoi(ev) != 0 ? 1 : 0;  // A/B: force graph replay on / off
+  if (const char* ev = getenv("SGDM_UP2")) e->use_up2 = atoi(ev) != 0;  // read before the weights are packed
   if (const char* ev = getenv("SGDM_SHARE_PREFIX")) e->share_prefix = atoi(ev) != 0;  // A/B: shared CFG prefix of guided plans
   if (build_topology(e.get())) return 1;
   *out = e.release();

@@ -1130,6 +1130,17 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   return 0;
 }
 
+bool conv_up2_applicable(int H, int W, int Cin, int Cout, int block_n) {
+  const int HW = H * W;
+  if ((Cin % 64) || block_n < 64 || (Cout % block_n) || Cout == 128) return false;  // (Cout = 128 layers run swap-AB)
+  if (W < 8 || (W % 8) || W > kTileM || (kTileM % W) || (HW % kTileM)) return false;  // whole rows of one image per tile
+  if (W < 32 ? (32 % W) != 0 : (W % 32) != 0) return false;                         // 32-pixel store chunks
+  const int bh = kTileM / W;
+  // two halo stages of (bh + 2) rows + two weight slots each (one CTA per tile: the larger case) beside 2 staging buffers
+  const int stage = (bh + 2) * W * 128 + 2 * block_n * 128;
+  return 2 * stage + 4 * 2 * kEpiBuf + kBarBytes + kBiasBytes <= kSmemLimit;
+}
+
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
   const cudaError_t e = l.pair ? launch_pdl(conv_gemm_kernel<2>, dim3(l.grid), dim3(kConvThreads), l.smem, stream, 2, l.p)
                                : launch_pdl(conv_gemm_kernel<1>, dim3(l.grid), dim3(kConvThreads), l.smem, stream, 1, l.p);
