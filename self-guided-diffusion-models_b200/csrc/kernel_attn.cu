@@ -48,7 +48,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 constexpr int kAttnQ = 128;       // queries per CTA
 constexpr int kAttnThreads = 256;  // 8 warps x 16 query rows
 
-template <int D>
+// D: head dim as the MMAs see it (multiple of 16); DR <= D: the real head dim (8 for 32 heads on 256 channels — the rows
+// are zero-extended to 16 in shared memory)
+template <int D, int DR = D>
 __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, int tkv_pad) {
   constexpr int LD = D + 8;  // padded row: conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tkv = a.n_extra + a.T;
-  constexpr int CPR = D / 8;  // 16-byte chunks per row
+  constexpr int CPR = D / 8;   // 16-byte chunks per row
+  constexpr int CPRR = DR / 8;  // ... that exist in global memory
 
   // ---- stage K, V (extra rows first, then the T self rows) and the Q tile: 16-byte cp.async,
   //      zero-fill for the padding rows
@@ -69,8 +72,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
     const int row = i / CPR, ch = i - row * CPR;
     op_t* dk = sK + row * LD + ch * 8;
     op_t* dv = sV + row * LD + ch * 8;
-    if (row < a.n_extra) {
-      const long o = (static_cast<long>(n) * a.n_extra + row) * D + ch * 8;
+    if (ch >= CPRR) {
+      *reinterpret_cast<uint4*>(dk) = zero4;
+      *reinterpret_cast<uint4*>(dv) = zero4;
+    } else if (row < a.n_extra) {
+      const long o = (static_cast<long>(n) * a.n_extra + row) * DR + ch * 8;
       cp_async16(dk, a.k_extra + o);
       cp_async16(dv, a.v_extra + o);
     } else if (row < Tkv) {
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
   for (int i = threadIdx.x; i < kAttnQ * CPR; i += kAttnThreads) {
     const int row = i / CPR, ch = i - row * CPR;
     op_t* dq = sQ + row * LD + ch * 8;
-    if (q0 + row < a.T)
+    if (q0 + row < a.T && ch < CPRR)
       cp_async16(dq, a.q + (static_cast<long>(n) * a.T + q0 + row) * a.q_row_stride + h * a.q_head_stride + ch * 8);
     else
       *reinterpret_cast<uint4*>(dq) = zero4;
@@ -180,11 +186,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
 #pragma unroll
   for (int nd = 0; nd < D / 8; ++nd) {
     const int d = nd * 8 + (lane & 3) * 2;
+    if (d >= DR) continue;
     if (r0 < a.T)
-      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r0) * a.o_row_stride + h * D + d) =
+      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r0) * a.o_row_stride + h * DR + d) =
           pack_op2(o[nd][0] * i0, o[nd][1] * i0);
     if (r1 < a.T)
-      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r1) * a.o_row_stride + h * D + d) =
+      *reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(n) * a.T + r1) * a.o_row_stride + h * DR + d) =
           pack_op2(o[nd][2] * i1, o[nd][3] * i1);
   }
 }
@@ -194,12 +201,13 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
   if (a.use_tc != 0 && attn_lr_tc_applicable(a)) return attn_lr_tc_launch(a, s);
   const int Tkv = a.n_extra + a.T;
   const int tkv_pad = (Tkv + 63) / 64 * 64;
-  if (a.D != 32 && a.D != 64 && a.D != 128) return 1;  // head dims of the reference configs (mc 64 / 128 / 256, 8 heads)
-  const int LD = a.D + 8;
+  // head dims of the reference configs (mc 64 / 128 / 256 with 8 heads: 32, 64, 128) and of num_heads = 32 (8, 16)
+  if (a.D != 8 && a.D != 16 && a.D != 32 && a.D != 64 && a.D != 128) return 1;
+  const int LD = (a.D < 16 ? 16 : a.D) + 8;
   const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + kAttnQ) * LD * sizeof(op_t);
   if (smem > 200 * 1024) return 1;
   const dim3 grid((a.T + kAttnQ - 1) / kAttnQ, a.heads, a.B);
-  static size_t max_set[3] = {0, 0, 0};  // opt-in dynamic smem limit, raised on demand
+  static size_t max_set[5] = {0, 0, 0, 0, 0};  // opt-in dynamic smem limit, raised on demand
   auto run = [&](auto kernel, size_t& limit) {
     if (smem > limit) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
@@ -208,7 +216,8 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
     }
     return launch_pdl(kernel, grid, dim3(kAttnThreads), smem, s, 1, a, tkv_pad) == cudaSuccess ? 0 : 1;
   };
-  if (a.D == 64 ? run(attn_kernel<64>, max_set[0]) : a.D == 32 ? run(attn_kernel<32>, max_set[1]) : run(attn_kernel<128>, max_set[2]))
+  if (a.D == 64 ? run(attn_kernel<64>, max_set[0]) : a.D == 32 ? run(attn_kernel<32>, max_set[1]) :
+      a.D == 128 ? run(attn_kernel<128>, max_set[2]) : a.D == 16 ? run(attn_kernel<16>, max_set[3]) : run(attn_kernel<16, 8>, max_set[4]))
     return 1;
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

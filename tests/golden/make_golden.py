@@ -65,6 +65,14 @@ CASES = {
              num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
              resblock_updown=False, cond_dim=0, condition_method="layout", layout_dim=21,
              context_dim=32, cond_token_num=0, scale_type="imagen"), 2),
+    # the attention layout of config/dynamic/unet.yaml (attention at ds 2 and 4, 32 heads: head dims 8 and 16) through the
+    # constructor the reference actually has (unet.yaml as written passes `num_classes` / `cond_mlp_divide`, which
+    # UNetModel.__init__ rejects with a TypeError)
+    "unet_heads32_ds24_tiny": (
+        dict(kind="unet_fast", image_size=16, in_channels=3, out_channels=3, model_channels=128,
+             num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[2, 4], num_heads=32,
+             resblock_updown=True, cond_dim=10, condition_method="label", layout_dim=0,
+             context_dim=None, cond_token_num=0, scale_type="imagen"), 2),
     # BASELINE.json configs at their true shapes (batch kept small: CPU reference)
     "cfg1_cifar_label": (
         dict(kind="unet_fast", image_size=32, in_channels=3, out_channels=3, model_channels=64,

@@ -219,6 +219,51 @@ def test_conv_head_folded_horizontal_taps(L, case):
         assert relerr(out, out2) < 2e-6
 
 
+BN192_CASES = [
+    # (B, H, W, Cin, Cout, ks, res, out, note)
+    (3, 16, 16, 384, 384, 3, True, "f32", "3x3 384 -> 384 at 16x16, residual, two 192-column tiles"),
+    (2, 32, 32, 128, 192, 3, False, "op", "3x3 128 -> 192 at 32x32, 16-bit out (three 64-channel chunks)"),
+    (5, 16, 16, 384, 1152, 1, False, "op", "1x1 qkv 384 -> 1152: six tiles, A-stationary"),
+    (4, 8, 8, 768, 384, 3, False, "f32", "3x3 768 -> 384 at 8x8 (tile spans two images)"),
+]
+
+
+@pytest.mark.parametrize("case", BN192_CASES, ids=[c[-1] for c in BN192_CASES])
+def test_conv_192_column_tiles(L, case):
+    """block_n = 192 (the engine's choice for 192 / 384 / 576 output channels): one CTA, CTA pair, policy; with the
+    epilogue's GroupNorm statistics."""
+    B, H, W, Cin, Cout, ks, with_res, out, note = case
+    g = torch.Generator(device="cuda").manual_seed(abs(hash(note)) % 2**31)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(L._op)
+    w = torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * ks * ks)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g) if with_res else None
+    wp, _ = pack_weight(L, w, None, 192)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=ks // 2)
+    if with_res:
+        ref = ref + res.permute(0, 3, 1, 2)
+    M = B * H * W
+    nblk = (M + 31) // 32
+    for label, pair in (("1-CTA", 0), ("CTA pair", 1), ("policy", -1)):
+        o32 = torch.full((B, H, W, Cout), float("nan"), device="cuda") if out == "f32" else None
+        oop = torch.zeros((B, H, W, Cout), dtype=L._op, device="cuda") if out == "op" else None
+        stats = torch.full((nblk, Cout // 4, 2), float("nan"), device="cuda")
+        L.sgdm_debug_set_conv_pair(pair)
+        try:
+            ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res),
+                                      1 if with_res else 0, P(o32), P(oop), None, 192, 0, P(stats), 4, None, None, 0))
+        finally:
+            L.sgdm_debug_set_conv_pair(-1)
+        torch.cuda.synchronize()
+        got = (o32 if o32 is not None else oop).float()
+        e = relerr(got.permute(0, 3, 1, 2), ref)
+        print(f"[conv block_n 192: {note}] {label} rel_l2={e:.3e}")
+        assert e < (out_tol(L, 2e-3) if out == "op" else 2e-5), label
+        blk = got.double().reshape(nblk, 32, Cout // 4, 4)
+        want = torch.stack([blk.sum((1, 3)), (blk * blk).sum((1, 3))], -1)
+        assert relerr(stats, want) < 1e-5, label
+
+
 UP2_CASES = [
     # (B, H, W, Cin, Cout, out, gran, note)  -- H, W are the LOW resolution
     (3, 16, 16, 128, 256, "f32", 4, "16x16 -> 32x32, N = 4 x 256, odd batch"),
@@ -226,6 +271,7 @@ UP2_CASES = [
     (2, 32, 32, 512, 512, "op", 0, "config-2 shape 512 -> 512, two n-tiles per parity, no statistics"),
     (1, 64, 64, 64, 128, "f32", 2, "64x64 -> 128x128 (2-row tiles), block_n 128"),
     (5, 8, 16, 192, 64, "f32", 2, "8x16 images, Cin = 192, N = 64"),
+    (3, 16, 16, 384, 384, "op", 4, "config-2 shape 384 -> 384 at 16x16: 192-column tiles, two per parity"),
     (40, 16, 16, 128, 256, "op", 4, "80 m-tiles x 4 parities: persistent loop, both accumulator stages"),
 ]
 
@@ -492,6 +538,11 @@ ATTN_CASES = [
     (1, 100, 4, 64, 5, True, "ragged T=100"),
     (2, 256, 8, 128, 0, False, "legacy, T=256 d=128 (unet_fast_s64: mc=256)"),
     (2, 64, 8, 128, 0, False, "legacy, T=64 d=128"),
+    (2, 256, 32, 8, 0, False, "32 heads on 256 channels: d=8 (zero-extended to 16)"),
+    (2, 64, 32, 16, 0, False, "32 heads on 512 channels: d=16"),
+    (1, 1024, 32, 8, 0, False, "T=1024 d=8 (64x64 images, attention at ds 2)"),
+    (1, 1024, 32, 16, 0, False, "T=1024 d=16"),
+    (2, 100, 4, 16, 5, True, "MQA d=16, ragged T, 5 extra keys"),
 ]
 
 
