@@ -50,12 +50,15 @@ typedef struct sgdm_config {
   int32_t cond_dim;
   int32_t layout_dim;     /* 0 | clusterlayout: 1 | stegoclusterlayout: 27 */
   int32_t context_dim;    /* unetca_fast: 32 */
-  int32_t cond_token_num; /* unetca_fast: 1 */
+  int32_t cond_token_num; /* unetca_fast: 1 (README runs) | 0 (layout-only) | N > 1: cond is [B, N, cond_dim] tokens */
   /* 0 (default): 16-bit GEMM operands, fp32 accumulation — the throughput path.
    * 1 ("fp16 x3"): every conv / GEMM on split operands (a_hi w_hi + a_hi w_lo + a_lo w_hi, ~22-bit operands, fp32
    *    accumulation) at ~3x the tensor work: for deterministic samplers (DDIM eta=0, PLMS) on ill-conditioned
    *    networks, where 16-bit operand rounding is amplified along the trajectory. */
   int32_t precision;
+  /* cond_token_num > 1 only: the vector fed to cond_mlp is token 0 (1, the reference config's value) or the mean over
+   * the tokens (0) (openaimodel_ca.py:1000-1006) */
+  int32_t use_cls_token_as_pooled;
 } sgdm_config;
 
 const char* sgdm_last_error(void);

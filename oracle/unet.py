@@ -241,7 +241,7 @@ def param_shapes(cfg):
     add = lambda n, *shape: out.append((n, tuple(shape)))
     has_cond = cd > 0 if not ca else cfg["cond_token_num"] > 0
     if has_cond:
-        add("null_cond_emb", 1, cd)
+        add("null_cond_emb", cfg["cond_token_num"] if ca and cfg["cond_token_num"] > 1 else 1, cd)
     if L > 0:
         add("null_layout_emb", 1, 1, H, H)
     add("time_embed.0.weight", ted, mc); add("time_embed.0.bias", ted)
@@ -336,6 +336,21 @@ def unet_forward(sd, cfg, x, timesteps, cond=None, layout=None, drop_mask=None, 
         if method == "layout":
             lm = torch.where(drop_mask[:, None, None, None], sd["null_layout_emb"], layout)
             x = torch.cat((x, lm), dim=1)
+        context = F.layer_norm(context, context.shape[-1:], sd["norm_cond.weight"], sd["norm_cond.bias"])
+    elif cfg["cond_token_num"] > 1:
+        # token condition [B, N, cond_dim] (openaimodel_ca.py:988-1012): masked against null_cond_emb [N, cond_dim],
+        # every token through the to_cond_tokens_2d MLP, pooled (CLS token or mean) into cond_mlp
+        assert cond.dim() == 3
+        tt = _lin(sd, "to_time_tokens.2", F.silu(_lin(sd, "to_time_tokens.0", t_emb)))
+        time_tokens = tt.reshape(b, 8, cfg["context_dim"])
+        cond_masked = torch.where(drop_mask[:, None, None], sd["null_cond_emb"], cond.float())
+        h2 = cond_masked
+        for i in (0, 2, 4):
+            h2 = F.silu(_lin(sd, f"to_cond_tokens_2d.{i}", h2))
+        cond_tokens = _lin(sd, "to_cond_tokens_2d.6", h2)
+        context = torch.cat([time_tokens, cond_tokens], 1)
+        pooled = cond_masked[:, 0, :] if cfg.get("use_cls_token_as_pooled", True) == True else cond_masked.mean(dim=1)  # noqa: E712
+        emb = emb + _mlp2(sd, "cond_mlp", pooled)
         context = F.layer_norm(context, context.shape[-1:], sd["norm_cond.weight"], sd["norm_cond.bias"])
     else:
         assert cfg["cond_token_num"] == 1 and cond.dim() == 2  # openaimodel_ca.py:960-961

@@ -33,6 +33,7 @@ class SgdmConfig(C.Structure):
         ("context_dim", C.c_int32),
         ("cond_token_num", C.c_int32),
         ("precision", C.c_int32),
+        ("use_cls_token_as_pooled", C.c_int32),
     ]
 
 

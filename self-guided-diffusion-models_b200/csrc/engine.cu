@@ -167,6 +167,7 @@ struct sgdm_engine {
   std::vector<void*> owned;
   bool device_ready = false;
   std::map<int, std::unique_ptr<Plan>> plans;  // key = 2 * batch rows + (shared-prefix variant)
+  int cond_w = 0;                               // floats per sample of the cond input: cond_dim (x cond_token_num if > 1)
   bool share_prefix = true;                     // SGDM_SHARE_PREFIX=0: A/B
   bool use_up2 = true;                          // SGDM_UP2=0: A/B (sub-pixel execution of upsample + conv)
   uint64_t plan_clock = 0;                      // LRU stamp source
@@ -289,9 +290,13 @@ int build_topology(sgdm_engine* e) {
   if (mc % 64) return fail("model_channels must be a multiple of 64 (got %d)", mc);
   if (c.n_channel_mult < 1 || c.n_channel_mult > 8) return fail("bad channel_mult");
   // unetca_fast: cond_token_num 1 (a [B, cond_dim] condition: cluster / attr / stego_attr ...) or 0 (no condition
-  // vector: the `layout`-only model, cond_dim == 0, openaimodel_ca.py:562-564,944-958)
-  if (e->ca && (c.context_dim <= 0 || !((c.cond_token_num == 1 && c.cond_dim > 0) || (c.cond_token_num == 0 && c.cond_dim == 0))))
-    return fail("unetca_fast: cond_token_num must be 1 (with cond_dim > 0) or 0 (with cond_dim == 0), and context_dim > 0");
+  // vector: the `layout`-only model, cond_dim == 0, openaimodel_ca.py:562-564,944-958), or N > 1 (a [B, N, cond_dim] token condition, e.g. patch features, :988-1012 — the
+  // reference concatenates no layout on that branch, so layout_dim must be 0)
+  if (e->ca && (c.context_dim <= 0 || !((c.cond_token_num >= 1 && c.cond_dim > 0) || (c.cond_token_num == 0 && c.cond_dim == 0))))
+    return fail("unetca_fast: cond_token_num must be >= 1 (with cond_dim > 0) or 0 (with cond_dim == 0), and context_dim > 0");
+  if (e->ca && c.cond_token_num > 1 && (c.layout_dim != 0 || 8 + c.cond_token_num > kMaxCtxTok))
+    return fail("unetca_fast: cond_token_num > 1 takes no layout input (openaimodel_ca.py:988-1012) and at most %d tokens", kMaxCtxTok - 8);
+  e->cond_w = c.cond_dim * (e->ca && c.cond_token_num > 1 ? c.cond_token_num : 1);
   if (!e->ca && c.layout_dim > 1) return fail("unet_fast supports clusterlayout (layout_dim 1) only (openaimodel.py:623)");
   if (c.precision != 0 && c.precision != 1) return fail("precision must be 0 (fp16 operands) or 1 (split fp16 x3), got %d", c.precision);
   e->x3 = c.precision == 1;
@@ -321,7 +326,7 @@ int build_topology(sgdm_engine* e) {
   } else {
     const int ctx = c.context_dim;
     const bool has_cond = c.cond_token_num > 0;
-    if (has_cond) add_param(e, "null_cond_emb", {1, c.cond_dim});
+    if (has_cond) add_param(e, "null_cond_emb", {c.cond_token_num > 1 ? c.cond_token_num : 1, c.cond_dim});
     if (c.layout_dim > 0) add_param(e, "null_layout_emb", {1, 1, c.image_size, c.image_size});
     add_param(e, "time_embed.0.weight", {ted, mc});
     add_param(e, "time_embed.0.bias", {ted});
@@ -341,7 +346,7 @@ int build_topology(sgdm_engine* e) {
       add_param(e, "to_cond_tokens.0.weight", {ctx * 8, c.cond_dim});
       add_param(e, "to_cond_tokens.0.bias", {ctx * 8});
       // to_cond_tokens_2d is built by the reference for every cond_token_num > 0 but only used
-      // when cond_token_num > 1 (openaimodel_ca.py:605-614,998): accepted, never read.
+      // when cond_token_num > 1 (openaimodel_ca.py:605-614,998): otherwise accepted, never read.
       const int mid = static_cast<int>(sqrt(static_cast<double>(ctx) * c.cond_dim));
       add_param(e, "to_cond_tokens_2d.0.weight", {mid, c.cond_dim});
       add_param(e, "to_cond_tokens_2d.0.bias", {mid});
@@ -499,6 +504,7 @@ int setup_device(sgdm_engine* e) {
     const std::string& n = p.name;
     if (n.rfind("time_embed.", 0) == 0 || n.rfind("mlp_cond.", 0) == 0 || n.rfind("cond_mlp.", 0) == 0 ||
         n.rfind("to_time_tokens.", 0) == 0 || n.rfind("to_cond_tokens.0", 0) == 0 || n.rfind("norm_cond.", 0) == 0 ||
+        (c.cond_token_num > 1 && n.rfind("to_cond_tokens_2d.", 0) == 0) ||
         n == "null_cond_emb" || n == "null_layout_emb")
       plain.push_back(n);
   }
@@ -1004,7 +1010,10 @@ struct Builder {
   }
 
   // extra key / value rows of every Attention_LR site: 8 time tokens (+ 8 condition tokens) + the null key
-  int n_ctx_rows() const { return (e->cfg.cond_token_num > 0 ? 16 : 8) + 1; }
+  int n_ctx_rows() const {
+    const int n = e->cfg.cond_token_num;
+    return 8 + (n == 0 ? 0 : n == 1 ? 8 : n) + 1;
+  }
 
   // buffers shared across the walk
   float* emb_out = nullptr;
@@ -1034,7 +1043,7 @@ struct Builder {
     // ---- prologue buffers
     op_t* x_in = static_cast<op_t*>(scratch("x_in", px * e->xin_c * sizeof(op_t)));
     float* t_emb = static_cast<float*>(scratch("t_emb", static_cast<size_t>(Bp) * mc * sizeof(float)));
-    float* cond_m = static_cast<float*>(scratch("cond_m", static_cast<size_t>(Bp) * (c.cond_dim + 1) * sizeof(float)));
+    float* cond_m = static_cast<float*>(scratch("cond_m", static_cast<size_t>(Bp) * (e->cond_w + 1) * sizeof(float)));
     float* hid = static_cast<float*>(scratch("hid", static_cast<size_t>(Bp) * ted * sizeof(float)));
     float* emb = static_cast<float*>(scratch("emb", static_cast<size_t>(Bp) * e->E * sizeof(float)));
     op_t* emb_act = static_cast<op_t*>(scratch("emb_act", static_cast<size_t>(Bp) * e->E * S * sizeof(op_t)));
@@ -1048,17 +1057,17 @@ struct Builder {
       pd.null_cond = c.cond_dim > 0 ? e->f32["null_cond_emb"] : nullptr;
       pd.null_layout = c.layout_dim > 0 ? e->f32["null_layout_emb"] : nullptr;
       pd.freqs = e->freqs;
-      pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = c.cond_dim; pd.mc = mc;
+      pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = e->cond_w; pd.mc = mc;
       pd.x_in = x_in; pd.t_emb = t_emb; pd.cond_masked = cond_m; pd.drop = drop;
       pd.im2col = e->first_im2col ? 1 : 0;
       pd.split3 = split3; pd.xc = e->xin_c;
     }
     auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,
-                   int silu_out, int accumulate) {
+                   int silu_out, int accumulate, int rows_per_sample = 1) {
       if (dry) return;
       const float* Wt = e->f32[std::string(wname) + ".weight"];
       const float* bs = e->f32[std::string(wname) + ".bias"];
-      const int M = Bp;
+      const int M = Bp * rows_per_sample;
       push([=](cudaStream_t s) {
         ++g_launches;
         return linear_f32_launch(in, in_stride, Wt, bs, out, out_stride, M, N, K, silu_out, accumulate, s);
@@ -1076,22 +1085,45 @@ struct Builder {
       const int ctx = c.context_dim;
       const bool has_cond = c.cond_token_num > 0;
       // cond_mlp ADDED to the time embedding (openaimodel_ca.py:594-598,976-977)
+      const int ntok = c.cond_token_num;  // > 1: cond_m is [Bp, ntok, cond_dim]
       if (has_cond) {
-        lin(cond_m, c.cond_dim, "cond_mlp.0", hid, ted, ted, c.cond_dim, 1, 0);
+        const float* pooled = cond_m;   // cond_token_num 1: the vector itself; > 1: the CLS token (row stride cond_w) ...
+        long pooled_stride = e->cond_w;
+        if (ntok > 1 && !c.use_cls_token_as_pooled) {  // ... or the mean over the tokens (:1000-1006)
+          float* pm = static_cast<float*>(scratch("cond_pool", static_cast<size_t>(Bp) * c.cond_dim * sizeof(float)));
+          const int B_ = Bp, cd_ = c.cond_dim;
+          push([=](cudaStream_t s) {
+            ++g_launches;
+            return token_mean_launch(cond_m, pm, B_, ntok, cd_, s);
+          });
+          pooled = pm;
+          pooled_stride = c.cond_dim;
+        }
+        lin(pooled, pooled_stride, "cond_mlp.0", hid, ted, ted, c.cond_dim, 1, 0);
         lin(hid, ted, "cond_mlp.2", emb, e->E, ted, ted, 0, 1);
       }
       // to_time_tokens / to_cond_tokens (:586-604,942,972); cond_token_num == 0: the context is the time tokens (:944-945)
       time_tokens = static_cast<float*>(scratch("time_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float)));
-      cond_tokens = has_cond ? static_cast<float*>(scratch("cond_tok", static_cast<size_t>(Bp) * 8 * ctx * sizeof(float))) : nullptr;
+      const int n_cond_tok = !has_cond ? 0 : ntok > 1 ? ntok : 8;
+      cond_tokens = has_cond ? static_cast<float*>(scratch("cond_tok", static_cast<size_t>(Bp) * n_cond_tok * ctx * sizeof(float))) : nullptr;
       lin(t_emb, mc, "to_time_tokens.0", hid, ted, mc, mc, 1, 0);
       lin(hid, ted, "to_time_tokens.2", time_tokens, 8 * ctx, 8 * ctx, mc, 0, 0);
-      if (has_cond) lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
+      if (has_cond && ntok == 1) lin(cond_m, c.cond_dim, "to_cond_tokens.0", cond_tokens, 8 * ctx, 8 * ctx, c.cond_dim, 0, 0);
+      if (ntok > 1) {  // to_cond_tokens_2d: a 4-layer MLP on every token (:605-614,998)
+        const int mid = static_cast<int>(sqrt(static_cast<double>(ctx) * c.cond_dim));
+        float* ha = static_cast<float*>(scratch("tok2d_a", static_cast<size_t>(Bp) * ntok * mid * sizeof(float)));
+        float* hb = static_cast<float*>(scratch("tok2d_b", static_cast<size_t>(Bp) * ntok * mid * sizeof(float)));
+        lin(cond_m, c.cond_dim, "to_cond_tokens_2d.0", ha, mid, mid, c.cond_dim, 1, 0, ntok);
+        lin(ha, mid, "to_cond_tokens_2d.2", hb, mid, mid, mid, 1, 0, ntok);
+        lin(hb, mid, "to_cond_tokens_2d.4", ha, mid, mid, mid, 1, 0, ntok);
+        lin(ha, mid, "to_cond_tokens_2d.6", cond_tokens, ctx, ctx, mid, 0, 0, ntok);
+      }
       // context K/V rows of every Attention_LR site (they depend on t / cond only): one launch, grid.y = sites
       CtxDesc cd;
       cd.time_tokens = time_tokens; cd.cond_tokens = cond_tokens;
       cd.norm_w = dry ? nullptr : e->f32["norm_cond.weight"]; cd.norm_b = dry ? nullptr : e->f32["norm_cond.bias"];
       cd.Bp = Bp; cd.ctx = ctx; cd.n_sites = static_cast<int>(e->attn_lr.size());
-      cd.n_tok = has_cond ? 16 : 8;
+      cd.n_tok = 8 + n_cond_tok;
       if (cd.n_sites > kMaxCtxSites) { fail("too many Attention_LR sites (%d)", cd.n_sites); err = 1; return; }
       for (int i = 0; i < cd.n_sites; ++i) {
         const AttnLRW& w = e->attn_lr[i];

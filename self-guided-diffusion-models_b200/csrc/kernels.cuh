@@ -107,15 +107,19 @@ struct CtxSite {                       // per Attention_LR site
 };
 struct CtxDesc {
   const float* time_tokens = nullptr;  // [Bp, 8*ctx]
-  const float* cond_tokens = nullptr;  // [Bp, 8*ctx]
+  const float* cond_tokens = nullptr;  // [Bp, (n_tok - 8)*ctx]
   const float* norm_w = nullptr;       // norm_cond [ctx]
   const float* norm_b = nullptr;
   int Bp = 0, ctx = 32, dh = 64;
-  int n_tok = 16;                      // context tokens: 8 time (+ 8 condition); k_out / v_out have n_tok + 1 rows per sample
+  int n_tok = 16;                      // context tokens: 8 time + the condition tokens (8 for cond_token_num 1, N for
+                                       // cond_token_num N > 1, none for 0); k_out / v_out have n_tok + 1 rows per sample
   int n_sites = 0;                     // all sites in one launch (grid.y)
   CtxSite site[kMaxCtxSites];
 };
 int context_kv_launch(const CtxDesc& d, cudaStream_t s);
+constexpr int kMaxCtxTok = 8 + 120;    // shared memory / one-thread-per-token LayerNorm of context_kv_kernel
+// out[b][j] = mean_t in[b][t][j] (cond_token_num > 1 with use_cls_token_as_pooled = False, openaimodel_ca.py:1004-1006)
+int token_mean_launch(const float* in, float* out, int B, int n_tok, int dim, cudaStream_t s);
 
 // ---- K10: guidance mix + sampler updates (fp32, bit-faithful op order) ----------------------
 // eps = (1-w) eps_u + w eps_c  ('imagen') | (1+w) eps_c - w eps_u ('cfg')   (openaimodel.py:853-859)

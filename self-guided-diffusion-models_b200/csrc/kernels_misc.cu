@@ -904,7 +904,7 @@ __global__ void context_kv_kernel(const CtxDesc d) {
   for (int i = threadIdx.x; i < nt * ctx; i += blockDim.x) {
     const int t = i / ctx, j = i - t * ctx;
     tok[i] = t < 8 ? d.time_tokens[(static_cast<long>(n) * 8 + t) * ctx + j]
-                   : d.cond_tokens[(static_cast<long>(n) * 8 + (t - 8)) * ctx + j];
+                   : d.cond_tokens[(static_cast<long>(n) * (nt - 8) + (t - 8)) * ctx + j];
   }
   __syncthreads();
   // two LayerNorms back to back (norm_cond, then to_context.0), one thread per token
@@ -923,31 +923,33 @@ __global__ void context_kv_kernel(const CtxDesc d) {
     }
   }
   __syncthreads();
-  // thread = output feature o: its weight row is read once (16-byte loads of whole lines) and used for all 16 tokens
-  // (token values are shared-memory broadcasts); same j-ascending summation order per output as before
+  // thread = output feature o: its weight row is read once per 16 tokens (16-byte loads of whole lines; token values
+  // are shared-memory broadcasts); j-ascending summation order per output
   for (int o = threadIdx.x; o < 2 * dh; o += blockDim.x) {
     const float* wr = w.lin_w + static_cast<long>(o) * ctx;
-    float acc[16];
     const float bias = w.lin_b[o];
+    for (int t0 = 0; t0 < nt; t0 += 16) {
+      float acc[16];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) acc[t] = bias;
-    for (int j = 0; j < ctx; j += 4) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+      for (int t = 0; t < 16; ++t) acc[t] = bias;
+      for (int j = 0; j < ctx; j += 4) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          if (t0 + t >= nt) break;
+          const float4 tv = *reinterpret_cast<const float4*>(tok + (t0 + t) * ctx + j);
+          acc[t] += tv.x * wv.x;
+          acc[t] += tv.y * wv.y;
+          acc[t] += tv.z * wv.z;
+          acc[t] += tv.w * wv.w;
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
-        if (t >= nt) break;
-        const float4 tv = *reinterpret_cast<const float4*>(tok + t * ctx + j);
-        acc[t] += tv.x * wv.x;
-        acc[t] += tv.y * wv.y;
-        acc[t] += tv.z * wv.z;
-        acc[t] += tv.w * wv.w;
+        if (t0 + t >= nt) break;
+        if (o < dh) w.k_out[(static_cast<long>(n) * rows + t0 + t) * dh + o] = to_op(acc[t]);
+        else w.v_out[(static_cast<long>(n) * rows + t0 + t) * dh + (o - dh)] = to_op(acc[t]);
       }
-    }
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      if (t >= nt) break;
-      if (o < dh) w.k_out[(static_cast<long>(n) * rows + t) * dh + o] = to_op(acc[t]);
-      else w.v_out[(static_cast<long>(n) * rows + t) * dh + (o - dh)] = to_op(acc[t]);
     }
   }
   for (int o = threadIdx.x; o < dh; o += blockDim.x) {
@@ -956,8 +958,23 @@ __global__ void context_kv_kernel(const CtxDesc d) {
   }
 }
 int context_kv_launch(const CtxDesc& d, cudaStream_t s) {
-  if (d.n_sites < 1 || d.n_sites > kMaxCtxSites || (d.ctx % 4) || (d.n_tok != 8 && d.n_tok != 16)) return 1;
-  context_kv_kernel<<<dim3(d.Bp, d.n_sites), 128, 16 * d.ctx * sizeof(float), s>>>(d);
+  if (d.n_sites < 1 || d.n_sites > kMaxCtxSites || (d.ctx % 4) || d.n_tok < 8 || d.n_tok > kMaxCtxTok) return 1;
+  context_kv_kernel<<<dim3(d.Bp, d.n_sites), 128, d.n_tok * d.ctx * sizeof(float), s>>>(d);
+  return SGDM_LAUNCH_OK();
+}
+
+__global__ void token_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int n_tok, int dim, long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const long b = i / dim;
+  const int j = static_cast<int>(i - b * dim);
+  float acc = 0.f;
+  for (int t = 0; t < n_tok; ++t) acc += in[(b * n_tok + t) * dim + j];
+  out[i] = acc / static_cast<float>(n_tok);
+}
+int token_mean_launch(const float* in, float* out, int B, int n_tok, int dim, cudaStream_t s) {
+  const long total = static_cast<long>(B) * dim;
+  token_mean_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, n_tok, dim, total);
   return SGDM_LAUNCH_OK();
 }
 

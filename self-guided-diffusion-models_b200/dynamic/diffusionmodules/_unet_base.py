@@ -300,8 +300,10 @@ class EngineUNet(nn.Module):
             if cond is None:
                 raise ValueError("cond is required")
             cond = cond.detach().to(x.device).to(torch.float32).contiguous()  # openaimodel.py:911
-            if cond.dim() != 2 or cond.shape[1] != self.cond_dim:
-                raise AssertionError(f"wtf? {tuple(cond.shape)}, {self.cond_dim}")
+            ntok = int(self._cfg.cond_token_num) if self._KIND == _lib.KIND_UNETCA_FAST else 1
+            want = (x.shape[0], ntok, self.cond_dim) if ntok > 1 else (x.shape[0], self.cond_dim)
+            if tuple(cond.shape) != want:
+                raise AssertionError(f"wtf? {tuple(cond.shape)}, expected {want}")
         else:
             cond = None
         if self._cfg.layout_dim > 0:

@@ -54,7 +54,6 @@ class UNetModel(EngineUNet):
         if dims != 2: unsupported.append("dims != 2")
         if not use_scale_shift_norm: unsupported.append("use_scale_shift_norm=False")
         if not use_ca_block: unsupported.append("use_ca_block=False")
-        if cond_token_num > 1: unsupported.append("cond_token_num > 1")
         if context_dim is None: unsupported.append("context_dim=None")
         if num_head_channels != -1: unsupported.append("num_head_channels")
         if resblock_updown: unsupported.append("resblock_updown")
@@ -63,11 +62,15 @@ class UNetModel(EngineUNet):
         if unsupported:
             raise NotImplementedError(
                 "sgdm_b200 unetca_fast covers config/dynamic/unetca_fast.yaml with the README overrides "
-                "(cond_token_num=1 or 0, context_dim=32); not built: " + ", ".join(unsupported))
+                "(any cond_token_num, context_dim=32); not built: " + ", ".join(unsupported))
         if cond_token_num == 0:
             assert cond_dim == 0  # openaimodel_ca.py:562-564: no condition vector (the `layout`-only / unconditional model)
             if condition_method == "clusterlayout":
                 raise NotImplementedError  # openaimodel_ca.py:947-948
+        if cond_token_num > 1 and condition_method in ("clusterlayout", "stegoclusterlayout", "layout"):
+            # openaimodel_ca.py:988-1012 concatenates no layout on this branch (and raises for clusterlayout), while the
+            # constructor still widens the first conv: the reference cannot run these combinations either
+            raise NotImplementedError("cond_token_num > 1 takes a [B, N, cond_dim] token condition and no layout")
         layout_dim = 0
         if condition_method in ["layout"]:
             layout_dim = condition.layout.layout_dim  # openaimodel_ca.py:634-641
@@ -85,12 +88,15 @@ class UNetModel(EngineUNet):
                  model_channels=model_channels, num_res_blocks=num_res_blocks, channel_mult=channel_mult,
                  attention_resolutions=attention_resolutions, num_heads=num_heads, resblock_updown=0,
                  cond_dim=cond_dim, layout_dim=layout_dim, context_dim=context_dim,
-                 cond_token_num=cond_token_num),
+                 cond_token_num=cond_token_num,
+                 use_cls_token_as_pooled=int(use_cls_token_as_pooled is True or use_cls_token_as_pooled == True)),
             condition, condition_method, precision)
 
     def forward(self, x, timesteps=None, cond_drop_prob=0.0, cond=None, layout=None):
         if self.cond_token_num == 1:
             assert cond is not None and len(cond.shape) == 2  # openaimodel_ca.py:960-961
+        elif self.cond_token_num > 1:
+            assert cond is not None and len(cond.shape) == 3  # [B, T, C], openaimodel_ca.py:989
         return self._forward_impl(x, timesteps, cond, layout, cond_drop_prob)
 
     def forward_with_cond_scale(self, x, t, cond_scale, cond=None, layout=None):

@@ -65,7 +65,7 @@ def noise_tape(shape, n_draws, seed=1234, noise_dropout=0.0):
     return tape
 
 
-def synthetic_batch(condition_method, batch, cond_dim, image_size, layout_dim=0, seed=4321):
+def synthetic_batch(condition_method, batch, cond_dim, image_size, layout_dim=0, seed=4321, cond_token_num=1):
     """A dataset-batch dict in the reference's formats:
     label/cluster: int64 one-hot [B,cond_dim]; clusterlayout: cluster one-hot +
     'lostbboxmask' {0,1} [B,1,H,W]; stegoclusterlayout: 'stegomask' one-hot
@@ -94,6 +94,11 @@ def synthetic_batch(condition_method, batch, cond_dim, image_size, layout_dim=0,
         onehot = F.one_hot(cls, k).permute(0, 3, 1, 2).contiguous()
         out["stegomask"] = onehot
         out["stego_attr"] = (onehot.flatten(2).sum(-1) > 0).long()
+    elif condition_method in ("attr", "feat", "patchfeat"):
+        # float features: one vector per sample, or `cond_token_num` > 1 tokens per sample ([B, N, cond_dim], the
+        # input of unetca_fast's to_cond_tokens_2d branch)
+        shape = (batch, cond_dim) if cond_token_num <= 1 else (batch, cond_token_num, cond_dim)
+        out[condition_method] = torch.randn(shape, generator=g)
     elif condition_method is None:
         pass
     else:

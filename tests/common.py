@@ -9,7 +9,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 UNET_CASES = [
     "unet_fast_label_tiny", "unet_fast_clusterlayout_tiny", "unetca_clusterlayout_tiny",
-    "unetca_stego_tiny", "unetca_layout_tiny", "unet_heads32_ds24_tiny", "cfg1_cifar_label", "cfg2_in64_label", "cfg4_voc_clusterlayout",
+    "unetca_stego_tiny", "unetca_layout_tiny", "unet_heads32_ds24_tiny", "unetca_tokens4_cls_tiny", "unetca_tokens12_mean_tiny",
+    "cfg1_cifar_label", "cfg2_in64_label", "cfg4_voc_clusterlayout",
     "cfg5_coco_stego",
 ]
 

@@ -65,6 +65,18 @@ CASES = {
              num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
              resblock_updown=False, cond_dim=0, condition_method="layout", layout_dim=21,
              context_dim=32, cond_token_num=0, scale_type="imagen"), 2),
+    # cond_token_num > 1: a [B, N, cond_dim] token condition through to_cond_tokens_2d (openaimodel_ca.py:988-1012), pooled by
+    # the CLS token (the config's use_cls_token_as_pooled=True) or by the mean over the tokens
+    "unetca_tokens4_cls_tiny": (
+        dict(kind="unetca_fast", image_size=16, in_channels=3, out_channels=3, model_channels=64,
+             num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
+             resblock_updown=False, cond_dim=24, condition_method="patchfeat", layout_dim=0,
+             context_dim=32, cond_token_num=4, use_cls_token_as_pooled=True, scale_type="imagen"), 2),
+    "unetca_tokens12_mean_tiny": (
+        dict(kind="unetca_fast", image_size=16, in_channels=3, out_channels=3, model_channels=64,
+             num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
+             resblock_updown=False, cond_dim=24, condition_method="patchfeat", layout_dim=0,
+             context_dim=32, cond_token_num=12, use_cls_token_as_pooled=False, scale_type="imagen"), 2),
     # the attention layout of config/dynamic/unet.yaml (attention at ds 2 and 4, 32 heads: head dims 8 and 16) through the
     # constructor the reference actually has (unet.yaml as written passes `num_classes` / `cond_mlp_divide`, which
     # UNetModel.__init__ rejects with a TypeError)
@@ -110,7 +122,7 @@ def build_reference_unet(cfg):
     else:  # config/dynamic/unetca_fast.yaml + README overrides
         m = ref_unetca.UNetModel(dropout=0.0, use_ca_block=True, transformer_depth=1, legacy=False,
                                  cond_token_num=cfg["cond_token_num"], context_dim=cfg["context_dim"],
-                                 use_cls_token_as_pooled=True, **common)
+                                 use_cls_token_as_pooled=cfg.get("use_cls_token_as_pooled", True), **common)
     return m.eval()
 
 
@@ -138,7 +150,7 @@ def make_inputs(cfg, batch, seed):
     x = torch.randn(batch, cfg["in_channels"], H, H, generator=g)
     t = torch.randint(0, 1000, (batch,), generator=g)
     data = synthetic.synthetic_batch(cfg["condition_method"], batch, cfg["cond_dim"], H,
-                                     cfg["layout_dim"], seed=seed + 1)
+                                     cfg["layout_dim"], seed=seed + 1, cond_token_num=cfg.get("cond_token_num") or 1)
     return x, t, data
 
 

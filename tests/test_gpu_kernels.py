@@ -543,6 +543,7 @@ ATTN_CASES = [
     (1, 1024, 32, 8, 0, False, "T=1024 d=8 (64x64 images, attention at ds 2)"),
     (1, 1024, 32, 16, 0, False, "T=1024 d=16"),
     (2, 100, 4, 16, 5, True, "MQA d=16, ragged T, 5 extra keys"),
+    (2, 256, 8, 64, 49, True, "MQA, 49 extra keys (cond_token_num 40: beyond the tcgen05 kernel's 32)"),
 ]
 
 

@@ -29,7 +29,7 @@ def build_model(cfg, precision=None):
         return openaimodel.UNetModel(dropout=0.1, resblock_updown=True, **common)
     return openaimodel_ca.UNetModel(dropout=0.0, use_ca_block=True, transformer_depth=1, legacy=False,
                                     cond_token_num=cfg["cond_token_num"], context_dim=cfg["context_dim"],
-                                    use_cls_token_as_pooled=True, **common)
+                                    use_cls_token_as_pooled=cfg.get("use_cls_token_as_pooled", True), **common)
 
 
 def test_library_exports_every_declared_symbol():
