@@ -498,31 +498,39 @@ def main():
         model.forward_with_cond_scale(xg, tg, **kw)
         torch.cuda.synchronize()
         _lib.check(lib.sgdm_set_profiling(model._h, 0))
-        kind, ms, fl, by = C.c_char_p(), C.c_double(), C.c_double(), C.c_double()
+        kind, ms, fl, by, fx = C.c_char_p(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         ops = []
         for j in range(lib.sgdm_profile_count(model._h)):
             _lib.check(lib.sgdm_profile_get(model._h, j, C.byref(kind), C.byref(ms), C.byref(fl), C.byref(by)))
+            _lib.check(lib.sgdm_profile_executed_flops(model._h, j, C.byref(fx)))
             ops.append(dict(i=j, kind=kind.value.decode(), ms=round(ms.value, 4), gflop=round(fl.value / 1e9, 2),
+                            gflop_executed=round(fx.value / 1e9, 2),
                             mbytes=round(by.value / 1e6, 1),
                             tflops=round(fl.value / (ms.value * 1e-3) / 1e12, 1) if ms.value > 0 and fl.value else None,
                             gbs=round(by.value / (ms.value * 1e-3) / 1e9, 1) if ms.value > 0 and by.value else None))
-            f = fam.setdefault(kind.value.decode(), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            f = fam.setdefault(kind.value.decode(), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, flops_exec=0.0))
             f["ms"] += ms.value; f["flops"] += fl.value; f["bytes"] += by.value; f["launches"] += 1
+            f["flops_exec"] += fx.value
         if args.dump_ops:
             with open(args.dump_ops, "w") as fh:
                 json.dump(ops, fh, indent=0)
         pk = peaks()
-        conv = dict(ms=0.0, flops=0.0, launches=0)
+        conv = dict(ms=0.0, flops=0.0, launches=0, flops_exec=0.0)
         for k_ in ("conv3x3", "gemm1x1"):
             if k_ in fam:
                 for q in conv:
                     conv[q] += fam[k_][q]
         total_ms = sum(f["ms"] for f in fam.values())
+        # `achieved`: ALGORITHMIC FLOPs (the reference's math these launches stand for) per second; `achieved_executed`:
+        # what the tensor pipe does (sub-pixel up-convs execute 4/9 of their definition, shared-prefix launches half)
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        ach_x = conv["flops_exec"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         traffic, traffic_src = ncu_conv_traffic() if args.config == 2 and B == 256 else (None, None)
         roof = dict(bound="tensor", kernel="conv_gemm_kernel (tcgen05 implicit GEMM: conv3x3 + 1x1/linear GEMMs)",
                     achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
-                    frac_of_burst=ach / pk["burst"] if pk.get("burst") else None, traffic=traffic,
+                    frac_of_burst=ach / pk["burst"] if pk.get("burst") else None,
+                    achieved_executed=ach_x, frac_executed=ach_x / pk["tflops"], executed_flops_per_step=conv["flops_exec"],
+                    traffic=traffic,
                     traffic_unit="bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step)",
                     traffic_source=traffic_src, algorithmic_bytes_per_launch=(fam.get("conv3x3", {}).get("bytes", 0.0) + fam.get("gemm1x1", {}).get("bytes", 0.0)) / max(conv["launches"], 1),
                     peak_source=pk["src"], launches_per_step=conv["launches"],

@@ -162,7 +162,11 @@ int sgdm_set_graph_mode(sgdm_handle h, int mode);
 int sgdm_fingerprint(void* stream, const void* const* dev_ptrs, const int64_t* dev_numel, int n, uint64_t* dev_out);
 int sgdm_set_profiling(sgdm_handle h, int on);
 int sgdm_profile_count(sgdm_handle h);
+/* launch i of the last profiled replay: kernel family, duration, ALGORITHMIC FLOPs (2 x MAC of the reference computation
+ * the launch stands for) and HBM bytes; sgdm_profile_executed_flops: what the tensor pipe executes for it (4/9 for a
+ * sub-pixel up-conv, half for a launch on the shared rows of a guided plan, 3x in the fp16x3 mode) */
 int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double* flops, double* bytes);
+int sgdm_profile_executed_flops(sgdm_handle h, int i, double* flops);
 
 /* Count of kernels launched by this library since load (claim for bench.py `gpu_launches`). */
 int64_t sgdm_launch_count(void);

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "sgdm_set_profiling": (_i, [_vp, _i]),
     "sgdm_profile_count": (_i, [_vp]),
     "sgdm_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
+    "sgdm_profile_executed_flops": (_i, [_vp, _i, C.POINTER(_d)]),
     "sgdm_launch_count": (_i64, []),
     "sgdm_debug_set_conv_pair": (_i, [_i]),
     "sgdm_debug_set_conv_timing": (_i, [_vp]),

@@ -107,8 +107,11 @@ struct Act {
 
 struct OpMeta {
   const char* kind;  // kernel family
-  double flops;      // algorithmic FLOPs (2*MAC, real channel counts) of this launch
+  double flops;      // algorithmic FLOPs of this launch: 2*MAC of the reference computation it stands for, real channel
+                     // counts (a sub-pixel up-conv counts the 9-tap conv on the upsampled tensor, a shared-prefix launch
+                     // the rows of both CFG halves)
   double bytes;      // algorithmic HBM bytes (read + write) of this launch
+  double flops_exec; // FLOPs the tensor pipe executes for it (sub-pixel: 4/9; shared prefix: half; fp16x3: 3x)
 };
 
 struct Plan {
@@ -731,10 +734,10 @@ struct Builder {
     c.stats = o.stats;
     c.out_op2 = o.p16;
   }
-  void push(Op op, const char* kind = "misc", double flops = 0, double bytes = 0) {
+  void push(Op op, const char* kind = "misc", double flops = 0, double bytes = 0, double flops_exec = -1) {
     if (dry) return;
     plan->ops.push_back(std::move(op));
-    plan->meta.push_back(OpMeta{kind, flops, bytes});
+    plan->meta.push_back(OpMeta{kind, flops, bytes, flops_exec < 0 ? flops : flops_exec});
   }
 
   void conv(ConvDesc d, int real_cin = 0) {
@@ -757,7 +760,10 @@ struct Builder {
     const double M = static_cast<double>(d.B) * d.Hout * d.Wout * (d.up2 ? 4 : 1);
     // algorithmic K: the reference's channel counts (split-precision mode executes 3x that)
     const double k_real = static_cast<double>(d.ks) * d.ks * (real_cin > 0 ? real_cin : d.Cin / S) + (d.in2 ? (d.C2 + (d.in2b ? d.C2b : 0)) / S : 0);
-    const double flops = 2.0 * M * d.Cout * k_real;
+    // executed: the rows and K this launch really multiplies (sub-pixel: 4 of 9 taps; split precision: 3x the channels)
+    const double flops_exec = 2.0 * M * d.Cout * (d.up2 ? 4.0 / 9.0 : 1.0) * k_real * S;
+    // algorithmic: a launch on the shared rows of a guided plan stands for both CFG halves of the reference
+    const double flops = 2.0 * M * d.Cout * k_real * (d.B < Bp ? static_cast<double>(Bp) / d.B : 1.0);
     const double in_px = static_cast<double>(d.B) * d.Hin * d.Win;
     const double bytes = in_px * d.Cin * 2 + (d.in2 ? M * (d.C2 + (d.in2b ? d.C2b : 0)) * 2 : 0) +
                          M * d.Cout * ((d.out_f32 || d.out_nchw) ? 4 : 2) + (d.out_op2 ? M * d.Cout * 2 : 0) +
@@ -765,7 +771,7 @@ struct Builder {
     push([l](cudaStream_t s) {
       ++g_launches;
       return conv_launch(*l, s);
-    }, d.ks == 3 ? "conv3x3" : "gemm1x1", flops, bytes);
+    }, d.ks == 3 ? "conv3x3" : "gemm1x1", flops, bytes, flops_exec);
   }
   void gn(GnDesc d) {
     if (d.B == 0) d.B = Bp;
@@ -1458,6 +1464,12 @@ int sgdm_set_profiling(sgdm_handle h, int on) {
   return 0;
 }
 int sgdm_profile_count(sgdm_handle h) { return h->last_profiled ? static_cast<int>(h->last_profiled->ops.size()) : 0; }
+int sgdm_profile_executed_flops(sgdm_handle h, int i, double* flops) {
+  Plan* p = h->last_profiled;
+  if (!p || i < 0 || i >= static_cast<int>(p->ops.size())) return fail("no profile recorded");
+  *flops = p->meta[i].flops_exec;
+  return 0;
+}
 int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double* flops, double* bytes) {
   Plan* p = h->last_profiled;
   if (!p || i < 0 || i >= static_cast<int>(p->ops.size()) || p->prof_ms.size() != p->ops.size())
