@@ -732,25 +732,37 @@ int expand3_launch(const op_t* src, op_t* dst, long rows, int C, cudaStream_t s)
 }
 
 // =========================================================================== fp32 linear
-// 64x64 output tile per 256-thread CTA, 4x4 per thread, K staged 16 at a time through smem.
-__global__ void linear_f32_kernel(const float* __restrict__ in, long in_stride, const float* __restrict__ W,
-                                  const float* __restrict__ bias, float* __restrict__ out, long out_stride, int M,
-                                  int N, int K, int silu_out, int accumulate) {
-  __shared__ float As[16][65];
-  __shared__ float Ws[16][65];
+// 64x64 output tile per 256-thread CTA, 4x4 per thread, K staged 32 at a time through smem; the next K tile is prefetched
+// into registers while the current one is multiplied (the K = 5000 cluster-condition MLP of config 3 was bound by the
+// exposed load latency of 312 unpipelined 16-wide tiles: 0.8 ms).  Per output the products are added in ascending k.
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ in, long in_stride, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ out, long out_stride, int M,
+                                                         int N, int K, int silu_out, int accumulate) {
+  constexpr int KT = 32;
+  __shared__ float As[KT][65];
+  __shared__ float Ws[KT][65];
   const int tm = blockIdx.y * 64, tn = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;  // loader: k within the tile, row (+ 8 j)
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int r = i >> 4, kk = i & 15;
-      const int m = tm + r, n = tn + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? in[m * in_stride + k] : 0.f;
-      Ws[kk][r] = (n < N && k < K) ? W[static_cast<long>(n) * K + k] : 0.f;
-    }
-    __syncthreads();
+  float pa[8], pw[8];
+  auto fetch = [&](int k0) {
+    const int k = k0 + lk;
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int j = 0; j < 8; ++j) {
+      const int m = tm + lr + 8 * j, n = tn + lr + 8 * j;
+      pa[j] = (m < M && k < K) ? in[m * in_stride + k] : 0.f;
+      pw[j] = (n < N && k < K) ? W[static_cast<long>(n) * K + k] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KT) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { As[lk][lr + 8 * j] = pa[j]; Ws[lk][lr + 8 * j] = pw[j]; }
+    __syncthreads();
+    if (k0 + KT < K) fetch(k0 + KT);
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
       float a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
