@@ -55,11 +55,23 @@ __device__ __forceinline__ float ex2f(float x) {
 // of one tile hide behind the arithmetic of the other, and S / PV of one tile overlap the softmax of the other.
 // Shared memory: Q | K | V | P_0 | P_1 = 224 KB (single Q/K/V stage: the loads of the next pair are issued a whole
 // softmax ahead of their first use, so a second stage would buy nothing).
+// kHalves = 2 (round 2, the default): TWO threads per query row — 8 softmax warps per tile, 18 warps per CTA.  The
+// source-level profile of the one-thread-per-row version (profiles/r02_ncu_src_attn_tc2.txt) showed pass 2 issuing in
+// 18 % of its cycles: 39 % fixed-latency dependency stalls, 20 % scoreboard (MUFU / TMEM results) with two softmax warps
+// per scheduler to choose from.  Each thread now owns 128 of the row's 256 keys (P blocks 2 h, 2 h + 1) and 32 of the 64
+// output dims; the row maximum and the row sum are exchanged through 2 KB of shared memory under a 64-thread named
+// barrier per (tile, lane quarter).
 constexpr int kTc2Threads = 320;
 constexpr int kTc2P = 4 * 16384;  // P_j: four K-major [128 x 64] blocks
-constexpr int kTc2Smem = 3 * kTcTile + 2 * kTc2P + 256;
+constexpr int kTc2Xch = 2 * 128 * 2 * 4;  // [tile][row][half] fp32 exchange slots
+constexpr int kTc2Smem = 3 * kTcTile + 2 * kTc2P + 256 + kTc2Xch;
 
-__global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int kHalves>
+__global__ void __launch_bounds__(64 + 256 * kHalves, 1) attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   pdl_launch_dependents();
@@ -83,9 +95,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_c
     mbar_init(v_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_ready[i], 1);
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_ready[i], 4 * kHalves);
       mbar_init(&o_ready[i], 1);
-      mbar_init(&tfree[i], 4);
+      mbar_init(&tfree[i], 4 * kHalves);
     }
     fence_barrier_init();
   }
@@ -165,12 +177,18 @@ __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_c
       }
     }
   } else {
-    const int j = warp >= 6 ? 1 : 0;
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const int sw = warp - 2;                 // softmax warp 0 .. 8 kHalves - 1
+    const int j = sw / (4 * kHalves);        // query tile
+    const int half = (sw >> 2) % kHalves;    // which half of the row's keys / output dims this thread owns
+    const int quarter = warp & 3;            // == TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;       // query row within the tile == TMEM lane
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * 256;
     const uint32_t x7 = r & 7;
     const uint32_t pbase = smem_u32(smem) + 3 * kTcTile + j * kTc2P + r * 128;
+    constexpr int NC = 8 / kHalves;          // 32-key chunks per thread
+    const int c0 = half * NC;
+    float* xch = reinterpret_cast<float*>(smem + 3 * kTcTile + 2 * kTc2P + 256) + (j * 128 + r) * 2;
+    const int bar_id = 1 + j * 4 + quarter;  // the two warps that share this tile's lane quarter
     for (int it = 0; it < n_my; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
       const uint32_t ph = it & 1;
@@ -182,19 +200,25 @@ __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_c
       // pass 1: row maximum over the 256 keys, four independent chains
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr, va);
+      tmem_ld_32x32(taddr + 32 * c0, va);
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < NC; c += 2) {
         tmem_ld_wait();
-        tmem_ld_32x32(taddr + 32 * (c + 1), vb);
+        tmem_ld_32x32(taddr + 32 * (c0 + c + 1), vb);
 #pragma unroll
         for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(va[i]));
         tmem_ld_wait();
-        tmem_ld_32x32(taddr + 32 * ((c + 2) & 7), va);  // after the last chunk: chunk 0 again, for pass 2
+        tmem_ld_32x32(taddr + 32 * (c0 + ((c + 2) % NC)), va);  // after the last chunk: the first again, for pass 2
 #pragma unroll
         for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(vb[i]));
       }
-      const float mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      float mrow = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (kHalves == 2) {  // row maximum over both halves
+        xch[half] = mrow;
+        named_bar_sync(bar_id, 64);
+        mrow = fmaxf(mrow, xch[half ^ 1]);
+      }
+      const float mb = mrow * p.scale_log2;
       // pass 2: exponentials (log2 domain), row sum, P as the 16-bit K-major operand
       float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial row sums
       auto exp_chunk = [&](const uint32_t(&v)[32], int c) {
@@ -213,41 +237,51 @@ __global__ void __launch_bounds__(kTc2Threads, 1) attn_tc2_kernel(const __grid_c
         }
       };
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < NC; c += 2) {
         tmem_ld_wait();
-        tmem_ld_32x32(taddr + 32 * (c + 1), vb);
-        exp_chunk(va, c);
+        tmem_ld_32x32(taddr + 32 * (c0 + c + 1), vb);
+        exp_chunk(va, c0 + c);
         tmem_ld_wait();
-        if (c + 2 < 8) tmem_ld_32x32(taddr + 32 * (c + 2), va);
-        exp_chunk(vb, c + 1);
+        if (c + 2 < NC) tmem_ld_32x32(taddr + 32 * (c0 + c + 2), va);
+        exp_chunk(vb, c0 + c + 1);
       }
-      const float inv_l = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+      float lrow = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[j]);
+      if (kHalves == 2) {
+        // row sum over both halves, through the same slots: the partner has read the maxima (it is past its pass 2 when it
+        // arrives here), and the next pair's maxima are written only after both warps have released the tile (tfree)
+        named_bar_sync(bar_id, 64);
+        xch[half] = lrow;
+        named_bar_sync(bar_id, 64);
+        lrow += xch[half ^ 1];
+      }
+      const float inv_l = 1.0f / lrow;
       mbar_wait(&o_ready[j], ph);
       tc_fence_after();
       {
-        // O_j row -> * 1/l -> 64 x 16-bit = 128 B of the output row
-        op_t* dst = p.out + (static_cast<long>(n) * kTcT + j * 128 + r) * p.o_row_stride + h * kTcD;
+        // O_j row -> * 1/l -> this thread's 64 / kHalves output dims (16-bit)
+        constexpr int ND = 2 / kHalves;  // 32-column TMEM loads per thread
+        op_t* dst = p.out + (static_cast<long>(n) * kTcT + j * 128 + r) * p.o_row_stride + h * kTcD + (kHalves == 2 ? 32 * half : 0);
         uint32_t v0[32], v1[32];
-        tmem_ld_32x32(taddr, v0);
-        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_32x32(taddr + (kHalves == 2 ? 32 * half : 0), v0);
+        if (ND == 2) tmem_ld_32x32(taddr + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tfree[j]);  // the values are in registers: tile j's TMEM columns are free
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t(&v)[32] = half == 0 ? v0 : v1;
+        for (int q = 0; q < ND; ++q) {
+          const uint32_t(&v)[32] = q == 0 ? v0 : v1;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 o = make_uint4(pack_op2(__uint_as_float(v[8 * c]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
                                        pack_op2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
                                        pack_op2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
                                        pack_op2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
-            *reinterpret_cast<uint4*>(dst + 32 * half + 8 * c) = o;
+            *reinterpret_cast<uint4*>(dst + 32 * q + 8 * c) = o;
           }
         }
       }
@@ -648,11 +682,15 @@ int attn_tc_launch(const AttnDesc& a, cudaStream_t s) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem) != cudaSuccess)
+      return 1;
     attr_set = true;
   }
   const int grid = p.pairs < kNumSMs ? p.pairs : kNumSMs;
-  const cudaError_t e = launch_pdl(attn_tc2_kernel, dim3(grid), dim3(kTc2Threads), kTc2Smem, s, 1, p);
+  static const int halves = [] { const char* ev = getenv("SGDM_ATTN_HALVES"); return ev && atoi(ev) == 1 ? 1 : 2; }();
+  const cudaError_t e = halves == 2 ? launch_pdl(attn_tc2_kernel<2>, dim3(grid), dim3(64 + 512), kTc2Smem, s, 1, p)
+                                    : launch_pdl(attn_tc2_kernel<1>, dim3(grid), dim3(64 + 256), kTc2Smem, s, 1, p);
   return e == cudaSuccess ? 0 : 1;
 }
 
