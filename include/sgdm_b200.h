@@ -242,6 +242,11 @@ int sgdm_k_attention(void* stream, const void* q, int64_t q_row_stride, int q_he
                      int64_t k_row_stride, int k_head_stride, const void* v, int64_t v_row_stride,
                      int v_head_stride, const void* k_extra, const void* v_extra, int n_extra, void* out,
                      int64_t o_row_stride, int B, int T, int heads, int D, float scale);
+/* the same through `splits` K slices (partial: splits * M * N floats of scratch; slices summed in ascending order, so
+ * the result is deterministic); splits < 0 = the engine's policy (skinny M x N, K >= 1024) */
+int sgdm_k_linear_f32_splitk(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
+                             float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate,
+                             float* partial, int splits);
 int sgdm_k_linear_f32(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
                       float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate);
 int sgdm_k_cast(void* stream, const float* src, void* dst_op, int B, int H, int W, int C, int up2);

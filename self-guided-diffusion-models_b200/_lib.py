@@ -95,6 +95,7 @@ PROTOTYPES = {
     "sgdm_k_layernorm_split3": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i]),
     "sgdm_k_attention": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _f]),
     "sgdm_k_linear_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i]),
+    "sgdm_k_linear_f32_splitk": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _i]),
     "sgdm_k_conv_up2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
     "sgdm_k_conv_head_hfold": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "sgdm_k_cast": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),

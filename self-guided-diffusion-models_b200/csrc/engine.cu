@@ -1070,13 +1070,17 @@ struct Builder {
     }
     auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,
                    int silu_out, int accumulate, int rows_per_sample = 1) {
+      // skinny and deep (the K = 1000 / 5000 condition MLPs at small batch): deterministic split-K through scratch
+      const int splits = linear_f32_splits(Bp * rows_per_sample, N, K);
+      float* part = splits > 1 ? static_cast<float*>(scratch("lin_partial", static_cast<size_t>(splits) * Bp * rows_per_sample * N * sizeof(float)))
+                               : nullptr;
       if (dry) return;
       const float* Wt = e->f32[std::string(wname) + ".weight"];
       const float* bs = e->f32[std::string(wname) + ".bias"];
       const int M = Bp * rows_per_sample;
       push([=](cudaStream_t s) {
-        ++g_launches;
-        return linear_f32_launch(in, in_stride, Wt, bs, out, out_stride, M, N, K, silu_out, accumulate, s);
+        g_launches += splits > 1 ? 2 : 1;
+        return linear_f32_launch(in, in_stride, Wt, bs, out, out_stride, M, N, K, silu_out, accumulate, s, part, splits);
       });
     };
     // time_embed (openaimodel.py:570-574,921-923)
@@ -1756,6 +1760,16 @@ int sgdm_k_linear_f32(void* stream, const float* in, int64_t in_stride, const fl
   ++g_launches;
   return linear_f32_launch(in, in_stride, W, bias, out, out_stride, M, N, K, silu_out, accumulate,
                            static_cast<cudaStream_t>(stream))
+             ? fail("linear launch failed")
+             : 0;
+}
+int sgdm_k_linear_f32_splitk(void* stream, const float* in, int64_t in_stride, const float* W, const float* bias,
+                             float* out, int64_t out_stride, int M, int N, int K, int silu_out, int accumulate,
+                             float* partial, int splits) {
+  g_launches += 2;
+  if (splits < 0) splits = linear_f32_splits(M, N, K);  // the engine's policy
+  return linear_f32_launch(in, in_stride, W, bias, out, out_stride, M, N, K, silu_out, accumulate,
+                           static_cast<cudaStream_t>(stream), partial, splits)
              ? fail("linear launch failed")
              : 0;
 }

@@ -65,8 +65,10 @@ int silu_cast_launch(const float* src, op_t* dst, long n, cudaStream_t s, int C 
 int expand3_launch(const op_t* src, op_t* dst, long rows, int C, cudaStream_t s);
 
 // ---- fp32 small linear: out[m, n] (+)= act(bias[n] + sum_k in[m,k] W[n,k]) -----------------
+int linear_f32_splits(int M, int N, int K);  // split-K policy (1 = none); partial: splits * M * N floats of scratch
 int linear_f32_launch(const float* in, long in_stride, const float* W, const float* bias, float* out,
-                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s);
+                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s,
+                      float* partial = nullptr, int splits = 1);
 
 // ---- prologue: CFG batch assembly (C1/C3/C4 rows of SURVEY §8a) ------------------------------
 struct PrepDesc {

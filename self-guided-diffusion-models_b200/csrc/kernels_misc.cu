@@ -737,8 +737,14 @@ int expand3_launch(const op_t* src, op_t* dst, long rows, int C, cudaStream_t s)
 // exposed load latency of 312 unpipelined 16-wide tiles: 0.8 ms).  Per output the products are added in ascending k.
 __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ in, long in_stride, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float* __restrict__ out, long out_stride, int M,
-                                                         int N, int K, int silu_out, int accumulate) {
+                                                         int N, int K, int silu_out, int accumulate, float* __restrict__ partial,
+                                                         int k_chunk) {
+  // split-K (gridDim.z > 1): this CTA multiplies k in [z * k_chunk, (z + 1) * k_chunk) and writes the raw partial sums
+  // to partial[z][m][n]; linear_reduce_kernel adds them in ascending z (deterministic), then bias / SiLU / accumulate
   constexpr int KT = 32;
+  const bool split = gridDim.z > 1;
+  const int k_lo = split ? static_cast<int>(blockIdx.z) * k_chunk : 0;
+  const int k_hi = split ? min(K, k_lo + k_chunk) : K;
   __shared__ float As[KT][65];
   __shared__ float Ws[KT][65];
   const int tm = blockIdx.y * 64, tn = blockIdx.x * 64;
@@ -751,16 +757,16 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int m = tm + lr + 8 * j, n = tn + lr + 8 * j;
-      pa[j] = (m < M && k < K) ? in[m * in_stride + k] : 0.f;
-      pw[j] = (n < N && k < K) ? W[static_cast<long>(n) * K + k] : 0.f;
+      pa[j] = (m < M && k < k_hi) ? in[m * in_stride + k] : 0.f;
+      pw[j] = (n < N && k < k_hi) ? W[static_cast<long>(n) * K + k] : 0.f;
     }
   };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += KT) {
+  if (k_lo < k_hi) fetch(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += KT) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { As[lk][lr + 8 * j] = pa[j]; Ws[lk][lr + 8 * j] = pw[j]; }
     __syncthreads();
-    if (k0 + KT < K) fetch(k0 + KT);
+    if (k0 + KT < k_hi) fetch(k0 + KT);
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
       float a[4], b[4];
@@ -773,12 +779,14 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
     }
     __syncthreads();
   }
+  float* pz = split ? partial + static_cast<long>(blockIdx.z) * M * N : nullptr;
   for (int i = 0; i < 4; ++i) {
     const int m = tm + ty * 4 + i;
     if (m >= M) continue;
     for (int j = 0; j < 4; ++j) {
       const int n = tn + tx * 4 + j;
       if (n >= N) continue;
+      if (split) { pz[static_cast<long>(m) * N + n] = acc[i][j]; continue; }
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
       if (silu_out) v = silu(v);
       float* o = out + m * out_stride + n;
@@ -786,10 +794,41 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
     }
   }
 }
+__global__ void linear_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ out, long out_stride, int M, int N, int silu_out, int accumulate) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long>(m) * N);
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += partial[static_cast<long>(z) * M * N + i];
+  float v = acc + (bias ? bias[n] : 0.f);
+  if (silu_out) v = silu(v);
+  float* o = out + m * out_stride + n;
+  *o = accumulate ? *o + v : v;
+}
+// how many K slices a skinny, deep Linear is cut into (1 = no split): enough CTAs to cover the SMs, slices of >= 256
+int linear_f32_splits(int M, int N, int K) {
+  const int ctas = ((N + 63) / 64) * ((M + 63) / 64);
+  if (K < 1024 || ctas >= 64) return 1;
+  int s = (128 + ctas - 1) / ctas;
+  if (s > K / 256) s = K / 256;
+  if (s > 16) s = 16;
+  return s < 2 ? 1 : s;
+}
 int linear_f32_launch(const float* in, long in_stride, const float* W, const float* bias, float* out,
-                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s) {
+                      long out_stride, int M, int N, int K, int silu_out, int accumulate, cudaStream_t s, float* partial,
+                      int splits) {
+  if (splits > 1 && partial != nullptr) {
+    const int k_chunk = ((K + splits - 1) / splits + 31) / 32 * 32;
+    linear_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64, splits), 256, 0, s>>>(in, in_stride, W, bias, out, out_stride, M,
+                                                                                N, K, silu_out, accumulate, partial, k_chunk);
+    const long total = static_cast<long>(M) * N;
+    linear_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, splits, bias, out, out_stride, M,
+                                                                                    N, silu_out, accumulate);
+    return SGDM_LAUNCH_OK();
+  }
   linear_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, s>>>(in, in_stride, W, bias, out, out_stride, M, N,
-                                                                      K, silu_out, accumulate);
+                                                                      K, silu_out, accumulate, nullptr, 0);
   return SGDM_LAUNCH_OK();
 }
 

@@ -674,6 +674,32 @@ def test_linear_f32(L):
         ref = (F.silu(lin) + lin).float()
         assert relerr(out[:, :N], ref) < 1e-5
         assert out[:, N:].abs().max() == 0
+    # split-K (the engine's path for the K = 1000 / 5000 condition MLPs at small batch): same values to fp32 rounding,
+    # bit-identical from run to run, exact for one-hot inputs
+    for M, N, K, splits in ((64, 256, 5000, 16), (64, 256, 5000, -1), (32, 512, 1000, 3), (7, 70, 1030, 4)):
+        x = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+        b = torch.randn(N, device="cuda", generator=g)
+        part = torch.full((16 * M * N,), float("nan"), device="cuda")
+        outs = []
+        for _ in range(2):
+            out = torch.zeros(M, N + 3, device="cuda")
+            ck(L, L.sgdm_k_linear_f32_splitk(S(), P(x), K, P(W), P(b), P(out), N + 3, M, N, K, 1, 0, P(part), splits))
+            ck(L, L.sgdm_k_linear_f32_splitk(S(), P(x), K, P(W), P(b), P(out), N + 3, M, N, K, 0, 1, P(part), splits))
+            torch.cuda.synchronize()
+            outs.append(out)
+        lin = F.linear(x.double(), W.double(), b.double())
+        assert relerr(outs[0][:, :N], (F.silu(lin) + lin).float()) < 1e-5
+        assert torch.equal(outs[0], outs[1]) and outs[0][:, N:].abs().max() == 0
+    idx = torch.randint(0, 5000, (8,), device="cuda", generator=g)
+    oh = F.one_hot(idx, 5000).float()
+    W = torch.randn(256, 5000, device="cuda", generator=g)
+    b = torch.randn(256, device="cuda", generator=g)
+    out = torch.zeros(8, 256, device="cuda")
+    part = torch.empty(16 * 8 * 256, device="cuda")
+    ck(L, L.sgdm_k_linear_f32_splitk(S(), P(oh), 5000, P(W), P(b), P(out), 256, 8, 256, 5000, 0, 0, P(part), -1))
+    torch.cuda.synchronize()
+    assert torch.equal(out, W[:, idx].t() + b)
     # one-hot input: the first Linear is an exact column gather
     idx = torch.randint(0, 1000, (16,), device="cuda", generator=g)
     oh = F.one_hot(idx, 1000).float()
