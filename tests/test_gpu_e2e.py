@@ -472,6 +472,48 @@ def test_full_size_properties_cfg2():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg4_voc_clusterlayout", "cfg5_coco_stego"])
+def test_full_size_properties_unetca(name):
+    """The same size-independent properties at the true shapes of BASELINE configs 4 / 5 (unetca_fast, 64x64, layout input,
+    Attention_LR on the tcgen05 kernel, sub-pixel Upsample convs): determinism, batch-composition invariance down to a
+    single sample, CFG linearity, the golden reference samples inside a larger batch."""
+    need_gpu()
+    from sgdm_b200 import synthetic
+
+    meta, a = load_unet_case(name)
+    cfg = meta["cfg"]
+    m = cuda_model(meta)
+    B = 20
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 3, 64, 64, generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    data = synthetic.synthetic_batch(cfg["condition_method"], B, cfg["cond_dim"], 64, cfg["layout_dim"], seed=10)
+    if cfg["condition_method"] == "clusterlayout":
+        kw = dict(cond=data["cluster"].float().cuda(), layout=data["lostbboxmask"].float().cuda())
+    else:
+        kw = dict(cond=data["stego_attr"].float().cuda(), layout=data["stegomask"].float().cuda())
+    cut = lambda lo, hi: {k: v[lo:hi].contiguous() for k, v in kw.items()}
+    e1 = m.forward_with_cond_scale(x, t, 2.0, **kw).clone()
+    e2 = m.forward_with_cond_scale(x, t, 2.0, **kw).clone()
+    assert torch.isfinite(e1).all() and torch.equal(e1, e2), "not deterministic"
+    for lo, hi in ((0, 1), (3, 8), (13, 20)):
+        sub = m.forward_with_cond_scale(x[lo:hi].contiguous(), t[lo:hi].contiguous(), 2.0, **cut(lo, hi))
+        assert torch.equal(sub, e1[lo:hi]), f"batch {hi - lo}: rel_l2 {rel_l2(sub.cpu(), e1[lo:hi].cpu()):.3e}"
+    c = m.forward_with_cond_scale(x, t, 1, **kw)
+    u = m.forward_with_cond_scale(x, t, 0, **kw)
+    assert rel_l2(((1 - 2.0) * u + 2.0 * c).cpu(), e1.cpu()) < 1e-5
+    # the golden reference's two samples, placed inside a larger batch
+    n = a["x"].shape[0]
+    xg = torch.cat([x[:7], a["x"].cuda(), x[7:]])
+    tg = torch.cat([t[:7], a["t"].cuda(), t[7:]])
+    kg = {k: torch.cat([v[:7], a["kw_" + k].float().cuda(), v[7:]]) for k, v in kw.items()}
+    eg = m.forward_with_cond_scale(xg, tg, 2.0, **kg)[7:7 + n]
+    err = rel_l2(eg.cpu(), a["eps_guided"])
+    print(f"[full size {name}] golden samples inside a batch of {B + n}: rel_l2 = {err:.3e}")
+    assert err <= EPS_TOL
+
+
+@pytest.mark.gpu
 def test_oracle_parity_on_fresh_seeded_inputs():
     """CUDA path vs the CPU oracle on inputs that are NOT in the golden files."""
     need_gpu()
