@@ -149,7 +149,9 @@ inline bool conv_should_swap(const ConvDesc& d) { return conv_can_swap(d); }
 
 // Can a "nearest-2x upsample, then 3x3 conv" whose LOW-resolution input is [*, H, W, Cin] run in the sub-pixel mode
 // (ConvDesc::up2)?  Independent of the batch size (halo tiles never span images).
-bool conv_up2_applicable(int H, int W, int Cin, int Cout, int block_n);
+// Returns 0 (no), 1 (halo geometry: >= 128 pixels per image, [4 Cout][9 Cin] weights) or 2 (dense geometry: tiles of whole
+// small images, a plain 2x2 conv per parity over [4 Cout][4 Cin] weights) = the value for ConvDesc::up2.
+int conv_up2_applicable(int H, int W, int Cin, int Cout, int block_n);
 
 // CTA pairs need two m-tiles to share a weight tile of >= 64 output channels (each CTA stages block_n/2 rows).
 inline bool conv_pair_ok(const ConvDesc& d) { return !d.swap_ab && d.block_n >= 64 && (d.block_n % 32) == 0; }

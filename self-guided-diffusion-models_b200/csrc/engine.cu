@@ -64,7 +64,7 @@ struct ResW {
   int cin = 0, cout = 0;
   bool up = false, down = false, skip = false;
   int hin = 0;      // input resolution (H = W) of an up block
-  bool up2 = false; // conv1 of an up block in the sub-pixel mode (ConvDesc::up2): w1 holds the [4 cout][9 cin] parity packing
+  int up2 = 0;      // conv1 of an up block in the sub-pixel mode (ConvDesc::up2: 1 halo / 2 dense geometry): w1 holds the parity packing
   float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *bskip = nullptr, *bfused = nullptr;
   op_t *w1 = nullptr, *w2 = nullptr;
@@ -84,7 +84,7 @@ struct AttnLRW {  // Attention_LR
 struct ConvW {
   int cin = 0, cin_pad = 0, cout = 0;
   int hin = 0;       // Upsample.conv: resolution (H = W) of the tensor being upsampled
-  bool up2 = false;  // Upsample.conv in the sub-pixel mode: w holds the parity packing
+  int up2 = 0;       // Upsample.conv in the sub-pixel mode (1 halo / 2 dense): w holds the parity packing
   op_t* w = nullptr;
   float* b = nullptr;
   op_t* w_hfold = nullptr;  // output head only: the [16][3 * cin_pad] packing of ConvDesc::hfold
@@ -460,10 +460,10 @@ std::function<int(const float*, cudaStream_t)> copy_loader(float* dst, int64_t n
     return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : 1;
   };
 }
-std::function<int(const float*, cudaStream_t)> pack_up2_loader(op_t* dst, int cout, int cin) {
+std::function<int(const float*, cudaStream_t)> pack_up2_loader(op_t* dst, int cout, int cin, int variant) {
   return [=](const float* src, cudaStream_t s) {
     ++g_launches;
-    return pack_conv_weight_up2_launch(src, dst, cout, cin, cin, s);
+    return pack_conv_weight_up2_launch(src, dst, cout, cin, cin, s, variant == 2 ? 1 : 0);
   };
 }
 std::function<int(const float*, cudaStream_t)> pack_loader(op_t* dst, int cout, int cin, int ks, int cin_pad,
@@ -546,9 +546,10 @@ int setup_device(sgdm_engine* e) {
       const int k1 = 9 * r.cin * S, k2 = (9 * r.cout + (r.skip ? r.cin : 0)) * S;
       const int np = conv_npad(r.cout, pick_block_n(r.cout));
       // up block: upsample + conv1 as four 2x2 parity convs on the low-resolution tensor (2.25x fewer MACs)
-      r.up2 = r.up && e->use_up2 && !e->x3 && conv_up2_applicable(r.hin, r.hin, r.cin, r.cout, pick_block_n(r.cout));
+      // (Cout = 128 layers keep the swap-AB geometry: an M128 x N128 MMA runs at half rate)
+      r.up2 = (r.up && e->use_up2 && !e->x3 && r.cout != 128) ? conv_up2_applicable(r.hin, r.hin, r.cin, r.cout, pick_block_n(r.cout)) : 0;
       if (dalloc(e, &r.w1, static_cast<size_t>(r.up2 ? 4 * r.cout : np) * k1) || dalloc(e, &r.w2, static_cast<size_t>(np) * k2)) return 1;
-      if (bind_loader(e, p + ".in_layers.2.weight", r.up2 ? pack_up2_loader(r.w1, r.cout, r.cin)
+      if (bind_loader(e, p + ".in_layers.2.weight", r.up2 ? pack_up2_loader(r.w1, r.cout, r.cin, r.up2)
                                                           : pack_loader(r.w1, r.cout, r.cin, 3, S * r.cin, k1, 0, nullptr, part(r.cin)))) return 1;
       if (bind_loader(e, p + ".out_layers.3.weight", pack_loader(r.w2, r.cout, r.cout, 3, S * r.cout, k2, 0, nullptr, part(r.cout)))) return 1;
       if (dalloc(e, &r.b2, r.cout) || dalloc(e, &r.bfused, r.cout)) return 1;
@@ -618,10 +619,10 @@ int setup_device(sgdm_engine* e) {
       const std::string pp = L.kind == L_DOWN ? p + ".op" : L.kind == L_UP ? p + ".conv" : p;
       if (e->x3) cw.cin_pad = L.kind == L_CONV_IN ? e->xin_c : 3 * cw.cin;  // split parts of cw.cin channels
       const int ktot = 9 * cw.cin_pad;
-      cw.up2 = L.kind == L_UP && e->use_up2 && !e->x3 && conv_up2_applicable(cw.hin, cw.hin, cw.cin, cw.cout, pick_block_n(cw.cout));
+      cw.up2 = (L.kind == L_UP && e->use_up2 && !e->x3 && cw.cout != 128) ? conv_up2_applicable(cw.hin, cw.hin, cw.cin, cw.cout, pick_block_n(cw.cout)) : 0;
       if (dalloc(e, &cw.w, static_cast<size_t>(cw.up2 ? 4 * cw.cout : conv_npad(cw.cout, pick_block_n(cw.cout))) * ktot)) return 1;
       if (bind_f32(e, pp + ".bias", &cw.b)) return 1;
-      if (cw.up2) return bind_loader(e, pp + ".weight", pack_up2_loader(cw.w, cw.cout, cw.cin));
+      if (cw.up2) return bind_loader(e, pp + ".weight", pack_up2_loader(cw.w, cw.cout, cw.cin, cw.up2));
       const int* map = (L.kind == L_CONV_IN && !e->x3) ? e->ci_map_first : nullptr;
       if (L.kind == L_CONV_IN && e->first_im2col) {
         // [Npad][64]: K = tap * (2 Cimg + L) + entry; the buffer (sized for the 3x3 packing) is reused
@@ -744,7 +745,7 @@ struct Builder {
     if (d.B == 0) d.B = Bp;
     d.block_n = pick_block_n(d.Cout);
     d.swap_ab = !d.up2 && conv_should_swap(d) ? 1 : 0;
-    if (d.up2) d.halo = 1;
+    if (d.up2) d.halo = d.up2 == 1 ? 1 : 0;
     d.stat_gran = stat_gran();
     // geometry (pair / halo / 32-channel K blocks / A-stationary): the kernel's own policy (conv.cuh, conv_prepare)
     if (d.hfold) { d.halo = 1; d.pair = 0; }
@@ -839,7 +840,7 @@ struct Builder {
     c1.in = g1; c1.Hin = Ho; c1.Win = Wo; c1.Cin = C * S; c1.w = r.w1; c1.ks = 3; c1.stride = 1; c1.pad = 1;
     c1.Hout = Ho; c1.Wout = Wo; c1.Cout = r.cout; c1.bias = r.b1; c1.stats = h1_stats;
     c1.B = Bb;
-    if (r.up2) { c1.Hin = H; c1.Win = W; c1.Hout = H; c1.Wout = W; c1.up2 = 1; }  // low-resolution grid, [B, 2H, 2W, C] output
+    if (r.up2) { c1.Hin = H; c1.Win = W; c1.Hout = H; c1.Wout = W; c1.up2 = r.up2; }  // low-resolution grid, [B, 2H, 2W, C] output
     if (split3) c1.out_f32 = h1f;
     else c1.out_op = h1;
     conv(c1);
@@ -993,7 +994,7 @@ struct Builder {
   Act resample_conv(const ConvW& cw, Act a, bool up) {
     const int Hc = up ? a.H * 2 : a.H, Wc = up ? a.W * 2 : a.W;  // conv input size
     const int Ho = up ? Hc : a.H / 2, Wo = up ? Wc : a.W / 2;
-    const bool up2 = up && cw.up2;
+    const bool up2 = up && cw.up2 != 0;
     op_t* raw = static_cast<op_t*>(scratch("raw_op", static_cast<size_t>(Bp) * (up2 ? a.H * a.W : Hc * Wc) * a.C * S * sizeof(op_t)));
     {
       const float* src = a.p;
@@ -1010,7 +1011,7 @@ struct Builder {
     c.in = raw; c.Hin = Hc; c.Win = Wc; c.Cin = a.C * S; c.w = cw.w; c.ks = 3; c.stride = up ? 1 : 2; c.pad = 1;
     c.Hout = Ho; c.Wout = Wo; c.Cout = cw.cout; c.bias = cw.b; c.out_f32 = o.p;
     attach_outputs(o, static_cast<size_t>(Bp) * Ho * Wo, c);
-    if (up2) { c.Hin = a.H; c.Win = a.W; c.Hout = a.H; c.Wout = a.W; c.up2 = 1; }
+    if (up2) { c.Hin = a.H; c.Win = a.W; c.Hout = a.H; c.Wout = a.W; c.up2 = cw.up2; }
     conv(c);
     return o;
   }
@@ -1643,15 +1644,17 @@ int sgdm_k_conv_up2(void* stream, const void* in, int B, int H, int W, int Cin, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   g_launches += 3;
   // (naive == 2: w_scratch already holds the packing — micro-benchmarks time the conv alone)
+  const int variant = conv_up2_applicable(H, W, Cin, Cout, pick_block_n(Cout));
+  if (!variant) return fail("the sub-pixel mode does not apply to this shape");
   if (naive != 2 && (cudaMemsetAsync(w_scratch, 0, static_cast<size_t>(4) * Cout * 9 * Cin * sizeof(op_t), st) != cudaSuccess ||
-                     pack_conv_weight_up2_launch(w, static_cast<op_t*>(w_scratch), Cout, Cin, Cin, st)))
+                     pack_conv_weight_up2_launch(w, static_cast<op_t*>(w_scratch), Cout, Cin, Cin, st, variant == 2 ? 1 : 0)))
     return fail("up2 weight pack failed");
   ConvDesc d;
   d.in = static_cast<const op_t*>(in); d.B = B; d.Hin = H; d.Win = W; d.Cin = Cin; d.w = static_cast<const op_t*>(w_scratch);
   d.ks = 3; d.stride = 1; d.pad = 1; d.Hout = H; d.Wout = W; d.Cout = Cout; d.bias = bias;
   d.out_f32 = out_f32; d.out_op = static_cast<op_t*>(out_op);
   d.stats = reinterpret_cast<float2*>(stats); d.stat_gran = stat_gran;
-  d.block_n = pick_block_n(Cout); d.up2 = 1; d.halo = 1; d.pair = g_conv_pair;
+  d.block_n = pick_block_n(Cout); d.up2 = variant; d.halo = variant == 1 ? 1 : 0; d.pair = g_conv_pair;
   d.timing = g_conv_timing;
   if (naive == 1) return conv_launch_naive(d, st) ? fail("naive conv launch failed") : 0;
   ConvLaunch l;

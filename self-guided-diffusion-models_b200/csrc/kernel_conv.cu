@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int b_rows = block_n / kCtas;  // weight rows this CTA loads
       // main K blocks: halo stages hold the three vertical taps of one (horizontal tap, chunk); plain stages hold
       // p.kps consecutive (tap, chunk) K blocks, each with its own activation tile and weight slot
-      const int n_blk = (p.hfold ? 1 : p.up2 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;  // up2: two horizontal taps per parity
+      // (sub-pixel mode, halo geometry: two horizontal taps per parity; dense geometry: a plain 2x2 conv, p.ks = 2)
+      const int n_blk = (p.hfold ? 1 : p.up2 == 1 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;
       const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       uint32_t a_it = 0;  // A-stationary: m-tiles loaded so far (parity of the resident slots)
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile)) {
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               const int tap = q_tap;  // halo: the horizontal tap s; otherwise the tap index r*ks+s
               cc = q_cc;
               const int r = p.halo ? 0 : q_r;
-              const int s_tap = p.hfold ? p.pad : p.halo ? tap + up_dx : tap - r * p.ks;  // hfold: no horizontal shift
+              const int s_tap = p.hfold ? p.pad : p.halo ? tap + up_dx : tap - r * p.ks + up_dx;  // hfold: no horizontal shift
+              const int r_ld = r + (p.halo ? 0 : up_dy);  // dense sub-pixel mode: the parity's vertical offset goes into the load
               if (++q_cc == p.kc1) {
                 q_cc = 0;
                 ++q_tap;
@@ -269,8 +271,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
               if (u == 0) kb0 = p.hfold ? cc : p.halo ? s_tap * p.kc1 + cc : q * p.kps;
               uint8_t* dst = act_dst + u * p.act_tx;
-              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
-              else tma_load_4d(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r - p.pad, img);
+              if (kCtas == 2) tma_load_4d_pair(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r_ld - p.pad, img);
+              else tma_load_4d(&p.tmA, &full[stage], dst, cc * p.kblk, s_tap - p.pad, y0 * p.stride + r_ld - p.pad, img);
             }
           } else {
             cc = (q - n_main) * p.tps2;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint64_t desc_hi = umma_smem_desc_hi(p.kblk == 32);
       uint32_t stage = 0, phase = 0, it = 0, a_it = 0;
       long long t_full = 0, t_acc = 0;
-      const int n_blk = (p.hfold ? 1 : p.up2 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;
+      const int n_blk = (p.hfold ? 1 : p.up2 == 1 ? 2 : p.halo ? p.ks : p.taps) * p.kc1;
       const int n_main = p.halo ? n_blk : (n_blk + p.kps - 1) / p.kps, n_st = n_main + (p.kc2 + p.tps2 - 1) / p.tps2;
       for (int tile = tile_first; tile < total_tiles; tile = tile_next(tile), ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -862,6 +864,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.Cin % 64 || (d.in2 && d.C2 % 64) || (d.in2b && (d.C2b % 64 || !d.in2)))
     return fail("channel counts must be multiples of 64");
   if (!(d.ks == 1 || d.ks == 3) || !(d.stride == 1 || d.stride == 2)) return fail("unsupported ks/stride");
+  // sub-pixel mode, dense geometry (up2 == 2): a plain 2x2 conv per parity over [4 Cout][4 Cin] weights
+  const int ks = d.up2 == 2 ? 2 : d.ks;
   if (d.block_n != 16 && (d.block_n % 32 || d.block_n > 256 || d.block_n <= 0)) return fail("bad block_n");
   const int HW = d.Hout * d.Wout;
   if (!d.swap_ab) {
@@ -887,7 +891,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const int bh = min(d.Hout, tile_px / bw);
   const int bn = tile_px / (bw * bh);
   // halo mode: 3x3 stride 1, tiles made of whole rows of one image, row pitch = whole swizzle atoms
-  bool halo = d.halo != 0 && d.ks == 3 && d.stride == 1 && bn == 1 && bw * bh == tile_px && (HW % tile_px) == 0 &&
+  bool halo = d.halo != 0 && d.up2 != 2 && d.ks == 3 && d.stride == 1 && bn == 1 && bw * bh == tile_px && (HW % tile_px) == 0 &&
               (d.Wout % 8) == 0 && bh + 2 <= 256;
   if (d.halo == 1 && !halo) return fail("halo mode needs a 3x3 stride-1 conv whose tiles are whole rows of one image");
   if (d.hfold && (!halo || !d.out_nchw || 3 * d.Cout > 16 || d.in2 || d.swap_ab || pair))
@@ -911,9 +915,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // tensor pipe 47 %), 576 KB with it.  ConvDesc::k32: -1 policy, 0 never, 1 force.
   const bool halo_ok = halo;
   if (d.up2) {
-    if (!halo || d.swap_ab || d.res || d.in2 || d.out_nchw || d.out_op2 || d.hfold || d.k32 == 1 || (d.Cout % d.block_n) ||
-        (HW % 32) || (d.Wout < 32 && (32 % d.Wout)) || (d.Wout > 32 && (d.Wout % 32)))
-      return fail("up2 (sub-pixel) mode needs the halo geometry, Cout % block_n == 0, no residual / skip / NCHW output");
+    if ((d.up2 == 1 && !halo) || d.ks != 3 || d.stride != 1 || d.swap_ab || d.res || d.in2 || d.out_nchw || d.out_op2 || d.hfold ||
+        d.k32 == 1 || d.a_stat == 1 || (d.Cout % d.block_n) || (HW % 32) || (d.Wout < 32 && (32 % d.Wout)) || (d.Wout > 32 && (d.Wout % 32)))
+      return fail("up2 (sub-pixel) mode needs a 3x3 stride-1 conv, Cout % block_n == 0, no residual / skip / NCHW output "
+                  "(up2 == 1: the halo geometry)");
   }
   int kblk = d.k32 == 1 ? 32 : 64;
   if (kblk == 32 && ((d.Cin % 32) || !halo_ok || pair || d.hfold)) return fail("k32 needs a halo-mode conv, one CTA per tile");
@@ -967,7 +972,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const int kps_max = 3;
   p.kps = 1;
   if (!p.halo && p.kblk == 64 && d.a_stat != 1) {
-    const int n_blk = d.ks * d.ks * (d.Cin / 64);
+    const int n_blk = ks * ks * (d.Cin / 64);
     // (three blocks per stage only as two 96..144 KB stages, like the halo ring; two blocks need three stages)
     for (int kps = min(kps_max, min(n_blk, 3)); kps >= 2; --kps) {
       const int stage_k = kps * (p.act_tx + p.wgt_bytes);
@@ -1028,7 +1033,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (encode_nhwc(&p.tmA2, d.in2, d.B, d.Hout, d.Wout, d.C2, bw, bh, bn, 1, err, errlen, kblk)) return 1;
     if (d.in2b && encode_nhwc(&p.tmA2b, d.in2b, d.B, d.Hout, d.Wout, d.C2b, bw, bh, bn, 1, err, errlen, kblk)) return 1;
   }
-  const int Ktot = d.hfold ? d.ks * d.Cin : d.ks * d.ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
+  const int Ktot = d.hfold ? d.ks * d.Cin : ks * ks * d.Cin + (d.in2 ? d.C2 + (d.in2b ? d.C2b : 0) : 0);
   const int npad = d.up2 ? 4 * d.Cout : conv_npad(d.Cout, d.block_n);
   {
     auto fn = get_encode_fn();
@@ -1050,13 +1055,13 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   p.Hout = d.Hout;
   p.stride = d.stride;
   p.pad = d.pad;
-  p.ks = d.ks;
-  p.taps = d.ks * d.ks;
+  p.ks = ks;
+  p.taps = ks * ks;
   p.kc1 = d.Cin / kblk;
   p.kc2a = d.in2 ? d.C2 / kblk : 0;
   p.kc2 = p.kc2a + (d.in2 && d.in2b ? d.C2b / kblk : 0);
   p.N_total = d.up2 ? 4 * d.Cout : d.Cout;
-  p.up2 = d.up2 ? 1 : 0;
+  p.up2 = d.up2;
   p.cout_real = d.Cout;
   p.ntpp = d.up2 ? d.Cout / d.block_n : 0;
   p.block_n = d.block_n;
@@ -1111,7 +1116,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // shared memory: as many K-block stages as fit beside the epilogue staging
   out->pair = pair ? 1 : 0;
   // (A-stationary: the work items of a CTA / pair are whole m-tiles)
-  if (d.up2 && (p.kblk != 64 || !p.halo)) return fail("up2 mode: unexpected geometry");
+  if (d.up2 && (p.kblk != 64 || (d.up2 == 1) != (p.halo != 0) || p.a_stat)) return fail("up2 mode: unexpected geometry");
   if (pair) {
     const int total = (p.m_tiles + 1) / 2 * (p.a_stat ? 1 : p.n_tiles);
     out->grid = 2 * (total < kNumSMs / 2 ? total : kNumSMs / 2);
@@ -1130,15 +1135,16 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   return 0;
 }
 
-bool conv_up2_applicable(int H, int W, int Cin, int Cout, int block_n) {
+int conv_up2_applicable(int H, int W, int Cin, int Cout, int block_n) {
   const int HW = H * W;
-  if ((Cin % 64) || block_n < 64 || (Cout % block_n) || Cout == 128) return false;  // (Cout = 128 layers run swap-AB)
-  if (W < 8 || (W % 8) || W > kTileM || (kTileM % W) || (HW % kTileM)) return false;  // whole rows of one image per tile
-  if (W < 32 ? (32 % W) != 0 : (W % 32) != 0) return false;                         // 32-pixel store chunks
+  if ((Cin % 64) || block_n < 64 || (Cout % block_n)) return 0;
+  if ((HW % 32) || (W < 32 ? (32 % W) != 0 : (W % 32) != 0)) return 0;         // 32-pixel store chunks, statistics blocks
+  if (HW < kTileM) return (kTileM % HW) == 0 && W >= 4 ? 2 : 0;                 // tiles of whole images: the dense geometry
+  if (W < 8 || (W % 8) || W > kTileM || (kTileM % W) || (HW % kTileM)) return 0;  // whole rows of one image per tile
   const int bh = kTileM / W;
   // two halo stages of (bh + 2) rows + two weight slots each (one CTA per tile: the larger case) beside 2 staging buffers
   const int stage = (bh + 2) * W * 128 + 2 * block_n * 128;
-  return 2 * stage + 4 * 2 * kEpiBuf + kBarBytes + kBiasBytes <= kSmemLimit;
+  return 2 * stage + 4 * 2 * kEpiBuf + kBarBytes + kBiasBytes <= kSmemLimit ? 1 : 0;
 }
 
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
@@ -1159,14 +1165,15 @@ __global__ void conv_naive_kernel(ConvDesc d, int npad) {
     const int W2 = 2 * d.Wout, H2 = 2 * d.Hout;
     const int X = px % W2, Y = (px / W2) % H2, b = px / (static_cast<long>(W2) * H2);
     const int dy = Y & 1, dx = X & 1, yy = Y >> 1, xx = X >> 1;
-    const op_t* wr = d.w + static_cast<long>((2 * dy + dx) * d.Cout + co) * (9 * d.Cin);
+    const int taps_k = d.up2 == 2 ? 4 : 9;  // dense geometry: [4 Cout][4 Cin], tap (a, b) at (a * 2 + b) * Cin
+    const op_t* wr = d.w + static_cast<long>((2 * dy + dx) * d.Cout + co) * (taps_k * d.Cin);
     float acc = 0.f;
     for (int R = dy; R <= dy + 1; ++R)
       for (int S = dx; S <= dx + 1; ++S) {
         const int iy = yy + R - 1, ix = xx + S - 1;
         if (iy < 0 || iy >= d.Hin || ix < 0 || ix >= d.Win) continue;
         const op_t* a = d.in + ((static_cast<long>(b) * d.Hin + iy) * d.Win + ix) * d.Cin;
-        const op_t* w = wr + (R * 3 + S) * d.Cin;
+        const op_t* w = wr + (d.up2 == 2 ? (R - dy) * 2 + (S - dx) : R * 3 + S) * d.Cin;
         for (int c = 0; c < d.Cin; ++c) acc += from_op(a[c]) * from_op(w[c]);
       }
     if (d.bias) acc += d.bias[co];

@@ -176,7 +176,7 @@ int pack_conv_weight_hfold_launch(const float* w, op_t* dst, int Cout, int Cin, 
 int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks, int cin_pad, int ktot, int k_off,
                             const int* ci_map, cudaStream_t s, int cin_part = 0);
 // sub-pixel packing of a 3x3 conv that follows a nearest-2x upsample (ConvDesc::up2): dst [4 Cout][9 cin_pad]
-int pack_conv_weight_up2_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s);
+int pack_conv_weight_up2_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s, int dense = 0);
 int add_bias_launch(const float* a, const float* b, float* out, int n, cudaStream_t s);
 // out[t] = 64-bit hash of the bits of fp32 tensor t (device pointer / element-count tables on the device)
 int fingerprint_launch(const void* const* ptrs, const long long* numel, int n, unsigned long long* out, cudaStream_t s);

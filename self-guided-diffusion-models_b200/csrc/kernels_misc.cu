@@ -1275,7 +1275,8 @@ int pack_conv_weight_launch(const float* w, op_t* dst, int Cout, int Cin, int ks
 // Sub-pixel packing (ConvDesc::up2): dst[(2 dy + dx) Cout + co][(R * 3 + S) * cin_pad + ci] = sum of w[co][ci][r][s] over
 // r in V(dy, R), s in V(dx, S) with V(0,0) = {0}, V(0,1) = {1,2}, V(1,1) = {0,1}, V(1,2) = {2}; the sums are formed in
 // fp32 and rounded once.  Taps a parity does not use stay zero (they are never read).
-__global__ void pack_conv_weight_up2_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin, int cin_pad) {
+__global__ void pack_conv_weight_up2_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cin, int cin_pad,
+                                            int dense) {
   const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   const long total = static_cast<long>(4) * Cout * 4 * Cin;
   if (idx >= total) return;
@@ -1292,11 +1293,13 @@ __global__ void pack_conv_weight_up2_kernel(const float* __restrict__ w, op_t* _
   float acc = 0.f;
   for (int r = r_lo; r <= r_hi; ++r)
     for (int s = s_lo; s <= s_hi; ++s) acc += wp[r * 3 + s];
-  dst[(static_cast<long>(par) * Cout + co) * (9 * cin_pad) + (R * 3 + S) * cin_pad + ci] = to_op(acc);
+  // dense (ConvDesc::up2 == 2): only the parity's own four taps, K = (a * 2 + b) * cin_pad + ci
+  if (dense) dst[(static_cast<long>(par) * Cout + co) * (4 * cin_pad) + ab * cin_pad + ci] = to_op(acc);
+  else dst[(static_cast<long>(par) * Cout + co) * (9 * cin_pad) + (R * 3 + S) * cin_pad + ci] = to_op(acc);
 }
-int pack_conv_weight_up2_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s) {
+int pack_conv_weight_up2_launch(const float* w, op_t* dst, int Cout, int Cin, int cin_pad, cudaStream_t s, int dense) {
   const long total = static_cast<long>(4) * Cout * 4 * Cin;
-  pack_conv_weight_up2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, cin_pad);
+  pack_conv_weight_up2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, cin_pad, dense);
   return SGDM_LAUNCH_OK();
 }
 __global__ void pack_first_conv_im2col_kernel(const float* __restrict__ w, op_t* __restrict__ dst, int Cout, int Cimg, int L) {

@@ -273,6 +273,10 @@ UP2_CASES = [
     (5, 8, 16, 192, 64, "f32", 2, "8x16 images, Cin = 192, N = 64"),
     (3, 16, 16, 384, 384, "op", 4, "config-2 shape 384 -> 384 at 16x16: 192-column tiles, two per parity"),
     (40, 16, 16, 128, 256, "op", 4, "80 m-tiles x 4 parities: persistent loop, both accumulator stages"),
+    (6, 8, 8, 256, 256, "f32", 4, "8x8 -> 16x16: dense geometry (plain 2x2 conv per parity), tile = 2 images"),
+    (5, 8, 8, 128, 512, "op", 4, "8x8, odd batch: ragged last tile, two n-tiles per parity, 16-bit out"),
+    (9, 4, 8, 64, 64, "f32", 2, "4x8 images: tile = 4 images, ragged, N = 64"),
+    (64, 8, 8, 512, 512, "op", 4, "config-2 shape 512 -> 512 at 8x8, 32 m-tiles"),
 ]
 
 
