@@ -118,6 +118,27 @@ __device__ __forceinline__ float2 unpack_op2(uint32_t v) {
 // x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (an IEEE divide would make the GroupNorm
 // apply pass issue-bound instead of HBM-bound); |error| <= ~2 ulp, far below the 16-bit output rounding.
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// Four SiLUs with ONE reciprocal: 1 / d_i = (1 / (d_0 d_1 d_2 d_3)) * prod_{j != i} d_j, d_i = 1 + 2^(-x_i log2 e).
+// 1.25 MUFU operations per element instead of 2: the GroupNorm apply pass with a 16-bit source moves 4 B per element
+// and was bound by the 16-lane MUFU at the power-capped clocks (4.7 instead of 6.1 TB/s).  The exponent is clamped at
+// 2^30 so that the product of four stays finite: for x < -20.8 the result is x * 2^-30 instead of ~x e^x, |error| < 2e-8 |x|.
+__device__ __forceinline__ void silu4(const float (&x)[4], float (&y)[4]) {
+  float d[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x[i] * -1.4426950408889634f, 30.0f)));
+    d[i] = 1.0f + e;
+  }
+  const float p01 = d[0] * d[1], p23 = d[2] * d[3];
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+  const float r01 = r * p23, r23 = r * p01;  // 1 / (d0 d1), 1 / (d2 d3)
+  y[0] = x[0] * (r01 * d[1]);
+  y[1] = x[1] * (r01 * d[0]);
+  y[2] = x[2] * (r23 * d[3]);
+  y[3] = x[3] * (r23 * d[2]);
+}
 
 // ---- shared-memory address / mbarrier -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

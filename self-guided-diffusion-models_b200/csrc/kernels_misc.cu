@@ -323,11 +323,20 @@ __global__ void __launch_bounds__(256, kMinBlocks) gn_apply_kernel(const GnApply
     }
   }
   auto xform = [&](const float (&v)[8], float (&y)[8]) {
+    if (a.silu) {  // SiLU with one reciprocal per four elements (common.cuh: silu4)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = v[j] * ka[j] + kb[j];
-      y[j] = a.silu ? silu(t) : t;
+      for (int q = 0; q < 2; ++q) {
+        float t[4], s[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = v[4 * q + j] * ka[4 * q + j] + kb[4 * q + j];
+        silu4(t, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[4 * q + j] = s[j];
+      }
+      return;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = v[j] * ka[j] + kb[j];
   };
   const int Ho = kResample == 1 ? a.H >> 1 : a.H, Wo = kResample == 1 ? a.W >> 1 : a.W;
   const int n_iter = Ho * Wo;  // pooled: output pixels; otherwise input pixels
