@@ -673,6 +673,10 @@ def test_bf16_operand_build_kernel_suite_and_eps():
     lib = os.path.join(root, "self-guided-diffusion-models_b200", "libsgdm_b200_bf16.so")
     if not os.path.exists(lib):
         pytest.skip("bf16 variant not built (__graft_entry__.build())")
+    # a variant left over from an older source state (built with SGDM_SKIP_BF16_BUILD=1 since) lacks newer symbols
+    stamps = [os.path.join(root, "build", "libsgdm_b200.sha256"), os.path.join(root, "build", "bf16", "libsgdm_b200_bf16.sha256")]
+    if all(os.path.exists(p) for p in stamps) and open(stamps[0]).read().strip() != open(stamps[1]).read().strip():
+        pytest.skip("bf16 variant is stale: run __graft_entry__.build() without SGDM_SKIP_BF16_BUILD")
     env = dict(os.environ, SGDM_LIB=lib)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-x", "-m", "gpu",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1500, cwd=root)
