@@ -1488,6 +1488,8 @@ int sgdm_profile_get(sgdm_handle h, int i, const char** kind, double* ms, double
 
 int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                  const float* layout, const uint8_t* drop, int B, float* eps_out) {
+  if (B == 0) return 0;  // empty batch: nothing to compute (the reference returns an empty tensor)
+  if (B < 0) return fail("negative batch size");
   Plan* plan = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (run_forward(h, s, x, t, cond, layout, drop, B, B, &plan)) return 1;
@@ -1497,6 +1499,12 @@ int sgdm_forward(sgdm_handle h, void* stream, const float* x, const int64_t* t, 
 }
 int sgdm_forward_guided(sgdm_handle h, void* stream, const float* x, const int64_t* t, const float* cond,
                         const float* layout, int B, const float** eps_c, const float** eps_u) {
+  if (B == 0) {  // empty batch: nothing to compute; the sampler update kernels are no-ops for it as well
+    *eps_c = nullptr;
+    *eps_u = nullptr;
+    return 0;
+  }
+  if (B < 0) return fail("negative batch size");
   Plan* plan = nullptr;
   if (run_forward(h, static_cast<cudaStream_t>(stream), x, t, cond, layout, nullptr, B, 2 * B, &plan)) return 1;
   const size_t n = static_cast<size_t>(B) * h->cfg.out_channels * h->cfg.image_size * h->cfg.image_size;

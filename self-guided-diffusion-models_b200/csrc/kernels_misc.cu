@@ -1068,6 +1068,7 @@ __global__ void mix_kernel(const MixDesc m, float* __restrict__ out, long per_sa
 }
 int mix_launch(const MixDesc& m, float* eps_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
+  if (total == 0) return 0;  // an empty batch is a no-op, like the reference's torch ops
   return launch_pdl(mix_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, eps_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
 
@@ -1110,6 +1111,7 @@ __global__ void ddim_step_kernel(const MixDesc m, const DdimCoef c, const StepEx
 int ddim_step_launch(const MixDesc& m, const DdimCoef& c, const StepExtras& ex, const float* x, const float* noise,
                      float* x_out, float* x0_out, float* eps_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
+  if (total == 0) return 0;
   return launch_pdl(ddim_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, c, ex, x, noise,
                     x_out, x0_out, eps_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
@@ -1138,6 +1140,7 @@ __global__ void ddpm_step_kernel(const MixDesc m, const DdpmCoef c, const StepEx
 int ddpm_step_launch(const MixDesc& m, const DdpmCoef& c, const StepExtras& ex, const float* x, const float* noise,
                      float* x_out, float* x0_out, int B, long per_sample, cudaStream_t s) {
   const long total = B * per_sample;
+  if (total == 0) return 0;
   return launch_pdl(ddpm_step_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, m, c, ex, x, noise,
                     x_out, x0_out, per_sample, total) == cudaSuccess ? 0 : 1;
 }
@@ -1196,6 +1199,7 @@ __global__ void __launch_bounds__(256) quantile_abs_kernel(const float* __restri
   }
 }
 int quantile_abs_launch(const float* x0, int B, long n, float q, float* s_out, cudaStream_t s) {
+  if (B == 0) return 0;
   quantile_abs_kernel<<<B, 256, 0, s>>>(x0, n, q, s_out);
   return SGDM_LAUNCH_OK();
 }
@@ -1208,6 +1212,7 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, unsigned char* __re
   out[i] = static_cast<unsigned char>(v);  // truncation, like .to(torch.uint8)
 }
 int to_uint8_launch(const float* x, unsigned char* out, long n, cudaStream_t s) {
+  if (n == 0) return 0;
   to_uint8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, out, n);
   return SGDM_LAUNCH_OK();
 }
@@ -1227,6 +1232,7 @@ __global__ void lincomb_kernel(const LincombArgs g, float* __restrict__ out, lon
 int lincomb_launch(const float* const* a, const float* c, int n_terms, float div, float* out, long n, cudaStream_t s,
                    int use_scale, float pre_scale) {
   if (n_terms < 1 || n_terms > 4) return 1;
+  if (n == 0) return 0;
   LincombArgs g;
   for (int k = 0; k < 4; ++k) { g.a[k] = k < n_terms ? a[k] : nullptr; g.c[k] = k < n_terms ? c[k] : 0.f; }
   g.n_terms = n_terms;
@@ -1247,6 +1253,7 @@ __global__ void pndm_transfer_kernel(const float* __restrict__ x, const float* _
   out[i] = __fadd_rn(xi, __fmul_rn(d, __fsub_rn(__fmul_rn(A, xi), __fmul_rn(B, et[i]))));
 }
 int pndm_transfer_launch(const float* x, const float* et, float d, float A, float B, float* out, long n, cudaStream_t s) {
+  if (n == 0) return 0;
   pndm_transfer_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, et, d, A, B, out, n);
   return SGDM_LAUNCH_OK();
 }

@@ -97,7 +97,7 @@ class DDIMSampler(object):
             self._extras = StepExtras(sampling_kwargs, x)
             out, x0 = torch.empty_like(x), torch.empty_like(x)
             self._step(_lib.current_stream(device), eps, int(index), 1 if sampling_kwargs["clip_denoised"] else 0,
-                       sampling_kwargs["temperature"], x, nz, out, x0, x.shape[0], x[0].numel())
+                       sampling_kwargs["temperature"], x, nz, out, x0, x.shape[0], x.shape[1:].numel())
         return out, x0, None
 
     @torch.no_grad()
@@ -115,7 +115,7 @@ class DDIMSampler(object):
         logs = log_indices(total, sampling_kwargs["log_num_per_prog"])
         eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device)
         clip = 1 if sampling_kwargs["clip_denoised"] else 0
-        per_sample = img[0].numel()
+        per_sample = img.shape[1:].numel()
         nxt = torch.empty_like(img)
         out = dict(pred_x0=[], x_inter=[])
         for i, step in enumerate(np.flip(timesteps)):
@@ -148,7 +148,7 @@ class DDIMSampler(object):
         logs = log_indices(total, sampling_kwargs["log_num_per_prog"])
         eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device)
         clip = 1 if sampling_kwargs["clip_denoised"] else 0
-        per_sample, n = img[0].numel(), img.numel()
+        per_sample, n = img.shape[1:].numel(), img.numel()
         temperature = sampling_kwargs["temperature"]
         old = []
         out = dict(pred_x0=[], x_inter=[])

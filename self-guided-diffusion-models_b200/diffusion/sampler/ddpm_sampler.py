@@ -107,10 +107,10 @@ class Schedule_DDPM(nn.Module):
                   tab["sigma"][i] if i != 0 else 0.0, temperature)
         stream = _lib.current_stream(device)
         extras = StepExtras(sampling_kwargs, x, noise_dropout=noise_dropout)
-        dyn, mul = extras.pointers(stream, 0, (pc, pu, w, w_ptr, st), c, x, x.shape[0], x[0].numel())
+        dyn, mul = extras.pointers(stream, 0, (pc, pu, w, w_ptr, st), c, x, x.shape[0], x.shape[1:].numel())
         _lib.check(_lib.lib().sgdm_ddpm_step_ex(stream, pc, pu, w, w_ptr, st, c,
                                                 1 if sampling_kwargs["clip_denoised"] else 0, x.data_ptr(), nz.data_ptr(),
-                                                out.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel(), dyn, mul))
+                                                out.data_ptr(), x0.data_ptr(), x.shape[0], x.shape[1:].numel(), dyn, mul))
         return out, x0, None
 
     @torch.no_grad()
@@ -146,7 +146,7 @@ class Schedule_DDPM(nn.Module):
         sigma = (0.5 * tab["posterior_log_variance_clipped"]).exp()
         eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device)
         clip = 1 if sampling_kwargs["clip_denoised"] else 0
-        per_sample = img[0].numel()
+        per_sample = img.shape[1:].numel()
         extras = StepExtras(sampling_kwargs, img, noise)
         out = dict(pred_x0=[], x_inter=[])
         for i in reversed(range(0, timesteps)):

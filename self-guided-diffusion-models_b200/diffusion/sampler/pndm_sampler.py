@@ -80,7 +80,7 @@ class PNDM_Sampler(object):
         sch, S = self.noise_scheduler, self.num_inference_steps
         B = shape[0]
         image = NoiseSource(shape, device, noise_tape).x_T().contiguous()
-        n, per_sample = image.numel(), image[0].numel()
+        n, per_sample = image.numel(), image.shape[1:].numel()
         eps_src = GuidedEps(denoise_sample_fn, denoise_sample_fn_kwargs, device)
 
         def guided(x, t_value):

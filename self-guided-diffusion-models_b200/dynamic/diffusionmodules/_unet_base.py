@@ -324,6 +324,8 @@ class EngineUNet(nn.Module):
         self.refresh_weights() if self.check_weights else self.sync_weights()
         x, t, cond, layout = self._prep_inputs(x, t, cond, layout)
         B = x.shape[0]
+        if B == 0:  # empty batch: the reference's torch ops return an empty tensor
+            return torch.empty((0, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
         drop = drop_mask.to(device=x.device, dtype=torch.uint8).contiguous()
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
@@ -385,6 +387,8 @@ class EngineUNet(nn.Module):
             return self.get_guided_score(z=eps_u, zc=eps_c, w=cond_scale)
         self.refresh_weights() if self.check_weights else self.sync_weights()
         x, t, cond, layout = self._prep_inputs(x, t, cond, layout)
+        if B == 0:
+            return torch.empty((0, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
         pc, pu = self.guided_pair_ptrs(x, t, cond, layout)
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
         w_ptr, w = None, 0.0
@@ -397,7 +401,7 @@ class EngineUNet(nn.Module):
             w_ptr = wt.data_ptr()
         else:
             w = float(cond_scale)
-        per_sample = out[0].numel()
+        per_sample = out.shape[1:].numel()
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().sgdm_mix(_lib.current_stream(x.device), pc, pu, w, w_ptr, self._scale_type(),
                                            _lib.ptr(out), B, per_sample))

@@ -514,6 +514,34 @@ def test_full_size_properties_unetca(name):
 
 
 @pytest.mark.gpu
+def test_empty_batch_is_a_no_op():
+    """B = 0 (a last, empty shard): the reference's torch ops return empty tensors; so do the UNet calls and a whole
+    trajectory here, without a kernel launch failing."""
+    need_gpu()
+    from sgdm_b200.diffusion import ddpm as ddpm_mod
+
+    meta, a = load_unet_case("unet_fast_label_tiny")
+    m = cuda_model(meta)
+    H = meta["cfg"]["image_size"]
+    x0 = torch.empty(0, 3, H, H, device="cuda")
+    t0 = torch.empty(0, dtype=torch.long, device="cuda")
+    c0 = a["kw_cond"][:0].cuda()
+    for cs in (2.0, 1, 0):
+        e = m.forward_with_cond_scale(x0, t0, cs, cond=c0)
+        assert tuple(e.shape) == (0, 3, H, H) and e.dtype == torch.float32
+    for method, T in (("native", 10), ("ddim", 1000)):
+        ld = ddpm_mod.LatentDiffusion(given_betas=None, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
+                                      v_posterior=0.0, parameterization="eps", device="cuda", num_timesteps=T, loss_type="l2")
+        ld.set_denoise_fn(m.forward, m.forward_with_cond_scale)
+        skw = dict(sampling_method=method, vis=None, ddim_eta=0.0, log_num_per_prog=10, clip_denoised=True, dtp=1,
+                   temperature=1.0, noise_dropout=0, random_sample_condition=False, return_inter_dict=False,
+                   disable_tqdm=True, num_timesteps=10)
+        samples, _ = ld.p_sample_loop(method, (0, 3, H, H), skw, denoise_sample_fn_kwargs=dict(cond=c0, cond_scale=2.0),
+                                      condition_kwargs=dict(cond_scale=2.0, condition_method="label"))
+        assert tuple(samples.shape) == (0, 3, H, H)
+
+
+@pytest.mark.gpu
 def test_oracle_parity_on_fresh_seeded_inputs():
     """CUDA path vs the CPU oracle on inputs that are NOT in the golden files."""
     need_gpu()
