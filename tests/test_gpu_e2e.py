@@ -514,6 +514,31 @@ def test_full_size_properties_unetca(name):
 
 
 @pytest.mark.gpu
+def test_large_batch_index_widths():
+    """Batch 768 at config-2 shapes (1536 rows through the guided plan, a 67 GB workspace): the largest concat tensor has
+    2.4e9 elements (> 2^31) and most tensors exceed 2^32 bytes, so any 32-bit index or byte offset on the path would show.
+    The first, middle and last samples must equal the same samples run alone, bit for bit."""
+    need_gpu()
+    from sgdm_b200 import synthetic
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~70 GB of free device memory")
+    meta, _ = load_unet_case("cfg2_in64_label")
+    m = cuda_model(meta)
+    B = 768
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, 3, 64, 64, generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    cond = synthetic.synthetic_batch("label", B, 1000, 64, seed=13)["label"].cuda()
+    e = m.forward_with_cond_scale(x, t, 2.0, cond=cond)
+    assert torch.isfinite(e).all()
+    for lo, hi in ((0, 2), (383, 386), (766, 768)):
+        sub = m.forward_with_cond_scale(x[lo:hi].contiguous(), t[lo:hi].contiguous(), 2.0, cond=cond[lo:hi].contiguous())
+        assert torch.equal(sub, e[lo:hi]), f"samples {lo}:{hi} differ: rel_l2 {rel_l2(sub.cpu(), e[lo:hi].cpu()):.3e}"
+
+
+@pytest.mark.gpu
 def test_empty_batch_is_a_no_op():
     """B = 0 (a last, empty shard): the reference's torch ops return empty tensors; so do the UNet calls and a whole
     trajectory here, without a kernel launch failing."""
