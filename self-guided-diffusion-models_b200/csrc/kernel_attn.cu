@@ -6,8 +6,9 @@
 // 1 null | T self], q scaled by d^-1/2) — SURVEY.md §2.3 rows K6/K7.
 //
 // One CTA = 128 queries of one (sample, head); 8 warps x 16 query rows.  K and V of the
-// sample (T_kv <= 320 rows incl. the extra context/null rows) are staged once in shared
-// memory with 16-byte cp.async; S = QK^T and O = PV run on mma.sync m16n8k16 (16-bit operands, fp32 accumulate);
+// sample are staged in shared memory with 16-byte cp.async — all T_kv rows at once when they fit (T_kv <= 320 incl. the
+// extra context/null rows at d = 64), otherwise in blocks of 256 keys that the online softmax walks one after the other
+// (T = 1024: 128x128 images with attention at ds 4); S = QK^T and O = PV run on mma.sync m16n8k16 (16-bit operands, fp32 accumulate);
 // the softmax is computed in fp32 over key chunks of 64 with running max / sum.
 // Attention is ~1 % of the UNet FLOPs.
 #include "attn.cuh"
@@ -51,14 +52,14 @@ constexpr int kAttnThreads = 256;  // 8 warps x 16 query rows
 // D: head dim as the MMAs see it (multiple of 16); DR <= D: the real head dim (8 for 32 heads on 256 channels — the rows
 // are zero-extended to 16 in shared memory)
 template <int D, int DR = D>
-__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, int tkv_pad) {
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, int tkv_pad, int kv_blk) {
   constexpr int LD = D + 8;  // padded row: conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_attn[];
   pdl_launch_dependents();
   pdl_wait();
-  op_t* sK = reinterpret_cast<op_t*>(smem_attn);
-  op_t* sV = sK + static_cast<long>(tkv_pad) * LD;
-  op_t* sQ = sV + static_cast<long>(tkv_pad) * LD;
+  op_t* sK = reinterpret_cast<op_t*>(smem_attn);   // kv_blk rows (a multiple of 64; == tkv_pad when everything fits)
+  op_t* sV = sK + static_cast<long>(kv_blk) * LD;
+  op_t* sQ = sV + static_cast<long>(kv_blk) * LD;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tkv = a.n_extra + a.T;
@@ -68,10 +69,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
   // ---- stage K, V (extra rows first, then the T self rows) and the Q tile: 16-byte cp.async,
   //      zero-fill for the padding rows
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < tkv_pad * CPR; i += kAttnThreads) {
-    const int row = i / CPR, ch = i - row * CPR;
-    op_t* dk = sK + row * LD + ch * 8;
-    op_t* dv = sV + row * LD + ch * 8;
+  auto stage_kv = [&](int kb0) {  // rows [kb0, kb0 + kv_blk) of the key / value sequence -> sK / sV
+  for (int i = threadIdx.x; i < kv_blk * CPR; i += kAttnThreads) {
+    const int lrow = i / CPR, ch = i - lrow * CPR, row = kb0 + lrow;
+    op_t* dk = sK + lrow * LD + ch * 8;
+    op_t* dv = sV + lrow * LD + ch * 8;
     if (ch >= CPRR) {
       *reinterpret_cast<uint4*>(dk) = zero4;
       *reinterpret_cast<uint4*>(dv) = zero4;
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
       *reinterpret_cast<uint4*>(dv) = zero4;
     }
   }
+  };
+  stage_kv(0);
   for (int i = threadIdx.x; i < kAttnQ * CPR; i += kAttnThreads) {
     const int row = i / CPR, ch = i - row * CPR;
     op_t* dq = sQ + row * LD + ch * 8;
@@ -99,7 +103,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  if (q0 + warp * 16 >= a.T) return;  // this warp's 16 query rows are all padding
+  // (a warp whose 16 query rows are all padding computes nothing but keeps taking part in the block-wide staging)
+  const bool active = q0 + warp * 16 < a.T;
 
   // ---- Q fragments (A operand, 16 x D per warp)
   uint32_t qf[D / 16][4];
@@ -114,8 +119,17 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
   const float sl = a.scale * 1.4426950408889634f;  // logits in log2 units
   const int mi = lane >> 3, lr = lane & 7;
 
-  const int nchunks = (Tkv + 63) / 64;
+  const int nchunks = (Tkv + 63) / 64, cpb = kv_blk / 64;  // 64-key chunks in all / per staged block
   for (int kc = 0; kc < nchunks; ++kc) {
+    if (kc > 0 && kc % cpb == 0) {  // next block of keys: everyone is done with the staged one
+      __syncthreads();
+      stage_kv(kc * 64);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    if (!active) continue;
+    const int kl = (kc % cpb) * 64;  // first row of this chunk inside the staged block
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         uint32_t b[4];
-        ldsm_x4(b, sK + (kc * 64 + np * 16 + (mi >> 1) * 8 + lr) * LD + ks * 16 + (mi & 1) * 8);
+        ldsm_x4(b, sK + (kl + np * 16 + (mi >> 1) * 8 + lr) * LD + ks * 16 + (mi & 1) * 8);
         mma16816(s[2 * np], qf[ks], b[0], b[1]);
         mma16816(s[2 * np + 1], qf[ks], b[2], b[3]);
       }
@@ -170,12 +184,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const AttnDesc a, in
 #pragma unroll
       for (int ndp = 0; ndp < D / 16; ++ndp) {
         uint32_t b[4];
-        ldsm_x4_t(b, sV + (kc * 64 + kk * 16 + (mi & 1) * 8 + lr) * LD + (ndp * 2 + (mi >> 1)) * 8);
+        ldsm_x4_t(b, sV + (kl + kk * 16 + (mi & 1) * 8 + lr) * LD + (ndp * 2 + (mi >> 1)) * 8);
         mma16816(o[2 * ndp], pf[kk], b[0], b[1]);
         mma16816(o[2 * ndp + 1], pf[kk], b[2], b[3]);
       }
     }
   }
+  if (!active) return;
   // ---- finalise: row sums across the 4 lanes of a row, normalise, store
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -204,7 +219,10 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
   // head dims of the reference configs (mc 64 / 128 / 256 with 8 heads: 32, 64, 128) and of num_heads = 32 (8, 16)
   if (a.D != 8 && a.D != 16 && a.D != 32 && a.D != 64 && a.D != 128) return 1;
   const int LD = (a.D < 16 ? 16 : a.D) + 8;
-  const size_t smem = (static_cast<size_t>(tkv_pad) * 2 + kAttnQ) * LD * sizeof(op_t);
+  // everything staged at once when it fits in 200 KB, else blocks of 256 keys
+  int kv_blk = tkv_pad;
+  if ((static_cast<size_t>(tkv_pad) * 2 + kAttnQ) * LD * sizeof(op_t) > 200 * 1024) kv_blk = 256;
+  const size_t smem = (static_cast<size_t>(kv_blk) * 2 + kAttnQ) * LD * sizeof(op_t);
   if (smem > 200 * 1024) return 1;
   const dim3 grid((a.T + kAttnQ - 1) / kAttnQ, a.heads, a.B);
   static size_t max_set[5] = {0, 0, 0, 0, 0};  // opt-in dynamic smem limit, raised on demand
@@ -214,7 +232,7 @@ int attn_launch(const AttnDesc& a, cudaStream_t s) {
         return 1;
       limit = smem;
     }
-    return launch_pdl(kernel, grid, dim3(kAttnThreads), smem, s, 1, a, tkv_pad) == cudaSuccess ? 0 : 1;
+    return launch_pdl(kernel, grid, dim3(kAttnThreads), smem, s, 1, a, tkv_pad, kv_blk) == cudaSuccess ? 0 : 1;
   };
   if (a.D == 64 ? run(attn_kernel<64>, max_set[0]) : a.D == 32 ? run(attn_kernel<32>, max_set[1]) :
       a.D == 128 ? run(attn_kernel<128>, max_set[2]) : a.D == 16 ? run(attn_kernel<16>, max_set[3]) : run(attn_kernel<16, 8>, max_set[4]))

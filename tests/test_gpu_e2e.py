@@ -606,6 +606,13 @@ VARIANT_CFGS = {
                                        num_res_blocks=2, channel_mult=[1, 2, 4], attention_resolutions=[4], num_heads=8,
                                        resblock_updown=True, cond_dim=5000, condition_method="cluster", layout_dim=0,
                                        context_dim=None, cond_token_num=0, scale_type="imagen"),
+    # 128x128 images (config/data/ffhq128.yaml) on config 2's UNet: one-row halo tiles at the top level, sub-pixel up-convs
+    # from 32x32 and 64x64, attention over T = 1024 tokens at ds 4 (keys staged in blocks)
+    "unet_fast at 128x128 (T=1024 attention)": dict(kind="unet_fast", image_size=128, in_channels=3, out_channels=3,
+                                                    model_channels=128, num_res_blocks=2, channel_mult=[1, 2, 4],
+                                                    attention_resolutions=[4], num_heads=8, resblock_updown=True, cond_dim=10,
+                                                    condition_method="label", layout_dim=0, context_dim=None,
+                                                    cond_token_num=0, scale_type="imagen", batch=1),
     # scale_type 'cfg' (openaimodel.py:857: (1 + w) eps_c - w eps_u) on the cross-attention UNet
     "unetca clusterlayout, scale_type=cfg": dict(kind="unetca_fast", image_size=32, in_channels=3, out_channels=3,
                                                  model_channels=64, num_res_blocks=2, channel_mult=[1, 2, 4],
@@ -639,7 +646,7 @@ def test_variant_configs_vs_oracle(name):
     m.load_state_dict(synthetic.synthetic_state_dict(shapes, 3))
     m = m.cuda().eval()
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    B, H = 2, cfg["image_size"]
+    B, H = cfg.get("batch", 2), cfg["image_size"]
     g = torch.Generator().manual_seed(91)
     x = torch.randn(B, 3, H, H, generator=g)
     t = torch.randint(0, 1000, (B,), generator=g)

@@ -548,6 +548,9 @@ ATTN_CASES = [
     (1, 1024, 32, 16, 0, False, "T=1024 d=16"),
     (2, 100, 4, 16, 5, True, "MQA d=16, ragged T, 5 extra keys"),
     (2, 256, 8, 64, 49, True, "MQA, 49 extra keys (cond_token_num 40: beyond the tcgen05 kernel's 32)"),
+    (1, 1024, 8, 64, 0, False, "T=1024 d=64 (128x128 images, attention at ds 4): keys staged in blocks of 256"),
+    (1, 1024, 4, 64, 17, True, "MQA T=1024 + 17 extra keys: ragged last key block"),
+    (2, 576, 2, 128, 0, False, "T=576 d=128: three key blocks, the last one partial"),
 ]
 
 
