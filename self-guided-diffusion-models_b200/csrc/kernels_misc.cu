@@ -523,23 +523,30 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = C >> 7;  // float4 per lane
+  // (fully unrolled with a predicate per slot: a runtime trip count put v[] into local memory — 128 B of stack)
   float4 v[8];
   float s = 0.f;
   const float4* xr = reinterpret_cast<const float4*>(x + row * C);
-  for (int j = 0; j < nv; ++j) {
-    v[j] = __ldg(xr + j * 32 + lane);
-    s += v[j].x + v[j].y + v[j].z + v[j].w;
-  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) v[j] = __ldg(xr + j * 32 + lane);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) s += v[j].x + v[j].y + v[j].z + v[j].w;
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
   float q = 0.f;
-  for (int j = 0; j < nv; ++j) {
-    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-    q += a * a + b * b + c * c + d * d;
-  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / C + 1e-5f);
-  for (int j = 0; j < nv; ++j) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j >= nv) break;
     const int c = (j * 32 + lane) * 4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -569,7 +576,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // Block = 8 warps = 32 consecutive rows (4 per warp); a lane's float4 j covers channels (j * 32 + lane) * 4 .. + 3,
 // i.e. one granule of 4 or two of 2; fixed summation order (rows of a warp, then the 8 warps in order).
 template <int kGran>
-__global__ void __launch_bounds__(256) layernorm_res_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 2) layernorm_res_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, const float* __restrict__ res,
                                                                   float* __restrict__ out, float2* __restrict__ stats, long rows,
                                                                   int C) {
@@ -598,6 +605,14 @@ __global__ void __launch_bounds__(256) layernorm_res_stats_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j < nv) v[j] = vn[j];
+    // the residual row does not depend on the statistics: its loads go out before the two warp reductions
+    float4 rv[8];
+    {
+      const float4* rr4 = reinterpret_cast<const float4*>(res + row * C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) rv[j] = __ldg(rr4 + j * 32 + lane);
+    }
     if (rr + 1 < 4) {
       const float4* xr = reinterpret_cast<const float4*>(x + (row + 1) * C);
 #pragma unroll
@@ -624,7 +639,7 @@ __global__ void __launch_bounds__(256) layernorm_res_stats_kernel(const float* _
         const int c = (j * 32 + lane) * 4;
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-        const float4 r = __ldg(reinterpret_cast<const float4*>(res + row * C + c));
+        const float4 r = rv[j];
         const float4 y = make_float4((v[j].x - mean) * rstd * g.x + b.x + r.x, (v[j].y - mean) * rstd * g.y + b.y + r.y,
                                      (v[j].z - mean) * rstd * g.z + b.z + r.z, (v[j].w - mean) * rstd * g.w + b.w + r.w);
         *reinterpret_cast<float4*>(out + row * C + c) = y;
