@@ -197,6 +197,9 @@ int pick_block_n(int cout) {
   static const bool bn192 = [] { const char* ev = getenv("SGDM_BN192"); return ev == nullptr || atoi(ev) != 0; }();
   if (cout % 256 == 0) return 256;
   if (bn192 && cout % 192 == 0) return 192;
+  // 640 (the q | kv GEMM of Attention_LR), 896, ...: 256-column tiles with a partial last one (zero weight rows, clipped
+  // stores) instead of 128-column tiles, whose MMAs run at half rate
+  if (cout >= 512 && cout % 128 == 0) return 256;
   for (int bn : {128, 64, 32})
     if (cout % bn == 0) return bn;
   return 0;

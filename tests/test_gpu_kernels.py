@@ -226,9 +226,14 @@ BN192_CASES = [
     (5, 16, 16, 384, 1152, 1, False, "op", "1x1 qkv 384 -> 1152: six tiles, A-stationary"),
     (4, 8, 8, 768, 384, 3, False, "f32", "3x3 768 -> 384 at 8x8 (tile spans two images)"),
 ]
+PARTIAL_TILE_CASES = [
+    (5, 16, 16, 512, 640, 1, False, "op", "1x1 q|kv 512 -> 640 as 256-column tiles: partial last tile"),
+    (3, 16, 16, 256, 896, 1, True, "f32", "1x1 256 -> 896, fp32 + residual, partial last tile"),
+    (2, 16, 16, 128, 640, 3, False, "op", "3x3 128 -> 640 (halo), partial last tile"),
+]
 
 
-@pytest.mark.parametrize("case", BN192_CASES, ids=[c[-1] for c in BN192_CASES])
+@pytest.mark.parametrize("case", BN192_CASES + PARTIAL_TILE_CASES, ids=[c[-1] for c in BN192_CASES + PARTIAL_TILE_CASES])
 def test_conv_192_column_tiles(L, case):
     """block_n = 192 (the engine's choice for 192 / 384 / 576 output channels): one CTA, CTA pair, policy; with the
     epilogue's GroupNorm statistics."""
@@ -238,7 +243,8 @@ def test_conv_192_column_tiles(L, case):
     w = torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * ks * ks)
     bias = torch.randn(Cout, device="cuda", generator=g)
     res = torch.randn(B, H, W, Cout, device="cuda", generator=g) if with_res else None
-    wp, _ = pack_weight(L, w, None, 192)
+    bn_t = 256 if case in PARTIAL_TILE_CASES else 192
+    wp, _ = pack_weight(L, w, None, bn_t)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(L._op).float(), bias, padding=ks // 2)
     if with_res:
         ref = ref + res.permute(0, 3, 1, 2)
@@ -251,7 +257,7 @@ def test_conv_192_column_tiles(L, case):
         L.sgdm_debug_set_conv_pair(pair)
         try:
             ck(L, L.sgdm_k_conv_stats(S(), P(x), B, H, W, Cin, None, 0, P(wp), ks, 1, H, W, Cout, P(bias), P(res),
-                                      1 if with_res else 0, P(o32), P(oop), None, 192, 0, P(stats), 4, None, None, 0))
+                                      1 if with_res else 0, P(o32), P(oop), None, bn_t, 0, P(stats), 4, None, None, 0))
         finally:
             L.sgdm_debug_set_conv_pair(-1)
         torch.cuda.synchronize()

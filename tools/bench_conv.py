@@ -105,6 +105,7 @@ SHAPES = {
     "conv 256->256 3x3 @32 B512": (512, 32, 256, 256, 3),
     "conv 512->512 3x3 @16 B512": (512, 16, 512, 512, 3),
     "first 64->128 3x3 @64 B512": (512, 64, 64, 128, 3),
+    "first conv as the K=64 im2col GEMM @64 B512": (512, 64, 64, 128, 1),
 }
 if os.environ.get("RESIDUAL"):
     # residual-epilogue experiments: fp32 out + residual + statistics
