@@ -521,7 +521,8 @@ int setup_device(sgdm_engine* e) {
   // fused emb projection
   const int S = e->S;                       // K expansion (3 in split-precision mode)
   auto part = [&](int cin) { return e->x3 ? cin : 0; };  // pack_conv_weight_launch's cin_part
-  if (dalloc(e, &e->w_emb, static_cast<size_t>(e->NE) * e->E * S) || dalloc(e, &e->b_emb, e->NE)) return 1;
+  // (rows up to the next multiple of the GEMM's tile width: the weight tensor map covers whole n-tiles)
+  if (dalloc(e, &e->w_emb, static_cast<size_t>(conv_npad(e->NE, pick_block_n(e->NE))) * e->E * S) || dalloc(e, &e->b_emb, e->NE)) return 1;
 
   // 3 + 3 (+1) input channels: the whole 3x3 neighbourhood fits the 64-channel input row
   e->first_im2col = !e->x3 && 9 * (2 * c.in_channels + c.layout_dim) <= 64;
