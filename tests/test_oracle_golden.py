@@ -165,3 +165,29 @@ def test_oracle_param_inventory_matches_reference(name):
     ref = {n: tuple(s) for n, s in meta["named_shapes"]}
     got = dict(ounet.param_shapes(meta["cfg"]))
     assert got == ref, (sorted(set(ref) ^ set(got))[:8], [k for k in ref if k in got and got[k] != ref[k]][:8])
+
+
+def test_subpixel_upconv_identity():
+    """The algebra behind ConvDesc::up2 (csrc/conv.cuh), in float64 on the CPU: conv3x3(nearest_2x(x)) equals, for output
+    parity (dy, dx), a 2x2 conv of x whose tap (a, b) is the sum of the 3x3 taps r in V(dy, a), s in V(dx, b) with
+    V(0,0) = {0}, V(0,1) = {1,2}, V(1,0) = {0,1}, V(1,1) = {2} — the nearest-2x upsample + conv of every up ResBlock
+    (openaimodel.py:214-216,304-307) and of unetca_fast's Upsample (openaimodel_ca.py:101-133) at 4/9 of the MACs."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(4, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    V = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    H, W = x.shape[2:]
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.empty_like(ref)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            k = torch.zeros(4, 5, 2, 2, dtype=torch.float64)
+            for a in (0, 1):
+                for c in (0, 1):
+                    k[:, :, a, c] = sum(w[:, :, r, s] for r in V[(dy, a)] for s in V[(dx, c)])
+            out[:, :, dy::2, dx::2] = F.conv2d(xp[:, :, dy:dy + H + 1, dx:dx + W + 1], k, b)
+    assert torch.allclose(out, ref, rtol=0, atol=1e-12)

@@ -28,14 +28,14 @@ class FakeDiffusion:
         return out, {"pred_x0": out.unsqueeze(0).repeat(3, 1, 1, 1, 1)}
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, B=7):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from sgdm_b200 import parallel
 
-    B = 7  # ragged: 4 + 3
+    # B = 7: ragged, 4 + 3;  B = 1: the second rank's shard is EMPTY (fewer samples than ranks)
     cond = torch.nn.functional.one_hot(torch.arange(B) % 5, 5)
     layout = torch.arange(B).float().view(B, 1, 1, 1).expand(B, 1, 4, 4).contiguous()
     w = torch.linspace(0.5, 2.0, B).view(B, 1, 1, 1)
@@ -66,11 +66,15 @@ def test_shard_bounds():
     assert shard_bounds(1024, 3, 8) == (384, 512)  # config 5: 128 per GPU
 
 
-def test_sample_sharded_world2_gloo():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("B", [7, 1])
+def test_sample_sharded_world2_gloo(B):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (50 if B == 1 else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, B)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(2))
