@@ -1071,6 +1071,7 @@ struct Builder {
       pd.Bp = Bp; pd.Cimg = c.in_channels; pd.H = H; pd.W = W; pd.L = c.layout_dim; pd.cond_dim = e->cond_w; pd.mc = mc;
       pd.x_in = x_in; pd.t_emb = t_emb; pd.cond_masked = cond_m; pd.drop = drop;
       pd.im2col = e->first_im2col ? 1 : 0;
+      pd.Bx = Bshare;  // a shared-prefix plan's first conv reads the B shared rows only
       pd.split3 = split3; pd.xc = e->xin_c;
     }
     auto lin = [&](const float* in, long in_stride, const char* wname, float* out, long out_stride, int N, int K,

@@ -81,6 +81,7 @@ struct PrepDesc {
   const float* null_layout = nullptr;   // [H*W]
   const float* freqs = nullptr;      // [mc/2] host-computed exp(-ln(1e4) i / half) (util.py:160-163)
   int B = 0, Bp = 0;                 // Bp = B or 2B; row r reads sample r % B
+  int Bx = 0;                        // rows of x_in to produce (0 = Bp): the shared rows of a guided plan
   int Cimg = 3, H = 0, W = 0, L = 0, cond_dim = 0, mc = 0;
   op_t* x_in = nullptr;              // NHWC op_t [Bp, H, W, 64]: [x_hi(Cimg) | x_lo(Cimg) | layout(L) | 0]
   // im2col: the 64 channels of pixel (y, x) hold the 3x3 neighbourhood instead, channel tap * (2 Cimg + L) + j =

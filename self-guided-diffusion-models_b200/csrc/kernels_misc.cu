@@ -860,59 +860,56 @@ int linear_f32_launch(const float* in, long in_stride, const float* W, const flo
 // x (NCHW fp32) -> NHWC op_t with 64 channels: [x_hi | x_lo | layout | 0].  x_lo = x - x_hi
 // restores the precision lost by the 16-bit rounding of the image (its weights duplicate
 // the image-channel weights), so the first conv sees x to ~2^-21.
-__global__ void prep_x_kernel(const PrepDesc d) {
-  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+// Eight threads per pixel, each builds one 16-byte slice (8 of the 64 slots) in registers: a warp writes 512 contiguous
+// bytes per store.  grid.y = row (sample of the doubled batch): no 64-bit division per thread; the (tap, entry) decode of
+// the 64 slots is a shared-memory table built once per block.  (The first version — one thread per pixel, the 64 slots
+// in a local-memory array, 128-byte-strided stores, a runtime division per slot — took 0.33 ms per step at batch 256.)
+// Only the rows the first conv consumes are produced (Bx: the shared rows of a guided plan).
+__global__ void __launch_bounds__(256) prep_x_kernel(const PrepDesc d) {
+  __shared__ int s_tab[64];  // per slot: (dy + 1) | (dx + 1) << 2 | entry << 4, or -1 for a slot that stays zero
+  const int ce = 2 * d.Cimg + d.L;
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x;
+    int code = -1;
+    if (d.im2col) {
+      const int tap = k / ce, j = k - tap * ce;
+      if (tap < 9) code = (tap / 3) | ((tap % 3) << 2) | (j << 4);
+    } else if (k < ce) {
+      code = 1 | (1 << 2) | (k << 4);  // the pixel itself
+    }
+    s_tab[k] = code;
+  }
+  __syncthreads();
   const int HW = d.H * d.W;
-  if (idx >= static_cast<long>(d.Bp) * HW) return;
-  const int r = idx / HW, pix = idx - static_cast<long>(r) * HW;
+  const int r = blockIdx.y;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pix = static_cast<int>(gid >> 3), t8 = static_cast<int>(gid & 7);
+  if (pix >= HW) return;
   const int b = r % d.B;
   const bool drop = d.drop && d.drop[r];
-  __align__(16) op_t v[64];
+  const int y = pix / d.W, x = pix - y * d.W;
+  const float* xb = d.x + static_cast<long>(b) * d.Cimg * HW;
+  float val[8];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) v[j] = to_op(0.f);
-  if (d.im2col) {
-    const int y = pix / d.W, x = pix - y * d.W, ce = 2 * d.Cimg + d.L;
-    // static indexing of v (registers): walk the 64 slots, decode (tap, entry) of each
-    int tap = 0, j = 0;
-#pragma unroll
-    for (int k = 0; k < 64; ++k) {
-      if (tap < 9) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
-          const int pp = yy * d.W + xx;
-          if (j < 2 * d.Cimg) {
-            const int c = j < d.Cimg ? j : j - d.Cimg;
-            const float xv = d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pp];
-            const op_t hi = to_op(xv);
-            v[k] = j < d.Cimg ? hi : to_op(xv - from_op(hi));
-          } else {
-            const int l = j - 2 * d.Cimg;
-            v[k] = to_op(drop ? d.null_layout[pp] : d.layout[(static_cast<long>(b) * d.L + l) * HW + pp]);
-          }
+  for (int i = 0; i < 8; ++i) {
+    const int code = s_tab[t8 * 8 + i];
+    float v = 0.f;
+    if (code >= 0) {
+      const int yy = y + (code & 3) - 1, xx = x + ((code >> 2) & 3) - 1, j = code >> 4;
+      if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
+        const int pp = yy * d.W + xx;
+        if (j < 2 * d.Cimg) {
+          const float xv = xb[(j < d.Cimg ? j : j - d.Cimg) * HW + pp];
+          v = j < d.Cimg ? xv : xv - from_op(to_op(xv));  // x_hi (rounded below) | x_lo = x - x_hi
+        } else {
+          v = drop ? d.null_layout[pp] : d.layout[(static_cast<long>(b) * d.L + (j - 2 * d.Cimg)) * HW + pp];
         }
-        if (++j == ce) { j = 0; ++tap; }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(d.x_in + idx * 64);
-    const uint4* srcv = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = srcv[q];
-    return;
+    val[i] = v;
   }
-  for (int c = 0; c < d.Cimg; ++c) {
-    const float xv = d.x[(static_cast<long>(b) * d.Cimg + c) * HW + pix];
-    const op_t hi = to_op(xv);
-    v[c] = hi;
-    v[d.Cimg + c] = to_op(xv - from_op(hi));
-  }
-  for (int l = 0; l < d.L; ++l) {
-    const float lv = drop ? d.null_layout[pix] : d.layout[(static_cast<long>(b) * d.L + l) * HW + pix];
-    v[2 * d.Cimg + l] = to_op(lv);
-  }
-  uint4* dst = reinterpret_cast<uint4*>(d.x_in + idx * 64);
-  const uint4* srcv = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dst[j] = srcv[j];
+  *reinterpret_cast<uint4*>(d.x_in + (static_cast<long>(r) * HW + pix) * 64 + t8 * 8) =
+      make_uint4(pack_op2(val[0], val[1]), pack_op2(val[2], val[3]), pack_op2(val[4], val[5]), pack_op2(val[6], val[7]));
 }
 // Split-precision first-conv input (engine precision 1): xc channels per pixel,
 // [hi(x, layout) | hi(x, layout) | lo(x, layout) | 0] with parts of Cimg + L channels (see store8_split3).
@@ -960,7 +957,9 @@ int prep_launch(const PrepDesc& d, cudaStream_t s) {
     prep_x_split_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
   } else {
     if (2 * d.Cimg + d.L > 64 || (d.im2col && 9 * (2 * d.Cimg + d.L) > 64)) return 1;
-    prep_x_kernel<<<static_cast<unsigned>((npx + 127) / 128), 128, 0, s>>>(d);
+    const int rows = d.Bx > 0 ? d.Bx : d.Bp;
+    if (rows > 65535) return 1;  // grid.y
+    prep_x_kernel<<<dim3(static_cast<unsigned>((d.H * d.W * 8 + 255) / 256), rows), 256, 0, s>>>(d);
   }
   const long ne = static_cast<long>(d.Bp) * (d.mc / 2) + static_cast<long>(d.Bp) * d.cond_dim;
   prep_emb_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, s>>>(d);
